@@ -1,0 +1,170 @@
+// G1 group law on device: y^2 = x^3 + 4 over Fp, extended-Jacobian "XYZZ" coordinates
+// (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; infinity <=> ZZ == 0).
+//
+// Replaces what the reference gets from gnark-crypto's G1Affine/G1Jac (call sites:
+// internal/multiexp/multiexp.go:20-26, internal/domain/fft.go:39,80-83).  All degenerate cases
+// (P+P, P+(-P), infinity operands) are handled exactly: spec vectors such as constant blobs and
+// verify_cell_kzg_proof_batch "same cell multiple times" do reach them.
+//
+// Cost in Fp multiplications (mul == sqr here): mixed add 10, full add 14, double 9.
+#pragma once
+#include "field.cuh"
+
+namespace kzg {
+
+// affine point in Montgomery form; infinity is encoded as (0,0) (not on the curve since b=4)
+struct G1Aff {
+    Fp x, y;
+    __device__ __forceinline__ bool is_inf() const { return x.is_zero() && y.is_zero(); }
+};
+
+struct G1 {
+    Fp X, Y, ZZ, ZZZ;
+
+    __device__ __forceinline__ bool is_inf() const { return ZZ.is_zero(); }
+    static __device__ __forceinline__ G1 infinity() {
+        G1 r; r.X = Fp::zero(); r.Y = Fp::zero(); r.ZZ = Fp::zero(); r.ZZZ = Fp::zero();
+        return r;
+    }
+    static __device__ __forceinline__ G1 from_affine(const G1Aff &a) {
+        G1 r;
+        if (a.is_inf()) return infinity();
+        r.X = a.x; r.Y = a.y; r.ZZ = Fp::one(); r.ZZZ = Fp::one();
+        return r;
+    }
+    __device__ __forceinline__ void neg_inplace() { Y = Fp::neg(Y); }
+};
+
+// 2*(x,y) from affine (mdbl-2008-s-1).  Cold path: kept out of line.
+__device__ __noinline__ void g1_dbl_affine(G1 *r, const G1Aff *a) {
+    Fp U = Fp::dbl(a->y);
+    Fp V = Fp::sqr(U);
+    Fp W = Fp::mul(U, V);
+    Fp S = Fp::mul(a->x, V);
+    Fp M = Fp::sqr(a->x);
+    M = Fp::add(Fp::dbl(M), M);
+    Fp X3 = Fp::sub(Fp::sqr(M), Fp::dbl(S));
+    r->Y = Fp::sub(Fp::mul(M, Fp::sub(S, X3)), Fp::mul(W, a->y));
+    r->X = X3;
+    r->ZZ = V;
+    r->ZZZ = W;
+}
+
+// r = 2*p (dbl-2008-s-1, a = 0)
+__device__ __forceinline__ G1 g1_dbl(const G1 &p) {
+    if (p.is_inf()) return p;
+    G1 r;
+    Fp U = Fp::dbl(p.Y);
+    Fp V = Fp::sqr(U);
+    Fp W = Fp::mul(U, V);
+    Fp S = Fp::mul(p.X, V);
+    Fp M = Fp::sqr(p.X);
+    M = Fp::add(Fp::dbl(M), M);
+    r.X = Fp::sub(Fp::sqr(M), Fp::dbl(S));
+    r.Y = Fp::sub(Fp::mul(M, Fp::sub(S, r.X)), Fp::mul(W, p.Y));
+    r.ZZ = Fp::mul(V, p.ZZ);
+    r.ZZZ = Fp::mul(W, p.ZZZ);
+    return r;
+}
+__device__ __noinline__ void g1_dbl_cold(G1 *r, const G1 *p) { *r = g1_dbl(*p); }
+
+// acc += (x2,y2)   (madd-2008-s); b must not be the infinity encoding unless checked by caller
+__device__ __forceinline__ void g1_add_affine(G1 &acc, const G1Aff &b) {
+    if (b.is_inf()) return;
+    if (acc.is_inf()) { acc.X = b.x; acc.Y = b.y; acc.ZZ = Fp::one(); acc.ZZZ = Fp::one(); return; }
+    Fp U2 = Fp::mul(b.x, acc.ZZ);
+    Fp S2 = Fp::mul(b.y, acc.ZZZ);
+    Fp Pd = Fp::sub(U2, acc.X);
+    Fp R = Fp::sub(S2, acc.Y);
+    if (Pd.is_zero()) {
+        if (R.is_zero()) g1_dbl_affine(&acc, &b);
+        else acc = G1::infinity();
+        return;
+    }
+    Fp PP = Fp::sqr(Pd);
+    Fp PPP = Fp::mul(Pd, PP);
+    Fp Q = Fp::mul(acc.X, PP);
+    Fp X3 = Fp::sub(Fp::sub(Fp::sqr(R), PPP), Fp::dbl(Q));
+    acc.Y = Fp::sub(Fp::mul(R, Fp::sub(Q, X3)), Fp::mul(acc.Y, PPP));
+    acc.X = X3;
+    acc.ZZ = Fp::mul(acc.ZZ, PP);
+    acc.ZZZ = Fp::mul(acc.ZZZ, PPP);
+}
+
+// a += b   (add-2008-s)
+__device__ __forceinline__ void g1_add(G1 &a, const G1 &b) {
+    if (b.is_inf()) return;
+    if (a.is_inf()) { a = b; return; }
+    Fp U1 = Fp::mul(a.X, b.ZZ);
+    Fp U2 = Fp::mul(b.X, a.ZZ);
+    Fp S1 = Fp::mul(a.Y, b.ZZZ);
+    Fp S2 = Fp::mul(b.Y, a.ZZZ);
+    Fp Pd = Fp::sub(U2, U1);
+    Fp R = Fp::sub(S2, S1);
+    if (Pd.is_zero()) {
+        if (R.is_zero()) { G1 t; g1_dbl_cold(&t, &a); a = t; }
+        else a = G1::infinity();
+        return;
+    }
+    Fp PP = Fp::sqr(Pd);
+    Fp PPP = Fp::mul(Pd, PP);
+    Fp Q = Fp::mul(U1, PP);
+    Fp X3 = Fp::sub(Fp::sub(Fp::sqr(R), PPP), Fp::dbl(Q));
+    a.Y = Fp::sub(Fp::mul(R, Fp::sub(Q, X3)), Fp::mul(S1, PPP));
+    a.X = X3;
+    a.ZZ = Fp::mul(Fp::mul(a.ZZ, b.ZZ), PP);
+    a.ZZZ = Fp::mul(Fp::mul(a.ZZZ, b.ZZZ), PPP);
+}
+// out-of-line full add for cold / code-size-sensitive call sites
+__device__ __noinline__ void g1_add_ool(G1 *a, const G1 *b) { g1_add(*a, *b); }
+
+// a^(e) for a public, fixed exponent given as plain little-endian 32-bit limbs
+__device__ __noinline__ Fp fp_pow(const Fp &a, const uint32_t *e, int nlimbs) {
+    Fp r = Fp::one();
+    bool started = false;
+    for (int i = nlimbs * 32 - 1; i >= 0; --i) {
+        if (started) r = Fp::sqr(r);
+        if ((e[i >> 5] >> (i & 31)) & 1) {
+            if (started) r = Fp::mul(r, a); else { r = a; started = true; }
+        }
+    }
+    return r;
+}
+__device__ __constant__ const uint32_t FP_PM2[12] = {0xffffaaa9u, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                                                     0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};   // p-2
+// (p+1)/4, for square roots (p = 3 mod 4)
+__device__ __constant__ const uint32_t FP_P1D4[12] = {0xffffeaabu, 0xee7fbfffu, 0xac54ffffu, 0x07aaffffu, 0x3dac3d89u, 0xd9cc34a8u,
+                                                      0x3ce144afu, 0xd91dd2e1u, 0x90d2eb35u, 0x92c6e9edu, 0x8e5ff9a6u, 0x0680447au};
+__device__ __forceinline__ Fp fp_inv(const Fp &a) { return fp_pow(a, FP_PM2, 12); }
+
+// XYZZ -> affine (one inversion).  x = X * ZZ^2 / ZZZ^2,  y = Y / ZZZ.
+__device__ __forceinline__ G1Aff g1_to_affine(const G1 &p) {
+    G1Aff r;
+    if (p.is_inf()) { r.x = Fp::zero(); r.y = Fp::zero(); return r; }
+    Fp i3 = fp_inv(p.ZZZ);
+    Fp i2 = Fp::mul(Fp::sqr(i3), Fp::sqr(p.ZZ));   // 1/ZZ
+    r.x = Fp::mul(p.X, i2);
+    r.y = Fp::mul(p.Y, i3);
+    return r;
+}
+
+// ZCash/gnark compressed encoding of an affine point (serialization.go:98-100 -> G1Affine.Bytes)
+__device__ __forceinline__ void g1_compress(uint8_t *out48, const G1Aff &a) {
+    uint32_t w[12];
+    if (a.is_inf()) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) w[i] = 0;
+        w[11] = 0xc0000000u;
+    } else {
+        Fp x = Fp::from_mont(a.x), y = Fp::from_mont(a.y);
+        bool largest = !Fp::geq_limbs(FP_HALF, y.v);   // y > (p-1)/2
+#pragma unroll
+        for (int i = 0; i < 12; ++i) w[i] = x.v[i];
+        w[11] |= 0x80000000u | (largest ? 0x20000000u : 0u);
+    }
+    uint32_t *o = reinterpret_cast<uint32_t *>(out48);   // 48-byte records are 4-byte aligned
+#pragma unroll
+    for (int i = 0; i < 12; ++i) o[i] = __byte_perm(w[11 - i], 0, 0x0123);   // big-endian
+}
+
+}  // namespace kzg

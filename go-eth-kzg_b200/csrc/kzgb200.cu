@@ -1,0 +1,373 @@
+// libkzgb200.so -- host side of the C ABI (include/kzgb200.h) and kernel launch plumbing.
+//
+// One context = one GPU.  All per-call scratch lives in a grow-only device arena owned by the
+// context; inputs are processed in chunks so the arena stays bounded regardless of batch size.
+#include "../../include/kzgb200.h"
+#include "../../include/kzgb200_debug.h"
+#include "msm.cuh"
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace kzg;
+
+static thread_local std::string g_last_error;
+static int set_err(int code, const char *what, cudaError_t e = cudaSuccess) {
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    g_last_error = buf;
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return set_err(KZGB200_ERR_CUDA, #call, e_); } while (0)
+
+static const int N_BLOB = 4096;
+
+// ===========================================================================================
+// kernels that belong to the API layer
+// ===========================================================================================
+namespace kzg {
+
+// trusted-setup ingestion: decompress n points; dst index optionally bit-reversed (api.go:131)
+__global__ void k_setup_decompress(const uint8_t *__restrict__ in, G1Aff *__restrict__ out, int n, int log_n_brp, int32_t *__restrict__ bad) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Aff a;
+    int32_t st = g1_decompress(a, in + (size_t)i * 48);
+    if (st != ST_OK) atomicMax(bad, st);
+    int dst = log_n_brp ? (int)(__brev((unsigned)i) >> (32 - log_n_brp)) : i;
+    out[dst] = a;
+}
+
+// blob bytes -> plain little-endian scalar limbs + canonical check (serialization.go:134-146)
+// one thread per scalar; status[blob] = NON_CANONICAL if any scalar >= r
+__global__ void k_blob_to_scalars(const uint8_t *__restrict__ blobs, uint32_t *__restrict__ scalars, int32_t *__restrict__ status, size_t n_scalars, int per_item) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_scalars) return;
+    uint32_t l[8];
+    load_be32(l, blobs + i * 32);
+    if (!fr_is_canonical(l)) atomicMax(&status[i / per_item], (int32_t)ST_NON_CANONICAL_SCALAR);
+    uint4 *o = reinterpret_cast<uint4 *>(scalars + i * 8);
+    o[0] = make_uint4(l[0], l[1], l[2], l[3]);
+    o[1] = make_uint4(l[4], l[5], l[6], l[7]);
+}
+
+// XYZZ sums -> 48-byte compressed points; items with a non-OK status get zero bytes
+__global__ void k_finalize_g1(const G1 *__restrict__ in, uint8_t *__restrict__ out48, const int32_t *__restrict__ status, size_t n, int per_status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t *o = out48 + i * 48;
+    if (status && status[i / per_status] != ST_OK) {
+        uint32_t *w = reinterpret_cast<uint32_t *>(o);
+        for (int k = 0; k < 12; ++k) w[k] = 0;
+        return;
+    }
+    g1_compress(o, g1_to_affine(in[i]));
+}
+
+// ---- debug / unit-test kernels (include/kzgb200_debug.h) ----------------------------------
+__global__ void k_dbg_fp_mul(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp x, y;
+    for (int k = 0; k < 12; ++k) { x.v[k] = a[i * 12 + k]; y.v[k] = b[i * 12 + k]; }
+    x = Fp::to_mont(x); y = Fp::to_mont(y);
+    Fp r = op == 0 ? Fp::mul(x, y) : op == 1 ? Fp::add(x, y) : op == 2 ? Fp::sub(x, y) : fp_inv(x);
+    r = Fp::from_mont(r);
+    for (int k = 0; k < 12; ++k) out[i * 12 + k] = r.v[k];
+}
+__global__ void k_dbg_fr_mul(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr x, y;
+    for (int k = 0; k < 8; ++k) { x.v[k] = a[i * 8 + k]; y.v[k] = b[i * 8 + k]; }
+    x = Fr::to_mont(x); y = Fr::to_mont(y);
+    Fr r = op == 0 ? Fr::mul(x, y) : op == 1 ? Fr::add(x, y) : Fr::sub(x, y);
+    r = Fr::from_mont(r);
+    for (int k = 0; k < 8; ++k) out[i * 8 + k] = r.v[k];
+}
+// out = a (op) b on compressed points: op 0 add (XYZZ+XYZZ), 1 mixed add, 2 double
+__global__ void k_dbg_g1_op(const uint8_t *a48, const uint8_t *b48, uint8_t *out48, int n, int op) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Aff a, b;
+    g1_decompress(a, a48 + i * 48);
+    g1_decompress(b, b48 + i * 48);
+    G1 A = G1::from_affine(a);
+    if (op == 0) { G1 B = G1::from_affine(b); G1 B2 = g1_dbl(B); g1_add(B2, B); /* 3b, non-trivial ZZ */
+                   G1 nb = B; nb.neg_inplace(); g1_add(B2, nb); g1_add(B2, nb); g1_add(A, B2); }
+    else if (op == 1) g1_add_affine(A, b);
+    else A = g1_dbl(A);
+    g1_compress(out48 + i * 48, g1_to_affine(A));
+}
+// dependency-free IMAD throughput probe: each thread runs `iters` x 8 independent mad chains
+__global__ void k_imad_peak(uint32_t *out, int iters, uint32_t seed) {
+    uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, a4 = a0 * 11, a5 = a0 * 13, a6 = a0 * 17, a7 = a0 * 19;
+    uint32_t m = blockIdx.x * 2654435761u + 12345u;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = a0 * m + a1; a1 = a1 * m + a2; a2 = a2 * m + a3; a3 = a3 * m + a0;
+            a4 = __umulhi(a4, m) + a5; a5 = __umulhi(a5, m) + a6; a6 = __umulhi(a6, m) + a7; a7 = __umulhi(a7, m) + a4;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
+}  // namespace kzg
+
+// ===========================================================================================
+// context
+// ===========================================================================================
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return set_err(KZGB200_ERR_CUDA, "cudaMalloc(scratch)", e);
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct kzgb200_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex mu;
+    // setup
+    G1Aff *g1_monomial = nullptr;      // natural order
+    G1Aff *g1_lagrange_brp = nullptr;  // bit-reversed order (api.go:131)
+    std::vector<uint8_t> g2_bytes;
+    MsmTable commit_tab{};
+    // scratch
+    DevBuf in_bytes, scalars, status, sums, out_bytes;
+    double init_ms = 0, last_device_ms = 0;
+    uint64_t launches = 0;
+};
+
+static bool is_device_ptr(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static int build_table(kzgb200_ctx *c, const G1Aff *pts, int npts, int window, MsmTable &tab) {
+    tab.npts = npts; tab.c = window; tab.W = (256 + window - 1) / window; tab.H = 1 << (window - 1);
+    size_t n_bases = (size_t)npts * tab.W;
+    G1 *bases = nullptr; G1Aff *bases_aff = nullptr;
+    CU(cudaMalloc(&bases, n_bases * sizeof(G1)));
+    CU(cudaMalloc(&bases_aff, n_bases * sizeof(G1Aff)));
+    CU(cudaMalloc(&tab.entries, tab.bytes()));
+    k_table_bases<<<(npts + 63) / 64, 64, 0, c->stream>>>(pts, npts, tab.c, tab.W, bases);
+    k_to_affine<<<(unsigned)((n_bases + 127) / 128), 128, 0, c->stream>>>(bases, bases_aff, n_bases);
+    size_t chunks = (tab.H + KZG_TABLE_CHUNK - 1) / KZG_TABLE_CHUNK;
+    size_t threads = n_bases * chunks;
+    k_table_fill<<<(unsigned)((threads + 63) / 64), 64, 0, c->stream>>>(bases_aff, n_bases, tab.H, tab.entries);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(bases); cudaFree(bases_aff);
+    return 0;
+}
+
+extern "C" {
+
+const char *kzgb200_last_error(void) { return g_last_error.c_str(); }
+
+void *kzgb200_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void kzgb200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+void kzgb200_ctx_free(kzgb200_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->g1_monomial); cudaFree(c->g1_lagrange_brp); cudaFree(c->commit_tab.entries);
+    c->in_bytes.release(); c->scalars.release(); c->status.release(); c->sums.release(); c->out_bytes.release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, const uint8_t *g2, size_t n_g2, const kzgb200_opts *opts) {
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    c->device = opts ? opts->device : 0;
+    if (c->device < 0 || c->device >= ndev) return set_err(KZGB200_ERR_CUDA, "no such CUDA device");
+    CU(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c->device));
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    c->g2_bytes.assign(g2, g2 + n_g2 * 96);
+
+    int cw = opts && opts->commit_window ? opts->commit_window : 0;
+    if (!cw) { const char *e = getenv("KZGB200_COMMIT_WINDOW"); cw = e ? atoi(e) : 13; }
+    if (cw < 4 || cw > 15) return set_err(KZGB200_ERR_ARGS, "commit_window must be in 4..15");
+
+    uint8_t *d_in = nullptr; int32_t *d_bad = nullptr;
+    CU(cudaMalloc(&d_in, 2 * N_BLOB * 48));
+    CU(cudaMalloc(&d_bad, sizeof(int32_t)));
+    CU(cudaMalloc(&c->g1_monomial, N_BLOB * sizeof(G1Aff)));
+    CU(cudaMalloc(&c->g1_lagrange_brp, N_BLOB * sizeof(G1Aff)));
+    CU(cudaMemsetAsync(d_bad, 0, sizeof(int32_t), c->stream));
+    CU(cudaMemcpyAsync(d_in, g1m, N_BLOB * 48, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_in + N_BLOB * 48, g1l, N_BLOB * 48, cudaMemcpyHostToDevice, c->stream));
+    k_setup_decompress<<<N_BLOB / 64, 64, 0, c->stream>>>(d_in, c->g1_monomial, N_BLOB, 0, d_bad);
+    k_setup_decompress<<<N_BLOB / 64, 64, 0, c->stream>>>(d_in + N_BLOB * 48, c->g1_lagrange_brp, N_BLOB, 12, d_bad);
+    c->launches += 2;
+    int32_t bad = 0;
+    CU(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_in); cudaFree(d_bad);
+    if (bad) return set_err(KZGB200_ERR_SETUP, "trusted setup: G1 point failed to decode");
+
+    int rc = build_table(c, c->g1_lagrange_brp, N_BLOB, cw, c->commit_tab);
+    if (rc) return rc;
+    return 0;
+}
+
+int kzgb200_ctx_new(const uint8_t *g1_monomial, const uint8_t *g1_lagrange, const uint8_t *g2_monomial, size_t n_g2,
+                    const kzgb200_opts *opts, kzgb200_ctx **out) {
+    if (!g1_monomial || !g1_lagrange || !g2_monomial || !out) return set_err(KZGB200_ERR_ARGS, "null argument");
+    *out = nullptr;
+    if (n_g2 < 65) return set_err(KZGB200_ERR_SETUP, "need at least 65 G2 points (api.go:93,115; kzg_multi/kzg_verify.go:92)");
+    auto t0 = std::chrono::steady_clock::now();
+    kzgb200_ctx *c = new kzgb200_ctx();
+    int rc = ctx_init(c, g1_monomial, g1_lagrange, g2_monomial, n_g2, opts);
+    if (rc) { kzgb200_ctx_free(c); return rc; }
+    c->init_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    *out = c;
+    return KZGB200_OK;
+}
+
+int kzgb200_get_info(kzgb200_ctx *c, kzgb200_info *o) {
+    if (!c || !o) return set_err(KZGB200_ERR_ARGS, "null argument");
+    memset(o, 0, sizeof *o);
+    o->device = c->device; o->sm_count = c->sm_count;
+    o->commit_window = c->commit_tab.c; o->commit_windows_per_scalar = c->commit_tab.W;
+    o->commit_table_bytes = c->commit_tab.bytes();
+    o->init_ms = c->init_ms; o->kernel_launches = c->launches;
+    return KZGB200_OK;
+}
+double kzgb200_last_device_ms(kzgb200_ctx *c) { return c ? c->last_device_ms : 0.0; }
+
+// -------------------------------------------------------------------------------------------
+// BlobToKZGCommitment (prove.go:13-34): DeserializeBlob -> MSM against the bit-reversed Lagrange
+// SRS -> compress.  Processed in chunks of CHUNK blobs.
+// -------------------------------------------------------------------------------------------
+static const size_t COMMIT_CHUNK = 1024;
+
+int kzgb200_blob_to_kzg_commitment(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint8_t *out48, int32_t *status) {
+    if (!c || (n && (!blobs || !out48 || !status))) return set_err(KZGB200_ERR_ARGS, "null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    c->last_device_ms = 0;
+    const bool in_dev = n && is_device_ptr(blobs), out_dev = n && is_device_ptr(out48), st_dev = n && is_device_ptr(status);
+    const size_t chunk = std::min(n, COMMIT_CHUNK);
+    if (n == 0) return KZGB200_OK;
+    int rc;
+    if (!in_dev && (rc = c->in_bytes.ensure(chunk * KZGB200_BYTES_PER_BLOB))) return rc;
+    if ((rc = c->scalars.ensure(chunk * N_BLOB * 32))) return rc;
+    if ((rc = c->status.ensure(chunk * sizeof(int32_t)))) return rc;
+    if ((rc = c->sums.ensure(chunk * sizeof(G1)))) return rc;
+    if (!out_dev && (rc = c->out_bytes.ensure(chunk * 48))) return rc;
+    const int TPB = 128;
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t m = std::min(chunk, n - off);
+        const uint8_t *d_blobs = blobs + off * KZGB200_BYTES_PER_BLOB;
+        if (!in_dev) {
+            CU(cudaMemcpyAsync(c->in_bytes.p, d_blobs, m * KZGB200_BYTES_PER_BLOB, cudaMemcpyHostToDevice, c->stream));
+            d_blobs = (const uint8_t *)c->in_bytes.p;
+        }
+        int32_t *d_status = st_dev ? status + off : (int32_t *)c->status.p;
+        uint8_t *d_out = out_dev ? out48 + off * 48 : (uint8_t *)c->out_bytes.p;
+        CU(cudaEventRecord(c->ev0, c->stream));
+        CU(cudaMemsetAsync(d_status, 0, m * sizeof(int32_t), c->stream));
+        size_t ns = m * N_BLOB;
+        k_blob_to_scalars<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(d_blobs, (uint32_t *)c->scalars.p, d_status, ns, N_BLOB);
+        k_msm_fixed<<<dim3(1, (unsigned)m), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->commit_tab, N_BLOB, 1,
+                                                                                  d_status, (G1 *)c->sums.p);
+        k_finalize_g1<<<(unsigned)((m + 63) / 64), 64, 0, c->stream>>>((const G1 *)c->sums.p, d_out, d_status, m, 1);
+        c->launches += 3;
+        CU(cudaEventRecord(c->ev1, c->stream));
+        CU(cudaGetLastError());
+        if (!out_dev) CU(cudaMemcpyAsync(out48 + off * 48, d_out, m * 48, cudaMemcpyDeviceToHost, c->stream));
+        if (!st_dev) CU(cudaMemcpyAsync(status + off, d_status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->last_device_ms += ms;
+    }
+    return KZGB200_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// debug entry points (include/kzgb200_debug.h)
+// -------------------------------------------------------------------------------------------
+static int dbg_binop(int which, const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op, int limbs) {
+    uint32_t *da, *db, *dout;
+    size_t bytes = (size_t)n * limbs * 4;
+    CU(cudaMalloc(&da, bytes)); CU(cudaMalloc(&db, bytes)); CU(cudaMalloc(&dout, bytes));
+    CU(cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice));
+    if (which == 0) k_dbg_fp_mul<<<(n + 63) / 64, 64>>>(da, db, dout, n, op);
+    else k_dbg_fr_mul<<<(n + 63) / 64, 64>>>(da, db, dout, n, op);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    return 0;
+}
+int kzgb200_dbg_fp_op(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op) { return dbg_binop(0, a, b, out, n, op, 12); }
+int kzgb200_dbg_fr_op(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op) { return dbg_binop(1, a, b, out, n, op, 8); }
+int kzgb200_dbg_g1_op(const uint8_t *a48, const uint8_t *b48, uint8_t *out48, int n, int op) {
+    uint8_t *da, *db, *dout;
+    size_t bytes = (size_t)n * 48;
+    CU(cudaMalloc(&da, bytes)); CU(cudaMalloc(&db, bytes)); CU(cudaMalloc(&dout, bytes));
+    CU(cudaMemcpy(da, a48, bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(db, b48, bytes, cudaMemcpyHostToDevice));
+    k_dbg_g1_op<<<(n + 31) / 32, 32>>>(da, db, dout, n, op);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out48, dout, bytes, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    return 0;
+}
+// measured device-wide 32-bit IMAD rate (results/s); the roofline denominator of SURVEY 8(d)
+int kzgb200_bench_imad(int device, double *imad_per_s, double *ms_out) {
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
+    int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    uint32_t *d; CU(cudaMalloc(&d, (size_t)blocks * threads * 4));
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    double best = 1e30;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0));
+        k_imad_peak<<<blocks, threads>>>(d, iters, 17u + rep);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms; CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    double ops = (double)blocks * threads * iters * 8.0 * 8.0;   // 8 unrolled x 8 mads
+    *imad_per_s = ops / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}
+
+}  // extern "C"

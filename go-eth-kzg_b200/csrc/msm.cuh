@@ -1,0 +1,171 @@
+// Fixed-base multi-scalar multiplication against full digit tables resident in HBM.
+//
+// Replaces internal/multiexp/multiexp.go:20-26 (-> gnark MultiExp, generic Pippenger) for the two
+// fixed bases of the hot path: the bit-reversed Lagrange SRS (internal/kzg/srs.go:56-62,
+// api.go:131) and the FK20 table (internal/kzg_multi/fk20/toeplitz.go:87,113-119).
+//
+// B200-first design: the bases never change, HBM is 180 GB, and a batch holds thousands of
+// blobs, so instead of Pippenger buckets (whose per-blob bucket state, 4096 x 192 B, fits no
+// shared memory and costs a 2*2^(c-1)-add reduction per blob) the table stores EVERY signed
+// digit multiple of every window of every base point in affine form:
+//     table[(j*W + k)*H + (d-1)] = d * 2^(c*k) * P_j      d = 1..H,  H = 2^(c-1),  W = ceil(256/c)
+// and an MSM is just n*W mixed additions of gathered table entries plus a log-depth reduction --
+// no buckets, no sorting, no atomics, no doublings.  c = 13 gives 32 GB for the 4096-point base.
+// Entries are 96-byte affine points (3 x 32 B sectors per gather); the gathers are random over
+// the table, so the kernel is IMAD-bound with ~100-300 GB/s of scattered HBM reads in flight.
+#pragma once
+#include "codec.cuh"
+
+namespace kzg {
+
+struct MsmTable {
+    G1Aff *entries;     // device
+    int npts, c, W, H;
+    size_t bytes() const { return (size_t)npts * W * H * sizeof(G1Aff); }
+};
+
+// signed-digit recoding state for one scalar (plain little-endian limbs, < 2^255)
+struct DigitStream {
+    uint32_t s[8];
+    uint32_t carry;
+    int c;
+    __device__ __forceinline__ void init(const uint32_t *limbs, int c_) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = limbs[i];
+        carry = 0; c = c_;
+    }
+    // digit of window k (must be called for k = 0,1,2,... in order); returns signed digit
+    __device__ __forceinline__ int next(int k) {
+        int bit = k * c;
+        int wi = bit >> 5, sh = bit & 31;
+        // dynamic limb index without local memory: select via unrolled compare
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { if (i == wi) lo = s[i]; if (i == wi + 1) hi = s[i]; }
+        uint32_t raw = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh) & ((1u << c) - 1u);
+        raw += carry;
+        int H = 1 << (c - 1);
+        if ((int)raw > H) { carry = 1; return (int)raw - (1 << c); }
+        carry = 0;
+        return (int)raw;
+    }
+};
+
+__device__ __forceinline__ G1Aff load_aff(const G1Aff *p) {
+    G1Aff r;
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 t[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) t[i] = __ldg(q + i);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        r.x.v[4 * i] = t[i].x; r.x.v[4 * i + 1] = t[i].y; r.x.v[4 * i + 2] = t[i].z; r.x.v[4 * i + 3] = t[i].w;
+        r.y.v[4 * i] = t[3 + i].x; r.y.v[4 * i + 1] = t[3 + i].y; r.y.v[4 * i + 2] = t[3 + i].z; r.y.v[4 * i + 3] = t[3 + i].w;
+    }
+    return r;
+}
+
+// One group of `group_pts` consecutive base points per (blockIdx.x = group, blockIdx.y = blob);
+// blockDim.x threads cooperate on a group.  Scalars: [blob][total_pts][8] plain limbs.
+// out: [blob][n_groups] XYZZ sums.
+//   commit:  group_pts = 4096, n_groups = 1
+//   FK20:    group_pts = 64,   n_groups = 128 (scalars already transposed to table order)
+extern __shared__ unsigned char msm_smem[];
+__global__ void __launch_bounds__(128) k_msm_fixed(const uint32_t *__restrict__ scalars, MsmTable tab, int group_pts,
+                                                    int n_groups, const int32_t *__restrict__ status, G1 *__restrict__ out) {
+    const int group = blockIdx.x, blob = blockIdx.y, t = threadIdx.x, T = blockDim.x;
+    if (status && status[blob] != ST_OK) return;
+    const int total = group_pts * n_groups;
+    const uint32_t *sc = scalars + ((size_t)blob * total + (size_t)group * group_pts) * 8;
+    G1 acc = G1::infinity();
+    for (int j = t; j < group_pts; j += T) {
+        DigitStream ds;
+        {
+            const uint4 *q = reinterpret_cast<const uint4 *>(sc + (size_t)j * 8);
+            uint4 a = __ldg(q), b = __ldg(q + 1);
+            uint32_t l[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            ds.init(l, tab.c);
+        }
+        const G1Aff *row = tab.entries + ((size_t)(group * group_pts + j) * tab.W) * tab.H;
+        for (int k = 0; k < tab.W; ++k) {
+            int d = ds.next(k);
+            if (d == 0) continue;
+            int mag = d < 0 ? -d : d;
+            G1Aff e = load_aff(row + (size_t)k * tab.H + (mag - 1));
+            if (d < 0) e.y = Fp::neg(e.y);
+            g1_add_affine(acc, e);
+        }
+    }
+    // block tree reduction through shared memory
+    G1 *sm = reinterpret_cast<G1 *>(msm_smem);
+    sm[t] = acc;
+    __syncthreads();
+    for (int s = T >> 1; s > 0; s >>= 1) {
+        if (t < s) g1_add_ool(&sm[t], &sm[t + s]);
+        __syncthreads();
+    }
+    if (t == 0) out[(size_t)blob * n_groups + group] = sm[0];
+}
+
+// ---- table construction (context init) ---------------------------------------------------
+// step 1: bases[(j*W + k)] = 2^(c*k) * P_j  in XYZZ
+__global__ void k_table_bases(const G1Aff *__restrict__ pts, int npts, int c, int W, G1 *__restrict__ bases) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= npts) return;
+    G1 q = G1::from_affine(pts[j]);
+    for (int k = 0; k < W; ++k) {
+        bases[(size_t)j * W + k] = q;
+        if (k + 1 < W) for (int i = 0; i < c; ++i) { G1 t2; g1_dbl_cold(&t2, &q); q = t2; }
+    }
+}
+// XYZZ -> affine, one thread per point (used only at init / for small batches)
+__global__ void k_to_affine(const G1 *__restrict__ in, G1Aff *__restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = g1_to_affine(in[i]);
+}
+// step 2: for base b = (j,k) and chunk q of CH digits: entries d = q*CH+1 .. q*CH+CH of d*Q_b,
+// batch-normalised with one inversion per chunk.
+#define KZG_TABLE_CHUNK 16
+__global__ void __launch_bounds__(64) k_table_fill(const G1Aff *__restrict__ bases_aff, size_t n_bases, int H, G1Aff *__restrict__ table) {
+    const int chunks = (H + KZG_TABLE_CHUNK - 1) / KZG_TABLE_CHUNK;
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_bases * chunks) return;
+    size_t b = gid / chunks;
+    int q = (int)(gid % chunks);
+    G1Aff Q = bases_aff[b];
+    G1Aff *dst = table + b * H + (size_t)q * KZG_TABLE_CHUNK;
+    int cnt = min(KZG_TABLE_CHUNK, H - q * KZG_TABLE_CHUNK);
+    if (Q.is_inf()) {
+        for (int i = 0; i < cnt; ++i) dst[i] = Q;
+        return;
+    }
+    // start = (q*CH) * Q by MSB-first double-and-add
+    G1 cur = G1::infinity();
+    unsigned d0 = (unsigned)q * KZG_TABLE_CHUNK;
+    for (int bit = 31 - __clz(d0 | 1); bit >= 0; --bit) {
+        G1 t2; g1_dbl_cold(&t2, &cur); cur = t2;
+        if ((d0 >> bit) & 1) g1_add_affine(cur, Q);
+    }
+    G1 pts[KZG_TABLE_CHUNK];
+    Fp pre[KZG_TABLE_CHUNK];
+    Fp run = Fp::one();
+    for (int i = 0; i < cnt; ++i) {
+        g1_add_affine(cur, Q);
+        pts[i] = cur;
+        pre[i] = run;
+        run = Fp::mul(run, cur.ZZZ);
+    }
+    Fp inv = fp_inv(run);
+    for (int i = cnt - 1; i >= 0; --i) {
+        Fp i3 = Fp::mul(inv, pre[i]);          // 1/ZZZ_i
+        inv = Fp::mul(inv, pts[i].ZZZ);
+        Fp i2 = Fp::mul(Fp::sqr(i3), Fp::sqr(pts[i].ZZ));
+        G1Aff a;
+        a.x = Fp::mul(pts[i].X, i2);
+        a.y = Fp::mul(pts[i].Y, i3);
+        dst[i] = a;
+    }
+}
+
+}  // namespace kzg

@@ -1,0 +1,188 @@
+"""ctypes binding of libkzgb200.so + a host-side mirror of the reference's `Context`.
+
+The reference's boundary is the Go method set of *goethkzg.Context (api.go:17-28, prove.go,
+verify.go, api_eip7594.go, api_eip.go).  No Go toolchain exists in this image, so this module is
+the executable stand-in for the cgo shim shown in INTEGRATION.md: same method names (snake_case),
+same argument meaning, and the same three-way outcome convention the reference's tests use
+(nil / kzg.ErrVerifyOpeningProof / any other error  ==  OK / VERIFY_FAILED / other status).
+
+There is NO CPU fallback: if libkzgb200.so is missing or no CUDA device is usable, construction
+raises.
+"""
+import ctypes, os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libkzgb200.so")
+SETUP = os.path.join(HERE, "data", "trusted_setup_4096.bin")
+
+BYTES_PER_BLOB = 131072
+BYTES_PER_CELL = 2048
+CELLS_PER_EXT_BLOB = 128
+
+OK, VERIFY_FAILED, NON_CANONICAL_SCALAR, BAD_G1_ENCODING, NOT_ON_CURVE, NOT_IN_SUBGROUP = 0, 1, 2, 3, 4, 5
+LENGTH_MISMATCH, BAD_CELL_INDEX, CELL_IDS_NOT_ASCENDING, NOT_ENOUGH_CELLS, BAD_ROW_INDEX = 6, 7, 8, 9, 10
+ERR_ARGS, ERR_SETUP, ERR_CUDA = 11, 12, 100
+
+
+class KzgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"kzgb200 error {code}: {msg}")
+        self.code = code
+
+
+class Opts(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int), ("commit_window", ctypes.c_int), ("fk20_window", ctypes.c_int),
+                ("reserved", ctypes.c_int * 5)]
+
+
+class Info(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int), ("sm_count", ctypes.c_int),
+                ("commit_window", ctypes.c_int), ("commit_windows_per_scalar", ctypes.c_int),
+                ("fk20_window", ctypes.c_int), ("fk20_windows_per_scalar", ctypes.c_int),
+                ("commit_table_bytes", ctypes.c_uint64), ("fk20_table_bytes", ctypes.c_uint64),
+                ("init_ms", ctypes.c_double), ("kernel_launches", ctypes.c_uint64)]
+
+
+_lib = None
+
+EXPORTS = [
+    "kzgb200_ctx_new", "kzgb200_ctx_free", "kzgb200_last_error", "kzgb200_host_alloc", "kzgb200_host_free",
+    "kzgb200_blob_to_kzg_commitment", "kzgb200_get_info", "kzgb200_last_device_ms",
+]
+
+
+def load_library():
+    """Loads the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            raise KzgError(ERR_CUDA, f"{SO} not built: run `python go-eth-kzg_b200/build.py`")
+        L = ctypes.CDLL(SO)
+        L.kzgb200_last_error.restype = ctypes.c_char_p
+        L.kzgb200_host_alloc.restype = ctypes.c_void_p
+        L.kzgb200_host_alloc.argtypes = [ctypes.c_size_t]
+        L.kzgb200_host_free.argtypes = [ctypes.c_void_p]
+        L.kzgb200_last_device_ms.restype = ctypes.c_double
+        L.kzgb200_last_device_ms.argtypes = [ctypes.c_void_p]
+        L.kzgb200_ctx_free.argtypes = [ctypes.c_void_p]
+        _lib = L
+    return _lib
+
+
+def load_trusted_setup(path=SETUP):
+    raw = open(path, "rb").read()
+    n = 4096 * 48
+    return raw[:n], raw[n:2 * n], raw[2 * n:]
+
+
+def _ptr(x):
+    """bytes / ctypes buffer / int address -> c_void_p"""
+    if isinstance(x, int):
+        return ctypes.c_void_p(x)
+    if isinstance(x, (bytes, bytearray)):
+        return ctypes.cast(ctypes.c_char_p(bytes(x)), ctypes.c_void_p)
+    return ctypes.cast(x, ctypes.c_void_p)
+
+
+class Context:
+    """Mirror of goethkzg.Context.  NewContext4096Secure (api.go:53) == Context()."""
+
+    def __init__(self, device=0, commit_window=0, fk20_window=0, setup_path=SETUP):
+        L = load_library()
+        self.L = L
+        m, l, g2 = load_trusted_setup(setup_path)
+        opts = Opts(device=device, commit_window=commit_window, fk20_window=fk20_window)
+        ctx = ctypes.c_void_p()
+        rc = L.kzgb200_ctx_new(m, l, g2, ctypes.c_size_t(len(g2) // 96), ctypes.byref(opts), ctypes.byref(ctx))
+        if rc != OK:
+            raise KzgError(rc, L.kzgb200_last_error().decode())
+        self.ctx = ctx
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.kzgb200_ctx_free(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise KzgError(rc, self.L.kzgb200_last_error().decode())
+
+    def info(self):
+        i = Info()
+        self._check(self.L.kzgb200_get_info(self.ctx, ctypes.byref(i)))
+        return {f[0]: getattr(i, f[0]) for f in Info._fields_}
+
+    def last_device_ms(self):
+        return self.L.kzgb200_last_device_ms(self.ctx)
+
+    # ---- raw batched calls on caller-provided addresses (host or device) -------------------
+    def raw_blob_to_kzg_commitment(self, blobs_ptr, n, out_ptr, status_ptr):
+        self._check(self.L.kzgb200_blob_to_kzg_commitment(self.ctx, _ptr(blobs_ptr), ctypes.c_size_t(n), _ptr(out_ptr), _ptr(status_ptr)))
+
+    # ---- batched, bytes in / bytes out ------------------------------------------------------
+    def blob_to_kzg_commitment_batch(self, blobs):
+        n = len(blobs)
+        if any(len(b) != BYTES_PER_BLOB for b in blobs):
+            raise KzgError(LENGTH_MISMATCH, "blob must be 131072 bytes")
+        out = ctypes.create_string_buffer(48 * max(n, 1))
+        st = (ctypes.c_int32 * max(n, 1))()
+        self.raw_blob_to_kzg_commitment(b"".join(blobs), n, out, st)
+        return [(st[i], out.raw[48 * i:48 * i + 48]) for i in range(n)]
+
+    # ---- single-item methods, named after the reference's Context methods --------------------
+    def blob_to_kzg_commitment(self, blob):
+        """Context.BlobToKZGCommitment (prove.go:13-34) -> (status, commitment48)"""
+        if len(blob) != BYTES_PER_BLOB:
+            return LENGTH_MISMATCH, None
+        st, c = self.blob_to_kzg_commitment_batch([blob])[0]
+        return st, c
+
+
+class Debug:
+    """include/kzgb200_debug.h"""
+
+    def __init__(self):
+        self.L = load_library()
+
+    @staticmethod
+    def _limbs(vals, n):
+        arr = (ctypes.c_uint32 * (len(vals) * n))()
+        for i, v in enumerate(vals):
+            for k in range(n):
+                arr[i * n + k] = (v >> (32 * k)) & 0xffffffff
+        return arr
+
+    @staticmethod
+    def _ints(arr, cnt, n):
+        return [sum(arr[i * n + k] << (32 * k) for k in range(n)) for i in range(cnt)]
+
+    def field_op(self, field, a, b, op):
+        n = 12 if field == "fp" else 8
+        fn = self.L.kzgb200_dbg_fp_op if field == "fp" else self.L.kzgb200_dbg_fr_op
+        A, B = self._limbs(a, n), self._limbs(b, n)
+        out = (ctypes.c_uint32 * (len(a) * n))()
+        rc = fn(A, B, out, len(a), op)
+        if rc:
+            raise KzgError(rc, self.L.kzgb200_last_error().decode())
+        return self._ints(out, len(a), n)
+
+    def g1_op(self, a48, b48, op):
+        n = len(a48)
+        out = ctypes.create_string_buffer(48 * n)
+        rc = self.L.kzgb200_dbg_g1_op(b"".join(a48), b"".join(b48), out, n, op)
+        if rc:
+            raise KzgError(rc, self.L.kzgb200_last_error().decode())
+        return [out.raw[48 * i:48 * i + 48] for i in range(n)]
+
+    def imad_peak(self, device=0):
+        v, ms = ctypes.c_double(), ctypes.c_double()
+        rc = self.L.kzgb200_bench_imad(device, ctypes.byref(v), ctypes.byref(ms))
+        if rc:
+            raise KzgError(rc, self.L.kzgb200_last_error().decode())
+        return v.value

@@ -1,0 +1,21 @@
+/* kzgb200 debug / unit-test hooks.  NOT part of the drop-in boundary: they exist so that
+ * tests/ can check the device field and group arithmetic against Python integers and the oracle
+ * one primitive at a time, and so that bench.py can measure the IMAD roofline denominator.
+ * Operands are plain (non-Montgomery) little-endian 32-bit limbs: 12 per Fp, 8 per Fr. */
+#ifndef KZGB200_DEBUG_H
+#define KZGB200_DEBUG_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* op: 0 mul, 1 add, 2 sub, 3 inverse of a (Fp only) */
+int kzgb200_dbg_fp_op(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op);
+int kzgb200_dbg_fr_op(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op);
+/* compressed points in/out. op: 0 a + b (XYZZ + XYZZ with non-trivial ZZ), 1 a + b (mixed), 2 2a */
+int kzgb200_dbg_g1_op(const uint8_t *a48, const uint8_t *b48, uint8_t *out48, int n, int op);
+/* dependency-free mad.lo/mad.hi microbenchmark: device-wide 32-bit IMAD results per second */
+int kzgb200_bench_imad(int device, double *imad_per_s, double *ms_out);
+#ifdef __cplusplus
+}
+#endif
+#endif
