@@ -47,12 +47,18 @@ __device__ __forceinline__ int32_t g1_decompress(G1Aff &out, const uint8_t *in48
     Fp x;
 #pragma unroll
     for (int i = 0; i < 12; ++i) x.v[i] = l[i];
-    x = Fp::to_mont(x);
+    {
+        Fp r2;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) r2.v[i] = FP_R2[i];
+        x = fp_mul_ni(x, r2);
+    }
     Fp four = Fp::one(); four = Fp::dbl(Fp::dbl(four));
-    Fp y2 = Fp::add(Fp::mul(Fp::sqr(x), x), four);
+    Fp y2 = Fp::add(fp_mul_ni(fp_mul_ni(x, x), x), four);
     Fp y = fp_pow(y2, FP_P1D4, 12);
-    if (!Fp::eq(Fp::sqr(y), y2)) return ST_NOT_ON_CURVE;
-    Fp yp = Fp::from_mont(y);
+    if (!Fp::eq(fp_mul_ni(y, y), y2)) return ST_NOT_ON_CURVE;
+    Fp o1 = Fp::zero(); o1.v[0] = 1;
+    Fp yp = fp_mul_ni(y, o1);
     bool largest = !Fp::geq_limbs(FP_HALF, yp.v);
     if (largest != (m == 5)) y = Fp::neg(y);
     out.x = x; out.y = y;

@@ -12,6 +12,21 @@
 
 namespace kzg {
 
+// Multiplication policies.  MulInline expands the ~600-instruction Montgomery product in place
+// (used only in the MSM inner loop, where the ~5% call overhead matters); MulCall goes through
+// one shared out-of-line copy (arguments and result stay in registers under the CUDA ABI), which
+// keeps every other kernel small enough for the 32 KB instruction cache and quick to compile.
+static __device__ __noinline__ Fp fp_mul_ni(Fp a, Fp b) { return Fp::mul(a, b); }
+static __device__ __noinline__ Fr fr_mul_ni(Fr a, Fr b) { return Fr::mul(a, b); }
+struct MulInline {
+    static __device__ __forceinline__ Fp mul(const Fp &a, const Fp &b) { return Fp::mul(a, b); }
+    static __device__ __forceinline__ Fp sqr(const Fp &a) { return Fp::mul(a, a); }
+};
+struct MulCall {
+    static __device__ __forceinline__ Fp mul(const Fp &a, const Fp &b) { return fp_mul_ni(a, b); }
+    static __device__ __forceinline__ Fp sqr(const Fp &a) { return fp_mul_ni(a, a); }
+};
+
 // affine point in Montgomery form; infinity is encoded as (0,0) (not on the curve since b=4)
 struct G1Aff {
     Fp x, y;
@@ -36,44 +51,45 @@ struct G1 {
 };
 
 // 2*(x,y) from affine (mdbl-2008-s-1).  Cold path: kept out of line.
-__device__ __noinline__ void g1_dbl_affine(G1 *r, const G1Aff *a) {
+static __device__ __noinline__ void g1_dbl_affine(G1 *r, const G1Aff *a) {
+    typedef MulCall M_;
     Fp U = Fp::dbl(a->y);
-    Fp V = Fp::sqr(U);
-    Fp W = Fp::mul(U, V);
-    Fp S = Fp::mul(a->x, V);
-    Fp M = Fp::sqr(a->x);
+    Fp V = M_::sqr(U);
+    Fp W = M_::mul(U, V);
+    Fp S = M_::mul(a->x, V);
+    Fp M = M_::sqr(a->x);
     M = Fp::add(Fp::dbl(M), M);
-    Fp X3 = Fp::sub(Fp::sqr(M), Fp::dbl(S));
-    r->Y = Fp::sub(Fp::mul(M, Fp::sub(S, X3)), Fp::mul(W, a->y));
+    Fp X3 = Fp::sub(M_::sqr(M), Fp::dbl(S));
+    r->Y = Fp::sub(M_::mul(M, Fp::sub(S, X3)), M_::mul(W, a->y));
     r->X = X3;
     r->ZZ = V;
     r->ZZZ = W;
 }
 
 // r = 2*p (dbl-2008-s-1, a = 0)
-__device__ __forceinline__ G1 g1_dbl(const G1 &p) {
+template <class M_ = MulCall> __device__ __forceinline__ G1 g1_dbl(const G1 &p) {
     if (p.is_inf()) return p;
     G1 r;
     Fp U = Fp::dbl(p.Y);
-    Fp V = Fp::sqr(U);
-    Fp W = Fp::mul(U, V);
-    Fp S = Fp::mul(p.X, V);
-    Fp M = Fp::sqr(p.X);
+    Fp V = M_::sqr(U);
+    Fp W = M_::mul(U, V);
+    Fp S = M_::mul(p.X, V);
+    Fp M = M_::sqr(p.X);
     M = Fp::add(Fp::dbl(M), M);
-    r.X = Fp::sub(Fp::sqr(M), Fp::dbl(S));
-    r.Y = Fp::sub(Fp::mul(M, Fp::sub(S, r.X)), Fp::mul(W, p.Y));
-    r.ZZ = Fp::mul(V, p.ZZ);
-    r.ZZZ = Fp::mul(W, p.ZZZ);
+    r.X = Fp::sub(M_::sqr(M), Fp::dbl(S));
+    r.Y = Fp::sub(M_::mul(M, Fp::sub(S, r.X)), M_::mul(W, p.Y));
+    r.ZZ = M_::mul(V, p.ZZ);
+    r.ZZZ = M_::mul(W, p.ZZZ);
     return r;
 }
-__device__ __noinline__ void g1_dbl_cold(G1 *r, const G1 *p) { *r = g1_dbl(*p); }
+static __device__ __noinline__ void g1_dbl_cold(G1 *r, const G1 *p) { *r = g1_dbl<MulCall>(*p); }
 
 // acc += (x2,y2)   (madd-2008-s); b must not be the infinity encoding unless checked by caller
-__device__ __forceinline__ void g1_add_affine(G1 &acc, const G1Aff &b) {
+template <class M_ = MulCall> __device__ __forceinline__ void g1_add_affine(G1 &acc, const G1Aff &b) {
     if (b.is_inf()) return;
     if (acc.is_inf()) { acc.X = b.x; acc.Y = b.y; acc.ZZ = Fp::one(); acc.ZZZ = Fp::one(); return; }
-    Fp U2 = Fp::mul(b.x, acc.ZZ);
-    Fp S2 = Fp::mul(b.y, acc.ZZZ);
+    Fp U2 = M_::mul(b.x, acc.ZZ);
+    Fp S2 = M_::mul(b.y, acc.ZZZ);
     Fp Pd = Fp::sub(U2, acc.X);
     Fp R = Fp::sub(S2, acc.Y);
     if (Pd.is_zero()) {
@@ -81,24 +97,24 @@ __device__ __forceinline__ void g1_add_affine(G1 &acc, const G1Aff &b) {
         else acc = G1::infinity();
         return;
     }
-    Fp PP = Fp::sqr(Pd);
-    Fp PPP = Fp::mul(Pd, PP);
-    Fp Q = Fp::mul(acc.X, PP);
-    Fp X3 = Fp::sub(Fp::sub(Fp::sqr(R), PPP), Fp::dbl(Q));
-    acc.Y = Fp::sub(Fp::mul(R, Fp::sub(Q, X3)), Fp::mul(acc.Y, PPP));
+    Fp PP = M_::sqr(Pd);
+    Fp PPP = M_::mul(Pd, PP);
+    Fp Q = M_::mul(acc.X, PP);
+    Fp X3 = Fp::sub(Fp::sub(M_::sqr(R), PPP), Fp::dbl(Q));
+    acc.Y = Fp::sub(M_::mul(R, Fp::sub(Q, X3)), M_::mul(acc.Y, PPP));
     acc.X = X3;
-    acc.ZZ = Fp::mul(acc.ZZ, PP);
-    acc.ZZZ = Fp::mul(acc.ZZZ, PPP);
+    acc.ZZ = M_::mul(acc.ZZ, PP);
+    acc.ZZZ = M_::mul(acc.ZZZ, PPP);
 }
 
 // a += b   (add-2008-s)
-__device__ __forceinline__ void g1_add(G1 &a, const G1 &b) {
+template <class M_ = MulCall> __device__ __forceinline__ void g1_add(G1 &a, const G1 &b) {
     if (b.is_inf()) return;
     if (a.is_inf()) { a = b; return; }
-    Fp U1 = Fp::mul(a.X, b.ZZ);
-    Fp U2 = Fp::mul(b.X, a.ZZ);
-    Fp S1 = Fp::mul(a.Y, b.ZZZ);
-    Fp S2 = Fp::mul(b.Y, a.ZZZ);
+    Fp U1 = M_::mul(a.X, b.ZZ);
+    Fp U2 = M_::mul(b.X, a.ZZ);
+    Fp S1 = M_::mul(a.Y, b.ZZZ);
+    Fp S2 = M_::mul(b.Y, a.ZZZ);
     Fp Pd = Fp::sub(U2, U1);
     Fp R = Fp::sub(S2, S1);
     if (Pd.is_zero()) {
@@ -106,26 +122,27 @@ __device__ __forceinline__ void g1_add(G1 &a, const G1 &b) {
         else a = G1::infinity();
         return;
     }
-    Fp PP = Fp::sqr(Pd);
-    Fp PPP = Fp::mul(Pd, PP);
-    Fp Q = Fp::mul(U1, PP);
-    Fp X3 = Fp::sub(Fp::sub(Fp::sqr(R), PPP), Fp::dbl(Q));
-    a.Y = Fp::sub(Fp::mul(R, Fp::sub(Q, X3)), Fp::mul(S1, PPP));
+    Fp PP = M_::sqr(Pd);
+    Fp PPP = M_::mul(Pd, PP);
+    Fp Q = M_::mul(U1, PP);
+    Fp X3 = Fp::sub(Fp::sub(M_::sqr(R), PPP), Fp::dbl(Q));
+    a.Y = Fp::sub(M_::mul(R, Fp::sub(Q, X3)), M_::mul(S1, PPP));
     a.X = X3;
-    a.ZZ = Fp::mul(Fp::mul(a.ZZ, b.ZZ), PP);
-    a.ZZZ = Fp::mul(Fp::mul(a.ZZZ, b.ZZZ), PPP);
+    a.ZZ = M_::mul(M_::mul(a.ZZ, b.ZZ), PP);
+    a.ZZZ = M_::mul(M_::mul(a.ZZZ, b.ZZZ), PPP);
 }
 // out-of-line full add for cold / code-size-sensitive call sites
-__device__ __noinline__ void g1_add_ool(G1 *a, const G1 *b) { g1_add(*a, *b); }
+static __device__ __noinline__ void g1_add_ool(G1 *a, const G1 *b) { g1_add<MulCall>(*a, *b); }
 
 // a^(e) for a public, fixed exponent given as plain little-endian 32-bit limbs
-__device__ __noinline__ Fp fp_pow(const Fp &a, const uint32_t *e, int nlimbs) {
+static __device__ __noinline__ Fp fp_pow(Fp a, const uint32_t *e, int nlimbs) {
     Fp r = Fp::one();
     bool started = false;
+#pragma unroll 1
     for (int i = nlimbs * 32 - 1; i >= 0; --i) {
-        if (started) r = Fp::sqr(r);
+        if (started) r = fp_mul_ni(r, r);
         if ((e[i >> 5] >> (i & 31)) & 1) {
-            if (started) r = Fp::mul(r, a); else { r = a; started = true; }
+            if (started) r = fp_mul_ni(r, a); else { r = a; started = true; }
         }
     }
     return r;
@@ -142,9 +159,9 @@ __device__ __forceinline__ G1Aff g1_to_affine(const G1 &p) {
     G1Aff r;
     if (p.is_inf()) { r.x = Fp::zero(); r.y = Fp::zero(); return r; }
     Fp i3 = fp_inv(p.ZZZ);
-    Fp i2 = Fp::mul(Fp::sqr(i3), Fp::sqr(p.ZZ));   // 1/ZZ
-    r.x = Fp::mul(p.X, i2);
-    r.y = Fp::mul(p.Y, i3);
+    Fp i2 = fp_mul_ni(fp_mul_ni(i3, i3), fp_mul_ni(p.ZZ, p.ZZ));   // 1/ZZ
+    r.x = fp_mul_ni(p.X, i2);
+    r.y = fp_mul_ni(p.Y, i3);
     return r;
 }
 
@@ -156,7 +173,8 @@ __device__ __forceinline__ void g1_compress(uint8_t *out48, const G1Aff &a) {
         for (int i = 0; i < 12; ++i) w[i] = 0;
         w[11] = 0xc0000000u;
     } else {
-        Fp x = Fp::from_mont(a.x), y = Fp::from_mont(a.y);
+        Fp o1 = Fp::zero(); o1.v[0] = 1;
+        Fp x = fp_mul_ni(a.x, o1), y = fp_mul_ni(a.y, o1);
         bool largest = !Fp::geq_limbs(FP_HALF, y.v);   // y > (p-1)/2
 #pragma unroll
         for (int i = 0; i < 12; ++i) w[i] = x.v[i];

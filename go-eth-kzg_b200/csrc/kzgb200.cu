@@ -5,6 +5,7 @@
 #include "../../include/kzgb200.h"
 #include "../../include/kzgb200_debug.h"
 #include "msm.cuh"
+#include "fk20.cuh"
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <chrono>
@@ -149,8 +150,11 @@ struct kzgb200_ctx {
     G1Aff *g1_lagrange_brp = nullptr;  // bit-reversed order (api.go:131)
     std::vector<uint8_t> g2_bytes;
     MsmTable commit_tab{};
+    MsmTable fk20_tab{};
+    Fr *roots = nullptr;               // w_8192^t, Montgomery
+    int8_t *glv_digits = nullptr;      // [128][2][KZG_GLV_DIGITS]
     // scratch
-    DevBuf in_bytes, scalars, status, sums, out_bytes;
+    DevBuf in_bytes, scalars, status, sums, out_bytes, coeffs, cells, proofs_xyzz;
     double init_ms = 0, last_device_ms = 0;
     uint64_t launches = 0;
 };
@@ -196,7 +200,9 @@ void kzgb200_ctx_free(kzgb200_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->g1_monomial); cudaFree(c->g1_lagrange_brp); cudaFree(c->commit_tab.entries);
+    cudaFree(c->fk20_tab.entries); cudaFree(c->roots); cudaFree(c->glv_digits);
     c->in_bytes.release(); c->scalars.release(); c->status.release(); c->sums.release(); c->out_bytes.release();
+    c->coeffs.release(); c->cells.release(); c->proofs_xyzz.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -240,6 +246,30 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
 
     int rc = build_table(c, c->g1_lagrange_brp, N_BLOB, cw, c->commit_tab);
     if (rc) return rc;
+
+    // Fr twiddles and GLV digit tables
+    CU(cudaMalloc(&c->roots, ROOTS_N * sizeof(Fr)));
+    CU(cudaMalloc(&c->glv_digits, sizeof(H_GLV_TW)));
+    CU(cudaMemcpyAsync(c->glv_digits, H_GLV_TW, sizeof(H_GLV_TW), cudaMemcpyHostToDevice, c->stream));
+    Fr gen; memcpy(gen.v, H_FR_W8192, sizeof gen.v);
+    k_init_roots<<<ROOTS_N / 128, 128, 0, c->stream>>>(c->roots, gen);
+    CU(cudaFuncSetAttribute(k_blob_ifft, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 32));
+    CU(cudaFuncSetAttribute(k_coset_fft_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 32));
+
+    // FK20 table (fk20.go:23-52, toeplitz.go:50-93): 64 G1 FFTs of size 128, then the window table
+    int fw = opts && opts->fk20_window ? opts->fk20_window : 0;
+    if (!fw) { const char *e = getenv("KZGB200_FK20_WINDOW"); fw = e ? atoi(e) : 12; }
+    if (fw < 4 || fw > 15) return set_err(KZGB200_ERR_ARGS, "fk20_window must be in 4..15");
+    G1 *fk_xyzz = nullptr; G1Aff *fk_aff = nullptr;
+    CU(cudaMalloc(&fk_xyzz, 8192 * sizeof(G1)));
+    CU(cudaMalloc(&fk_aff, 8192 * sizeof(G1Aff)));
+    k_fk20_table_fft<<<64, 64, 0, c->stream>>>(c->g1_monomial, fk_xyzz, c->glv_digits);
+    k_to_affine<<<8192 / 128, 128, 0, c->stream>>>(fk_xyzz, fk_aff, 8192);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    rc = build_table(c, fk_aff, 8192, fw, c->fk20_tab);
+    cudaFree(fk_xyzz); cudaFree(fk_aff);
+    if (rc) return rc;
     return 0;
 }
 
@@ -263,6 +293,8 @@ int kzgb200_get_info(kzgb200_ctx *c, kzgb200_info *o) {
     o->device = c->device; o->sm_count = c->sm_count;
     o->commit_window = c->commit_tab.c; o->commit_windows_per_scalar = c->commit_tab.W;
     o->commit_table_bytes = c->commit_tab.bytes();
+    o->fk20_window = c->fk20_tab.c; o->fk20_windows_per_scalar = c->fk20_tab.W;
+    o->fk20_table_bytes = c->fk20_tab.bytes();
     o->init_ms = c->init_ms; o->kernel_launches = c->launches;
     return KZGB200_OK;
 }
@@ -302,7 +334,7 @@ int kzgb200_blob_to_kzg_commitment(kzgb200_ctx *c, const uint8_t *blobs, size_t 
         CU(cudaMemsetAsync(d_status, 0, m * sizeof(int32_t), c->stream));
         size_t ns = m * N_BLOB;
         k_blob_to_scalars<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(d_blobs, (uint32_t *)c->scalars.p, d_status, ns, N_BLOB);
-        k_msm_fixed<<<dim3(1, (unsigned)m), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->commit_tab, N_BLOB, 1,
+        k_msm_fixed<<<dim3(1, (unsigned)m), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->commit_tab, N_BLOB, 1, TPB,
                                                                                   d_status, (G1 *)c->sums.p);
         k_finalize_g1<<<(unsigned)((m + 63) / 64), 64, 0, c->stream>>>((const G1 *)c->sums.p, d_out, d_status, m, 1);
         c->launches += 3;
@@ -315,6 +347,77 @@ int kzgb200_blob_to_kzg_commitment(kzgb200_ctx *c, const uint8_t *blobs, size_t 
         c->last_device_ms += ms;
     }
     return KZGB200_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// ComputeCells / ComputeCellsAndKZGProofs (api_eip7594.go:12-52)
+// -------------------------------------------------------------------------------------------
+static const size_t CELLS_CHUNK = 256;
+
+static int cells_and_proofs(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, uint8_t *out_proofs, int32_t *status) {
+    if (!c || (n && (!blobs || !out_cells || !status))) return set_err(KZGB200_ERR_ARGS, "null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    c->last_device_ms = 0;
+    if (n == 0) return KZGB200_OK;
+    const bool in_dev = is_device_ptr(blobs), cells_dev = is_device_ptr(out_cells), st_dev = is_device_ptr(status);
+    const bool proofs_dev = out_proofs && is_device_ptr(out_proofs);
+    const size_t chunk = std::min(n, CELLS_CHUNK);
+    int rc;
+    if (!in_dev && (rc = c->in_bytes.ensure(chunk * KZGB200_BYTES_PER_BLOB))) return rc;
+    if ((rc = c->coeffs.ensure(chunk * N_BLOB * sizeof(Fr)))) return rc;
+    if ((rc = c->status.ensure(chunk * sizeof(int32_t)))) return rc;
+    if (!cells_dev && (rc = c->cells.ensure(chunk * 262144))) return rc;
+    if (out_proofs) {
+        if ((rc = c->scalars.ensure(chunk * 8192 * 32))) return rc;
+        if ((rc = c->sums.ensure(chunk * 128 * sizeof(G1)))) return rc;
+        if ((rc = c->proofs_xyzz.ensure(chunk * 128 * sizeof(G1)))) return rc;
+        if (!proofs_dev && (rc = c->out_bytes.ensure(chunk * 128 * 48))) return rc;
+    }
+    Fr inv4096; memcpy(inv4096.v, H_FR_INV4096, sizeof inv4096.v);
+    Fr inv128p; memcpy(inv128p.v, H_FR_INV128_PLAIN, sizeof inv128p.v);
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t m = std::min(chunk, n - off);
+        const uint8_t *d_blobs = blobs + off * KZGB200_BYTES_PER_BLOB;
+        if (!in_dev) {
+            CU(cudaMemcpyAsync(c->in_bytes.p, d_blobs, m * KZGB200_BYTES_PER_BLOB, cudaMemcpyHostToDevice, c->stream));
+            d_blobs = (const uint8_t *)c->in_bytes.p;
+        }
+        int32_t *d_status = st_dev ? status + off : (int32_t *)c->status.p;
+        uint8_t *d_cells = cells_dev ? out_cells + off * 262144 : (uint8_t *)c->cells.p;
+        uint8_t *d_proofs = !out_proofs ? nullptr : proofs_dev ? out_proofs + off * 6144 : (uint8_t *)c->out_bytes.p;
+        CU(cudaEventRecord(c->ev0, c->stream));
+        k_blob_ifft<<<(unsigned)m, KZG_NTT_THREADS, 4096 * 32, c->stream>>>(d_blobs, (Fr *)c->coeffs.p, d_status, c->roots, inv4096);
+        k_coset_fft_cells<<<(unsigned)m, KZG_NTT_THREADS, 4096 * 32, c->stream>>>((const Fr *)c->coeffs.p, d_blobs, d_cells, d_status, c->roots);
+        c->launches += 2;
+        if (out_proofs) {
+            k_fk20_rows<<<dim3(64, (unsigned)m), 64, 0, c->stream>>>((const Fr *)c->coeffs.p, (uint32_t *)c->scalars.p, d_status, c->roots, inv128p);
+            const int TPB = 128, L = 8;
+            k_msm_fixed<<<dim3(128 / (TPB / L), (unsigned)m), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->fk20_tab, 64, 128, L,
+                                                                                                    d_status, (G1 *)c->sums.p);
+            k_fk20_g1fft<<<(unsigned)m, 64, 0, c->stream>>>((const G1 *)c->sums.p, (G1 *)c->proofs_xyzz.p, d_status, c->glv_digits);
+            size_t np = m * 128;
+            k_finalize_g1<<<(unsigned)((np + 63) / 64), 64, 0, c->stream>>>((const G1 *)c->proofs_xyzz.p, d_proofs, d_status, np, 128);
+            c->launches += 4;
+        }
+        CU(cudaEventRecord(c->ev1, c->stream));
+        CU(cudaGetLastError());
+        if (!cells_dev) CU(cudaMemcpyAsync(out_cells + off * 262144, d_cells, m * 262144, cudaMemcpyDeviceToHost, c->stream));
+        if (out_proofs && !proofs_dev) CU(cudaMemcpyAsync(out_proofs + off * 6144, d_proofs, m * 6144, cudaMemcpyDeviceToHost, c->stream));
+        if (!st_dev) CU(cudaMemcpyAsync(status + off, d_status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->last_device_ms += ms;
+    }
+    return KZGB200_OK;
+}
+
+int kzgb200_compute_cells(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, int32_t *status) {
+    return cells_and_proofs(c, blobs, n, out_cells, nullptr, status);
+}
+int kzgb200_compute_cells_and_kzg_proofs(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, uint8_t *out_proofs, int32_t *status) {
+    if (n && !out_proofs) return set_err(KZGB200_ERR_ARGS, "null argument");
+    return cells_and_proofs(c, blobs, n, out_cells, out_proofs, status);
 }
 
 // -------------------------------------------------------------------------------------------

@@ -65,46 +65,50 @@ __device__ __forceinline__ G1Aff load_aff(const G1Aff *p) {
     return r;
 }
 
-// One group of `group_pts` consecutive base points per (blockIdx.x = group, blockIdx.y = blob);
-// blockDim.x threads cooperate on a group.  Scalars: [blob][total_pts][8] plain limbs.
-// out: [blob][n_groups] XYZZ sums.
-//   commit:  group_pts = 4096, n_groups = 1
-//   FK20:    group_pts = 64,   n_groups = 128 (scalars already transposed to table order)
+// Generic launch shape: blockIdx.y = blob; each block of blockDim.x threads serves
+// blockDim.x / L groups of `group_pts` consecutive base points, L lanes cooperating per group.
+// Scalars: [blob][n_groups*group_pts][8] plain limbs (table order).  out: [blob][n_groups] XYZZ.
+//   commit:  group_pts = 4096, n_groups = 1,   L = blockDim.x
+//   FK20:    group_pts = 64,   n_groups = 128, L = 8 (16 groups per 128-thread block)
 extern __shared__ unsigned char msm_smem[];
 __global__ void __launch_bounds__(128) k_msm_fixed(const uint32_t *__restrict__ scalars, MsmTable tab, int group_pts,
-                                                    int n_groups, const int32_t *__restrict__ status, G1 *__restrict__ out) {
-    const int group = blockIdx.x, blob = blockIdx.y, t = threadIdx.x, T = blockDim.x;
+                                                    int n_groups, int L, const int32_t *__restrict__ status, G1 *__restrict__ out) {
+    const int blob = blockIdx.y, t = threadIdx.x;
     if (status && status[blob] != ST_OK) return;
+    const int lane = t & (L - 1);
+    const int group = blockIdx.x * (blockDim.x / L) + t / L;
     const int total = group_pts * n_groups;
-    const uint32_t *sc = scalars + ((size_t)blob * total + (size_t)group * group_pts) * 8;
     G1 acc = G1::infinity();
-    for (int j = t; j < group_pts; j += T) {
-        DigitStream ds;
-        {
-            const uint4 *q = reinterpret_cast<const uint4 *>(sc + (size_t)j * 8);
-            uint4 a = __ldg(q), b = __ldg(q + 1);
-            uint32_t l[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            ds.init(l, tab.c);
-        }
-        const G1Aff *row = tab.entries + ((size_t)(group * group_pts + j) * tab.W) * tab.H;
-        for (int k = 0; k < tab.W; ++k) {
-            int d = ds.next(k);
-            if (d == 0) continue;
-            int mag = d < 0 ? -d : d;
-            G1Aff e = load_aff(row + (size_t)k * tab.H + (mag - 1));
-            if (d < 0) e.y = Fp::neg(e.y);
-            g1_add_affine(acc, e);
+    if (group < n_groups) {
+        const uint32_t *sc = scalars + ((size_t)blob * total + (size_t)group * group_pts) * 8;
+        for (int j = lane; j < group_pts; j += L) {
+            DigitStream ds;
+            {
+                const uint4 *q = reinterpret_cast<const uint4 *>(sc + (size_t)j * 8);
+                uint4 a = __ldg(q), b = __ldg(q + 1);
+                uint32_t l[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                ds.init(l, tab.c);
+            }
+            const G1Aff *row = tab.entries + ((size_t)(group * group_pts + j) * tab.W) * tab.H;
+            for (int k = 0; k < tab.W; ++k) {
+                int d = ds.next(k);
+                if (d == 0) continue;
+                int mag = d < 0 ? -d : d;
+                G1Aff e = load_aff(row + (size_t)k * tab.H + (mag - 1));
+                if (d < 0) e.y = Fp::neg(e.y);
+                g1_add_affine<MulInline>(acc, e);
+            }
         }
     }
-    // block tree reduction through shared memory
+    // tree reduction over the L lanes of each group through shared memory
     G1 *sm = reinterpret_cast<G1 *>(msm_smem);
     sm[t] = acc;
     __syncthreads();
-    for (int s = T >> 1; s > 0; s >>= 1) {
-        if (t < s) g1_add_ool(&sm[t], &sm[t + s]);
+    for (int s = L >> 1; s > 0; s >>= 1) {
+        if (lane < s) g1_add_ool(&sm[t], &sm[t + s]);
         __syncthreads();
     }
-    if (t == 0) out[(size_t)blob * n_groups + group] = sm[0];
+    if (lane == 0 && group < n_groups) out[(size_t)blob * n_groups + group] = sm[t];
 }
 
 // ---- table construction (context init) ---------------------------------------------------
@@ -115,7 +119,7 @@ __global__ void k_table_bases(const G1Aff *__restrict__ pts, int npts, int c, in
     G1 q = G1::from_affine(pts[j]);
     for (int k = 0; k < W; ++k) {
         bases[(size_t)j * W + k] = q;
-        if (k + 1 < W) for (int i = 0; i < c; ++i) { G1 t2; g1_dbl_cold(&t2, &q); q = t2; }
+        if (k + 1 < W) for (int i = 0; i < c; ++i) q = g1_dbl(q);
     }
 }
 // XYZZ -> affine, one thread per point (used only at init / for small batches)
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(64) k_table_fill(const G1Aff *__restrict__ bas
     G1 cur = G1::infinity();
     unsigned d0 = (unsigned)q * KZG_TABLE_CHUNK;
     for (int bit = 31 - __clz(d0 | 1); bit >= 0; --bit) {
-        G1 t2; g1_dbl_cold(&t2, &cur); cur = t2;
+        cur = g1_dbl(cur);
         if ((d0 >> bit) & 1) g1_add_affine(cur, Q);
     }
     G1 pts[KZG_TABLE_CHUNK];
@@ -154,16 +158,16 @@ __global__ void __launch_bounds__(64) k_table_fill(const G1Aff *__restrict__ bas
         g1_add_affine(cur, Q);
         pts[i] = cur;
         pre[i] = run;
-        run = Fp::mul(run, cur.ZZZ);
+        run = fp_mul_ni(run, cur.ZZZ);
     }
     Fp inv = fp_inv(run);
     for (int i = cnt - 1; i >= 0; --i) {
-        Fp i3 = Fp::mul(inv, pre[i]);          // 1/ZZZ_i
-        inv = Fp::mul(inv, pts[i].ZZZ);
-        Fp i2 = Fp::mul(Fp::sqr(i3), Fp::sqr(pts[i].ZZ));
+        Fp i3 = fp_mul_ni(inv, pre[i]);          // 1/ZZZ_i
+        inv = fp_mul_ni(inv, pts[i].ZZZ);
+        Fp i2 = fp_mul_ni(fp_mul_ni(i3, i3), fp_mul_ni(pts[i].ZZ, pts[i].ZZ));
         G1Aff a;
-        a.x = Fp::mul(pts[i].X, i2);
-        a.y = Fp::mul(pts[i].Y, i3);
+        a.x = fp_mul_ni(pts[i].X, i2);
+        a.y = fp_mul_ni(pts[i].Y, i3);
         dst[i] = a;
     }
 }

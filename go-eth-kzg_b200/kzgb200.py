@@ -48,6 +48,7 @@ _lib = None
 EXPORTS = [
     "kzgb200_ctx_new", "kzgb200_ctx_free", "kzgb200_last_error", "kzgb200_host_alloc", "kzgb200_host_free",
     "kzgb200_blob_to_kzg_commitment", "kzgb200_get_info", "kzgb200_last_device_ms",
+    "kzgb200_compute_cells", "kzgb200_compute_cells_and_kzg_proofs",
 ]
 
 
@@ -125,7 +126,29 @@ class Context:
     def raw_blob_to_kzg_commitment(self, blobs_ptr, n, out_ptr, status_ptr):
         self._check(self.L.kzgb200_blob_to_kzg_commitment(self.ctx, _ptr(blobs_ptr), ctypes.c_size_t(n), _ptr(out_ptr), _ptr(status_ptr)))
 
+    def raw_compute_cells_and_kzg_proofs(self, blobs_ptr, n, cells_ptr, proofs_ptr, status_ptr):
+        self._check(self.L.kzgb200_compute_cells_and_kzg_proofs(self.ctx, _ptr(blobs_ptr), ctypes.c_size_t(n), _ptr(cells_ptr),
+                                                                _ptr(proofs_ptr), _ptr(status_ptr)))
+
+    def raw_compute_cells(self, blobs_ptr, n, cells_ptr, status_ptr):
+        self._check(self.L.kzgb200_compute_cells(self.ctx, _ptr(blobs_ptr), ctypes.c_size_t(n), _ptr(cells_ptr), _ptr(status_ptr)))
+
     # ---- batched, bytes in / bytes out ------------------------------------------------------
+    def compute_cells_and_kzg_proofs_batch(self, blobs, proofs=True):
+        n = len(blobs)
+        if any(len(b) != BYTES_PER_BLOB for b in blobs):
+            raise KzgError(LENGTH_MISMATCH, "blob must be 131072 bytes")
+        cells = ctypes.create_string_buffer(262144 * max(n, 1))
+        st = (ctypes.c_int32 * max(n, 1))()
+        if proofs:
+            pr = ctypes.create_string_buffer(6144 * max(n, 1))
+            self.raw_compute_cells_and_kzg_proofs(b"".join(blobs), n, cells, pr, st)
+            craw, praw = cells.raw, pr.raw
+            return [(st[i], craw[262144 * i:262144 * (i + 1)], praw[6144 * i:6144 * (i + 1)]) for i in range(n)]
+        self.raw_compute_cells(b"".join(blobs), n, cells, st)
+        craw = cells.raw
+        return [(st[i], craw[262144 * i:262144 * (i + 1)]) for i in range(n)]
+
     def blob_to_kzg_commitment_batch(self, blobs):
         n = len(blobs)
         if any(len(b) != BYTES_PER_BLOB for b in blobs):
@@ -133,7 +156,8 @@ class Context:
         out = ctypes.create_string_buffer(48 * max(n, 1))
         st = (ctypes.c_int32 * max(n, 1))()
         self.raw_blob_to_kzg_commitment(b"".join(blobs), n, out, st)
-        return [(st[i], out.raw[48 * i:48 * i + 48]) for i in range(n)]
+        oraw = out.raw
+        return [(st[i], oraw[48 * i:48 * i + 48]) for i in range(n)]
 
     # ---- single-item methods, named after the reference's Context methods --------------------
     def blob_to_kzg_commitment(self, blob):
@@ -142,6 +166,18 @@ class Context:
             return LENGTH_MISMATCH, None
         st, c = self.blob_to_kzg_commitment_batch([blob])[0]
         return st, c
+
+    def compute_cells(self, blob):
+        """Context.ComputeCells (api_eip7594.go:12-26) -> (status, cells[128*2048])"""
+        if len(blob) != BYTES_PER_BLOB:
+            return LENGTH_MISMATCH, None
+        return self.compute_cells_and_kzg_proofs_batch([blob], proofs=False)[0]
+
+    def compute_cells_and_kzg_proofs(self, blob):
+        """Context.ComputeCellsAndKZGProofs (api_eip7594.go:28-52) -> (status, cells, proofs[128*48])"""
+        if len(blob) != BYTES_PER_BLOB:
+            return LENGTH_MISMATCH, None, None
+        return self.compute_cells_and_kzg_proofs_batch([blob])[0]
 
 
 class Debug:

@@ -1,0 +1,52 @@
+"""ComputeCells / ComputeCellsAndKZGProofs through the C ABI on the GPU."""
+import pytest
+import oracle_lib
+from golden_util import cases
+from vector_runner import run_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import kzgb200
+    c = kzgb200.Context(commit_window=8, fk20_window=8)
+    yield c
+    c.close()
+
+
+def test_spec_vectors_compute_cells_and_kzg_proofs(ctx):
+    bad = []
+    for c in cases("compute_cells_and_kzg_proofs"):
+        got, exp = run_case(ctx, c)
+        if got != exp:
+            bad.append(c["name"])
+    assert not bad, bad
+
+
+def test_compute_cells_agrees_with_cells_and_proofs(ctx):
+    # consensus_specs_test.go:389-397: ComputeCells must agree with ComputeCellsAndKZGProofs
+    blob = oracle_lib.rand_blob(7 << 20)
+    st1, cells1 = ctx.compute_cells(blob)
+    st2, cells2, _ = ctx.compute_cells_and_kzg_proofs(blob)
+    assert st1 == st2 == 0 and cells1 == cells2
+    assert cells1[:131072] == blob      # first 64 cells are the blob itself
+
+
+def test_random_blobs_match_oracle(ctx):
+    o = oracle_lib.get_oracle()
+    blobs = [oracle_lib.rand_blob(b << 20) for b in range(3)]
+    got = ctx.compute_cells_and_kzg_proofs_batch(blobs)
+    for b, (st, cells, proofs) in zip(blobs, got):
+        est, ecells, eproofs = o.compute_cells_and_kzg_proofs(b)
+        assert st == est == 0
+        assert cells == ecells
+        assert proofs == eproofs
+
+
+def test_bad_blob_in_batch(ctx):
+    good = oracle_lib.rand_blob(5)
+    bad = bytes([0xff]) * 32 + good[32:]
+    got = ctx.compute_cells_and_kzg_proofs_batch([good, bad, good])
+    assert got[0][0] == 0 and got[2][0] == 0 and got[0][1:] == got[2][1:]
+    assert got[1][0] == 2 and got[1][1] == bytes(262144) and got[1][2] == bytes(6144)
