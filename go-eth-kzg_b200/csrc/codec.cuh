@@ -65,4 +65,33 @@ __device__ __forceinline__ int32_t g1_decompress(G1Aff &out, const uint8_t *in48
     return ST_OK;
 }
 
+// Subgroup membership of an on-curve affine point (the check gnark's SetBytes performs,
+// serialization.go:108-115).  Endomorphism test (M. Scott, "A note on group membership tests for
+// G1, G2 and GT on BLS pairing-friendly curves", 2021): P is in G1  <=>  phi2(P) == [-x^2]P where
+// phi2(x,y) = (beta^2 x, y) and x = -0xd201000000010000.  Cost: 126 doublings + 10 additions.
+static __device__ __noinline__ bool g1_in_subgroup(const G1Aff *pa, const uint32_t *beta2) {
+    G1Aff a = *pa;
+    if (a.is_inf()) return true;
+    G1 q = G1::from_affine(a);
+#pragma unroll 1
+    for (int rep = 0; rep < 2; ++rep) {               // q = [|x|] q, twice
+        G1 base = q;
+        // |x| = 0xd201000000010000, MSB first after the leading 1: bits 62..0
+        const unsigned long long X_ABS = 0xd201000000010000ULL;
+#pragma unroll 1
+        for (int bit = 62; bit >= 0; --bit) {
+            q = g1_dbl(q);
+            if ((X_ABS >> bit) & 1) g1_add(q, base);
+        }
+    }
+    // need q == -phi2(P) = (beta2*x, -y)
+    if (q.is_inf()) return false;
+    Fp b2;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) b2.v[i] = beta2[i];
+    Fp ex = fp_mul_ni(fp_mul_ni(b2, a.x), q.ZZ);
+    Fp ey = fp_mul_ni(Fp::neg(a.y), q.ZZZ);
+    return Fp::eq(ex, q.X) && Fp::eq(ey, q.Y);
+}
+
 }  // namespace kzg

@@ -1,0 +1,285 @@
+// EIP-4844 single-point opening path on device: Fiat-Shamir challenge, barycentric evaluation,
+// quotient polynomial.  The quotient is then committed with k_msm_fixed (msm.cuh).
+//
+// Replaces fiatshamir.go:22-40, internal/domain/domain.go:163-235
+// (EvaluateLagrangePolynomialWithIndex) and internal/kzg/kzg_prove.go:14-180 (Open,
+// computeQuotientPolyOutsideDomain / OnDomain).
+#pragma once
+#include "ntt.cuh"
+
+namespace kzg {
+
+// ---- SHA-256 (FIPS 180-4), one thread per message -------------------------------------------
+__device__ __constant__ const uint32_t SHA_K[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+    0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+    0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+    0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+    0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+    0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+
+__device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+
+// one compression; w[16] holds the big-endian message words and is clobbered
+__device__ __forceinline__ void sha256_block(uint32_t *h, uint32_t *w) {
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        if (i >= 16) {
+            uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+            uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+            uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+            w[i & 15] = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+        }
+        uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+        uint32_t ch = (e & f) ^ (~e & g);
+        uint32_t t1 = hh + S1 + ch + SHA_K[i] + w[i & 15];
+        uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+        uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t t2 = S0 + mj;
+        hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+
+// computeChallenge (fiatshamir.go:22-33): SHA-256("FSBLOBVERIFY_V1_" || u128_be(4096) || blob || commitment)
+// reduced mod r, written as plain little-endian limbs.  One thread per blob.
+// message = 32 + 131072 + 48 = 131152 bytes = 2049 full blocks + 16 bytes, then padding.
+__global__ void k_fiat_shamir(const uint8_t *__restrict__ blobs, const uint8_t *__restrict__ commitments, uint32_t *__restrict__ z_out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    uint32_t w[16];
+    const uint32_t *bw = reinterpret_cast<const uint32_t *>(blobs + i * 131072);
+    const uint32_t *cw = reinterpret_cast<const uint32_t *>(commitments + i * 48);
+    // block 0: domain separator (16 B) + 16-byte big-endian 4096 + first 32 bytes of the blob
+    w[0] = 0x4653424c; w[1] = 0x4f425645; w[2] = 0x52494659; w[3] = 0x5f56315f;   // "FSBLOBVERIFY_V1_"
+    w[4] = 0; w[5] = 0; w[6] = 0; w[7] = 4096;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[8 + k] = __byte_perm(bw[k], 0, 0x0123);
+    sha256_block(h, w);
+    // blocks 1..2047: blob bytes 32 + 64(b-1) .. ; the blob has 131072-32 = 131040 bytes left = 2047 blocks + 32 bytes
+#pragma unroll 1
+    for (int b = 0; b < 2047; ++b) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(bw + 8 + 16 * b);
+        uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
+        w[0] = __byte_perm(v0.x, 0, 0x0123); w[1] = __byte_perm(v0.y, 0, 0x0123); w[2] = __byte_perm(v0.z, 0, 0x0123); w[3] = __byte_perm(v0.w, 0, 0x0123);
+        w[4] = __byte_perm(v1.x, 0, 0x0123); w[5] = __byte_perm(v1.y, 0, 0x0123); w[6] = __byte_perm(v1.z, 0, 0x0123); w[7] = __byte_perm(v1.w, 0, 0x0123);
+        w[8] = __byte_perm(v2.x, 0, 0x0123); w[9] = __byte_perm(v2.y, 0, 0x0123); w[10] = __byte_perm(v2.z, 0, 0x0123); w[11] = __byte_perm(v2.w, 0, 0x0123);
+        w[12] = __byte_perm(v3.x, 0, 0x0123); w[13] = __byte_perm(v3.y, 0, 0x0123); w[14] = __byte_perm(v3.z, 0, 0x0123); w[15] = __byte_perm(v3.w, 0, 0x0123);
+        sha256_block(h, w);
+    }
+    // block 2048: last 32 blob bytes + first 32 commitment bytes
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = __byte_perm(bw[32768 - 8 + k], 0, 0x0123);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[8 + k] = __byte_perm(cw[k], 0, 0x0123);
+    sha256_block(h, w);
+    // block 2049: last 16 commitment bytes + 0x80 + zeros + 64-bit length (131152*8 = 1049216 bits)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = __byte_perm(cw[8 + k], 0, 0x0123);
+    w[4] = 0x80000000u;
+#pragma unroll
+    for (int k = 5; k < 15; ++k) w[k] = 0;
+    w[14] = 0; w[15] = 131152u * 8u;
+    sha256_block(h, w);
+    // digest (big-endian) -> integer mod r (fr.SetBytes reduces): digest < 2^256 < 3r, so <= 2 subtractions
+    uint32_t l[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) l[k] = h[7 - k];
+    for (int rep = 0; rep < 3; ++rep) {
+        if (Fr::geq_limbs(l, FR_MOD)) {
+            l[0] = ptx_sub_cc(l[0], FR_MOD[0]);
+#pragma unroll
+            for (int k = 1; k < 7; ++k) l[k] = ptx_subc_cc(l[k], FR_MOD[k]);
+            l[7] = ptx_subc(l[7], FR_MOD[7]);
+        }
+    }
+    uint32_t *o = z_out + i * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = l[k];
+}
+
+// 32-byte big-endian scalars -> plain limbs with canonical check (DeserializeScalar, serialization.go:153-159)
+__global__ void k_scalars_from_be(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, int32_t *__restrict__ status, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t l[8];
+    load_be32(l, in + i * 32);
+    if (!fr_is_canonical(l)) atomicMax(&status[i], (int32_t)ST_NON_CANONICAL_SCALAR);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[i * 8 + k] = l[k];
+}
+
+// a^-1 in Fr by Fermat (a != 0)
+__device__ __constant__ const uint32_t FR_RM2[8] = {0xffffffffu, 0xfffffffeu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+static __device__ __noinline__ Fr fr_inv(Fr a) {
+    Fr r = Fr::one();
+    bool started = false;
+#pragma unroll 1
+    for (int i = 254; i >= 0; --i) {
+        if (started) r = fr_mul_ni(r, r);
+        if ((FR_RM2[i >> 5] >> (i & 31)) & 1) {
+            if (started) r = fr_mul_ni(r, a); else { r = a; started = true; }
+        }
+    }
+    return r;
+}
+
+// block-wide inclusive product scan helper over KZG_NTT_THREADS values held in planes sm[8][T]
+// (Hillis-Steele; `dir` +1 = prefix, -1 = suffix).  Returns this thread's inclusive product.
+__device__ __forceinline__ Fr block_scan_mul(uint32_t *sm, Fr v, int tid, int dir) {
+    constexpr int T = KZG_NTT_THREADS;
+    sm_store<T>(sm, tid, v);
+    __syncthreads();
+#pragma unroll 1
+    for (int off = 1; off < T; off <<= 1) {
+        int src = tid - dir * off;
+        Fr o; bool have = src >= 0 && src < T;
+        if (have) o = sm_load<T>(sm, src);
+        __syncthreads();
+        if (have) { v = fr_mul_ni(v, o); sm_store<T>(sm, tid, v); }
+        __syncthreads();
+    }
+    return v;
+}
+
+// Open (internal/kzg/kzg_prove.go:14-44) for one blob per CTA.
+//   in : blob bytes (Lagrange evaluations over the bit-reversed domain), z (plain limbs)
+//   out: y (32 B big-endian, optional), quotient scalars as plain limbs [4096][8] for k_msm_fixed
+// status[blob] must be pre-set (OK or an earlier error); non-canonical blob sets it here.
+__global__ void __launch_bounds__(KZG_NTT_THREADS) k_eval_quotient(const uint8_t *__restrict__ blobs, const uint32_t *__restrict__ z_limbs,
+                                                                   const Fr *__restrict__ roots, int32_t *__restrict__ status,
+                                                                   uint32_t *__restrict__ quotient, uint8_t *__restrict__ y_out, Fr inv_n) {
+    constexpr int T = KZG_NTT_THREADS, PER = 4096 / T;
+    __shared__ uint32_t sm[8 * T];
+    __shared__ int s_index;
+    __shared__ uint32_t s_y[8];
+    const int blob = blockIdx.x, tid = threadIdx.x;
+    if (status[blob] != ST_OK) return;
+    if (tid == 0) s_index = -1;
+    Fr r2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r2.v[i] = FR_R2[i];
+    Fr z;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z.v[i] = z_limbs[(size_t)blob * 8 + i];
+    z = fr_mul_ni(z, r2);
+    __syncthreads();
+    // this thread owns elements i = tid*PER + k (contiguous, so the sequential Montgomery trick runs in-thread)
+    Fr f[PER], w[PER], den[PER];
+    int bad = 0;
+    const uint8_t *src = blobs + (size_t)blob * 131072;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        int i = tid * PER + k;
+        Fr x;
+        load_be32(x.v, src + i * 32);
+        if (!fr_is_canonical(x.v)) bad = 1;
+        f[k] = fr_mul_ni(x, r2);
+        int t = (int)(__brev((unsigned)i) >> 20) * 2;          // bit-reversed 4096-domain: w_4096^brp(i) = w_8192^(2 brp(i))
+        w[k] = ld_fr(roots + t);
+        den[k] = Fr::sub(z, w[k]);
+        if (den[k].is_zero()) { s_index = i; den[k] = Fr::one(); }   // z is in the domain (domain.go:163-171)
+    }
+    bad = __syncthreads_or(bad);
+    if (bad) { if (tid == 0) status[blob] = ST_NON_CANONICAL_SCALAR; return; }
+    const int index = s_index;
+    // ---- batch inversion of den over the whole block ------------------------------------------
+    Fr pre[PER];
+    Fr run = den[0];
+    pre[0] = Fr::one();
+#pragma unroll
+    for (int k = 1; k < PER; ++k) { pre[k] = run; run = fr_mul_ni(run, den[k]); }
+    Fr inc = block_scan_mul(sm, run, tid, +1);
+    Fr excl_pre = Fr::one();
+    if (tid > 0) excl_pre = sm_load<T>(sm, tid - 1);
+    Fr total = sm_load<T>(sm, T - 1);
+    __syncthreads();
+    block_scan_mul(sm, run, tid, -1);
+    Fr excl_suf = Fr::one();
+    if (tid < T - 1) excl_suf = sm_load<T>(sm, tid + 1);
+    __syncthreads();
+    (void)inc;
+    Fr inv_total = fr_inv(total);
+    Fr c = fr_mul_ni(fr_mul_ni(inv_total, excl_pre), excl_suf);    // 1 / (product of this thread's PER elements)
+    Fr inv[PER];
+#pragma unroll
+    for (int k = PER - 1; k >= 0; --k) { inv[k] = fr_mul_ni(c, pre[k]); c = fr_mul_ni(c, den[k]); }
+    // ---- evaluation -----------------------------------------------------------------------------
+    Fr y;
+    if (index >= 0) {
+        if (index / PER == tid) {
+#pragma unroll
+            for (int k = 0; k < PER; ++k) if (k == index % PER) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) s_y[q] = f[k].v[q];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) y.v[q] = s_y[q];
+    } else {
+        Fr acc = Fr::zero();
+#pragma unroll
+        for (int k = 0; k < PER; ++k) acc = Fr::add(acc, fr_mul_ni(fr_mul_ni(f[k], w[k]), inv[k]));
+        // block sum
+        sm_store<T>(sm, tid, acc);
+        __syncthreads();
+        for (int s = T >> 1; s > 0; s >>= 1) {
+            if (tid < s) sm_store<T>(sm, tid, Fr::add(sm_load<T>(sm, tid), sm_load<T>(sm, tid + s)));
+            __syncthreads();
+        }
+        Fr sum = sm_load<T>(sm, 0);
+        __syncthreads();
+        Fr zn = z;
+#pragma unroll 1
+        for (int i = 0; i < 12; ++i) zn = fr_mul_ni(zn, zn);                 // z^4096
+        y = fr_mul_ni(fr_mul_ni(Fr::sub(zn, Fr::one()), inv_n), sum);
+    }
+    Fr one_plain = Fr::zero(); one_plain.v[0] = 1;
+    if (tid == 0 && y_out) {
+        Fr yp = fr_mul_ni(y, one_plain);
+        store_be32(y_out + (size_t)blob * 32, yp.v);
+    }
+    // ---- quotient ---------------------------------------------------------------------------------
+    // outside: q_i = (f_i - y)/(w_i - z) = -(f_i - y) * inv_i                    (kzg_prove.go:81-111)
+    // on domain (index m): same for i != m (den_m was replaced by 1), and
+    //   q_m = sum_{i != m} -q_i * w_i / w_m                                       (kzg_prove.go:118-180)
+    Fr q[PER];
+    Fr qm_acc = Fr::zero();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        int i = tid * PER + k;
+        q[k] = Fr::neg(fr_mul_ni(Fr::sub(f[k], y), inv[k]));
+        if (index >= 0) {
+            if (i == index) q[k] = Fr::zero();
+            else qm_acc = Fr::sub(qm_acc, fr_mul_ni(q[k], w[k]));
+        }
+    }
+    if (index >= 0) {
+        sm_store<T>(sm, tid, qm_acc);
+        __syncthreads();
+        for (int s = T >> 1; s > 0; s >>= 1) {
+            if (tid < s) sm_store<T>(sm, tid, Fr::add(sm_load<T>(sm, tid), sm_load<T>(sm, tid + s)));
+            __syncthreads();
+        }
+        Fr tot = sm_load<T>(sm, 0);
+        // 1 / w_m = w_8192^(8192 - 2 brp(m))
+        int t = (int)(__brev((unsigned)index) >> 20) * 2;
+        Fr inv_wm = ld_fr(roots + ((ROOTS_N - t) & (ROOTS_N - 1)));
+        Fr qm = fr_mul_ni(tot, inv_wm);
+#pragma unroll
+        for (int k = 0; k < PER; ++k) if (tid * PER + k == index) q[k] = qm;
+    }
+    uint32_t *dst = quotient + (size_t)blob * 4096 * 8;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        Fr p = fr_mul_ni(q[k], one_plain);
+        uint4 *o = reinterpret_cast<uint4 *>(dst + (size_t)(tid * PER + k) * 8);
+        o[0] = make_uint4(p.v[0], p.v[1], p.v[2], p.v[3]);
+        o[1] = make_uint4(p.v[4], p.v[5], p.v[6], p.v[7]);
+    }
+}
+
+}  // namespace kzg

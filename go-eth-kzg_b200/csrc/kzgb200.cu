@@ -6,6 +6,8 @@
 #include "../../include/kzgb200_debug.h"
 #include "msm.cuh"
 #include "fk20.cuh"
+#include "kzg4844.cuh"
+#include "recover.cuh"
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <chrono>
@@ -72,6 +74,24 @@ __global__ void k_finalize_g1(const G1 *__restrict__ in, uint8_t *__restrict__ o
     g1_compress(o, g1_to_affine(in[i]));
 }
 
+// decompress + (optional) subgroup check of n compressed points; first error per status slot wins.
+// out may be null (validation only: prove.go:56-60 discards the point).
+__global__ void k_g1_check(const uint8_t *__restrict__ in48, G1Aff *__restrict__ out, int32_t *__restrict__ status, size_t n, int per_status, int subgroup) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Aff a;
+    int32_t st = g1_decompress(a, in48 + i * 48);
+    if (st == ST_OK && subgroup && !g1_in_subgroup(&a, FP_BETA2)) st = ST_NOT_IN_SUBGROUP;
+    if (st != ST_OK) atomicCAS(&status[i / per_status], (int32_t)ST_OK, st);
+    if (out) out[i] = a;
+}
+// zero the y outputs of failed items
+__global__ void k_zero_failed(uint8_t *__restrict__ out, const int32_t *__restrict__ status, size_t n, int bytes_per_item) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || status[i] == ST_OK) return;
+    for (int k = 0; k < bytes_per_item; ++k) out[i * bytes_per_item + k] = 0;
+}
+
 // ---- debug / unit-test kernels (include/kzgb200_debug.h) ----------------------------------
 __global__ void k_dbg_fp_mul(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -107,18 +127,47 @@ __global__ void k_dbg_g1_op(const uint8_t *a48, const uint8_t *b48, uint8_t *out
     else A = g1_dbl(A);
     g1_compress(out48 + i * 48, g1_to_affine(A));
 }
-// dependency-free IMAD throughput probe: each thread runs `iters` x 8 independent mad chains
-__global__ void k_imad_peak(uint32_t *out, int iters, uint32_t seed) {
-    uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, a4 = a0 * 11, a5 = a0 * 13, a6 = a0 * 17, a7 = a0 * 19;
-    uint32_t m = blockIdx.x * 2654435761u + 12345u;
-    for (int i = 0; i < iters; ++i) {
+// dependency-free integer multiply-add throughput probes: 8 independent chains per thread.
+// MODE 0: mad.lo.u32   1: mad.hi.u32   2: mad.wide.u32 (32x32+64 -> 64, one IMAD.WIDE)
+template <int MODE> __global__ void k_imad_peak(uint32_t *out, int iters, uint32_t seed) {
+    uint32_t m = blockIdx.x * 2654435761u + 12345u + seed;
+    if (MODE < 2) {
+        uint32_t a[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            a0 = a0 * m + a1; a1 = a1 * m + a2; a2 = a2 * m + a3; a3 = a3 * m + a0;
-            a4 = __umulhi(a4, m) + a5; a5 = __umulhi(a5, m) + a6; a6 = __umulhi(a6, m) + a7; a7 = __umulhi(a7, m) + a4;
+        for (int k = 0; k < 8; ++k) a[k] = seed * (2 * k + 3) + threadIdx.x;
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (MODE == 0) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(m), "r"(a[(k + 1) & 7]));
+                    else asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(m), "r"(a[(k + 1) & 7]));
+                }
+            }
         }
+        uint32_t x = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x ^= a[k];
+        out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+    } else {
+        unsigned long long a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = (unsigned long long)seed * (2 * k + 3) + threadIdx.x;
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    uint32_t lo = (uint32_t)a[k];
+                    asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[k]) : "r"(lo), "r"(m));
+                }
+            }
+        }
+        unsigned long long x = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x ^= a[k];
+        out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)(x ^ (x >> 32));
     }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
 }
 
 }  // namespace kzg
@@ -153,10 +202,38 @@ struct kzgb200_ctx {
     MsmTable fk20_tab{};
     Fr *roots = nullptr;               // w_8192^t, Montgomery
     int8_t *glv_digits = nullptr;      // [128][2][KZG_GLV_DIGITS]
+    Fr *pow7 = nullptr, *ipow7 = nullptr;   // 7^k, 7^-k (erasure_code.go:58 coset generator)
     // scratch
-    DevBuf in_bytes, scalars, status, sums, out_bytes, coeffs, cells, proofs_xyzz;
+    DevBuf in_bytes, scalars, status, sums, out_bytes, coeffs, cells, proofs_xyzz, in_small, in_small2, zbuf, ybuf;
+    DevBuf rec_a, rec_b, rec_meta, rec_zev, rec_czinv;
     double init_ms = 0, last_device_ms = 0;
     uint64_t launches = 0;
+    // per-kernel-class device timing of the last call (CUDA events on `stream`)
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> mark_cls;
+    size_t n_marks = 0;
+    double class_ms[KZGB200_N_KERNEL_CLASSES] = {0};
+    void marks_reset() { n_marks = 0; mark_cls.clear(); }
+    // the segment that starts here belongs to kernel class `cls` (-1 = end marker)
+    int mark(int cls) {
+        if (n_marks == ev_pool.size()) {
+            cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return 1;
+            ev_pool.push_back(e);
+        }
+        if (cudaEventRecord(ev_pool[n_marks], stream) != cudaSuccess) return 1;
+        mark_cls.push_back(cls); ++n_marks;
+        return 0;
+    }
+    void marks_collect() {   // stream must be synchronised
+        for (size_t i = 0; i + 1 < n_marks; ++i) {
+            float ms = 0;
+            if (mark_cls[i] >= 0 && cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]) == cudaSuccess) {
+                class_ms[mark_cls[i]] += ms; last_device_ms += ms;
+            }
+        }
+        marks_reset();
+    }
+    void timing_reset() { last_device_ms = 0; for (double &x : class_ms) x = 0; marks_reset(); }
 };
 
 static bool is_device_ptr(const void *p) {
@@ -203,6 +280,10 @@ void kzgb200_ctx_free(kzgb200_ctx *c) {
     cudaFree(c->fk20_tab.entries); cudaFree(c->roots); cudaFree(c->glv_digits);
     c->in_bytes.release(); c->scalars.release(); c->status.release(); c->sums.release(); c->out_bytes.release();
     c->coeffs.release(); c->cells.release(); c->proofs_xyzz.release();
+    c->in_small.release(); c->in_small2.release(); c->zbuf.release(); c->ybuf.release();
+    c->rec_a.release(); c->rec_b.release(); c->rec_meta.release(); c->rec_zev.release(); c->rec_czinv.release();
+    cudaFree(c->pow7); cudaFree(c->ipow7);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -253,6 +334,16 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
     CU(cudaMemcpyAsync(c->glv_digits, H_GLV_TW, sizeof(H_GLV_TW), cudaMemcpyHostToDevice, c->stream));
     Fr gen; memcpy(gen.v, H_FR_W8192, sizeof gen.v);
     k_init_roots<<<ROOTS_N / 128, 128, 0, c->stream>>>(c->roots, gen);
+    CU(cudaMalloc(&c->pow7, 8192 * sizeof(Fr)));
+    CU(cudaMalloc(&c->ipow7, 8192 * sizeof(Fr)));
+    {
+        Fr seven, inv7; memcpy(seven.v, H_FR_SEVEN, sizeof seven.v); memcpy(inv7.v, H_FR_INV7, sizeof inv7.v);
+        k_init_pow7<<<8192 / 128, 128, 0, c->stream>>>(c->pow7, c->ipow7, seven, inv7);
+        c->launches += 1;
+    }
+    CU(cudaFuncSetAttribute(k_half_dit_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 32));
+    CU(cudaFuncSetAttribute(k_half_dif_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 32));
+    CU(cudaFuncSetAttribute(k_cells_from_coeffs, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 32));
     CU(cudaFuncSetAttribute(k_blob_ifft, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 32));
     CU(cudaFuncSetAttribute(k_coset_fft_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 32));
 
@@ -299,6 +390,11 @@ int kzgb200_get_info(kzgb200_ctx *c, kzgb200_info *o) {
     return KZGB200_OK;
 }
 double kzgb200_last_device_ms(kzgb200_ctx *c) { return c ? c->last_device_ms : 0.0; }
+int kzgb200_last_kernel_ms(kzgb200_ctx *c, double *out) {
+    if (!c || !out) return set_err(KZGB200_ERR_ARGS, "null argument");
+    for (int i = 0; i < KZGB200_N_KERNEL_CLASSES; ++i) out[i] = c->class_ms[i];
+    return KZGB200_OK;
+}
 
 // -------------------------------------------------------------------------------------------
 // BlobToKZGCommitment (prove.go:13-34): DeserializeBlob -> MSM against the bit-reversed Lagrange
@@ -310,7 +406,7 @@ int kzgb200_blob_to_kzg_commitment(kzgb200_ctx *c, const uint8_t *blobs, size_t 
     if (!c || (n && (!blobs || !out48 || !status))) return set_err(KZGB200_ERR_ARGS, "null argument");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
-    c->last_device_ms = 0;
+    c->timing_reset();
     const bool in_dev = n && is_device_ptr(blobs), out_dev = n && is_device_ptr(out48), st_dev = n && is_device_ptr(status);
     const size_t chunk = std::min(n, COMMIT_CHUNK);
     if (n == 0) return KZGB200_OK;
@@ -330,35 +426,133 @@ int kzgb200_blob_to_kzg_commitment(kzgb200_ctx *c, const uint8_t *blobs, size_t 
         }
         int32_t *d_status = st_dev ? status + off : (int32_t *)c->status.p;
         uint8_t *d_out = out_dev ? out48 + off * 48 : (uint8_t *)c->out_bytes.p;
-        CU(cudaEventRecord(c->ev0, c->stream));
+        c->mark(KZGB200_KC_FR);
         CU(cudaMemsetAsync(d_status, 0, m * sizeof(int32_t), c->stream));
         size_t ns = m * N_BLOB;
         k_blob_to_scalars<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(d_blobs, (uint32_t *)c->scalars.p, d_status, ns, N_BLOB);
+        c->mark(KZGB200_KC_MSM);
         k_msm_fixed<<<dim3(1, (unsigned)m), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->commit_tab, N_BLOB, 1, TPB,
                                                                                   d_status, (G1 *)c->sums.p);
+        c->mark(KZGB200_KC_FINALIZE);
         k_finalize_g1<<<(unsigned)((m + 63) / 64), 64, 0, c->stream>>>((const G1 *)c->sums.p, d_out, d_status, m, 1);
         c->launches += 3;
-        CU(cudaEventRecord(c->ev1, c->stream));
+        c->mark(-1);
         CU(cudaGetLastError());
         if (!out_dev) CU(cudaMemcpyAsync(out48 + off * 48, d_out, m * 48, cudaMemcpyDeviceToHost, c->stream));
         if (!st_dev) CU(cudaMemcpyAsync(status + off, d_status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
-        float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-        c->last_device_ms += ms;
+        c->marks_collect();
     }
     return KZGB200_OK;
 }
 
 // -------------------------------------------------------------------------------------------
+// ComputeKZGProof (prove.go:85-111) and ComputeBlobKZGProof (prove.go:46-77)
+// -------------------------------------------------------------------------------------------
+// stage a (possibly host) input buffer on the device
+static int stage_in(kzgb200_ctx *c, const void *user, size_t bytes, DevBuf &buf, const void **dev) {
+    if (is_device_ptr(user)) { *dev = user; return 0; }
+    int rc = buf.ensure(bytes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(buf.p, user, bytes, cudaMemcpyHostToDevice, c->stream));
+    *dev = buf.p;
+    return 0;
+}
+
+static int open_common(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *z32, const uint8_t *commitments, size_t n,
+                       uint8_t *out_proof, uint8_t *out_y, int32_t *status) {
+    if (!c || (n && (!blobs || !out_proof || !status || (!z32 && !commitments)))) return set_err(KZGB200_ERR_ARGS, "null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    c->timing_reset();
+    if (n == 0) return KZGB200_OK;
+    const bool out_dev = is_device_ptr(out_proof), st_dev = is_device_ptr(status), y_dev = out_y && is_device_ptr(out_y);
+    const size_t chunk = std::min(n, COMMIT_CHUNK);
+    int rc;
+    if ((rc = c->scalars.ensure(chunk * N_BLOB * 32))) return rc;
+    if ((rc = c->status.ensure(chunk * sizeof(int32_t)))) return rc;
+    if ((rc = c->sums.ensure(chunk * sizeof(G1)))) return rc;
+    if ((rc = c->zbuf.ensure(chunk * 32))) return rc;
+    if ((rc = c->ybuf.ensure(chunk * 32))) return rc;
+    if (!out_dev && (rc = c->out_bytes.ensure(chunk * 48))) return rc;
+    Fr inv4096; memcpy(inv4096.v, H_FR_INV4096, sizeof inv4096.v);
+    const int TPB = 128;
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t m = std::min(chunk, n - off);
+        const void *d_blobs, *d_aux;
+        if ((rc = stage_in(c, blobs + off * KZGB200_BYTES_PER_BLOB, m * KZGB200_BYTES_PER_BLOB, c->in_bytes, &d_blobs))) return rc;
+        if (z32) { if ((rc = stage_in(c, z32 + off * 32, m * 32, c->in_small, &d_aux))) return rc; }
+        else { if ((rc = stage_in(c, commitments + off * 48, m * 48, c->in_small, &d_aux))) return rc; }
+        int32_t *d_status = st_dev ? status + off : (int32_t *)c->status.p;
+        uint8_t *d_out = out_dev ? out_proof + off * 48 : (uint8_t *)c->out_bytes.p;
+        uint8_t *d_y = !out_y ? nullptr : y_dev ? out_y + off * 32 : (uint8_t *)c->ybuf.p;
+        unsigned gb = (unsigned)((m + 63) / 64);
+        c->mark(KZGB200_KC_FR);
+        CU(cudaMemsetAsync(d_status, 0, m * sizeof(int32_t), c->stream));
+        if (d_y) CU(cudaMemsetAsync(d_y, 0, m * 32, c->stream));
+        if (z32) {
+            k_scalars_from_be<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_aux, (uint32_t *)c->zbuf.p, d_status, m);
+            c->launches += 1;
+        } else {
+            k_g1_check<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_aux, nullptr, d_status, m, 1, 1);
+            k_fiat_shamir<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_blobs, (const uint8_t *)d_aux, (uint32_t *)c->zbuf.p, m);
+            c->launches += 2;
+        }
+        k_eval_quotient<<<(unsigned)m, KZG_NTT_THREADS, 0, c->stream>>>((const uint8_t *)d_blobs, (const uint32_t *)c->zbuf.p, c->roots, d_status,
+                                                                         (uint32_t *)c->scalars.p, d_y, inv4096);
+        c->mark(KZGB200_KC_MSM);
+        k_msm_fixed<<<dim3(1, (unsigned)m), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->commit_tab, N_BLOB, 1, TPB,
+                                                                                  d_status, (G1 *)c->sums.p);
+        c->mark(KZGB200_KC_FINALIZE);
+        k_finalize_g1<<<gb, 64, 0, c->stream>>>((const G1 *)c->sums.p, d_out, d_status, m, 1);
+        if (d_y) { k_zero_failed<<<gb, 64, 0, c->stream>>>(d_y, d_status, m, 32); c->launches += 1; }
+        c->launches += 3;
+        c->mark(-1);
+        CU(cudaGetLastError());
+        if (!out_dev) CU(cudaMemcpyAsync(out_proof + off * 48, d_out, m * 48, cudaMemcpyDeviceToHost, c->stream));
+        if (out_y && !y_dev) CU(cudaMemcpyAsync(out_y + off * 32, d_y, m * 32, cudaMemcpyDeviceToHost, c->stream));
+        if (!st_dev) CU(cudaMemcpyAsync(status + off, d_status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->marks_collect();
+    }
+    return KZGB200_OK;
+}
+
+int kzgb200_compute_kzg_proof(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *z32, size_t n, uint8_t *out_proof48, uint8_t *out_y32, int32_t *status) {
+    if (n && (!z32 || !out_y32)) return set_err(KZGB200_ERR_ARGS, "null argument");
+    return open_common(c, blobs, z32, nullptr, n, out_proof48, out_y32, status);
+}
+int kzgb200_compute_blob_kzg_proof(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *commitments48, size_t n, uint8_t *out48, int32_t *status) {
+    if (n && !commitments48) return set_err(KZGB200_ERR_ARGS, "null argument");
+    return open_common(c, blobs, nullptr, commitments48, n, out48, nullptr, status);
+}
+
+// -------------------------------------------------------------------------------------------
 // ComputeCells / ComputeCellsAndKZGProofs (api_eip7594.go:12-52)
 // -------------------------------------------------------------------------------------------
-static const size_t CELLS_CHUNK = 256;
+static const size_t CELLS_CHUNK = 1024;
+
+// coefficients (c->coeffs) -> 128 compressed proofs per blob (fk20.go:76-124); buffers must be sized by the caller
+static void launch_fk20_proofs(kzgb200_ctx *c, size_t m, const int32_t *d_status, uint8_t *d_proofs) {
+    Fr inv128p; memcpy(inv128p.v, H_FR_INV128_PLAIN, sizeof inv128p.v);
+    k_fk20_rows<<<dim3(64, (unsigned)m), 64, 0, c->stream>>>((const Fr *)c->coeffs.p, (uint32_t *)c->scalars.p, d_status, c->roots, inv128p);
+    const int TPB = 128, L = 8;
+    c->mark(KZGB200_KC_MSM);
+    k_msm_fixed<<<dim3(128 / (TPB / L), (unsigned)m), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->fk20_tab, 64, 128, L,
+                                                                                            d_status, (G1 *)c->sums.p);
+    c->mark(KZGB200_KC_G1FFT);
+    k_fk20_g1fft<<<(unsigned)m, 64, 0, c->stream>>>((const G1 *)c->sums.p, (G1 *)c->proofs_xyzz.p, d_status, c->glv_digits);
+    size_t np = m * 128;
+    c->mark(KZGB200_KC_FINALIZE);
+    k_finalize_g1<<<(unsigned)((np + 63) / 64), 64, 0, c->stream>>>((const G1 *)c->proofs_xyzz.p, d_proofs, d_status, np, 128);
+    c->launches += 4;
+}
 
 static int cells_and_proofs(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, uint8_t *out_proofs, int32_t *status) {
     if (!c || (n && (!blobs || !out_cells || !status))) return set_err(KZGB200_ERR_ARGS, "null argument");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
-    c->last_device_ms = 0;
+    c->timing_reset();
     if (n == 0) return KZGB200_OK;
     const bool in_dev = is_device_ptr(blobs), cells_dev = is_device_ptr(out_cells), st_dev = is_device_ptr(status);
     const bool proofs_dev = out_proofs && is_device_ptr(out_proofs);
@@ -375,7 +569,6 @@ static int cells_and_proofs(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint
         if (!proofs_dev && (rc = c->out_bytes.ensure(chunk * 128 * 48))) return rc;
     }
     Fr inv4096; memcpy(inv4096.v, H_FR_INV4096, sizeof inv4096.v);
-    Fr inv128p; memcpy(inv128p.v, H_FR_INV128_PLAIN, sizeof inv128p.v);
     for (size_t off = 0; off < n; off += chunk) {
         size_t m = std::min(chunk, n - off);
         const uint8_t *d_blobs = blobs + off * KZGB200_BYTES_PER_BLOB;
@@ -386,28 +579,18 @@ static int cells_and_proofs(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint
         int32_t *d_status = st_dev ? status + off : (int32_t *)c->status.p;
         uint8_t *d_cells = cells_dev ? out_cells + off * 262144 : (uint8_t *)c->cells.p;
         uint8_t *d_proofs = !out_proofs ? nullptr : proofs_dev ? out_proofs + off * 6144 : (uint8_t *)c->out_bytes.p;
-        CU(cudaEventRecord(c->ev0, c->stream));
+        c->mark(KZGB200_KC_FR);
         k_blob_ifft<<<(unsigned)m, KZG_NTT_THREADS, 4096 * 32, c->stream>>>(d_blobs, (Fr *)c->coeffs.p, d_status, c->roots, inv4096);
         k_coset_fft_cells<<<(unsigned)m, KZG_NTT_THREADS, 4096 * 32, c->stream>>>((const Fr *)c->coeffs.p, d_blobs, d_cells, d_status, c->roots);
         c->launches += 2;
-        if (out_proofs) {
-            k_fk20_rows<<<dim3(64, (unsigned)m), 64, 0, c->stream>>>((const Fr *)c->coeffs.p, (uint32_t *)c->scalars.p, d_status, c->roots, inv128p);
-            const int TPB = 128, L = 8;
-            k_msm_fixed<<<dim3(128 / (TPB / L), (unsigned)m), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->fk20_tab, 64, 128, L,
-                                                                                                    d_status, (G1 *)c->sums.p);
-            k_fk20_g1fft<<<(unsigned)m, 64, 0, c->stream>>>((const G1 *)c->sums.p, (G1 *)c->proofs_xyzz.p, d_status, c->glv_digits);
-            size_t np = m * 128;
-            k_finalize_g1<<<(unsigned)((np + 63) / 64), 64, 0, c->stream>>>((const G1 *)c->proofs_xyzz.p, d_proofs, d_status, np, 128);
-            c->launches += 4;
-        }
-        CU(cudaEventRecord(c->ev1, c->stream));
+        if (out_proofs) launch_fk20_proofs(c, m, d_status, d_proofs);
+        c->mark(-1);
         CU(cudaGetLastError());
         if (!cells_dev) CU(cudaMemcpyAsync(out_cells + off * 262144, d_cells, m * 262144, cudaMemcpyDeviceToHost, c->stream));
         if (out_proofs && !proofs_dev) CU(cudaMemcpyAsync(out_proofs + off * 6144, d_proofs, m * 6144, cudaMemcpyDeviceToHost, c->stream));
         if (!st_dev) CU(cudaMemcpyAsync(status + off, d_status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
-        float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-        c->last_device_ms += ms;
+        c->marks_collect();
     }
     return KZGB200_OK;
 }
@@ -418,6 +601,106 @@ int kzgb200_compute_cells(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint8_
 int kzgb200_compute_cells_and_kzg_proofs(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, uint8_t *out_proofs, int32_t *status) {
     if (n && !out_proofs) return set_err(KZGB200_ERR_ARGS, "null argument");
     return cells_and_proofs(c, blobs, n, out_cells, out_proofs, status);
+}
+
+// -------------------------------------------------------------------------------------------
+// RecoverCellsAndComputeKZGProofs / RecoverCells (api_eip7594.go:93-161, api_eip.go:8-15)
+// cell_ids and counts are read on the host (validation order of api_eip7594.go:93-113).
+// -------------------------------------------------------------------------------------------
+static const size_t RECOVER_CHUNK = 256;
+
+int kzgb200_recover_cells_and_kzg_proofs(kzgb200_ctx *c, const uint64_t *cell_ids, const uint64_t *counts, const uint8_t *cells, size_t n,
+                                         uint8_t *out_cells, uint8_t *out_proofs, int32_t *status) {
+    if (!c || (n && (!counts || !out_cells || !status))) return set_err(KZGB200_ERR_ARGS, "null argument");
+    if (n && (is_device_ptr(cell_ids) || is_device_ptr(counts))) return set_err(KZGB200_ERR_ARGS, "cell_ids/counts must be host pointers");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    c->timing_reset();
+    if (n == 0) return KZGB200_OK;
+    const bool cells_in_dev = cells && is_device_ptr(cells), cells_dev = is_device_ptr(out_cells), st_dev = is_device_ptr(status);
+    const bool proofs_dev = out_proofs && is_device_ptr(out_proofs);
+    // host-side validation + metadata
+    std::vector<int32_t> h_status(n, KZGB200_OK), h_slot(n * 128, -1);
+    std::vector<uint8_t> h_present(n * 128, 0);
+    std::vector<uint64_t> h_base(n, 0);
+    uint64_t base = 0;
+    for (size_t b = 0; b < n; ++b) {
+        const uint64_t *ids = cell_ids + base;
+        uint64_t cnt = counts[b];
+        h_base[b] = base;
+        int st = KZGB200_OK;
+        for (uint64_t i = 1; i < cnt && !st; ++i) if (ids[i] <= ids[i - 1]) st = KZGB200_CELL_IDS_NOT_ASCENDING;
+        for (uint64_t i = 0; i < cnt && !st; ++i) if (ids[i] >= 128) st = KZGB200_BAD_CELL_INDEX;
+        if (!st && cnt < 64) st = KZGB200_NOT_ENOUGH_CELLS;
+        if (!st) for (uint64_t i = 0; i < cnt; ++i) { h_present[b * 128 + ids[i]] = 1; h_slot[b * 128 + ids[i]] = (int32_t)i; }
+        h_status[b] = st;
+        base += cnt;
+    }
+    const uint64_t total_cells = base;
+    if (total_cells && !cells) return set_err(KZGB200_ERR_ARGS, "null argument");
+    const size_t chunk = std::min(n, RECOVER_CHUNK);
+    int rc;
+    if ((rc = c->rec_a.ensure(chunk * 8192 * sizeof(Fr)))) return rc;
+    if ((rc = c->rec_b.ensure(chunk * 8192 * sizeof(Fr)))) return rc;
+    if ((rc = c->rec_zev.ensure(chunk * 128 * sizeof(Fr)))) return rc;
+    if ((rc = c->rec_czinv.ensure(chunk * 128 * sizeof(Fr)))) return rc;
+    if ((rc = c->rec_meta.ensure(chunk * (128 * 4 + 128 + 8)))) return rc;
+    if ((rc = c->coeffs.ensure(chunk * N_BLOB * sizeof(Fr)))) return rc;
+    if ((rc = c->status.ensure(chunk * sizeof(int32_t)))) return rc;
+    if (!cells_dev && (rc = c->cells.ensure(chunk * 262144))) return rc;
+    if (out_proofs) {
+        if ((rc = c->scalars.ensure(chunk * 8192 * 32))) return rc;
+        if ((rc = c->sums.ensure(chunk * 128 * sizeof(G1)))) return rc;
+        if ((rc = c->proofs_xyzz.ensure(chunk * 128 * sizeof(G1)))) return rc;
+        if (!proofs_dev && (rc = c->out_bytes.ensure(chunk * 128 * 48))) return rc;
+    }
+    Fr inv8192; memcpy(inv8192.v, H_FR_INV8192, sizeof inv8192.v);
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t m = std::min(chunk, n - off);
+        // cells of this chunk are contiguous in the flat input
+        uint64_t c0 = h_base[off], c1 = off + m < n ? h_base[off + m] : total_cells;
+        const uint8_t *d_cells_in = nullptr;
+        if (c1 > c0) {
+            if (cells_in_dev) d_cells_in = cells + c0 * 2048;
+            else {
+                if ((rc = c->in_bytes.ensure((c1 - c0) * 2048))) return rc;
+                CU(cudaMemcpyAsync(c->in_bytes.p, cells + c0 * 2048, (c1 - c0) * 2048, cudaMemcpyHostToDevice, c->stream));
+                d_cells_in = (const uint8_t *)c->in_bytes.p;
+            }
+        }
+        int32_t *d_slot = (int32_t *)c->rec_meta.p;
+        uint8_t *d_present = (uint8_t *)(d_slot + chunk * 128);
+        uint64_t *d_base = (uint64_t *)(d_present + chunk * 128);
+        std::vector<uint64_t> rel(m);
+        for (size_t b = 0; b < m; ++b) rel[b] = h_base[off + b] - c0;
+        int32_t *d_status = st_dev ? status + off : (int32_t *)c->status.p;
+        CU(cudaMemcpyAsync(d_slot, h_slot.data() + off * 128, m * 128 * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_present, h_present.data() + off * 128, m * 128, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_base, rel.data(), m * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_status, h_status.data() + off, m * 4, cudaMemcpyHostToDevice, c->stream));
+        uint8_t *d_cells = cells_dev ? out_cells + off * 262144 : (uint8_t *)c->cells.p;
+        uint8_t *d_proofs = !out_proofs ? nullptr : proofs_dev ? out_proofs + off * 6144 : (uint8_t *)c->out_bytes.p;
+        Fr *A = (Fr *)c->rec_a.p, *B = (Fr *)c->rec_b.p;
+        c->mark(KZGB200_KC_FR);
+        k_rec_vanishing<<<(unsigned)m, 128, 0, c->stream>>>(d_present, d_status, c->roots, c->pow7, (Fr *)c->rec_zev.p, (Fr *)c->rec_czinv.p);
+        k_rec_scale<<<dim3(8192 / 256, (unsigned)m), 256, 0, c->stream>>>(d_cells_in, d_slot, d_base, (const Fr *)c->rec_zev.p, d_status, A);
+        k_half_dit_inv<<<dim3(2, (unsigned)m), KZG_NTT_THREADS, 4096 * 32, c->stream>>>(A, B, d_status, c->roots);
+        k_inv_combine<<<dim3(4096 / 256, (unsigned)m), 256, 0, c->stream>>>(B, A, d_status, c->roots, c->pow7, inv8192, 1);
+        k_half_dif_fwd<<<dim3(2, (unsigned)m), KZG_NTT_THREADS, 4096 * 32, c->stream>>>(A, B, d_status, c->roots, (const Fr *)c->rec_czinv.p);
+        k_half_dit_inv<<<dim3(2, (unsigned)m), KZG_NTT_THREADS, 4096 * 32, c->stream>>>(B, A, d_status, c->roots);
+        k_inv_combine<<<dim3(4096 / 256, (unsigned)m), 256, 0, c->stream>>>(A, (Fr *)c->coeffs.p, d_status, c->roots, c->ipow7, inv8192, 0);
+        k_cells_from_coeffs<<<dim3(2, (unsigned)m), KZG_NTT_THREADS, 4096 * 32, c->stream>>>((const Fr *)c->coeffs.p, d_cells, d_status, c->roots);
+        c->launches += 8;
+        if (out_proofs) launch_fk20_proofs(c, m, d_status, d_proofs);
+        c->mark(-1);
+        CU(cudaGetLastError());
+        if (!cells_dev) CU(cudaMemcpyAsync(out_cells + off * 262144, d_cells, m * 262144, cudaMemcpyDeviceToHost, c->stream));
+        if (out_proofs && !proofs_dev) CU(cudaMemcpyAsync(out_proofs + off * 6144, d_proofs, m * 6144, cudaMemcpyDeviceToHost, c->stream));
+        if (!st_dev) CU(cudaMemcpyAsync(status + off, d_status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->marks_collect();
+    }
+    return KZGB200_OK;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -451,7 +734,7 @@ int kzgb200_dbg_g1_op(const uint8_t *a48, const uint8_t *b48, uint8_t *out48, in
     return 0;
 }
 // measured device-wide 32-bit IMAD rate (results/s); the roofline denominator of SURVEY 8(d)
-int kzgb200_bench_imad(int device, double *imad_per_s, double *ms_out) {
+int kzgb200_bench_imad(int device, int mode, double *imad_per_s, double *ms_out) {
     CU(cudaSetDevice(device));
     cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
     int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
@@ -460,7 +743,9 @@ int kzgb200_bench_imad(int device, double *imad_per_s, double *ms_out) {
     double best = 1e30;
     for (int rep = 0; rep < 5; ++rep) {
         CU(cudaEventRecord(e0));
-        k_imad_peak<<<blocks, threads>>>(d, iters, 17u + rep);
+        if (mode == 0) k_imad_peak<0><<<blocks, threads>>>(d, iters, 17u + rep);
+        else if (mode == 1) k_imad_peak<1><<<blocks, threads>>>(d, iters, 17u + rep);
+        else k_imad_peak<2><<<blocks, threads>>>(d, iters, 17u + rep);
         CU(cudaEventRecord(e1));
         CU(cudaEventSynchronize(e1));
         float ms; CU(cudaEventElapsedTime(&ms, e0, e1));

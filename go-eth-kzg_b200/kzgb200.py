@@ -48,7 +48,8 @@ _lib = None
 EXPORTS = [
     "kzgb200_ctx_new", "kzgb200_ctx_free", "kzgb200_last_error", "kzgb200_host_alloc", "kzgb200_host_free",
     "kzgb200_blob_to_kzg_commitment", "kzgb200_get_info", "kzgb200_last_device_ms",
-    "kzgb200_compute_cells", "kzgb200_compute_cells_and_kzg_proofs",
+    "kzgb200_compute_cells", "kzgb200_compute_cells_and_kzg_proofs", "kzgb200_last_kernel_ms",
+    "kzgb200_compute_kzg_proof", "kzgb200_compute_blob_kzg_proof", "kzgb200_recover_cells_and_kzg_proofs",
 ]
 
 
@@ -122,6 +123,13 @@ class Context:
     def last_device_ms(self):
         return self.L.kzgb200_last_device_ms(self.ctx)
 
+    KERNEL_CLASSES = ["fr", "msm", "g1fft", "finalize", "verify"]
+
+    def last_kernel_ms(self):
+        arr = (ctypes.c_double * 8)()
+        self._check(self.L.kzgb200_last_kernel_ms(self.ctx, arr))
+        return {k: arr[i] for i, k in enumerate(self.KERNEL_CLASSES)}
+
     # ---- raw batched calls on caller-provided addresses (host or device) -------------------
     def raw_blob_to_kzg_commitment(self, blobs_ptr, n, out_ptr, status_ptr):
         self._check(self.L.kzgb200_blob_to_kzg_commitment(self.ctx, _ptr(blobs_ptr), ctypes.c_size_t(n), _ptr(out_ptr), _ptr(status_ptr)))
@@ -159,6 +167,41 @@ class Context:
         oraw = out.raw
         return [(st[i], oraw[48 * i:48 * i + 48]) for i in range(n)]
 
+    def compute_kzg_proof_batch(self, blobs, zs):
+        n = len(blobs)
+        proofs = ctypes.create_string_buffer(48 * max(n, 1))
+        ys = ctypes.create_string_buffer(32 * max(n, 1))
+        st = (ctypes.c_int32 * max(n, 1))()
+        self._check(self.L.kzgb200_compute_kzg_proof(self.ctx, _ptr(b"".join(blobs)), _ptr(b"".join(zs)), ctypes.c_size_t(n),
+                                                     _ptr(proofs), _ptr(ys), _ptr(st)))
+        praw, yraw = proofs.raw, ys.raw
+        return [(st[i], praw[48 * i:48 * i + 48], yraw[32 * i:32 * i + 32]) for i in range(n)]
+
+    def compute_blob_kzg_proof_batch(self, blobs, commitments):
+        n = len(blobs)
+        proofs = ctypes.create_string_buffer(48 * max(n, 1))
+        st = (ctypes.c_int32 * max(n, 1))()
+        self._check(self.L.kzgb200_compute_blob_kzg_proof(self.ctx, _ptr(b"".join(blobs)), _ptr(b"".join(commitments)), ctypes.c_size_t(n),
+                                                          _ptr(proofs), _ptr(st)))
+        praw = proofs.raw
+        return [(st[i], praw[48 * i:48 * i + 48]) for i in range(n)]
+
+    def recover_cells_and_kzg_proofs_batch(self, ids_list, cells_list, proofs=True):
+        """ids_list[i] / cells_list[i]: the cell ids and 2048-byte cells provided for blob i"""
+        n = len(ids_list)
+        flat_ids = [x for ids in ids_list for x in ids]
+        ids = (ctypes.c_uint64 * max(len(flat_ids), 1))(*flat_ids)
+        counts = (ctypes.c_uint64 * max(n, 1))(*[len(x) for x in ids_list])
+        cells = b"".join(c for cl in cells_list for c in cl)
+        oc = ctypes.create_string_buffer(262144 * max(n, 1))
+        op = ctypes.create_string_buffer(6144 * max(n, 1)) if proofs else None
+        st = (ctypes.c_int32 * max(n, 1))()
+        self._check(self.L.kzgb200_recover_cells_and_kzg_proofs(self.ctx, ids, counts, _ptr(cells) if cells else None, ctypes.c_size_t(n),
+                                                                _ptr(oc), _ptr(op) if proofs else None, _ptr(st)))
+        craw = oc.raw
+        praw = op.raw if proofs else None
+        return [(st[i], craw[262144 * i:262144 * (i + 1)]) + ((praw[6144 * i:6144 * (i + 1)],) if proofs else ()) for i in range(n)]
+
     # ---- single-item methods, named after the reference's Context methods --------------------
     def blob_to_kzg_commitment(self, blob):
         """Context.BlobToKZGCommitment (prove.go:13-34) -> (status, commitment48)"""
@@ -166,6 +209,32 @@ class Context:
             return LENGTH_MISMATCH, None
         st, c = self.blob_to_kzg_commitment_batch([blob])[0]
         return st, c
+
+    def compute_kzg_proof(self, blob, z):
+        """Context.ComputeKZGProof (prove.go:85-111) -> (status, proof48, y32)"""
+        if len(blob) != BYTES_PER_BLOB or len(z) != 32:
+            return LENGTH_MISMATCH, None, None
+        return self.compute_kzg_proof_batch([blob], [z])[0]
+
+    def compute_blob_kzg_proof(self, blob, commitment):
+        """Context.ComputeBlobKZGProof (prove.go:46-77) -> (status, proof48)"""
+        if len(blob) != BYTES_PER_BLOB or len(commitment) != 48:
+            return LENGTH_MISMATCH, None
+        return self.compute_blob_kzg_proof_batch([blob], [commitment])[0]
+
+    def recover_cells_and_kzg_proofs(self, cell_ids, cells):
+        """Context.RecoverCellsAndComputeKZGProofs (api_eip7594.go:144-161) -> (status, cells, proofs)"""
+        if len(cell_ids) != len(cells):
+            return LENGTH_MISMATCH, None, None      # ErrNumCellIDsNotEqualNumCells (api_eip7594.go:94)
+        if any(len(c) != BYTES_PER_CELL for c in cells):
+            return LENGTH_MISMATCH, None, None
+        return self.recover_cells_and_kzg_proofs_batch([list(cell_ids)], [list(cells)])[0]
+
+    def recover_cells(self, cell_ids, cells):
+        """Context.RecoverCells (api_eip.go:8-15) -> (status, cells)"""
+        if len(cell_ids) != len(cells) or any(len(c) != BYTES_PER_CELL for c in cells):
+            return LENGTH_MISMATCH, None
+        return self.recover_cells_and_kzg_proofs_batch([list(cell_ids)], [list(cells)], proofs=False)[0]
 
     def compute_cells(self, blob):
         """Context.ComputeCells (api_eip7594.go:12-26) -> (status, cells[128*2048])"""
@@ -216,9 +285,10 @@ class Debug:
             raise KzgError(rc, self.L.kzgb200_last_error().decode())
         return [out.raw[48 * i:48 * i + 48] for i in range(n)]
 
-    def imad_peak(self, device=0):
+    def imad_peak(self, device=0, mode=0):
+        """instructions*lanes per second for mad.lo (0), mad.hi (1), mad.wide (2)"""
         v, ms = ctypes.c_double(), ctypes.c_double()
-        rc = self.L.kzgb200_bench_imad(device, ctypes.byref(v), ctypes.byref(ms))
+        rc = self.L.kzgb200_bench_imad(device, mode, ctypes.byref(v), ctypes.byref(ms))
         if rc:
             raise KzgError(rc, self.L.kzgb200_last_error().decode())
         return v.value

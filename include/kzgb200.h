@@ -139,6 +139,17 @@ typedef struct kzgb200_info {
 } kzgb200_info;
 int kzgb200_get_info(kzgb200_ctx *ctx, kzgb200_info *out);
 
+/* Kernel classes for kzgb200_last_kernel_ms: CUDA-event time per class during the LAST call */
+enum kzgb200_kernel_class {
+    KZGB200_KC_FR = 0,        /* byte codec + Fr NTT / scalar preparation kernels */
+    KZGB200_KC_MSM = 1,       /* k_msm_fixed (fixed-base digit-table MSM) */
+    KZGB200_KC_G1FFT = 2,     /* G1 FFT-128 pair of the FK20 pipeline */
+    KZGB200_KC_FINALIZE = 3,  /* to-affine + compression */
+    KZGB200_KC_VERIFY = 4,    /* decompression, subgroup checks, pairing */
+    KZGB200_N_KERNEL_CLASSES = 8
+};
+int kzgb200_last_kernel_ms(kzgb200_ctx *ctx, double out[KZGB200_N_KERNEL_CLASSES]);
+
 /* Time of the device-side part of the LAST API call on this context, measured with CUDA events
  * on the context's stream (kernels only, excluding H2D/D2H when inputs were host buffers) */
 double kzgb200_last_device_ms(kzgb200_ctx *ctx);

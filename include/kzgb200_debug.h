@@ -13,8 +13,9 @@ int kzgb200_dbg_fp_op(const uint32_t *a, const uint32_t *b, uint32_t *out, int n
 int kzgb200_dbg_fr_op(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op);
 /* compressed points in/out. op: 0 a + b (XYZZ + XYZZ with non-trivial ZZ), 1 a + b (mixed), 2 2a */
 int kzgb200_dbg_g1_op(const uint8_t *a48, const uint8_t *b48, uint8_t *out48, int n, int op);
-/* dependency-free mad.lo/mad.hi microbenchmark: device-wide 32-bit IMAD results per second */
-int kzgb200_bench_imad(int device, double *imad_per_s, double *ms_out);
+/* dependency-free integer multiply-add microbenchmark: device-wide instructions*lanes per second.
+ * mode 0: mad.lo.u32 (IMAD), 1: mad.hi.u32 (IMAD.HI), 2: mad.wide.u32 (IMAD.WIDE, 32x32+64) */
+int kzgb200_bench_imad(int device, int mode, double *per_s, double *ms_out);
 #ifdef __cplusplus
 }
 #endif
