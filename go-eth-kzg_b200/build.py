@@ -24,11 +24,29 @@ def needs_build():
     return any(os.path.getmtime(f) > t for f in _deps())
 
 
+# per-file extra flags.  kzgb200_verify.cu: ptxas -O1 (see the header of that file)
+PER_FILE = {"kzgb200_verify.cu": ["-Xptxas", "-O1"]}
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + _sources()
+    extra = os.environ.get("KZGB200_NVCC_EXTRA", "").split()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs, objs = [], []
+    for src in _sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        flags = [f for f in NVCC_FLAGS if f != "-shared"]
+        cmd = [nvcc] + flags + PER_FILE.get(os.path.basename(src), []) + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        print("[kzgb200] " + " ".join(cmd), file=sys.stderr)
+        procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    cmd = [nvcc, "-Wno-deprecated-gpu-targets", "-shared", "-o", SO] + objs
     print("[kzgb200] " + " ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
     return SO

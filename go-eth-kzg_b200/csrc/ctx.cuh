@@ -1,0 +1,133 @@
+// Shared host-side definitions of libkzgb200.so: error plumbing, the context object, staging helpers.
+// Included by both translation units (kzgb200.cu: setup + proving paths at full optimisation;
+// kzgb200_verify.cu: verification paths, built with -Xptxas -O1 -- see build.py for why).
+#pragma once
+#include "../../include/kzgb200.h"
+#include "../../include/kzgb200_debug.h"
+#include "msm.cuh"
+#include "fk20.cuh"
+#include "kzg4844.cuh"
+#include "recover.cuh"
+#include "pairing.cuh"
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <random>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace kzg;
+
+std::string &kzgb200_err_slot();   // thread-local last-error text (defined in kzgb200.cu)
+static inline int set_err(int code, const char *what, cudaError_t e = cudaSuccess) {
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    kzgb200_err_slot() = buf;
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return set_err(KZGB200_ERR_CUDA, #call, e_); } while (0)
+
+static const int N_BLOB = 4096;
+
+namespace kzg {
+// decompress + (optional) subgroup check of n compressed points; first error per status slot wins.
+// out may be null (validation only: prove.go:56-60 discards the point).
+static __global__ void k_g1_check(const uint8_t *__restrict__ in48, G1Aff *__restrict__ out, int32_t *__restrict__ status, size_t n, int per_status, int subgroup) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Aff a;
+    int32_t st = g1_decompress(a, in48 + i * 48);
+    if (st == ST_OK && subgroup && !g1_in_subgroup(&a, FP_BETA2)) st = ST_NOT_IN_SUBGROUP;
+    if (st != ST_OK) atomicCAS(&status[i / per_status], (int32_t)ST_OK, st);
+    if (out) out[i] = a;
+}
+
+}  // namespace kzg
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return set_err(KZGB200_ERR_CUDA, "cudaMalloc(scratch)", e);
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct kzgb200_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex mu;
+    // setup
+    G1Aff *g1_monomial = nullptr;      // natural order
+    G1Aff *g1_lagrange_brp = nullptr;  // bit-reversed order (api.go:131)
+    std::vector<uint8_t> g2_bytes;
+    MsmTable commit_tab{};
+    MsmTable fk20_tab{};
+    Fr *roots = nullptr;               // w_8192^t, Montgomery
+    int8_t *glv_digits = nullptr;      // [128][2][KZG_GLV_DIGITS]
+    Fr *pow7 = nullptr, *ipow7 = nullptr;   // 7^k, 7^-k (erasure_code.go:58 coset generator)
+    PairingConsts *pairing = nullptr;       // Frobenius constants + line tables of G2, [s]G2, [s^64]G2
+    MsmTable mono64_tab{};                  // digit table of monomial G1[0..63] (kzg_multi/srs.go:143-149)
+    std::mt19937_64 rng{std::random_device{}()};
+    // scratch
+    DevBuf in_bytes, scalars, status, sums, out_bytes, coeffs, cells, proofs_xyzz, in_small, in_small2, zbuf, ybuf;
+    DevBuf rec_a, rec_b, rec_meta, rec_zev, rec_czinv;
+    DevBuf v_aff1, v_aff2, v_T, v_fr, v_meta, v_S, v_W, v_partial, v_in2, v_in3, v_st2;
+    double init_ms = 0, last_device_ms = 0;
+    uint64_t launches = 0;
+    // per-kernel-class device timing of the last call (CUDA events on `stream`)
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> mark_cls;
+    size_t n_marks = 0;
+    double class_ms[KZGB200_N_KERNEL_CLASSES] = {0};
+    void marks_reset() { n_marks = 0; mark_cls.clear(); }
+    // the segment that starts here belongs to kernel class `cls` (-1 = end marker)
+    int mark(int cls) {
+        if (n_marks == ev_pool.size()) {
+            cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return 1;
+            ev_pool.push_back(e);
+        }
+        if (cudaEventRecord(ev_pool[n_marks], stream) != cudaSuccess) return 1;
+        mark_cls.push_back(cls); ++n_marks;
+        return 0;
+    }
+    void marks_collect() {   // stream must be synchronised
+        for (size_t i = 0; i + 1 < n_marks; ++i) {
+            float ms = 0;
+            if (mark_cls[i] >= 0 && cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]) == cudaSuccess) {
+                class_ms[mark_cls[i]] += ms; last_device_ms += ms;
+            }
+        }
+        marks_reset();
+    }
+    void timing_reset() { last_device_ms = 0; for (double &x : class_ms) x = 0; marks_reset(); }
+};
+
+static inline bool is_device_ptr(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// stage a (possibly host) input buffer on the device
+static inline int stage_in(kzgb200_ctx *c, const void *user, size_t bytes, DevBuf &buf, const void **dev) {
+    if (is_device_ptr(user)) { *dev = user; return 0; }
+    int rc = buf.ensure(bytes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(buf.p, user, bytes, cudaMemcpyHostToDevice, c->stream));
+    *dev = buf.p;
+    return 0;
+}
+

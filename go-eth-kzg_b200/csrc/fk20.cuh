@@ -28,7 +28,7 @@ namespace kzg {
 // ---- Fr side -----------------------------------------------------------------------------
 // grid = blobs, block = NTT_THREADS, dynamic smem = 4096*32 B
 #define KZG_NTT_THREADS 512
-__global__ void __launch_bounds__(KZG_NTT_THREADS) k_blob_ifft(const uint8_t *__restrict__ blobs, Fr *__restrict__ coeffs,
+static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_blob_ifft(const uint8_t *__restrict__ blobs, Fr *__restrict__ coeffs,
                                                                int32_t *__restrict__ status, const Fr *__restrict__ roots, Fr inv_n) {
     extern __shared__ uint32_t sm[];
     const int blob = blockIdx.x, tid = threadIdx.x;
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(KZG_NTT_THREADS) k_blob_ifft(const uint8_t *__
 }
 
 // cells[blob] = blob bytes || brp(coset FFT) ; failed blobs get zeros
-__global__ void __launch_bounds__(KZG_NTT_THREADS) k_coset_fft_cells(const Fr *__restrict__ coeffs, const uint8_t *__restrict__ blobs,
+static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_coset_fft_cells(const Fr *__restrict__ coeffs, const uint8_t *__restrict__ blobs,
                                                                      uint8_t *__restrict__ cells, const int32_t *__restrict__ status,
                                                                      const Fr *__restrict__ roots) {
     extern __shared__ uint32_t sm[];
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(KZG_NTT_THREADS) k_coset_fft_cells(const Fr *_
 }
 
 // grid = (64 rows, blobs), block = 64.  scalars[blob][q][row] = plain( FFT128(circulant row)[brp q] / 128 )
-__global__ void __launch_bounds__(64) k_fk20_rows(const Fr *__restrict__ coeffs, uint32_t *__restrict__ scalars,
+static __global__ void __launch_bounds__(64) k_fk20_rows(const Fr *__restrict__ coeffs, uint32_t *__restrict__ scalars,
                                                   const int32_t *__restrict__ status, const Fr *__restrict__ roots, Fr inv128_plain) {
     __shared__ uint32_t sm[128 * 8];
     const int row = blockIdx.x, blob = blockIdx.y, tid = threadIdx.x;
@@ -171,7 +171,7 @@ __device__ __forceinline__ void g1_fft128_smem(G1 *pts, const int8_t *__restrict
 // init: FK20 table rows.  grid = 64 (vector index i), block = 64.
 // S_i[m] = monomial[4031 - i - 64 m], m = 0..62, padded to 128 with the identity (fk20.go:29-33,
 // 141-167; toeplitz.go:76-87).  Output: fk_pts[q*64 + i] = FFT128(S_i)[brp q], affine.
-__global__ void __launch_bounds__(64) k_fk20_table_fft(const G1Aff *__restrict__ monomial, G1 *__restrict__ fk_pts, const int8_t *__restrict__ digits) {
+static __global__ void __launch_bounds__(64) k_fk20_table_fft(const G1Aff *__restrict__ monomial, G1 *__restrict__ fk_pts, const int8_t *__restrict__ digits) {
     __shared__ G1 pts[128];
     const int i = blockIdx.x, tid = threadIdx.x;
     for (int m = tid; m < 128; m += 64) pts[m] = m < 63 ? G1::from_affine(monomial[4031 - i - 64 * m]) : G1::infinity();
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(64) k_fk20_table_fft(const G1Aff *__restrict__
 }
 
 // per blob: u' (brp) --IFFT--> h --truncate/pad--> --FFT--> proofs (brp).  grid = blobs, block = 64
-__global__ void __launch_bounds__(64) k_fk20_g1fft(const G1 *__restrict__ u, G1 *__restrict__ proofs, const int32_t *__restrict__ status,
+static __global__ void __launch_bounds__(64) k_fk20_g1fft(const G1 *__restrict__ u, G1 *__restrict__ proofs, const int32_t *__restrict__ status,
                                                    const int8_t *__restrict__ digits) {
     __shared__ G1 pts[128];
     const int blob = blockIdx.x, tid = threadIdx.x;

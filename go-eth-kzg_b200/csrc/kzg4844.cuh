@@ -45,7 +45,7 @@ __device__ __forceinline__ void sha256_block(uint32_t *h, uint32_t *w) {
 // computeChallenge (fiatshamir.go:22-33): SHA-256("FSBLOBVERIFY_V1_" || u128_be(4096) || blob || commitment)
 // reduced mod r, written as plain little-endian limbs.  One thread per blob.
 // message = 32 + 131072 + 48 = 131152 bytes = 2049 full blocks + 16 bytes, then padding.
-__global__ void k_fiat_shamir(const uint8_t *__restrict__ blobs, const uint8_t *__restrict__ commitments, uint32_t *__restrict__ z_out, size_t n) {
+static __global__ void k_fiat_shamir(const uint8_t *__restrict__ blobs, const uint8_t *__restrict__ commitments, uint32_t *__restrict__ z_out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
@@ -101,7 +101,7 @@ __global__ void k_fiat_shamir(const uint8_t *__restrict__ blobs, const uint8_t *
 }
 
 // 32-byte big-endian scalars -> plain limbs with canonical check (DeserializeScalar, serialization.go:153-159)
-__global__ void k_scalars_from_be(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, int32_t *__restrict__ status, size_t n) {
+static __global__ void k_scalars_from_be(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, int32_t *__restrict__ status, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t l[8];
@@ -146,11 +146,13 @@ __device__ __forceinline__ Fr block_scan_mul(uint32_t *sm, Fr v, int tid, int di
 
 // Open (internal/kzg/kzg_prove.go:14-44) for one blob per CTA.
 //   in : blob bytes (Lagrange evaluations over the bit-reversed domain), z (plain limbs)
-//   out: y (32 B big-endian, optional), quotient scalars as plain limbs [4096][8] for k_msm_fixed
+//   out: y (32 B big-endian and/or plain limbs, optional), quotient scalars as plain limbs
+//        [4096][8] for k_msm_fixed (optional: null = EvaluateLagrangePolynomial only)
 // status[blob] must be pre-set (OK or an earlier error); non-canonical blob sets it here.
-__global__ void __launch_bounds__(KZG_NTT_THREADS) k_eval_quotient(const uint8_t *__restrict__ blobs, const uint32_t *__restrict__ z_limbs,
+static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_eval_quotient(const uint8_t *__restrict__ blobs, const uint32_t *__restrict__ z_limbs,
                                                                    const Fr *__restrict__ roots, int32_t *__restrict__ status,
-                                                                   uint32_t *__restrict__ quotient, uint8_t *__restrict__ y_out, Fr inv_n) {
+                                                                   uint32_t *__restrict__ quotient, uint8_t *__restrict__ y_out,
+                                                                   uint32_t *__restrict__ y_limbs, Fr inv_n) {
     constexpr int T = KZG_NTT_THREADS, PER = 4096 / T;
     __shared__ uint32_t sm[8 * T];
     __shared__ int s_index;
@@ -238,10 +240,15 @@ __global__ void __launch_bounds__(KZG_NTT_THREADS) k_eval_quotient(const uint8_t
         y = fr_mul_ni(fr_mul_ni(Fr::sub(zn, Fr::one()), inv_n), sum);
     }
     Fr one_plain = Fr::zero(); one_plain.v[0] = 1;
-    if (tid == 0 && y_out) {
+    if (tid == 0 && (y_out || y_limbs)) {
         Fr yp = fr_mul_ni(y, one_plain);
-        store_be32(y_out + (size_t)blob * 32, yp.v);
+        if (y_out) store_be32(y_out + (size_t)blob * 32, yp.v);
+        if (y_limbs) {
+#pragma unroll
+            for (int q8 = 0; q8 < 8; ++q8) y_limbs[(size_t)blob * 8 + q8] = yp.v[q8];
+        }
     }
+    if (!quotient) return;      // evaluation only (verify.go:69, 128)
     // ---- quotient ---------------------------------------------------------------------------------
     // outside: q_i = (f_i - y)/(w_i - z) = -(f_i - y) * inv_i                    (kzg_prove.go:81-111)
     // on domain (index m): same for i != m (den_m was replaced by 1), and

@@ -1,36 +1,12 @@
-// libkzgb200.so -- host side of the C ABI (include/kzgb200.h) and kernel launch plumbing.
+// libkzgb200.so -- host side of the C ABI (include/kzgb200.h): context creation and the
+// commit / prove / cells / recovery entry points.  The verification entry points live in
+// kzgb200_verify.cu.
 //
 // One context = one GPU.  All per-call scratch lives in a grow-only device arena owned by the
 // context; inputs are processed in chunks so the arena stays bounded regardless of batch size.
-#include "../../include/kzgb200.h"
-#include "../../include/kzgb200_debug.h"
-#include "msm.cuh"
-#include "fk20.cuh"
-#include "kzg4844.cuh"
-#include "recover.cuh"
-#include <cuda_runtime.h>
-#include <algorithm>
-#include <chrono>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <mutex>
-#include <string>
-#include <vector>
+#include "ctx.cuh"
 
-using namespace kzg;
-
-static thread_local std::string g_last_error;
-static int set_err(int code, const char *what, cudaError_t e = cudaSuccess) {
-    char buf[512];
-    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
-    else snprintf(buf, sizeof buf, "%s", what);
-    g_last_error = buf;
-    return code;
-}
-#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return set_err(KZGB200_ERR_CUDA, #call, e_); } while (0)
-
-static const int N_BLOB = 4096;
+std::string &kzgb200_err_slot() { static thread_local std::string s; return s; }
 
 // ===========================================================================================
 // kernels that belong to the API layer
@@ -38,7 +14,7 @@ static const int N_BLOB = 4096;
 namespace kzg {
 
 // trusted-setup ingestion: decompress n points; dst index optionally bit-reversed (api.go:131)
-__global__ void k_setup_decompress(const uint8_t *__restrict__ in, G1Aff *__restrict__ out, int n, int log_n_brp, int32_t *__restrict__ bad) {
+static __global__ void k_setup_decompress(const uint8_t *__restrict__ in, G1Aff *__restrict__ out, int n, int log_n_brp, int32_t *__restrict__ bad) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     G1Aff a;
@@ -50,7 +26,7 @@ __global__ void k_setup_decompress(const uint8_t *__restrict__ in, G1Aff *__rest
 
 // blob bytes -> plain little-endian scalar limbs + canonical check (serialization.go:134-146)
 // one thread per scalar; status[blob] = NON_CANONICAL if any scalar >= r
-__global__ void k_blob_to_scalars(const uint8_t *__restrict__ blobs, uint32_t *__restrict__ scalars, int32_t *__restrict__ status, size_t n_scalars, int per_item) {
+static __global__ void k_blob_to_scalars(const uint8_t *__restrict__ blobs, uint32_t *__restrict__ scalars, int32_t *__restrict__ status, size_t n_scalars, int per_item) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_scalars) return;
     uint32_t l[8];
@@ -62,7 +38,7 @@ __global__ void k_blob_to_scalars(const uint8_t *__restrict__ blobs, uint32_t *_
 }
 
 // XYZZ sums -> 48-byte compressed points; items with a non-OK status get zero bytes
-__global__ void k_finalize_g1(const G1 *__restrict__ in, uint8_t *__restrict__ out48, const int32_t *__restrict__ status, size_t n, int per_status) {
+static __global__ void k_finalize_g1(const G1 *__restrict__ in, uint8_t *__restrict__ out48, const int32_t *__restrict__ status, size_t n, int per_status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t *o = out48 + i * 48;
@@ -74,26 +50,15 @@ __global__ void k_finalize_g1(const G1 *__restrict__ in, uint8_t *__restrict__ o
     g1_compress(o, g1_to_affine(in[i]));
 }
 
-// decompress + (optional) subgroup check of n compressed points; first error per status slot wins.
-// out may be null (validation only: prove.go:56-60 discards the point).
-__global__ void k_g1_check(const uint8_t *__restrict__ in48, G1Aff *__restrict__ out, int32_t *__restrict__ status, size_t n, int per_status, int subgroup) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    G1Aff a;
-    int32_t st = g1_decompress(a, in48 + i * 48);
-    if (st == ST_OK && subgroup && !g1_in_subgroup(&a, FP_BETA2)) st = ST_NOT_IN_SUBGROUP;
-    if (st != ST_OK) atomicCAS(&status[i / per_status], (int32_t)ST_OK, st);
-    if (out) out[i] = a;
-}
 // zero the y outputs of failed items
-__global__ void k_zero_failed(uint8_t *__restrict__ out, const int32_t *__restrict__ status, size_t n, int bytes_per_item) {
+static __global__ void k_zero_failed(uint8_t *__restrict__ out, const int32_t *__restrict__ status, size_t n, int bytes_per_item) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || status[i] == ST_OK) return;
     for (int k = 0; k < bytes_per_item; ++k) out[i * bytes_per_item + k] = 0;
 }
 
 // ---- debug / unit-test kernels (include/kzgb200_debug.h) ----------------------------------
-__global__ void k_dbg_fp_mul(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op) {
+static __global__ void k_dbg_fp_mul(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fp x, y;
@@ -103,7 +68,7 @@ __global__ void k_dbg_fp_mul(const uint32_t *a, const uint32_t *b, uint32_t *out
     r = Fp::from_mont(r);
     for (int k = 0; k < 12; ++k) out[i * 12 + k] = r.v[k];
 }
-__global__ void k_dbg_fr_mul(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op) {
+static __global__ void k_dbg_fr_mul(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fr x, y;
@@ -114,7 +79,7 @@ __global__ void k_dbg_fr_mul(const uint32_t *a, const uint32_t *b, uint32_t *out
     for (int k = 0; k < 8; ++k) out[i * 8 + k] = r.v[k];
 }
 // out = a (op) b on compressed points: op 0 add (XYZZ+XYZZ), 1 mixed add, 2 double
-__global__ void k_dbg_g1_op(const uint8_t *a48, const uint8_t *b48, uint8_t *out48, int n, int op) {
+static __global__ void k_dbg_g1_op(const uint8_t *a48, const uint8_t *b48, uint8_t *out48, int n, int op) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     G1Aff a, b;
@@ -127,9 +92,10 @@ __global__ void k_dbg_g1_op(const uint8_t *a48, const uint8_t *b48, uint8_t *out
     else A = g1_dbl(A);
     g1_compress(out48 + i * 48, g1_to_affine(A));
 }
+
 // dependency-free integer multiply-add throughput probes: 8 independent chains per thread.
 // MODE 0: mad.lo.u32   1: mad.hi.u32   2: mad.wide.u32 (32x32+64 -> 64, one IMAD.WIDE)
-template <int MODE> __global__ void k_imad_peak(uint32_t *out, int iters, uint32_t seed) {
+template <int MODE> static __global__ void k_imad_peak(uint32_t *out, int iters, uint32_t seed) {
     uint32_t m = blockIdx.x * 2654435761u + 12345u + seed;
     if (MODE < 2) {
         uint32_t a[8];
@@ -172,76 +138,6 @@ template <int MODE> __global__ void k_imad_peak(uint32_t *out, int iters, uint32
 
 }  // namespace kzg
 
-// ===========================================================================================
-// context
-// ===========================================================================================
-struct DevBuf {
-    void *p = nullptr; size_t cap = 0;
-    int ensure(size_t bytes) {
-        if (bytes <= cap) return 0;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e != cudaSuccess) return set_err(KZGB200_ERR_CUDA, "cudaMalloc(scratch)", e);
-        cap = bytes;
-        return 0;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-struct kzgb200_ctx {
-    int device = 0, sm_count = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::mutex mu;
-    // setup
-    G1Aff *g1_monomial = nullptr;      // natural order
-    G1Aff *g1_lagrange_brp = nullptr;  // bit-reversed order (api.go:131)
-    std::vector<uint8_t> g2_bytes;
-    MsmTable commit_tab{};
-    MsmTable fk20_tab{};
-    Fr *roots = nullptr;               // w_8192^t, Montgomery
-    int8_t *glv_digits = nullptr;      // [128][2][KZG_GLV_DIGITS]
-    Fr *pow7 = nullptr, *ipow7 = nullptr;   // 7^k, 7^-k (erasure_code.go:58 coset generator)
-    // scratch
-    DevBuf in_bytes, scalars, status, sums, out_bytes, coeffs, cells, proofs_xyzz, in_small, in_small2, zbuf, ybuf;
-    DevBuf rec_a, rec_b, rec_meta, rec_zev, rec_czinv;
-    double init_ms = 0, last_device_ms = 0;
-    uint64_t launches = 0;
-    // per-kernel-class device timing of the last call (CUDA events on `stream`)
-    std::vector<cudaEvent_t> ev_pool;
-    std::vector<int> mark_cls;
-    size_t n_marks = 0;
-    double class_ms[KZGB200_N_KERNEL_CLASSES] = {0};
-    void marks_reset() { n_marks = 0; mark_cls.clear(); }
-    // the segment that starts here belongs to kernel class `cls` (-1 = end marker)
-    int mark(int cls) {
-        if (n_marks == ev_pool.size()) {
-            cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return 1;
-            ev_pool.push_back(e);
-        }
-        if (cudaEventRecord(ev_pool[n_marks], stream) != cudaSuccess) return 1;
-        mark_cls.push_back(cls); ++n_marks;
-        return 0;
-    }
-    void marks_collect() {   // stream must be synchronised
-        for (size_t i = 0; i + 1 < n_marks; ++i) {
-            float ms = 0;
-            if (mark_cls[i] >= 0 && cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]) == cudaSuccess) {
-                class_ms[mark_cls[i]] += ms; last_device_ms += ms;
-            }
-        }
-        marks_reset();
-    }
-    void timing_reset() { last_device_ms = 0; for (double &x : class_ms) x = 0; marks_reset(); }
-};
-
-static bool is_device_ptr(const void *p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
-}
-
 static int build_table(kzgb200_ctx *c, const G1Aff *pts, int npts, int window, MsmTable &tab) {
     tab.npts = npts; tab.c = window; tab.W = (256 + window - 1) / window; tab.H = 1 << (window - 1);
     size_t n_bases = (size_t)npts * tab.W;
@@ -263,7 +159,7 @@ static int build_table(kzgb200_ctx *c, const G1Aff *pts, int npts, int window, M
 
 extern "C" {
 
-const char *kzgb200_last_error(void) { return g_last_error.c_str(); }
+const char *kzgb200_last_error(void) { return kzgb200_err_slot().c_str(); }
 
 void *kzgb200_host_alloc(size_t bytes) {
     void *p = nullptr;
@@ -282,7 +178,9 @@ void kzgb200_ctx_free(kzgb200_ctx *c) {
     c->coeffs.release(); c->cells.release(); c->proofs_xyzz.release();
     c->in_small.release(); c->in_small2.release(); c->zbuf.release(); c->ybuf.release();
     c->rec_a.release(); c->rec_b.release(); c->rec_meta.release(); c->rec_zev.release(); c->rec_czinv.release();
-    cudaFree(c->pow7); cudaFree(c->ipow7);
+    cudaFree(c->pow7); cudaFree(c->ipow7); cudaFree(c->pairing); cudaFree(c->mono64_tab.entries);
+    c->v_aff1.release(); c->v_aff2.release(); c->v_T.release(); c->v_fr.release(); c->v_meta.release(); c->v_S.release();
+    c->v_W.release(); c->v_partial.release(); c->v_in2.release(); c->v_in3.release(); c->v_st2.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -360,6 +258,26 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
     CU(cudaGetLastError());
     rc = build_table(c, fk_aff, 8192, fw, c->fk20_tab);
     cudaFree(fk_xyzz); cudaFree(fk_aff);
+    if (rc) return rc;
+
+    // verification constants: G2 line tables (GPU, one thread per point) and the 64-point monomial table
+    {
+        uint8_t h_g2[3 * 96];
+        memcpy(h_g2, g2, 96); memcpy(h_g2 + 96, g2 + 96, 96); memcpy(h_g2 + 192, g2 + 64 * 96, 96);
+        uint8_t *d_g2 = nullptr; int32_t *d_bad2 = nullptr;
+        CU(cudaMalloc(&d_g2, sizeof h_g2)); CU(cudaMalloc(&d_bad2, 4));
+        CU(cudaMalloc(&c->pairing, sizeof(PairingConsts)));
+        CU(cudaMemsetAsync(d_bad2, 0, 4, c->stream));
+        CU(cudaMemcpyAsync(d_g2, h_g2, sizeof h_g2, cudaMemcpyHostToDevice, c->stream));
+        k_g2_prepare<<<1, 4, 0, c->stream>>>(d_g2, c->pairing, d_bad2);
+        c->launches += 1;
+        int32_t bad2 = 0;
+        CU(cudaMemcpyAsync(&bad2, d_bad2, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(d_g2); cudaFree(d_bad2);
+        if (bad2) return set_err(KZGB200_ERR_SETUP, "trusted setup: G2 point failed to decode");
+    }
+    rc = build_table(c, c->g1_monomial, 64, 10, c->mono64_tab);
     if (rc) return rc;
     return 0;
 }
@@ -449,16 +367,6 @@ int kzgb200_blob_to_kzg_commitment(kzgb200_ctx *c, const uint8_t *blobs, size_t 
 // -------------------------------------------------------------------------------------------
 // ComputeKZGProof (prove.go:85-111) and ComputeBlobKZGProof (prove.go:46-77)
 // -------------------------------------------------------------------------------------------
-// stage a (possibly host) input buffer on the device
-static int stage_in(kzgb200_ctx *c, const void *user, size_t bytes, DevBuf &buf, const void **dev) {
-    if (is_device_ptr(user)) { *dev = user; return 0; }
-    int rc = buf.ensure(bytes);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(buf.p, user, bytes, cudaMemcpyHostToDevice, c->stream));
-    *dev = buf.p;
-    return 0;
-}
-
 static int open_common(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *z32, const uint8_t *commitments, size_t n,
                        uint8_t *out_proof, uint8_t *out_y, int32_t *status) {
     if (!c || (n && (!blobs || !out_proof || !status || (!z32 && !commitments)))) return set_err(KZGB200_ERR_ARGS, "null argument");
@@ -499,7 +407,7 @@ static int open_common(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *z32,
             c->launches += 2;
         }
         k_eval_quotient<<<(unsigned)m, KZG_NTT_THREADS, 0, c->stream>>>((const uint8_t *)d_blobs, (const uint32_t *)c->zbuf.p, c->roots, d_status,
-                                                                         (uint32_t *)c->scalars.p, d_y, inv4096);
+                                                                         (uint32_t *)c->scalars.p, d_y, nullptr, inv4096);
         c->mark(KZGB200_KC_MSM);
         k_msm_fixed<<<dim3(1, (unsigned)m), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->commit_tab, N_BLOB, 1, TPB,
                                                                                   d_status, (G1 *)c->sums.p);

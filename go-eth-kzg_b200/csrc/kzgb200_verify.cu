@@ -1,0 +1,347 @@
+// libkzgb200.so -- verification entry points of the C ABI (include/kzgb200.h).
+//
+// Separate translation unit because it is compiled with `-Xptxas -O1`: at ptxas' default level
+// nvcc 12.9 miscompiles k_verify_single (the caller of the scalar multiplication mixes a stale
+// register into the reloaded point; caught by the reference's verify_kzg_proof vectors, gone at
+// -O1, PTX identical).  These kernels are latency-bound one-thread-per-check code, so the lower
+// optimisation level costs nothing measurable; the throughput kernels stay in kzgb200.cu.
+#include "ctx.cuh"
+#include "verify.cuh"
+
+namespace kzg {
+static __global__ void k_dbg_g1_mul(const uint8_t *p48, const uint8_t *s32, uint8_t *out48, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Aff a; g1_decompress(a, p48 + i * 48);
+    uint32_t k[8]; load_be32(k, s32 + i * 32);
+    G1 P = G1::from_affine(a), r;
+    g1_mul_scalar(&r, &P, k);
+    g1_compress(out48 + i * 48, g1_to_affine(r));
+}
+static __global__ void k_dbg_pairing(const PairingConsts *pc, const uint8_t *a48, const int *qa, const uint8_t *b48, const int *qb, int *out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Aff a, b;
+    g1_decompress(a, a48 + i * 48); g1_decompress(b, b48 + i * 48);
+    out[i] = pairing_check2(pc, &a, qa[i], &b, qb[i]) ? 1 : 0;
+}
+static __global__ void k_dbg_dump_pairing(const PairingConsts *pc, uint32_t *out) {
+    // gamma[1] (24 limbs, plain), then q[0].A[0], q[0].B[0], q[0].A[67] (24 limbs each)
+    Fp o1 = Fp::zero(); o1.v[0] = 1;
+    const Fp2 *src[4] = {&pc->gamma[1], &pc->q[0].A[0], &pc->q[0].B[0], &pc->q[0].A[67]};
+    for (int s = 0; s < 4; ++s) {
+        Fp a = fp_mul_ni(src[s]->c0, o1), b = fp_mul_ni(src[s]->c1, o1);
+        for (int k = 0; k < 12; ++k) { out[s * 24 + k] = a.v[k]; out[s * 24 + 12 + k] = b.v[k]; }
+    }
+}
+}  // namespace kzg
+
+extern "C" {
+
+// -------------------------------------------------------------------------------------------
+// Verifiers (verify.go:12-169, api_eip7594.go:163-265)
+// -------------------------------------------------------------------------------------------
+static const size_t VERIFY_CHUNK = 1024;
+
+// shared front end: decode commitments/proofs, obtain z and y (given, or Fiat-Shamir + evaluation)
+//   blobs == nullptr: z32/y32 given (VerifyKZGProof); else z = challenge, y = p(z)
+// leaves: v_aff1 = commitments, v_aff2 = proofs, zbuf = z limbs, ybuf = y limbs, d_status filled
+static int verify_front(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm48, const uint8_t *z32, const uint8_t *y32, const uint8_t *pf48,
+                        size_t m, int32_t *d_status) {
+    int rc;
+    const void *d_cm, *d_pf, *d_blobs = nullptr, *d_z = nullptr, *d_y = nullptr;
+    if ((rc = stage_in(c, cm48, m * 48, c->in_small, &d_cm))) return rc;
+    if ((rc = stage_in(c, pf48, m * 48, c->in_small2, &d_pf))) return rc;
+    if (blobs) { if ((rc = stage_in(c, blobs, m * KZGB200_BYTES_PER_BLOB, c->in_bytes, &d_blobs))) return rc; }
+    else {
+        if ((rc = stage_in(c, z32, m * 32, c->v_in2, &d_z))) return rc;
+        if ((rc = stage_in(c, y32, m * 32, c->v_in3, &d_y))) return rc;
+    }
+    if ((rc = c->v_aff1.ensure(m * sizeof(G1Aff)))) return rc;
+    if ((rc = c->v_aff2.ensure(m * sizeof(G1Aff)))) return rc;
+    if ((rc = c->zbuf.ensure(m * 32))) return rc;
+    if ((rc = c->ybuf.ensure(m * 32))) return rc;
+    unsigned gb = (unsigned)((m + 63) / 64);
+    Fr inv4096; memcpy(inv4096.v, H_FR_INV4096, sizeof inv4096.v);
+    c->mark(KZGB200_KC_VERIFY);
+    CU(cudaMemsetAsync(d_status, 0, m * sizeof(int32_t), c->stream));
+    if (!blobs) {
+        k_scalars_from_be<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_y, (uint32_t *)c->ybuf.p, d_status, m);
+        k_scalars_from_be<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_z, (uint32_t *)c->zbuf.p, d_status, m);
+        c->launches += 2;
+    }
+    k_g1_check<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_cm, (G1Aff *)c->v_aff1.p, d_status, m, 1, 1);
+    k_g1_check<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_pf, (G1Aff *)c->v_aff2.p, d_status, m, 1, 1);
+    c->launches += 2;
+    if (blobs) {
+        c->mark(KZGB200_KC_FR);
+        k_fiat_shamir<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_blobs, (const uint8_t *)d_cm, (uint32_t *)c->zbuf.p, m);
+        k_eval_quotient<<<(unsigned)m, KZG_NTT_THREADS, 0, c->stream>>>((const uint8_t *)d_blobs, (const uint32_t *)c->zbuf.p, c->roots, d_status,
+                                                                         nullptr, nullptr, (uint32_t *)c->ybuf.p, inv4096);
+        c->launches += 2;
+    }
+    return 0;
+}
+
+static int verify_independent(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm48, const uint8_t *z32, const uint8_t *y32,
+                              const uint8_t *pf48, size_t n, int32_t *status) {
+    if (!c || (n && (!cm48 || !pf48 || !status || (!blobs && (!z32 || !y32))))) return set_err(KZGB200_ERR_ARGS, "null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    c->timing_reset();
+    if (n == 0) return KZGB200_OK;
+    const bool st_dev = is_device_ptr(status);
+    const size_t chunk = std::min(n, VERIFY_CHUNK);
+    int rc;
+    if ((rc = c->status.ensure(chunk * sizeof(int32_t)))) return rc;
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t m = std::min(chunk, n - off);
+        int32_t *d_status = st_dev ? status + off : (int32_t *)c->status.p;
+        if ((rc = verify_front(c, blobs ? blobs + off * KZGB200_BYTES_PER_BLOB : nullptr, cm48 + off * 48, z32 ? z32 + off * 32 : nullptr,
+                               y32 ? y32 + off * 32 : nullptr, pf48 + off * 48, m, d_status))) return rc;
+        c->mark(KZGB200_KC_VERIFY);
+        k_verify_single<<<(unsigned)((m + 63) / 64), 64, 0, c->stream>>>((const G1Aff *)c->v_aff1.p, (const G1Aff *)c->v_aff2.p, (const uint32_t *)c->zbuf.p,
+                                                                          (const uint32_t *)c->ybuf.p, c->g1_monomial, c->pairing, d_status, m);
+        c->launches += 1;
+        c->mark(-1);
+        CU(cudaGetLastError());
+        if (!st_dev) CU(cudaMemcpyAsync(status + off, d_status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->marks_collect();
+    }
+    return KZGB200_OK;
+}
+
+int kzgb200_verify_kzg_proof(kzgb200_ctx *c, const uint8_t *commitments48, const uint8_t *z32, const uint8_t *y32, const uint8_t *proofs48, size_t n, int32_t *status) {
+    if (n && (!z32 || !y32)) return set_err(KZGB200_ERR_ARGS, "null argument");
+    return verify_independent(c, nullptr, commitments48, z32, y32, proofs48, n, status);
+}
+int kzgb200_verify_blob_kzg_proof(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *commitments48, const uint8_t *proofs48, size_t n, int32_t *status) {
+    if (n && !blobs) return set_err(KZGB200_ERR_ARGS, "null argument");
+    return verify_independent(c, blobs, commitments48, nullptr, nullptr, proofs48, n, status);
+}
+
+static void random_scalar_plain(kzgb200_ctx *c, uint32_t *limbs) {   // 248 uniformly random bits (< r)
+    for (int i = 0; i < 4; ++i) { uint64_t v = c->rng(); limbs[2 * i] = (uint32_t)v; limbs[2 * i + 1] = (uint32_t)(v >> 32); }
+    limbs[7] &= 0x00ffffffu;
+    if (!(limbs[0] | limbs[1] | limbs[2] | limbs[3])) limbs[0] = 1;
+}
+
+// VerifyBlobKZGProofBatch (verify.go:88-145 + internal/kzg/kzg_verify.go:111-202): one verdict
+int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm48, const uint8_t *pf48, size_t n, int32_t *result) {
+    if (!c || !result || (n && (!blobs || !cm48 || !pf48))) return set_err(KZGB200_ERR_ARGS, "null argument");
+    if (is_device_ptr(result)) return set_err(KZGB200_ERR_ARGS, "result must be a host pointer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    c->timing_reset();
+    *result = KZGB200_OK;
+    if (n == 0) return KZGB200_OK;                       // kzg_verify.go:120-122
+    int rc;
+    if ((rc = c->status.ensure(n * sizeof(int32_t)))) return rc;
+    if ((rc = c->v_T.ensure(3 * n * sizeof(G1)))) return rc;
+    if ((rc = c->v_fr.ensure(n * sizeof(Fr)))) return rc;
+    if ((rc = c->v_st2.ensure(sizeof(int32_t)))) return rc;
+    // the per-blob front end runs in chunks (bounded staging), all writing into full-size arrays
+    if ((rc = c->v_aff1.ensure(n * sizeof(G1Aff)))) return rc;
+    if ((rc = c->v_aff2.ensure(n * sizeof(G1Aff)))) return rc;
+    if ((rc = c->zbuf.ensure(n * 32))) return rc;
+    if ((rc = c->ybuf.ensure(n * 32))) return rc;
+    {
+        // verify_front works on [0, m): run it per chunk with shifted base pointers by temporarily offsetting the buffers
+        const size_t chunk = std::min(n, VERIFY_CHUNK);
+        DevBuf a1 = c->v_aff1, a2 = c->v_aff2, zb = c->zbuf, yb = c->ybuf;
+        for (size_t off = 0; off < n; off += chunk) {
+            size_t m = std::min(chunk, n - off);
+            c->v_aff1.p = (char *)a1.p + off * sizeof(G1Aff); c->v_aff1.cap = a1.cap - off * sizeof(G1Aff);
+            c->v_aff2.p = (char *)a2.p + off * sizeof(G1Aff); c->v_aff2.cap = a2.cap - off * sizeof(G1Aff);
+            c->zbuf.p = (char *)zb.p + off * 32; c->zbuf.cap = zb.cap - off * 32;
+            c->ybuf.p = (char *)yb.p + off * 32; c->ybuf.cap = yb.cap - off * 32;
+            rc = verify_front(c, blobs + off * KZGB200_BYTES_PER_BLOB, cm48 + off * 48, nullptr, nullptr, pf48 + off * 48, m, (int32_t *)c->status.p + off);
+            if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = set_err(KZGB200_ERR_CUDA, "sync");
+            c->v_aff1 = a1; c->v_aff2 = a2; c->zbuf = zb; c->ybuf = yb;
+            if (rc) return rc;
+        }
+    }
+    std::vector<int32_t> h_status(n);
+    CU(cudaMemcpyAsync(h_status.data(), c->status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; ++i) if (h_status[i] != KZGB200_OK) { *result = h_status[i]; c->marks_collect(); return KZGB200_OK; }   // first failing element (verify.go:102-119)
+    uint32_t r_plain[8];
+    random_scalar_plain(c, r_plain);
+    if (n == 1) { memset(r_plain, 0, sizeof r_plain); r_plain[0] = 1; }
+    // Montgomery form of r on the host: r * R mod p needs big arithmetic; let the kernel convert
+    Fr r_dev; memcpy(r_dev.v, r_plain, sizeof r_plain);
+    c->mark(KZGB200_KC_VERIFY);
+    k_rlc_terms<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>((const G1Aff *)c->v_aff1.p, (const G1Aff *)c->v_aff2.p, (const uint32_t *)c->zbuf.p,
+                                                                  (const uint32_t *)c->ybuf.p, r_dev, (const int32_t *)c->status.p, (G1 *)c->v_T.p, (Fr *)c->v_fr.p, n);
+    k_rlc_finish<<<1, 128, 0, c->stream>>>((const G1 *)c->v_T.p, (const Fr *)c->v_fr.p, n, c->g1_monomial, c->pairing, (int32_t *)c->v_st2.p);
+    c->launches += 2;
+    c->mark(-1);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(result, c->v_st2.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->marks_collect();
+    return KZGB200_OK;
+}
+
+// VerifyCellKZGProofBatch (api_eip7594.go:163-265 + internal/kzg_multi/kzg_verify.go:16-105)
+// cell_indices and batch_offsets (n_batches+1 entries) are read on the host.
+int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitments48, const uint64_t *cell_indices, const uint8_t *cells,
+                                        const uint8_t *proofs48, size_t N, const uint64_t *batch_offsets, size_t nb, int32_t *results) {
+    if (!c || (nb && (!batch_offsets || !results)) || (N && (!commitments48 || !cell_indices || !cells || !proofs48)))
+        return set_err(KZGB200_ERR_ARGS, "null argument");
+    if (N && (is_device_ptr(cell_indices) || is_device_ptr(batch_offsets))) return set_err(KZGB200_ERR_ARGS, "cell_indices/batch_offsets must be host pointers");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    c->timing_reset();
+    if (nb == 0) return KZGB200_OK;
+    const bool res_dev = is_device_ptr(results);
+    int rc;
+    // ---- host: commitments for de-duplication -------------------------------------------------
+    std::vector<uint8_t> h_cm_copy;
+    const uint8_t *h_cm = commitments48;
+    if (N && is_device_ptr(commitments48)) {
+        h_cm_copy.resize(N * 48);
+        CU(cudaMemcpy(h_cm_copy.data(), commitments48, N * 48, cudaMemcpyDeviceToHost));
+        h_cm = h_cm_copy.data();
+    }
+    std::vector<int32_t> h_bstatus(nb, KZGB200_OK);
+    std::vector<uint32_t> batch_of(N), order(N), row_cells(N);
+    std::vector<uint64_t> batch_start(nb), col_off(nb * 128 + 1, 0), batch_row_off(nb + 1, 0), row_off(1, 0), item_start, item_end, batch_item_off(nb + 1, 0);
+    std::vector<uint8_t> uniq_bytes;
+    const uint64_t ITEM = 512;
+    size_t ord_pos = 0, rc_pos = 0;
+    for (size_t b = 0; b < nb; ++b) {
+        uint64_t lo = batch_offsets[b], hi = batch_offsets[b + 1];
+        if (hi < lo || hi > N) return set_err(KZGB200_ERR_ARGS, "batch_offsets not monotone / out of range");
+        batch_start[b] = lo;
+        // de-duplicate on raw bytes, first-seen order (api_eip7594.go:238-265)
+        std::unordered_map<std::string, uint32_t> seen;
+        std::vector<std::vector<uint32_t>> rows;
+        std::vector<std::vector<uint32_t>> cols(128);
+        for (uint64_t k = lo; k < hi; ++k) {
+            batch_of[k] = (uint32_t)b;
+            std::string key((const char *)h_cm + k * 48, 48);
+            auto it = seen.find(key);
+            uint32_t row;
+            if (it == seen.end()) { row = (uint32_t)rows.size(); seen.emplace(key, row); rows.emplace_back(); uniq_bytes.insert(uniq_bytes.end(), key.begin(), key.end()); }
+            else row = it->second;
+            rows[row].push_back((uint32_t)k);
+            if (cell_indices[k] >= 128) h_bstatus[b] = KZGB200_BAD_CELL_INDEX;      // api_eip7594.go:184-188
+            else cols[cell_indices[k]].push_back((uint32_t)k);
+        }
+        for (int cidx = 0; cidx < 128; ++cidx) {
+            for (uint32_t k : cols[cidx]) order[ord_pos++] = k;
+            col_off[b * 128 + cidx + 1] = ord_pos;
+        }
+        for (auto &rw : rows) { for (uint32_t k : rw) row_cells[rc_pos++] = k; row_off.push_back(rc_pos); }
+        batch_row_off[b + 1] = row_off.size() - 1;
+        for (uint64_t s = lo; s < hi; s += ITEM) { item_start.push_back(s); item_end.push_back(std::min(hi, s + ITEM)); }
+        batch_item_off[b + 1] = item_start.size();
+    }
+    // cells with an out-of-range index were skipped in `order`; col_off stays consistent because ord_pos only counts placed cells
+    const size_t U = row_off.size() - 1, n_items = item_start.size();
+    std::vector<uint32_t> r_plain(nb * 8);
+    for (size_t b = 0; b < nb; ++b) random_scalar_plain(c, &r_plain[b * 8]);
+    std::vector<uint32_t> row_batch(U);
+    for (size_t b = 0; b < nb; ++b) for (uint64_t rw = batch_row_off[b]; rw < batch_row_off[b + 1]; ++rw) row_batch[rw] = (uint32_t)b;
+
+    // ---- device buffers ---------------------------------------------------------------------------
+    const void *d_cells, *d_proofs;
+    if ((rc = stage_in(c, cells, N * 2048, c->in_bytes, &d_cells))) return rc;
+    if ((rc = stage_in(c, proofs48, N * 48, c->in_small, &d_proofs))) return rc;
+    if ((rc = c->in_small2.ensure(std::max<size_t>(U, 1) * 48))) return rc;
+    if (U) CU(cudaMemcpyAsync(c->in_small2.p, uniq_bytes.data(), U * 48, cudaMemcpyHostToDevice, c->stream));
+    // meta arena layout
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) & ~(size_t)255; return at; };
+    size_t o_idx = take(N * 8), o_batch_of = take(N * 4), o_bstart = take(nb * 8), o_order = take(N * 4), o_col = take((nb * 128 + 1) * 8);
+    size_t o_rowc = take(N * 4), o_rowoff = take((U + 1) * 8), o_browoff = take((nb + 1) * 8), o_is = take(n_items * 8), o_ie = take(n_items * 8);
+    size_t o_bio = take((nb + 1) * 8), o_r = take(nb * 32), o_bst = take(nb * 4), o_cst = take(std::max<size_t>(N, 1) * 4), o_ust = take(std::max<size_t>(U, 1) * 4);
+    size_t o_rowb = take(std::max<size_t>(U, 1) * 4), o_res = take(nb * 4);
+    if ((rc = c->v_meta.ensure(o))) return rc;
+    char *M = (char *)c->v_meta.p;
+    auto up = [&](size_t at, const void *src, size_t bytes) { return bytes ? cudaMemcpyAsync(M + at, src, bytes, cudaMemcpyHostToDevice, c->stream) : cudaSuccess; };
+    CU(up(o_idx, cell_indices, N * 8)); CU(up(o_batch_of, batch_of.data(), N * 4)); CU(up(o_bstart, batch_start.data(), nb * 8));
+    CU(up(o_order, order.data(), N * 4)); CU(up(o_col, col_off.data(), (nb * 128 + 1) * 8)); CU(up(o_rowc, row_cells.data(), N * 4));
+    CU(up(o_rowoff, row_off.data(), (U + 1) * 8)); CU(up(o_browoff, batch_row_off.data(), (nb + 1) * 8));
+    CU(up(o_is, item_start.data(), n_items * 8)); CU(up(o_ie, item_end.data(), n_items * 8)); CU(up(o_bio, batch_item_off.data(), (nb + 1) * 8));
+    CU(up(o_r, r_plain.data(), nb * 32)); CU(up(o_bst, h_bstatus.data(), nb * 4)); CU(up(o_rowb, row_batch.data(), U * 4));
+    CU(cudaMemsetAsync(M + o_cst, 0, std::max<size_t>(N, 1) * 4, c->stream));
+    CU(cudaMemsetAsync(M + o_ust, 0, std::max<size_t>(U, 1) * 4, c->stream));
+    if ((rc = c->v_aff1.ensure(std::max<size_t>(U, 1) * sizeof(G1Aff)))) return rc;
+    if ((rc = c->v_aff2.ensure(std::max<size_t>(N, 1) * sizeof(G1Aff)))) return rc;
+    if ((rc = c->v_T.ensure(std::max<size_t>(N, 1) * sizeof(G1)))) return rc;
+    if ((rc = c->v_fr.ensure(std::max<size_t>(N, 1) * sizeof(Fr)))) return rc;
+    if ((rc = c->v_S.ensure(nb * 128 * sizeof(G1)))) return rc;
+    if ((rc = c->v_W.ensure(nb * 128 * sizeof(G1)))) return rc;
+    if ((rc = c->v_partial.ensure(std::max<size_t>(n_items, 1) * 64 * sizeof(Fr)))) return rc;
+    if ((rc = c->scalars.ensure(nb * 64 * 32))) return rc;
+    if ((rc = c->sums.ensure(nb * sizeof(G1)))) return rc;
+    Fr inv64; memcpy(inv64.v, H_FR_INV64, sizeof inv64.v);
+    int32_t *d_cst = (int32_t *)(M + o_cst), *d_ust = (int32_t *)(M + o_ust), *d_bst = (int32_t *)(M + o_bst), *d_res = (int32_t *)(M + o_res);
+    c->mark(KZGB200_KC_VERIFY);
+    if (U) k_g1_check<<<(unsigned)((U + 63) / 64), 64, 0, c->stream>>>((const uint8_t *)c->in_small2.p, (G1Aff *)c->v_aff1.p, d_ust, U, 1, 1);
+    if (N) {
+        unsigned gN = (unsigned)((N + 63) / 64);
+        k_g1_check<<<gN, 64, 0, c->stream>>>((const uint8_t *)d_proofs, (G1Aff *)c->v_aff2.p, d_cst, N, 1, 1);
+        k_cell_rpow_plain<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>((const uint32_t *)(M + o_r), (const uint32_t *)(M + o_batch_of), (const uint64_t *)(M + o_bstart), (Fr *)c->v_fr.p, N);
+        k_cell_proof_terms<<<gN, 64, 0, c->stream>>>((const G1Aff *)c->v_aff2.p, (const Fr *)c->v_fr.p, d_cst, (G1 *)c->v_T.p, N);
+        c->mark(KZGB200_KC_FR);
+        k_cell_interp<<<(unsigned)n_items, 256, 0, c->stream>>>((const uint8_t *)d_cells, (const uint64_t *)(M + o_idx), (const Fr *)c->v_fr.p, (const uint64_t *)(M + o_is),
+                                                                (const uint64_t *)(M + o_ie), c->roots, inv64, d_cst, (Fr *)c->v_partial.p);
+        c->launches += 4;
+    }
+    k_cell_interp_reduce<<<(unsigned)nb, 64, 0, c->stream>>>((const Fr *)c->v_partial.p, (const uint64_t *)(M + o_bio), (uint32_t *)c->scalars.p);
+    c->mark(KZGB200_KC_MSM);
+    k_msm_fixed<<<dim3(1, (unsigned)nb), 32, 32 * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p);
+    c->mark(KZGB200_KC_VERIFY);
+    k_cell_columns<<<(unsigned)nb, 128, 0, c->stream>>>((const G1 *)c->v_T.p, (const uint32_t *)(M + o_order), (const uint64_t *)(M + o_col), c->glv_digits, (G1 *)c->v_S.p, (G1 *)c->v_W.p);
+    if (N) k_merge_status<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(d_cst, (const uint32_t *)(M + o_batch_of), d_bst, N);
+    if (U) k_merge_status<<<(unsigned)((U + 127) / 128), 128, 0, c->stream>>>(d_ust, (const uint32_t *)(M + o_rowb), d_bst, U);
+    k_cell_finish<<<(unsigned)((nb + 31) / 32), 32, 0, c->stream>>>((const G1 *)c->v_S.p, (const G1 *)c->v_W.p, (const G1 *)c->sums.p, (const G1Aff *)c->v_aff1.p,
+                                                                     (const uint64_t *)(M + o_rowoff), (const uint64_t *)(M + o_browoff), (const uint32_t *)(M + o_rowc),
+                                                                     (const Fr *)c->v_fr.p, c->pairing, d_bst, d_res, nb);
+    c->launches += 6;
+    c->mark(-1);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(results, d_res, nb * 4, res_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->marks_collect();
+    return KZGB200_OK;
+}
+
+int kzgb200_dbg_g1_mul(const uint8_t *p48, const uint8_t *s32, uint8_t *out48, int n) {
+    uint8_t *dp, *ds, *dout;
+    CU(cudaMalloc(&dp, n * 48)); CU(cudaMalloc(&ds, n * 32)); CU(cudaMalloc(&dout, n * 48));
+    CU(cudaMemcpy(dp, p48, n * 48, cudaMemcpyHostToDevice)); CU(cudaMemcpy(ds, s32, n * 32, cudaMemcpyHostToDevice));
+    k_dbg_g1_mul<<<(n + 31) / 32, 32>>>(dp, ds, dout, n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out48, dout, n * 48, cudaMemcpyDeviceToHost));
+    cudaFree(dp); cudaFree(ds); cudaFree(dout);
+    return 0;
+}
+int kzgb200_dbg_pairing(kzgb200_ctx *c, const uint8_t *a48, const int *qa, const uint8_t *b48, const int *qb, int *out, int n) {
+    uint8_t *da, *db; int *dqa, *dqb, *dout;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMalloc(&da, n * 48)); CU(cudaMalloc(&db, n * 48)); CU(cudaMalloc(&dqa, n * 4)); CU(cudaMalloc(&dqb, n * 4)); CU(cudaMalloc(&dout, n * 4));
+    CU(cudaMemcpy(da, a48, n * 48, cudaMemcpyHostToDevice)); CU(cudaMemcpy(db, b48, n * 48, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dqa, qa, n * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(dqb, qb, n * 4, cudaMemcpyHostToDevice));
+    k_dbg_pairing<<<(n + 31) / 32, 32>>>(c->pairing, da, dqa, db, dqb, dout, n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, dout, n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dqa); cudaFree(dqb); cudaFree(dout);
+    return 0;
+}
+int kzgb200_dbg_dump_pairing(kzgb200_ctx *c, uint32_t *out96) {
+    uint32_t *d;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMalloc(&d, 96 * 4));
+    k_dbg_dump_pairing<<<1, 1>>>(c->pairing, d);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out96, d, 96 * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return 0;
+}
+
+}  // extern "C"

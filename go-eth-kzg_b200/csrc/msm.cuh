@@ -71,7 +71,7 @@ __device__ __forceinline__ G1Aff load_aff(const G1Aff *p) {
 //   commit:  group_pts = 4096, n_groups = 1,   L = blockDim.x
 //   FK20:    group_pts = 64,   n_groups = 128, L = 8 (16 groups per 128-thread block)
 extern __shared__ unsigned char msm_smem[];
-__global__ void __launch_bounds__(128) k_msm_fixed(const uint32_t *__restrict__ scalars, MsmTable tab, int group_pts,
+static __global__ void __launch_bounds__(128) k_msm_fixed(const uint32_t *__restrict__ scalars, MsmTable tab, int group_pts,
                                                     int n_groups, int L, const int32_t *__restrict__ status, G1 *__restrict__ out) {
     const int blob = blockIdx.y, t = threadIdx.x;
     if (status && status[blob] != ST_OK) return;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(128) k_msm_fixed(const uint32_t *__restrict__ 
 
 // ---- table construction (context init) ---------------------------------------------------
 // step 1: bases[(j*W + k)] = 2^(c*k) * P_j  in XYZZ
-__global__ void k_table_bases(const G1Aff *__restrict__ pts, int npts, int c, int W, G1 *__restrict__ bases) {
+static __global__ void k_table_bases(const G1Aff *__restrict__ pts, int npts, int c, int W, G1 *__restrict__ bases) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= npts) return;
     G1 q = G1::from_affine(pts[j]);
@@ -123,7 +123,7 @@ __global__ void k_table_bases(const G1Aff *__restrict__ pts, int npts, int c, in
     }
 }
 // XYZZ -> affine, one thread per point (used only at init / for small batches)
-__global__ void k_to_affine(const G1 *__restrict__ in, G1Aff *__restrict__ out, size_t n) {
+static __global__ void k_to_affine(const G1 *__restrict__ in, G1Aff *__restrict__ out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     out[i] = g1_to_affine(in[i]);
@@ -131,7 +131,7 @@ __global__ void k_to_affine(const G1 *__restrict__ in, G1Aff *__restrict__ out, 
 // step 2: for base b = (j,k) and chunk q of CH digits: entries d = q*CH+1 .. q*CH+CH of d*Q_b,
 // batch-normalised with one inversion per chunk.
 #define KZG_TABLE_CHUNK 16
-__global__ void __launch_bounds__(64) k_table_fill(const G1Aff *__restrict__ bases_aff, size_t n_bases, int H, G1Aff *__restrict__ table) {
+static __global__ void __launch_bounds__(64) k_table_fill(const G1Aff *__restrict__ bases_aff, size_t n_bases, int H, G1Aff *__restrict__ table) {
     const int chunks = (H + KZG_TABLE_CHUNK - 1) / KZG_TABLE_CHUNK;
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n_bases * chunks) return;

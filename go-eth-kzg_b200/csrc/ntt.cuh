@@ -76,7 +76,7 @@ __device__ __forceinline__ void ntt_smem(uint32_t *sm, const Fr *__restrict__ ro
 }
 
 // roots[t] = w_8192^t, one thread per t (square-and-multiply from the generator)
-__global__ void k_init_roots(Fr *roots, Fr gen_mont) {
+static __global__ void k_init_roots(Fr *roots, Fr gen_mont) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ROOTS_N) return;
     Fr r = Fr::one();

@@ -19,7 +19,7 @@
 namespace kzg {
 
 // pow7[k] = 7^k (k < 8192) and ipow7[k] = 7^-k, Montgomery; one thread per k
-__global__ void k_init_pow7(Fr *pow7, Fr *ipow7, Fr seven, Fr inv7) {
+static __global__ void k_init_pow7(Fr *pow7, Fr *ipow7, Fr seven, Fr inv7) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 8192) return;
     Fr a = Fr::one(), b = Fr::one();
@@ -32,7 +32,7 @@ __global__ void k_init_pow7(Fr *pow7, Fr *ipow7, Fr seven, Fr inv7) {
 
 // K0: per blob (128 threads): vanishing polynomial of the missing cells and its two evaluation
 // tables.  present[blob][c] != 0 marks provided cells.  Outputs zev[blob][128], czinv[blob][128].
-__global__ void __launch_bounds__(128) k_rec_vanishing(const uint8_t *__restrict__ present, const int32_t *__restrict__ status,
+static __global__ void __launch_bounds__(128) k_rec_vanishing(const uint8_t *__restrict__ present, const int32_t *__restrict__ status,
                                                        const Fr *__restrict__ roots, const Fr *__restrict__ pow7,
                                                        Fr *__restrict__ zev, Fr *__restrict__ czinv) {
     __shared__ uint32_t za[128 * 8];   // Zs coefficients (limb planes), later FFT workspace
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) k_rec_vanishing(const uint8_t *__restrict
 
 // K1: ez[blob][i] = E_brp[i] * zev[cell(i)]  (zero for missing cells); canonical check of the cells.
 // cell_slot[blob][c] = index of cell c inside this blob's provided cells (-1 if missing); cells_base[blob] = first cell.
-__global__ void k_rec_scale(const uint8_t *__restrict__ cells, const int32_t *__restrict__ cell_slot, const uint64_t *__restrict__ cells_base,
+static __global__ void k_rec_scale(const uint8_t *__restrict__ cells, const int32_t *__restrict__ cell_slot, const uint64_t *__restrict__ cells_base,
                             const Fr *__restrict__ zev, int32_t *__restrict__ status, Fr *__restrict__ ez) {
     const int blob = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // 0..8191
@@ -109,7 +109,7 @@ __global__ void k_rec_scale(const uint8_t *__restrict__ cells, const int32_t *__
 
 // size-4096 inverse DIT on one half of a brp-ordered size-8192 input.  grid = (2, blobs).
 // out half h, natural order, unscaled:  h=0 -> A[k] (even samples), h=1 -> B[k] (odd samples)
-__global__ void __launch_bounds__(KZG_NTT_THREADS) k_half_dit_inv(const Fr *__restrict__ in, Fr *__restrict__ out, const int32_t *__restrict__ status,
+static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_half_dit_inv(const Fr *__restrict__ in, Fr *__restrict__ out, const int32_t *__restrict__ status,
                                                                   const Fr *__restrict__ roots) {
     extern __shared__ uint32_t sm[];
     const int h = blockIdx.x, blob = blockIdx.y, tid = threadIdx.x;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(KZG_NTT_THREADS) k_half_dit_inv(const Fr *__re
 // final radix-2 stage of the inverse size-8192 DIT fused with 1/8192 and a per-index scale table:
 //   X[k] = (A[k] + w^-k B[k]) / 8192 * scale[k],  X[k+4096] = (A[k] - w^-k B[k]) / 8192 * scale[k+4096]
 // upper == 0: only k < 4096 is produced and written densely to out[blob][4096] (the coefficients).
-__global__ void k_inv_combine(const Fr *__restrict__ ab, Fr *__restrict__ out, const int32_t *__restrict__ status, const Fr *__restrict__ roots,
+static __global__ void k_inv_combine(const Fr *__restrict__ ab, Fr *__restrict__ out, const int32_t *__restrict__ status, const Fr *__restrict__ roots,
                               const Fr *__restrict__ scale, Fr inv_n, int upper) {
     const int blob = blockIdx.y;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;   // 0..4095
@@ -145,7 +145,7 @@ __global__ void k_inv_combine(const Fr *__restrict__ ab, Fr *__restrict__ out, c
 
 // forward size-8192 DIF: first radix-2 stage on load, then a size-4096 DIF in shared memory;
 // output (brp order) multiplied by percell[blob][pos >> 6].  grid = (2, blobs).
-__global__ void __launch_bounds__(KZG_NTT_THREADS) k_half_dif_fwd(const Fr *__restrict__ in, Fr *__restrict__ out, const int32_t *__restrict__ status,
+static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_half_dif_fwd(const Fr *__restrict__ in, Fr *__restrict__ out, const int32_t *__restrict__ status,
                                                                   const Fr *__restrict__ roots, const Fr *__restrict__ percell) {
     extern __shared__ uint32_t sm[];
     const int h = blockIdx.x, blob = blockIdx.y, tid = threadIdx.x;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(KZG_NTT_THREADS) k_half_dif_fwd(const Fr *__re
 
 // all 128 cells from monomial coefficients (fk20.go:58-74): cells 0..63 = brp(FFT_4096(c)),
 // cells 64..127 = brp(FFT_4096(c_j w_8192^j)).  grid = (2, blobs).
-__global__ void __launch_bounds__(KZG_NTT_THREADS) k_cells_from_coeffs(const Fr *__restrict__ coeffs, uint8_t *__restrict__ cells,
+static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_cells_from_coeffs(const Fr *__restrict__ coeffs, uint8_t *__restrict__ cells,
                                                                        const int32_t *__restrict__ status, const Fr *__restrict__ roots) {
     extern __shared__ uint32_t sm[];
     const int h = blockIdx.x, blob = blockIdx.y, tid = threadIdx.x;

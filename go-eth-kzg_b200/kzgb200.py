@@ -50,6 +50,8 @@ EXPORTS = [
     "kzgb200_blob_to_kzg_commitment", "kzgb200_get_info", "kzgb200_last_device_ms",
     "kzgb200_compute_cells", "kzgb200_compute_cells_and_kzg_proofs", "kzgb200_last_kernel_ms",
     "kzgb200_compute_kzg_proof", "kzgb200_compute_blob_kzg_proof", "kzgb200_recover_cells_and_kzg_proofs",
+    "kzgb200_verify_kzg_proof", "kzgb200_verify_blob_kzg_proof", "kzgb200_verify_blob_kzg_proof_batch",
+    "kzgb200_verify_cell_kzg_proof_batch",
 ]
 
 
@@ -202,6 +204,34 @@ class Context:
         praw = op.raw if proofs else None
         return [(st[i], craw[262144 * i:262144 * (i + 1)]) + ((praw[6144 * i:6144 * (i + 1)],) if proofs else ()) for i in range(n)]
 
+    def verify_kzg_proof_batch(self, commitments, zs, ys, proofs):
+        """n independent VerifyKZGProof checks -> list of statuses"""
+        n = len(commitments)
+        st = (ctypes.c_int32 * max(n, 1))()
+        self._check(self.L.kzgb200_verify_kzg_proof(self.ctx, _ptr(b"".join(commitments)), _ptr(b"".join(zs)), _ptr(b"".join(ys)),
+                                                    _ptr(b"".join(proofs)), ctypes.c_size_t(n), st))
+        return list(st[:n])
+
+    def verify_blob_kzg_proof_each(self, blobs, commitments, proofs):
+        """n independent VerifyBlobKZGProof checks (== VerifyBlobKZGProofBatchPar's work) -> statuses"""
+        n = len(blobs)
+        st = (ctypes.c_int32 * max(n, 1))()
+        self._check(self.L.kzgb200_verify_blob_kzg_proof(self.ctx, _ptr(b"".join(blobs)), _ptr(b"".join(commitments)), _ptr(b"".join(proofs)),
+                                                         ctypes.c_size_t(n), st))
+        return list(st[:n])
+
+    def verify_cell_kzg_proof_batches(self, commitments, cell_indices, cells, proofs, batch_offsets):
+        """several independent VerifyCellKZGProofBatch verdicts in one call -> list of statuses"""
+        N = len(cells)
+        nb = len(batch_offsets) - 1
+        idx = (ctypes.c_uint64 * max(N, 1))(*cell_indices)
+        offs = (ctypes.c_uint64 * (nb + 1))(*batch_offsets)
+        res = (ctypes.c_int32 * max(nb, 1))()
+        self._check(self.L.kzgb200_verify_cell_kzg_proof_batch(self.ctx, _ptr(b"".join(commitments)) if N else None, idx,
+                                                               _ptr(b"".join(cells)) if N else None, _ptr(b"".join(proofs)) if N else None,
+                                                               ctypes.c_size_t(N), offs, ctypes.c_size_t(nb), res))
+        return list(res[:nb])
+
     # ---- single-item methods, named after the reference's Context methods --------------------
     def blob_to_kzg_commitment(self, blob):
         """Context.BlobToKZGCommitment (prove.go:13-34) -> (status, commitment48)"""
@@ -235,6 +265,48 @@ class Context:
         if len(cell_ids) != len(cells) or any(len(c) != BYTES_PER_CELL for c in cells):
             return LENGTH_MISMATCH, None
         return self.recover_cells_and_kzg_proofs_batch([list(cell_ids)], [list(cells)], proofs=False)[0]
+
+    def verify_kzg_proof(self, commitment, z, y, proof):
+        """Context.VerifyKZGProof (verify.go:12-41) -> status (OK / VERIFY_FAILED / error)"""
+        if len(commitment) != 48 or len(z) != 32 or len(y) != 32 or len(proof) != 48:
+            return LENGTH_MISMATCH
+        return self.verify_kzg_proof_batch([commitment], [z], [y], [proof])[0]
+
+    def verify_blob_kzg_proof(self, blob, commitment, proof):
+        """Context.VerifyBlobKZGProof (verify.go:48-82) -> status"""
+        if len(blob) != BYTES_PER_BLOB or len(commitment) != 48 or len(proof) != 48:
+            return LENGTH_MISMATCH
+        return self.verify_blob_kzg_proof_each([blob], [commitment], [proof])[0]
+
+    def verify_blob_kzg_proof_batch(self, blobs, commitments, proofs):
+        """Context.VerifyBlobKZGProofBatch (verify.go:88-145): ONE verdict -> status"""
+        if not (len(blobs) == len(commitments) == len(proofs)):
+            return LENGTH_MISMATCH                         # ErrBatchLengthCheck (verify.go:91-95)
+        if any(len(b) != BYTES_PER_BLOB for b in blobs) or any(len(x) != 48 for x in commitments) or any(len(x) != 48 for x in proofs):
+            return LENGTH_MISMATCH
+        n = len(blobs)
+        res = ctypes.c_int32(0)
+        self._check(self.L.kzgb200_verify_blob_kzg_proof_batch(self.ctx, _ptr(b"".join(blobs)) if n else None, _ptr(b"".join(commitments)) if n else None,
+                                                               _ptr(b"".join(proofs)) if n else None, ctypes.c_size_t(n), ctypes.byref(res)))
+        return res.value
+
+    def verify_blob_kzg_proof_batch_par(self, blobs, commitments, proofs):
+        """Context.VerifyBlobKZGProofBatchPar (verify.go:152-169): n independent checks, first error wins"""
+        if not (len(blobs) == len(commitments) == len(proofs)):
+            return LENGTH_MISMATCH
+        for st in self.verify_blob_kzg_proof_each(blobs, commitments, proofs):
+            if st != OK:
+                return st
+        return OK
+
+    def verify_cell_kzg_proof_batch(self, commitments, cell_indices, cells, proofs):
+        """Context.VerifyCellKZGProofBatch (api_eip7594.go:163-215): one verdict -> status"""
+        n = len(commitments)
+        if not (n == len(cell_indices) == len(cells) == len(proofs)):
+            return LENGTH_MISMATCH                         # ErrBatchLengthCheck (api_eip7594.go:167-171)
+        if any(len(x) != 48 for x in commitments) or any(len(x) != BYTES_PER_CELL for x in cells) or any(len(x) != 48 for x in proofs):
+            return LENGTH_MISMATCH
+        return self.verify_cell_kzg_proof_batches(commitments, cell_indices, cells, proofs, [0, n])[0]
 
     def compute_cells(self, blob):
         """Context.ComputeCells (api_eip7594.go:12-26) -> (status, cells[128*2048])"""

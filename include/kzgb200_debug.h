@@ -13,6 +13,13 @@ int kzgb200_dbg_fp_op(const uint32_t *a, const uint32_t *b, uint32_t *out, int n
 int kzgb200_dbg_fr_op(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op);
 /* compressed points in/out. op: 0 a + b (XYZZ + XYZZ with non-trivial ZZ), 1 a + b (mixed), 2 2a */
 int kzgb200_dbg_g1_op(const uint8_t *a48, const uint8_t *b48, uint8_t *out48, int n, int op);
+/* out = [scalar] point (generic 255-bit scalar multiplication kernel) */
+int kzgb200_dbg_g1_mul(const uint8_t *p48, const uint8_t *s32, uint8_t *out48, int n);
+/* out[i] = 1 iff e(a_i, Q[qa_i]) * e(b_i, Q[qb_i]) == 1, Q = {G2, [s]G2, [s^64]G2} of the context */
+struct kzgb200_ctx;
+int kzgb200_dbg_pairing(struct kzgb200_ctx *ctx, const uint8_t *a48, const int *qa, const uint8_t *b48, const int *qb, int *out, int n);
+/* gamma[1], lines[0].A[0], lines[0].B[0], lines[0].A[67] as 4 x (c0,c1) x 12 plain limbs */
+int kzgb200_dbg_dump_pairing(struct kzgb200_ctx *ctx, uint32_t *out96);
 /* dependency-free integer multiply-add microbenchmark: device-wide instructions*lanes per second.
  * mode 0: mad.lo.u32 (IMAD), 1: mad.hi.u32 (IMAD.HI), 2: mad.wide.u32 (IMAD.WIDE, 32x32+64) */
 int kzgb200_bench_imad(int device, int mode, double *per_s, double *ms_out);

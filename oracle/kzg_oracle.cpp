@@ -688,3 +688,36 @@ int ko_pairing_check(const uint8_t *g1s, const uint8_t *g2s, size_t n) {
 }
 
 }  // extern "C"
+
+// debug: gamma = (1+u)^((p-1)/6) and the first/last Miller line coefficients of a G2 point,
+// as 4 x (c0,c1) x 48 big-endian bytes, for comparison with the device precomputation
+extern "C" int ko_dbg_dump_pairing(const uint8_t *g2_96, uint8_t *out) {
+    init_all();
+    G2Affine Q;
+    if (g2_decompress(Q, g2_96)) return -1;
+    Fp2 vals[4];
+    vals[0] = frob_tab().g1[1];
+    G2Affine T = Q;
+    int li = 0;
+    for (int i = 62; i >= 0; --i) {
+        Fp2 lambda = (T.x.sqr().dbl() + T.x.sqr()) * T.y.dbl().inv();
+        Fp2 A = lambda * T.x - T.y, B = lambda.neg();
+        if (li == 0) { vals[1] = A; vals[2] = B; }
+        if (li == 67) vals[3] = A;
+        ++li;
+        Fp2 x3 = lambda.sqr() - T.x.dbl();
+        Fp2 y3 = lambda * (T.x - x3) - T.y;
+        T = {x3, y3, false};
+        if ((BLS_X_ABS >> i) & 1) {
+            Fp2 lam2 = (Q.y - T.y) * (Q.x - T.x).inv();
+            Fp2 A2 = lam2 * T.x - T.y;
+            if (li == 67) vals[3] = A2;
+            ++li;
+            Fp2 x4 = lam2.sqr() - T.x - Q.x;
+            Fp2 y4 = lam2 * (T.x - x4) - T.y;
+            T = {x4, y4, false};
+        }
+    }
+    for (int s = 0; s < 4; ++s) { vals[s].c0.to_bytes_be(out + s * 96); vals[s].c1.to_bytes_be(out + s * 96 + 48); }
+    return li;
+}
