@@ -181,7 +181,7 @@ static __global__ void __launch_bounds__(64) k_fk20_table_fft(const G1Aff *__res
 }
 
 // per blob: u' (brp) --IFFT--> h --truncate/pad--> --FFT--> proofs (brp).  grid = blobs, block = 64
-static __global__ void __launch_bounds__(64) k_fk20_g1fft(const G1 *__restrict__ u, G1 *__restrict__ proofs, const int32_t *__restrict__ status,
+template <int MINB> static __global__ void __launch_bounds__(64, MINB) k_fk20_g1fft(const G1 *__restrict__ u, G1 *__restrict__ proofs, const int32_t *__restrict__ status,
                                                    const int8_t *__restrict__ digits) {
     __shared__ G1 pts[128];
     const int blob = blockIdx.x, tid = threadIdx.x;

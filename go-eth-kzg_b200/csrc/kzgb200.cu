@@ -449,7 +449,10 @@ static void launch_fk20_proofs(kzgb200_ctx *c, size_t m, const int32_t *d_status
     k_msm_fixed<<<dim3(128 / (TPB / L), (unsigned)m), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->fk20_tab, 64, 128, L,
                                                                                             d_status, (G1 *)c->sums.p);
     c->mark(KZGB200_KC_G1FFT);
-    k_fk20_g1fft<<<(unsigned)m, 64, 0, c->stream>>>((const G1 *)c->sums.p, (G1 *)c->proofs_xyzz.p, d_status, c->glv_digits);
+    static const int minb = [] { const char *e = getenv("KZGB200_G1FFT_MINB"); return e ? atoi(e) : 4; }();
+    if (minb >= 8) k_fk20_g1fft<8><<<(unsigned)m, 64, 0, c->stream>>>((const G1 *)c->sums.p, (G1 *)c->proofs_xyzz.p, d_status, c->glv_digits);
+    else if (minb >= 6) k_fk20_g1fft<6><<<(unsigned)m, 64, 0, c->stream>>>((const G1 *)c->sums.p, (G1 *)c->proofs_xyzz.p, d_status, c->glv_digits);
+    else k_fk20_g1fft<4><<<(unsigned)m, 64, 0, c->stream>>>((const G1 *)c->sums.p, (G1 *)c->proofs_xyzz.p, d_status, c->glv_digits);
     size_t np = m * 128;
     c->mark(KZGB200_KC_FINALIZE);
     k_finalize_g1<<<(unsigned)((np + 63) / 64), 64, 0, c->stream>>>((const G1 *)c->proofs_xyzz.p, d_proofs, d_status, np, 128);
@@ -515,7 +518,7 @@ int kzgb200_compute_cells_and_kzg_proofs(kzgb200_ctx *c, const uint8_t *blobs, s
 // RecoverCellsAndComputeKZGProofs / RecoverCells (api_eip7594.go:93-161, api_eip.go:8-15)
 // cell_ids and counts are read on the host (validation order of api_eip7594.go:93-113).
 // -------------------------------------------------------------------------------------------
-static const size_t RECOVER_CHUNK = 256;
+static const size_t RECOVER_CHUNK = 1024;
 
 int kzgb200_recover_cells_and_kzg_proofs(kzgb200_ctx *c, const uint64_t *cell_ids, const uint64_t *counts, const uint8_t *cells, size_t n,
                                          uint8_t *out_cells, uint8_t *out_proofs, int32_t *status) {
