@@ -54,9 +54,9 @@ __device__ __forceinline__ int32_t g1_decompress(G1Aff &out, const uint8_t *in48
         x = fp_mul_ni(x, r2);
     }
     Fp four = Fp::one(); four = Fp::dbl(Fp::dbl(four));
-    Fp y2 = Fp::add(fp_mul_ni(fp_mul_ni(x, x), x), four);
+    Fp y2 = Fp::add(fp_mul_ni(fp_sqr_ni(x), x), four);
     Fp y = fp_pow(y2, FP_P1D4, 12);
-    if (!Fp::eq(fp_mul_ni(y, y), y2)) return ST_NOT_ON_CURVE;
+    if (!Fp::eq(fp_sqr_ni(y), y2)) return ST_NOT_ON_CURVE;
     Fp o1 = Fp::zero(); o1.v[0] = 1;
     Fp yp = fp_mul_ni(y, o1);
     bool largest = !Fp::geq_limbs(FP_HALF, yp.v);

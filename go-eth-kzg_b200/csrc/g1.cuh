@@ -18,13 +18,15 @@ namespace kzg {
 // keeps every other kernel small enough for the 32 KB instruction cache and quick to compile.
 static __device__ __noinline__ Fp fp_mul_ni(Fp a, Fp b) { return Fp::mul(a, b); }
 static __device__ __noinline__ Fr fr_mul_ni(Fr a, Fr b) { return Fr::mul(a, b); }
+static __device__ __noinline__ Fp fp_sqr_ni(Fp a) { return Fp::sqr(a); }
+static __device__ __noinline__ Fr fr_sqr_ni(Fr a) { return Fr::sqr(a); }
 struct MulInline {
     static __device__ __forceinline__ Fp mul(const Fp &a, const Fp &b) { return Fp::mul(a, b); }
-    static __device__ __forceinline__ Fp sqr(const Fp &a) { return Fp::mul(a, a); }
+    static __device__ __forceinline__ Fp sqr(const Fp &a) { return Fp::sqr(a); }
 };
 struct MulCall {
     static __device__ __forceinline__ Fp mul(const Fp &a, const Fp &b) { return fp_mul_ni(a, b); }
-    static __device__ __forceinline__ Fp sqr(const Fp &a) { return fp_mul_ni(a, a); }
+    static __device__ __forceinline__ Fp sqr(const Fp &a) { return fp_sqr_ni(a); }
 };
 
 // affine point in Montgomery form; infinity is encoded as (0,0) (not on the curve since b=4)
@@ -140,7 +142,7 @@ static __device__ __noinline__ Fp fp_pow(Fp a, const uint32_t *e, int nlimbs) {
     bool started = false;
 #pragma unroll 1
     for (int i = nlimbs * 32 - 1; i >= 0; --i) {
-        if (started) r = fp_mul_ni(r, r);
+        if (started) r = fp_sqr_ni(r);
         if ((e[i >> 5] >> (i & 31)) & 1) {
             if (started) r = fp_mul_ni(r, a); else { r = a; started = true; }
         }
@@ -159,7 +161,7 @@ __device__ __forceinline__ G1Aff g1_to_affine(const G1 &p) {
     G1Aff r;
     if (p.is_inf()) { r.x = Fp::zero(); r.y = Fp::zero(); return r; }
     Fp i3 = fp_inv(p.ZZZ);
-    Fp i2 = fp_mul_ni(fp_mul_ni(i3, i3), fp_mul_ni(p.ZZ, p.ZZ));   // 1/ZZ
+    Fp i2 = fp_mul_ni(fp_sqr_ni(i3), fp_sqr_ni(p.ZZ));   // 1/ZZ
     r.x = fp_mul_ni(p.X, i2);
     r.y = fp_mul_ni(p.Y, i3);
     return r;

@@ -118,7 +118,7 @@ static __device__ __noinline__ Fr fr_inv(Fr a) {
     bool started = false;
 #pragma unroll 1
     for (int i = 254; i >= 0; --i) {
-        if (started) r = fr_mul_ni(r, r);
+        if (started) r = fr_sqr_ni(r);
         if ((FR_RM2[i >> 5] >> (i & 31)) & 1) {
             if (started) r = fr_mul_ni(r, a); else { r = a; started = true; }
         }
@@ -236,7 +236,7 @@ static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_eval_quotient(const 
         __syncthreads();
         Fr zn = z;
 #pragma unroll 1
-        for (int i = 0; i < 12; ++i) zn = fr_mul_ni(zn, zn);                 // z^4096
+        for (int i = 0; i < 12; ++i) zn = fr_sqr_ni(zn);                 // z^4096
         y = fr_mul_ni(fr_mul_ni(Fr::sub(zn, Fr::one()), inv_n), sum);
     }
     Fr one_plain = Fr::zero(); one_plain.v[0] = 1;

@@ -64,7 +64,7 @@ static __global__ void k_dbg_fp_mul(const uint32_t *a, const uint32_t *b, uint32
     Fp x, y;
     for (int k = 0; k < 12; ++k) { x.v[k] = a[i * 12 + k]; y.v[k] = b[i * 12 + k]; }
     x = Fp::to_mont(x); y = Fp::to_mont(y);
-    Fp r = op == 0 ? Fp::mul(x, y) : op == 1 ? Fp::add(x, y) : op == 2 ? Fp::sub(x, y) : fp_inv(x);
+    Fp r = op == 0 ? Fp::mul(x, y) : op == 1 ? Fp::add(x, y) : op == 2 ? Fp::sub(x, y) : op == 3 ? fp_inv(x) : Fp::sqr(x);
     r = Fp::from_mont(r);
     for (int k = 0; k < 12; ++k) out[i * 12 + k] = r.v[k];
 }
@@ -74,7 +74,7 @@ static __global__ void k_dbg_fr_mul(const uint32_t *a, const uint32_t *b, uint32
     Fr x, y;
     for (int k = 0; k < 8; ++k) { x.v[k] = a[i * 8 + k]; y.v[k] = b[i * 8 + k]; }
     x = Fr::to_mont(x); y = Fr::to_mont(y);
-    Fr r = op == 0 ? Fr::mul(x, y) : op == 1 ? Fr::add(x, y) : Fr::sub(x, y);
+    Fr r = op == 0 ? Fr::mul(x, y) : op == 1 ? Fr::add(x, y) : op == 2 ? Fr::sub(x, y) : Fr::sqr(x);
     r = Fr::from_mont(r);
     for (int k = 0; k < 8; ++k) out[i * 8 + k] = r.v[k];
 }

@@ -71,7 +71,7 @@ __device__ __forceinline__ G1Aff load_aff(const G1Aff *p) {
 //   commit:  group_pts = 4096, n_groups = 1,   L = blockDim.x
 //   FK20:    group_pts = 64,   n_groups = 128, L = 8 (16 groups per 128-thread block)
 extern __shared__ unsigned char msm_smem[];
-static __global__ void __launch_bounds__(128) k_msm_fixed(const uint32_t *__restrict__ scalars, MsmTable tab, int group_pts,
+static __global__ void __launch_bounds__(128, 4) k_msm_fixed(const uint32_t *__restrict__ scalars, MsmTable tab, int group_pts,
                                                     int n_groups, int L, const int32_t *__restrict__ status, G1 *__restrict__ out) {
     const int blob = blockIdx.y, t = threadIdx.x;
     if (status && status[blob] != ST_OK) return;
@@ -164,7 +164,7 @@ static __global__ void __launch_bounds__(64) k_table_fill(const G1Aff *__restric
     for (int i = cnt - 1; i >= 0; --i) {
         Fp i3 = fp_mul_ni(inv, pre[i]);          // 1/ZZZ_i
         inv = fp_mul_ni(inv, pts[i].ZZZ);
-        Fp i2 = fp_mul_ni(fp_mul_ni(i3, i3), fp_mul_ni(pts[i].ZZ, pts[i].ZZ));
+        Fp i2 = fp_mul_ni(fp_sqr_ni(i3), fp_mul_ni(pts[i].ZZ, pts[i].ZZ));
         G1Aff a;
         a.x = fp_mul_ni(pts[i].X, i2);
         a.y = fp_mul_ni(pts[i].Y, i3);

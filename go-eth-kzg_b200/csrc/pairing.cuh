@@ -43,7 +43,7 @@ static __device__ __noinline__ Fp2 fp2_sqr(Fp2 a) {
 }
 __device__ __forceinline__ Fp2 fp2_mul_fp(const Fp2 &a, const Fp &s) { Fp2 r; r.c0 = fp_mul_ni(a.c0, s); r.c1 = fp_mul_ni(a.c1, s); return r; }
 static __device__ __noinline__ Fp2 fp2_inv(Fp2 a) {
-    Fp n = fp_inv(Fp::add(fp_mul_ni(a.c0, a.c0), fp_mul_ni(a.c1, a.c1)));
+    Fp n = fp_inv(Fp::add(fp_sqr_ni(a.c0), fp_sqr_ni(a.c1)));
     Fp2 r; r.c0 = fp_mul_ni(a.c0, n); r.c1 = Fp::neg(fp_mul_ni(a.c1, n));
     return r;
 }
@@ -199,7 +199,7 @@ static __device__ __noinline__ void miller2(Fp12 *f, const G1Aff *P0, const G2Li
 // ---- context init: G2 decompression + line precomputation (one thread per fixed G2 point) --------
 static __device__ __noinline__ bool fp_sqrt_checked(Fp *out, Fp a) {
     Fp s = fp_pow(a, FP_P1D4, 12);
-    if (!Fp::eq(fp_mul_ni(s, s), a)) return false;
+    if (!Fp::eq(fp_sqr_ni(s), a)) return false;
     *out = s;
     return true;
 }
@@ -220,7 +220,7 @@ static __device__ __noinline__ bool fp2_sqrt(Fp2 *out, const Fp2 *pa) {
         if (fp_sqrt_checked(&s, Fp::neg(a.c0))) { out->c0 = Fp::zero(); out->c1 = s; return true; }
         return false;
     }
-    Fp n = Fp::add(fp_mul_ni(a.c0, a.c0), fp_mul_ni(a.c1, a.c1));
+    Fp n = Fp::add(fp_sqr_ni(a.c0), fp_sqr_ni(a.c1));
     if (!fp_sqrt_checked(&s, n)) return false;
     Fp d = fp_mul_ni(Fp::add(a.c0, s), inv2), x0;
     if (!fp_sqrt_checked(&x0, d)) {

@@ -24,7 +24,7 @@ static __global__ void k_init_pow7(Fr *pow7, Fr *ipow7, Fr seven, Fr inv7) {
     if (t >= 8192) return;
     Fr a = Fr::one(), b = Fr::one();
     for (int bit = 12; bit >= 0; --bit) {
-        a = fr_mul_ni(a, a); b = fr_mul_ni(b, b);
+        a = fr_sqr_ni(a); b = fr_sqr_ni(b);
         if ((t >> bit) & 1) { a = fr_mul_ni(a, seven); b = fr_mul_ni(b, inv7); }
     }
     pow7[t] = a; ipow7[t] = b;

@@ -64,7 +64,7 @@ static __device__ __noinline__ Fr fr_pow_u64(Fr base, unsigned long long e) {
     Fr r = Fr::one();
 #pragma unroll 1
     for (int bit = 63 - __clzll(e | 1ULL); bit >= 0; --bit) {
-        r = fr_mul_ni(r, r);
+        r = fr_sqr_ni(r);
         if ((e >> bit) & 1) r = fr_mul_ni(r, base);
     }
     return r;

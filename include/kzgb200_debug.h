@@ -8,7 +8,7 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
-/* op: 0 mul, 1 add, 2 sub, 3 inverse of a (Fp only) */
+/* op: 0 mul, 1 add, 2 sub, 3 inverse of a (Fp only), 4 square of a */
 int kzgb200_dbg_fp_op(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op);
 int kzgb200_dbg_fr_op(const uint32_t *a, const uint32_t *b, uint32_t *out, int n, int op);
 /* compressed points in/out. op: 0 a + b (XYZZ + XYZZ with non-trivial ZZ), 1 a + b (mixed), 2 2a */

@@ -27,6 +27,7 @@ def test_field_ops(dbg, field, mod):
     assert dbg.field_op(field, a, b, 0) == [x * y % mod for x, y in zip(a, b)]
     assert dbg.field_op(field, a, b, 1) == [(x + y) % mod for x, y in zip(a, b)]
     assert dbg.field_op(field, a, b, 2) == [(x - y) % mod for x, y in zip(a, b)]
+    assert dbg.field_op(field, a, b, 4) == [x * x % mod for x in a]        # dedicated squaring
 
 
 def test_fp_inverse(dbg):
