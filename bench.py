@@ -357,6 +357,13 @@ def main():
                      "frac_of_wide_multiply_rate": achieved / (2 * peaks["mad_wide"]) if achieved else None,
                      "work_model": "executed: %d pts x %d windows x 10 Fp-mul x 588 IMAD = %.0f M IMAD/blob in this kernel" % (npts, W_used, msm_imad / 1e6),
                      "hbm_table_gather": {"achieved": npts * W_used * 96.0 * B / (msm_ms * 1e-3) / 1e9 if msm_ms else None, "unit": "GB/s", "peak": hbm_peak}})
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("cells_proofs" if uses_fk20 else "commit")
+            if tr and tr["window_bits"] == c_used:
+                roof["traffic"] = tr["bytes_per_launch"]
+                roof["traffic_note"] = "ncu dram bytes per 1024-blob launch of k_msm_fixed (profiles/r01_ncu_full_headline.md); algorithmic gather bytes %d" % tr["algorithmic_gather_bytes_per_launch"]
+        except Exception:
+            pass
         cfg.update({"window_bits": c_used, "windows_per_scalar": W_used, "table_bytes": tab["commit_table_bytes"] if uses_commit else tab["fk20_table_bytes"]})
     else:
         top = max(kms, key=kms.get) if kms else None

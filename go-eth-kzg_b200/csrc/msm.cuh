@@ -71,7 +71,7 @@ __device__ __forceinline__ G1Aff load_aff(const G1Aff *p) {
 //   commit:  group_pts = 4096, n_groups = 1,   L = blockDim.x
 //   FK20:    group_pts = 64,   n_groups = 128, L = 8 (16 groups per 128-thread block)
 extern __shared__ unsigned char msm_smem[];
-static __global__ void __launch_bounds__(128, 4) k_msm_fixed(const uint32_t *__restrict__ scalars, MsmTable tab, int group_pts,
+static __global__ void __launch_bounds__(128) k_msm_fixed(const uint32_t *__restrict__ scalars, MsmTable tab, int group_pts,
                                                     int n_groups, int L, const int32_t *__restrict__ status, G1 *__restrict__ out) {
     const int blob = blockIdx.y, t = threadIdx.x;
     if (status && status[blob] != ST_OK) return;
