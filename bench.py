@@ -151,8 +151,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="cells_proofs", choices=sorted(METRIC))
     ap.add_argument("--blobs", type=int, default=0, help="blobs per GPU per step")
-    ap.add_argument("--commit-window", type=int, default=13)
-    ap.add_argument("--fk20-window", type=int, default=13)
+    ap.add_argument("--commit-window", type=int, default=15)
+    ap.add_argument("--fk20-window", type=int, default=14)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

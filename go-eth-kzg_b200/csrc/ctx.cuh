@@ -66,7 +66,7 @@ struct DevBuf {
 
 struct kzgb200_ctx {
     int device = 0, sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::mutex mu;
     // setup

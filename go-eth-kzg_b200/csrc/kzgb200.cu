@@ -181,6 +181,7 @@ void kzgb200_ctx_free(kzgb200_ctx *c) {
     cudaFree(c->pow7); cudaFree(c->ipow7); cudaFree(c->pairing); cudaFree(c->mono64_tab.entries);
     c->v_aff1.release(); c->v_aff2.release(); c->v_T.release(); c->v_fr.release(); c->v_meta.release(); c->v_S.release();
     c->v_W.release(); c->v_partial.release(); c->v_in2.release(); c->v_in3.release(); c->v_st2.release();
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -198,6 +199,7 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
     CU(cudaGetDeviceProperties(&prop, c->device));
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
     c->g2_bytes.assign(g2, g2 + n_g2 * 96);
@@ -441,21 +443,18 @@ int kzgb200_compute_blob_kzg_proof(kzgb200_ctx *c, const uint8_t *blobs, const u
 static const size_t CELLS_CHUNK = 1024;
 
 // coefficients (c->coeffs) -> 128 compressed proofs per blob (fk20.go:76-124); buffers must be sized by the caller
-static void launch_fk20_proofs(kzgb200_ctx *c, size_t m, const int32_t *d_status, uint8_t *d_proofs) {
+static void launch_fk20_proofs(kzgb200_ctx *c, cudaStream_t st, size_t m, const Fr *coeffs, uint32_t *scalars, G1 *sums, G1 *pxyzz,
+                               const int32_t *d_status, uint8_t *d_proofs, bool marks) {
     Fr inv128p; memcpy(inv128p.v, H_FR_INV128_PLAIN, sizeof inv128p.v);
-    k_fk20_rows<<<dim3(64, (unsigned)m), 64, 0, c->stream>>>((const Fr *)c->coeffs.p, (uint32_t *)c->scalars.p, d_status, c->roots, inv128p);
+    k_fk20_rows<<<dim3(64, (unsigned)m), 64, 0, st>>>(coeffs, scalars, d_status, c->roots, inv128p);
     const int TPB = 128, L = 8;
-    c->mark(KZGB200_KC_MSM);
-    k_msm_fixed<<<dim3(128 / (TPB / L), (unsigned)m), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->fk20_tab, 64, 128, L,
-                                                                                            d_status, (G1 *)c->sums.p);
-    c->mark(KZGB200_KC_G1FFT);
-    static const int minb = [] { const char *e = getenv("KZGB200_G1FFT_MINB"); return e ? atoi(e) : 4; }();
-    if (minb >= 8) k_fk20_g1fft<8><<<(unsigned)m, 64, 0, c->stream>>>((const G1 *)c->sums.p, (G1 *)c->proofs_xyzz.p, d_status, c->glv_digits);
-    else if (minb >= 6) k_fk20_g1fft<6><<<(unsigned)m, 64, 0, c->stream>>>((const G1 *)c->sums.p, (G1 *)c->proofs_xyzz.p, d_status, c->glv_digits);
-    else k_fk20_g1fft<4><<<(unsigned)m, 64, 0, c->stream>>>((const G1 *)c->sums.p, (G1 *)c->proofs_xyzz.p, d_status, c->glv_digits);
+    if (marks) c->mark(KZGB200_KC_MSM);
+    k_msm_fixed<<<dim3(128 / (TPB / L), (unsigned)m), TPB, TPB * sizeof(G1), st>>>(scalars, c->fk20_tab, 64, 128, L, d_status, sums);
+    if (marks) c->mark(KZGB200_KC_G1FFT);
+    k_fk20_g1fft<4><<<(unsigned)m, 64, 0, st>>>(sums, pxyzz, d_status, c->glv_digits);
     size_t np = m * 128;
-    c->mark(KZGB200_KC_FINALIZE);
-    k_finalize_g1<<<(unsigned)((np + 63) / 64), 64, 0, c->stream>>>((const G1 *)c->proofs_xyzz.p, d_proofs, d_status, np, 128);
+    if (marks) c->mark(KZGB200_KC_FINALIZE);
+    k_finalize_g1<<<(unsigned)((np + 63) / 64), 64, 0, st>>>(pxyzz, d_proofs, d_status, np, 128);
     c->launches += 4;
 }
 
@@ -494,10 +493,18 @@ static int cells_and_proofs(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint
         k_blob_ifft<<<(unsigned)m, KZG_NTT_THREADS, 4096 * 32, c->stream>>>(d_blobs, (Fr *)c->coeffs.p, d_status, c->roots, inv4096);
         k_coset_fft_cells<<<(unsigned)m, KZG_NTT_THREADS, 4096 * 32, c->stream>>>((const Fr *)c->coeffs.p, d_blobs, d_cells, d_status, c->roots);
         c->launches += 2;
-        if (out_proofs) launch_fk20_proofs(c, m, d_status, d_proofs);
+        // the cells are final after the second kernel: their D2H (the bulk of the output bytes) runs on
+        // the copy stream underneath the FK20 kernels
+        if (!cells_dev) {
+            CU(cudaEventRecord(c->ev0, c->stream));
+            CU(cudaStreamWaitEvent(c->copy_stream, c->ev0, 0));
+            CU(cudaMemcpyAsync(out_cells + off * 262144, d_cells, m * 262144, cudaMemcpyDeviceToHost, c->copy_stream));
+            CU(cudaEventRecord(c->ev1, c->copy_stream));
+        }
+        if (out_proofs) launch_fk20_proofs(c, c->stream, m, (const Fr *)c->coeffs.p, (uint32_t *)c->scalars.p, (G1 *)c->sums.p, (G1 *)c->proofs_xyzz.p, d_status, d_proofs, true);
         c->mark(-1);
         CU(cudaGetLastError());
-        if (!cells_dev) CU(cudaMemcpyAsync(out_cells + off * 262144, d_cells, m * 262144, cudaMemcpyDeviceToHost, c->stream));
+        if (!cells_dev) CU(cudaStreamWaitEvent(c->stream, c->ev1, 0));      // the staging buffer is reused by the next chunk
         if (out_proofs && !proofs_dev) CU(cudaMemcpyAsync(out_proofs + off * 6144, d_proofs, m * 6144, cudaMemcpyDeviceToHost, c->stream));
         if (!st_dev) CU(cudaMemcpyAsync(status + off, d_status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
@@ -602,7 +609,7 @@ int kzgb200_recover_cells_and_kzg_proofs(kzgb200_ctx *c, const uint64_t *cell_id
         k_inv_combine<<<dim3(4096 / 256, (unsigned)m), 256, 0, c->stream>>>(A, (Fr *)c->coeffs.p, d_status, c->roots, c->ipow7, inv8192, 0);
         k_cells_from_coeffs<<<dim3(2, (unsigned)m), KZG_NTT_THREADS, 4096 * 32, c->stream>>>((const Fr *)c->coeffs.p, d_cells, d_status, c->roots);
         c->launches += 8;
-        if (out_proofs) launch_fk20_proofs(c, m, d_status, d_proofs);
+        if (out_proofs) launch_fk20_proofs(c, c->stream, m, (const Fr *)c->coeffs.p, (uint32_t *)c->scalars.p, (G1 *)c->sums.p, (G1 *)c->proofs_xyzz.p, d_status, d_proofs, true);
         c->mark(-1);
         CU(cudaGetLastError());
         if (!cells_dev) CU(cudaMemcpyAsync(out_cells + off * 262144, d_cells, m * 262144, cudaMemcpyDeviceToHost, c->stream));
