@@ -25,7 +25,7 @@ def needs_build():
 
 
 # per-file extra flags.  kzgb200_verify.cu: ptxas -O1 (see the header of that file)
-PER_FILE = {"kzgb200_verify.cu": ["-Xptxas", "-O1"]}
+PER_FILE = {"kzgb200_verify.cu": os.environ.get("KZGB200_VERIFY_FLAGS", "-Xptxas -O1").split()}
 
 
 def build(force=False, verbose=False):

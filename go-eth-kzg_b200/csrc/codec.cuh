@@ -72,25 +72,25 @@ __device__ __forceinline__ int32_t g1_decompress(G1Aff &out, const uint8_t *in48
 static __device__ __noinline__ bool g1_in_subgroup(const G1Aff *pa, const uint32_t *beta2) {
     G1Aff a = *pa;
     if (a.is_inf()) return true;
-    G1 q = G1::from_affine(a);
+    G1J q; q.X = a.x; q.Y = a.y; q.Z = Fp::one();
+    const unsigned long long X_ABS = 0xd201000000010000ULL;
 #pragma unroll 1
     for (int rep = 0; rep < 2; ++rep) {               // q = [|x|] q, twice
-        G1 base = q;
-        // |x| = 0xd201000000010000, MSB first after the leading 1: bits 62..0
-        const unsigned long long X_ABS = 0xd201000000010000ULL;
+        G1JT base = jac_cache(q);
 #pragma unroll 1
-        for (int bit = 62; bit >= 0; --bit) {
-            q = g1_dbl(q);
-            if ((X_ABS >> bit) & 1) g1_add(q, base);
+        for (int bit = 62; bit >= 0; --bit) {          // |x| MSB first after the leading 1
+            jac_dbl(q);
+            if ((X_ABS >> bit) & 1) jac_add(q, base);
         }
     }
-    // need q == -phi2(P) = (beta2*x, -y)
-    if (q.is_inf()) return false;
+    // need q == -phi2(P) = (beta2*x, -y):  X == beta2*x*Z^2,  Y == -y*Z^3
+    if (q.Z.is_zero()) return false;
     Fp b2;
 #pragma unroll
     for (int i = 0; i < 12; ++i) b2.v[i] = beta2[i];
-    Fp ex = fp_mul_ni(fp_mul_ni(b2, a.x), q.ZZ);
-    Fp ey = fp_mul_ni(Fp::neg(a.y), q.ZZZ);
+    Fp zz = fp_sqr_ni(q.Z);
+    Fp ex = fp_mul_ni(fp_mul_ni(b2, a.x), zz);
+    Fp ey = fp_mul_ni(Fp::neg(a.y), fp_mul_ni(zz, q.Z));
     return Fp::eq(ex, q.X) && Fp::eq(ey, q.Y);
 }
 

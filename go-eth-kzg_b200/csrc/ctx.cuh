@@ -80,7 +80,6 @@ struct kzgb200_ctx {
     Fr *pow7 = nullptr, *ipow7 = nullptr;   // 7^k, 7^-k (erasure_code.go:58 coset generator)
     PairingConsts *pairing = nullptr;       // Frobenius constants + line tables of G2, [s]G2, [s^64]G2
     MsmTable mono64_tab{};                  // digit table of monomial G1[0..63] (kzg_multi/srs.go:143-149)
-    std::mt19937_64 rng{std::random_device{}()};
     // scratch
     DevBuf in_bytes, scalars, status, sums, out_bytes, coeffs, cells, proofs_xyzz, in_small, in_small2, zbuf, ybuf;
     DevBuf rec_a, rec_b, rec_meta, rec_zev, rec_czinv;

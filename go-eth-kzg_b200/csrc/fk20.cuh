@@ -107,58 +107,11 @@ static __global__ void __launch_bounds__(64) k_fk20_rows(const Fr *__restrict__ 
 }
 
 // ---- G1 side -----------------------------------------------------------------------------
-// Twiddle multiplications run in Jacobian coordinates (x = X/Z^2, y = Y/Z^3): a doubling is
-// 2M + 5S there against 6M + 3S in XYZZ, and a twiddle multiplication is 132 doublings + ~62
-// additions.  Table entries cache Z^2 and Z^3 so an addition is 11M + 3S.
-struct G1J { Fp X, Y, Z; };
-struct G1JT { Fp X, Y, Z, ZZ, ZZZ; };
-
-__device__ __forceinline__ void jac_dbl(G1J &p) {          // dbl-2009-l, a = 0; no-op on infinity (Z = 0 stays 0)
-    Fp A = fp_sqr_ni(p.X), B = fp_sqr_ni(p.Y), C = fp_sqr_ni(B);
-    Fp t = Fp::add(p.X, B);
-    Fp D = Fp::dbl(Fp::sub(Fp::sub(fp_sqr_ni(t), A), C));
-    Fp E = Fp::add(Fp::dbl(A), A);
-    Fp F = fp_sqr_ni(E);
-    Fp Z3 = Fp::dbl(fp_mul_ni(p.Y, p.Z));
-    p.X = Fp::sub(F, Fp::dbl(D));
-    Fp C8 = Fp::dbl(Fp::dbl(Fp::dbl(C)));
-    p.Y = Fp::sub(fp_mul_ni(E, Fp::sub(D, p.X)), C8);
-    p.Z = Z3;
-}
-__device__ __forceinline__ void jac_add(G1J &a, const G1JT &b) {   // b is never the point at infinity
-    if (a.Z.is_zero()) { a.X = b.X; a.Y = b.Y; a.Z = b.Z; return; }
-    Fp Z1Z1 = fp_sqr_ni(a.Z);
-    Fp U1 = fp_mul_ni(a.X, b.ZZ), U2 = fp_mul_ni(b.X, Z1Z1);
-    Fp S1 = fp_mul_ni(a.Y, b.ZZZ), S2 = fp_mul_ni(fp_mul_ni(b.Y, a.Z), Z1Z1);
-    Fp H = Fp::sub(U2, U1), r = Fp::sub(S2, S1);
-    if (H.is_zero()) {
-        if (r.is_zero()) { a.X = b.X; a.Y = b.Y; a.Z = b.Z; jac_dbl(a); }
-        else a.Z = Fp::zero();
-        return;
-    }
-    Fp HH = fp_sqr_ni(H), HHH = fp_mul_ni(H, HH), V = fp_mul_ni(U1, HH);
-    Fp X3 = Fp::sub(Fp::sub(fp_sqr_ni(r), HHH), Fp::dbl(V));
-    a.Y = Fp::sub(fp_mul_ni(r, Fp::sub(V, X3)), fp_mul_ni(S1, HHH));
-    a.X = X3;
-    a.Z = fp_mul_ni(fp_mul_ni(a.Z, b.Z), H);
-}
-__device__ __forceinline__ G1JT jac_cache(const G1J &p) {
-    G1JT t; t.X = p.X; t.Y = p.Y; t.Z = p.Z; t.ZZ = fp_sqr_ni(p.Z); t.ZZZ = fp_mul_ni(t.ZZ, p.Z);
-    return t;
-}
-
 // P = [w_128^t] P with the precomputed GLV digits dig[2][KZG_GLV_DIGITS] (top window first)
 static __device__ __noinline__ void g1_mul_twiddle(G1 *pp, const int8_t *__restrict__ dig) {
     G1 P = *pp;
     if (P.is_inf()) return;
-    // XYZZ -> Jacobian with Z = ZZ*ZZZ:  X' = X*ZZ*ZZZ^2,  Y' = Y*ZZ^3*ZZZ^2
-    G1J base;
-    {
-        Fp t = fp_sqr_ni(P.ZZZ);
-        base.Z = fp_mul_ni(P.ZZ, P.ZZZ);
-        base.X = fp_mul_ni(fp_mul_ni(P.X, P.ZZ), t);
-        base.Y = fp_mul_ni(fp_mul_ni(P.Y, fp_mul_ni(fp_sqr_ni(P.ZZ), P.ZZ)), t);
-    }
+    G1J base = jac_from_xyzz(P);
     G1JT tab[8];
     tab[0] = jac_cache(base);
     { G1J d = base; jac_dbl(d); tab[1] = jac_cache(d); }
@@ -188,9 +141,7 @@ static __device__ __noinline__ void g1_mul_twiddle(G1 *pp, const int8_t *__restr
             jac_add(acc, t);
         }
     }
-    G1 out;
-    out.X = acc.X; out.Y = acc.Y; out.ZZ = fp_sqr_ni(acc.Z); out.ZZZ = fp_mul_ni(out.ZZ, acc.Z);
-    *pp = out;
+    *pp = jac_to_xyzz(acc);
 }
 
 // radix-2 stages of a size-128 G1 FFT on points in shared memory, 64 threads.

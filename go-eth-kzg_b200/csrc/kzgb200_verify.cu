@@ -121,8 +121,10 @@ int kzgb200_verify_blob_kzg_proof(kzgb200_ctx *c, const uint8_t *blobs, const ui
     return verify_independent(c, blobs, commitments48, nullptr, nullptr, proofs48, n, status);
 }
 
-static void random_scalar_plain(kzgb200_ctx *c, uint32_t *limbs) {   // 248 uniformly random bits (< r)
-    for (int i = 0; i < 4; ++i) { uint64_t v = c->rng(); limbs[2 * i] = (uint32_t)v; limbs[2 * i + 1] = (uint32_t)(v >> 32); }
+static void random_scalar_plain(kzgb200_ctx *c, uint32_t *limbs) {   // 248 random bits from the OS entropy source (std::random_device -> /dev/urandom)
+    (void)c;
+    std::random_device rd;
+    for (int i = 0; i < 8; ++i) limbs[i] = rd();
     limbs[7] &= 0x00ffffffu;
     if (!(limbs[0] | limbs[1] | limbs[2] | limbs[3])) limbs[0] = 1;
 }
@@ -166,14 +168,12 @@ int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *blobs, co
     CU(cudaMemcpyAsync(h_status.data(), c->status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     for (size_t i = 0; i < n; ++i) if (h_status[i] != KZGB200_OK) { *result = h_status[i]; c->marks_collect(); return KZGB200_OK; }   // first failing element (verify.go:102-119)
-    uint32_t r_plain[8];
-    random_scalar_plain(c, r_plain);
-    if (n == 1) { memset(r_plain, 0, sizeof r_plain); r_plain[0] = 1; }
-    // Montgomery form of r on the host: r * R mod p needs big arithmetic; let the kernel convert
-    Fr r_dev; memcpy(r_dev.v, r_plain, sizeof r_plain);
+    uint32_t seed[8];
+    random_scalar_plain(c, seed);
+    Fr r_dev; memcpy(r_dev.v, seed, sizeof seed);      // PRF seed for the 128-bit coefficients; n == 1 uses coefficient 1 (kzg_verify.go:125-127)
     c->mark(KZGB200_KC_VERIFY);
     k_rlc_terms<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>((const G1Aff *)c->v_aff1.p, (const G1Aff *)c->v_aff2.p, (const uint32_t *)c->zbuf.p,
-                                                                  (const uint32_t *)c->ybuf.p, r_dev, (const int32_t *)c->status.p, (G1 *)c->v_T.p, (Fr *)c->v_fr.p, n);
+                                                                  (const uint32_t *)c->ybuf.p, r_dev, n == 1 ? 1 : 0, (const int32_t *)c->status.p, (G1 *)c->v_T.p, (Fr *)c->v_fr.p, n);
     k_rlc_finish<<<1, 128, 0, c->stream>>>((const G1 *)c->v_T.p, (const Fr *)c->v_fr.p, n, c->g1_monomial, c->pairing, (int32_t *)c->v_st2.p);
     c->launches += 2;
     c->mark(-1);
@@ -241,8 +241,7 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     }
     // cells with an out-of-range index were skipped in `order`; col_off stays consistent because ord_pos only counts placed cells
     const size_t U = row_off.size() - 1, n_items = item_start.size();
-    std::vector<uint32_t> r_plain(nb * 8);
-    for (size_t b = 0; b < nb; ++b) random_scalar_plain(c, &r_plain[b * 8]);
+    Fr seed_dev; random_scalar_plain(c, seed_dev.v);   // PRF seed of this call's 128-bit coefficients
     std::vector<uint32_t> row_batch(U);
     for (size_t b = 0; b < nb; ++b) for (uint64_t rw = batch_row_off[b]; rw < batch_row_off[b + 1]; ++rw) row_batch[rw] = (uint32_t)b;
 
@@ -257,7 +256,7 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) & ~(size_t)255; return at; };
     size_t o_idx = take(N * 8), o_batch_of = take(N * 4), o_bstart = take(nb * 8), o_order = take(N * 4), o_col = take((nb * 128 + 1) * 8);
     size_t o_rowc = take(N * 4), o_rowoff = take((U + 1) * 8), o_browoff = take((nb + 1) * 8), o_is = take(n_items * 8), o_ie = take(n_items * 8);
-    size_t o_bio = take((nb + 1) * 8), o_r = take(nb * 32), o_bst = take(nb * 4), o_cst = take(std::max<size_t>(N, 1) * 4), o_ust = take(std::max<size_t>(U, 1) * 4);
+    size_t o_bio = take((nb + 1) * 8), o_bst = take(nb * 4), o_cst = take(std::max<size_t>(N, 1) * 4), o_ust = take(std::max<size_t>(U, 1) * 4);
     size_t o_rowb = take(std::max<size_t>(U, 1) * 4), o_res = take(nb * 4);
     if ((rc = c->v_meta.ensure(o))) return rc;
     char *M = (char *)c->v_meta.p;
@@ -266,7 +265,7 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     CU(up(o_order, order.data(), N * 4)); CU(up(o_col, col_off.data(), (nb * 128 + 1) * 8)); CU(up(o_rowc, row_cells.data(), N * 4));
     CU(up(o_rowoff, row_off.data(), (U + 1) * 8)); CU(up(o_browoff, batch_row_off.data(), (nb + 1) * 8));
     CU(up(o_is, item_start.data(), n_items * 8)); CU(up(o_ie, item_end.data(), n_items * 8)); CU(up(o_bio, batch_item_off.data(), (nb + 1) * 8));
-    CU(up(o_r, r_plain.data(), nb * 32)); CU(up(o_bst, h_bstatus.data(), nb * 4)); CU(up(o_rowb, row_batch.data(), U * 4));
+    CU(up(o_bst, h_bstatus.data(), nb * 4)); CU(up(o_rowb, row_batch.data(), U * 4));
     CU(cudaMemsetAsync(M + o_cst, 0, std::max<size_t>(N, 1) * 4, c->stream));
     CU(cudaMemsetAsync(M + o_ust, 0, std::max<size_t>(U, 1) * 4, c->stream));
     if ((rc = c->v_aff1.ensure(std::max<size_t>(U, 1) * sizeof(G1Aff)))) return rc;
@@ -285,7 +284,7 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     if (N) {
         unsigned gN = (unsigned)((N + 63) / 64);
         k_g1_check<<<gN, 64, 0, c->stream>>>((const uint8_t *)d_proofs, (G1Aff *)c->v_aff2.p, d_cst, N, 1, 1);
-        k_cell_rpow_plain<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>((const uint32_t *)(M + o_r), (const uint32_t *)(M + o_batch_of), (const uint64_t *)(M + o_bstart), (Fr *)c->v_fr.p, N);
+        k_cell_coeffs<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(seed_dev, (const uint32_t *)(M + o_batch_of), (const uint64_t *)(M + o_bstart), (Fr *)c->v_fr.p, N);
         k_cell_proof_terms<<<gN, 64, 0, c->stream>>>((const G1Aff *)c->v_aff2.p, (const Fr *)c->v_fr.p, d_cst, (G1 *)c->v_T.p, N);
         c->mark(KZGB200_KC_FR);
         k_cell_interp<<<(unsigned)n_items, 256, 0, c->stream>>>((const uint8_t *)d_cells, (const uint64_t *)(M + o_idx), (const Fr *)c->v_fr.p, (const uint64_t *)(M + o_is),

@@ -14,39 +14,55 @@
 
 namespace kzg {
 
-// [k]P, k plain 8-limb integer (< 2^256), 4-bit fixed windows.  Arguments and result are passed BY
-// VALUE on purpose: with an out-pointer into the caller's frame, nvcc 12.9 produced a caller that
-// combined stale registers with the freshly written stack slot (caught by the verify_kzg_proof
-// vectors); value semantics keep the data flow explicit.
+// [k]P for a plain little-endian scalar of 4*nwin bits (nwin = 64: full 256-bit, 32: 128-bit
+// randomisers), 4-bit fixed windows, Jacobian doublings.  Arguments and result are passed BY VALUE
+// on purpose (see kzgb200_verify.cu): value semantics keep the data flow explicit for the compiler.
 struct Scalar256 { uint32_t v[8]; };
-static __device__ __noinline__ G1 g1_mul_scalar_v(G1 P, Scalar256 ks) {
+static __device__ __noinline__ G1 g1_mul_scalar_v(G1 P, Scalar256 ks, int nwin) {
     const uint32_t *k = ks.v;
-    G1 acc = G1::infinity();
-    if (P.is_inf()) return acc;
-    G1 tab[15];
-    tab[0] = P;
+    if (P.is_inf()) return G1::infinity();
+    G1J base = jac_from_xyzz(P);
+    G1JT tab[15];
+    tab[0] = jac_cache(base);
 #pragma unroll 1
     for (int i = 1; i < 15; ++i) {
-        if (i & 1) tab[i] = g1_dbl(tab[i >> 1]);            // (i+1) even: 2 * ((i+1)/2)
-        else { G1 t = tab[i - 1]; g1_add(t, P); tab[i] = t; }
+        G1J t;
+        if (i & 1) { t.X = tab[i >> 1].X; t.Y = tab[i >> 1].Y; t.Z = tab[i >> 1].Z; jac_dbl(t); }     // (i+1) even: 2 * ((i+1)/2)
+        else { t.X = tab[i - 1].X; t.Y = tab[i - 1].Y; t.Z = tab[i - 1].Z; jac_add(t, tab[0]); }
+        tab[i] = jac_cache(t);
     }
+    G1J acc; acc.X = Fp::zero(); acc.Y = Fp::zero(); acc.Z = Fp::zero();
 #pragma unroll 1
-    for (int w = 63; w >= 0; --w) {
-        if (w != 63) {
+    for (int w = nwin - 1; w >= 0; --w) {
+        if (w != nwin - 1) {
 #pragma unroll 1
-            for (int i = 0; i < 4; ++i) acc = g1_dbl(acc);
+            for (int i = 0; i < 4; ++i) jac_dbl(acc);
         }
         unsigned d = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
-        if (d) g1_add(acc, tab[d - 1]);
+        if (d) jac_add(acc, tab[d - 1]);
     }
-    return acc;
+    return jac_to_xyzz(acc);
 }
-__device__ __forceinline__ void g1_mul_scalar(G1 *out, const G1 *pp, const uint32_t *k) {
+__device__ __forceinline__ void g1_mul_scalar(G1 *out, const G1 *pp, const uint32_t *k, int nwin = 64) {
     Scalar256 ks;
 #pragma unroll
     for (int i = 0; i < 8; ++i) ks.v[i] = k[i];
-    G1 r = g1_mul_scalar_v(*pp, ks);
+    G1 r = g1_mul_scalar_v(*pp, ks, nwin);
     *out = r;
+}
+// 128-bit pseudo-random coefficient: first 16 bytes of SHA-256(seed32 || a || b).  The seed is fresh
+// host randomness per API call, so the coefficients are unpredictable to whoever chose the inputs
+// (the reference uses powers of one random r, internal/kzg/kzg_verify.go:136-141; any coefficients
+// that are independent of the inputs give the same soundness bound).
+__device__ __forceinline__ void prf128(uint32_t *out4, const uint32_t *seed8, unsigned long long a, unsigned long long b) {
+    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = seed8[i];
+    w[8] = (uint32_t)(a >> 32); w[9] = (uint32_t)a; w[10] = (uint32_t)(b >> 32); w[11] = (uint32_t)b;
+    w[12] = 0x80000000u; w[13] = 0; w[14] = 0; w[15] = 48 * 8;
+    sha256_block(h, w);
+    out4[0] = h[0]; out4[1] = h[1]; out4[2] = h[2]; out4[3] = h[3] | 1u;   // never zero
 }
 
 __device__ __forceinline__ Fr fr_to_mont(const uint32_t *plain) {
@@ -91,22 +107,24 @@ static __global__ void __launch_bounds__(64) k_verify_single(const G1Aff *__rest
 }
 
 // ---- EIP-4844 RLC batch (kzg_verify.go:111-231) -------------------------------------------------
-// per item i: r^i, T1 = [r^i]pi_i, T2 = [r^i]C_i, T3 = [r^i z_i]pi_i, fy = r^i y_i
+// per item i: 128-bit coefficient r_i = PRF(seed, i); T1 = [r_i]pi_i, T2 = [r_i]C_i, T3 = [r_i z_i]pi_i, fy = r_i y_i
 static __global__ void __launch_bounds__(64) k_rlc_terms(const G1Aff *__restrict__ commitments, const G1Aff *__restrict__ proofs,
-                                                  const uint32_t *__restrict__ z, const uint32_t *__restrict__ y, Fr r_plain,
+                                                  const uint32_t *__restrict__ z, const uint32_t *__restrict__ y, Fr seed, int unit_coeff,
                                                   const int32_t *__restrict__ status, G1 *__restrict__ T, Fr *__restrict__ fy, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     G1 inf = G1::infinity();
     if (status[i] != ST_OK) { T[i] = inf; T[n + i] = inf; T[2 * n + i] = inf; fy[i] = Fr::zero(); return; }
-    Fr ri = fr_pow_u64(fr_to_mont(r_plain.v), i);
+    Fr rip = Fr::zero();                         // plain 128-bit coefficient r_i
+    if (unit_coeff) rip.v[0] = 1; else prf128(rip.v, seed.v, 0, i);
+    Fr ri = fr_to_mont(rip.v);
     Fr rz = fr_mul_ni(ri, fr_to_mont(z + i * 8));
     fy[i] = fr_mul_ni(ri, fr_to_mont(y + i * 8));
-    Fr rip = fr_from_mont(ri), rzp = fr_from_mont(rz);
+    Fr rzp = fr_from_mont(rz);
     G1 Pi = G1::from_affine(proofs[i]), C = G1::from_affine(commitments[i]), t;
-    g1_mul_scalar(&t, &Pi, rip.v); T[i] = t;
-    g1_mul_scalar(&t, &C, rip.v); T[n + i] = t;
-    g1_mul_scalar(&t, &Pi, rzp.v); T[2 * n + i] = t;
+    g1_mul_scalar(&t, &Pi, rip.v, 32); T[i] = t;
+    g1_mul_scalar(&t, &C, rip.v, 32); T[n + i] = t;
+    g1_mul_scalar(&t, &Pi, rzp.v, 64); T[2 * n + i] = t;
 }
 // one block: sums, final combination and the pairing check
 static __global__ void __launch_bounds__(128) k_rlc_finish(const G1 *__restrict__ T, const Fr *__restrict__ fy, size_t n,
@@ -150,21 +168,15 @@ static __global__ void __launch_bounds__(128) k_rlc_finish(const G1 *__restrict_
 }
 
 // ---- EIP-7594 cell batch (kzg_multi/kzg_verify.go:16-105) ---------------------------------------
-// rpow[cell] = r_batch^(position in batch), Montgomery
-static __global__ void k_cell_rpow(const Fr *__restrict__ r_batch, const uint32_t *__restrict__ batch_of, const uint64_t *__restrict__ batch_start,
-                            Fr *__restrict__ rpow, size_t n) {
+// rpow[cell] = 128-bit coefficient PRF(seed, batch, position in batch), Montgomery form
+static __global__ void k_cell_coeffs(Fr seed, const uint32_t *__restrict__ batch_of, const uint64_t *__restrict__ batch_start,
+                                     Fr *__restrict__ rpow, size_t n) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     uint32_t b = batch_of[k];
-    rpow[k] = fr_pow_u64(r_batch[b], k - batch_start[b]);
-}
-// same, r given as plain limbs (converted here)
-static __global__ void k_cell_rpow_plain(const uint32_t *__restrict__ r_plain, const uint32_t *__restrict__ batch_of, const uint64_t *__restrict__ batch_start,
-                                  Fr *__restrict__ rpow, size_t n) {
-    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    uint32_t b = batch_of[k];
-    rpow[k] = fr_pow_u64(fr_to_mont(r_plain + (size_t)b * 8), k - batch_start[b]);
+    Fr p = Fr::zero();
+    prf128(p.v, seed.v, b, k - batch_start[b]);
+    rpow[k] = fr_to_mont(p.v);
 }
 // batch_status[group_of[i]] = max(., status[i])  (any error in a batch makes the batch an error)
 static __global__ void k_merge_status(const int32_t *__restrict__ status, const uint32_t *__restrict__ group_of, int32_t *__restrict__ batch_status, size_t n) {
@@ -179,9 +191,9 @@ static __global__ void __launch_bounds__(64) k_cell_proof_terms(const G1Aff *__r
     if (k >= n) return;
     G1 t = G1::infinity();
     if (status[k] == ST_OK) {
-        Fr rp = fr_from_mont(rpow[k]);
+        Fr rp = fr_from_mont(rpow[k]);          // 128-bit
         G1 P = G1::from_affine(proofs[k]);
-        g1_mul_scalar(&t, &P, rp.v);
+        g1_mul_scalar(&t, &P, rp.v, 32);
     }
     T[k] = t;
 }
