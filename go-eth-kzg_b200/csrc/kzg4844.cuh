@@ -58,16 +58,26 @@ static __global__ void k_fiat_shamir(const uint8_t *__restrict__ blobs, const ui
 #pragma unroll
     for (int k = 0; k < 8; ++k) w[8 + k] = __byte_perm(bw[k], 0, 0x0123);
     sha256_block(h, w);
-    // blocks 1..2047: blob bytes 32 + 64(b-1) .. ; the blob has 131072-32 = 131040 bytes left = 2047 blocks + 32 bytes
-#pragma unroll 1
-    for (int b = 0; b < 2047; ++b) {
-        const uint4 *q = reinterpret_cast<const uint4 *>(bw + 8 + 16 * b);
+    // blocks 1..2047: blob bytes 32 + 64(b-1) .. ; the blob has 131072-32 = 131040 bytes left = 2047 blocks + 32 bytes.
+    // Each thread streams its own blob (lane stride 128 KB), so the next block's 64 bytes are
+    // requested one iteration ahead to keep a load in flight under the 64 rounds of compute.
+    {
+        const uint4 *q = reinterpret_cast<const uint4 *>(bw + 8);
         uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
-        w[0] = __byte_perm(v0.x, 0, 0x0123); w[1] = __byte_perm(v0.y, 0, 0x0123); w[2] = __byte_perm(v0.z, 0, 0x0123); w[3] = __byte_perm(v0.w, 0, 0x0123);
-        w[4] = __byte_perm(v1.x, 0, 0x0123); w[5] = __byte_perm(v1.y, 0, 0x0123); w[6] = __byte_perm(v1.z, 0, 0x0123); w[7] = __byte_perm(v1.w, 0, 0x0123);
-        w[8] = __byte_perm(v2.x, 0, 0x0123); w[9] = __byte_perm(v2.y, 0, 0x0123); w[10] = __byte_perm(v2.z, 0, 0x0123); w[11] = __byte_perm(v2.w, 0, 0x0123);
-        w[12] = __byte_perm(v3.x, 0, 0x0123); w[13] = __byte_perm(v3.y, 0, 0x0123); w[14] = __byte_perm(v3.z, 0, 0x0123); w[15] = __byte_perm(v3.w, 0, 0x0123);
-        sha256_block(h, w);
+#pragma unroll 1
+        for (int b = 0; b < 2047; ++b) {
+            uint4 n0 = v0, n1 = v1, n2 = v2, n3 = v3;
+            if (b + 1 < 2047) {
+                const uint4 *qn = reinterpret_cast<const uint4 *>(bw + 8 + 16 * (b + 1));
+                n0 = __ldg(qn); n1 = __ldg(qn + 1); n2 = __ldg(qn + 2); n3 = __ldg(qn + 3);
+            }
+            w[0] = __byte_perm(v0.x, 0, 0x0123); w[1] = __byte_perm(v0.y, 0, 0x0123); w[2] = __byte_perm(v0.z, 0, 0x0123); w[3] = __byte_perm(v0.w, 0, 0x0123);
+            w[4] = __byte_perm(v1.x, 0, 0x0123); w[5] = __byte_perm(v1.y, 0, 0x0123); w[6] = __byte_perm(v1.z, 0, 0x0123); w[7] = __byte_perm(v1.w, 0, 0x0123);
+            w[8] = __byte_perm(v2.x, 0, 0x0123); w[9] = __byte_perm(v2.y, 0, 0x0123); w[10] = __byte_perm(v2.z, 0, 0x0123); w[11] = __byte_perm(v2.w, 0, 0x0123);
+            w[12] = __byte_perm(v3.x, 0, 0x0123); w[13] = __byte_perm(v3.y, 0, 0x0123); w[14] = __byte_perm(v3.z, 0, 0x0123); w[15] = __byte_perm(v3.w, 0, 0x0123);
+            sha256_block(h, w);
+            v0 = n0; v1 = n1; v2 = n2; v3 = n3;
+        }
     }
     // block 2048: last 32 blob bytes + first 32 commitment bytes
 #pragma unroll
@@ -203,7 +213,11 @@ static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_eval_quotient(const 
     if (tid < T - 1) excl_suf = sm_load<T>(sm, tid + 1);
     __syncthreads();
     (void)inc;
-    Fr inv_total = fr_inv(total);
+    // one Fermat inversion per blob (thread 0), broadcast through shared memory
+    if (tid == 0) { Fr it = fr_inv(total); sm_store<T>(sm, 0, it); }
+    __syncthreads();
+    Fr inv_total = sm_load<T>(sm, 0);
+    __syncthreads();
     Fr c = fr_mul_ni(fr_mul_ni(inv_total, excl_pre), excl_suf);    // 1 / (product of this thread's PER elements)
     Fr inv[PER];
 #pragma unroll

@@ -320,7 +320,7 @@ int kzgb200_last_kernel_ms(kzgb200_ctx *c, double *out) {
 // BlobToKZGCommitment (prove.go:13-34): DeserializeBlob -> MSM against the bit-reversed Lagrange
 // SRS -> compress.  Processed in chunks of CHUNK blobs.
 // -------------------------------------------------------------------------------------------
-static const size_t COMMIT_CHUNK = 1024;
+static const size_t COMMIT_CHUNK = 4096;
 
 int kzgb200_blob_to_kzg_commitment(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint8_t *out48, int32_t *status) {
     if (!c || (n && (!blobs || !out48 || !status))) return set_err(KZGB200_ERR_ARGS, "null argument");
@@ -405,7 +405,7 @@ static int open_common(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *z32,
             c->launches += 1;
         } else {
             k_g1_check<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_aux, nullptr, d_status, m, 1, 1);
-            k_fiat_shamir<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_blobs, (const uint8_t *)d_aux, (uint32_t *)c->zbuf.p, m);
+            k_fiat_shamir<<<(unsigned)((m + 31) / 32), 32, 0, c->stream>>>((const uint8_t *)d_blobs, (const uint8_t *)d_aux, (uint32_t *)c->zbuf.p, m);
             c->launches += 2;
         }
         k_eval_quotient<<<(unsigned)m, KZG_NTT_THREADS, 0, c->stream>>>((const uint8_t *)d_blobs, (const uint32_t *)c->zbuf.p, c->roots, d_status,

@@ -41,7 +41,7 @@ extern "C" {
 // -------------------------------------------------------------------------------------------
 // Verifiers (verify.go:12-169, api_eip7594.go:163-265)
 // -------------------------------------------------------------------------------------------
-static const size_t VERIFY_CHUNK = 1024;
+static const size_t VERIFY_CHUNK = 4096;
 
 // shared front end: decode commitments/proofs, obtain z and y (given, or Fiat-Shamir + evaluation)
 //   blobs == nullptr: z32/y32 given (VerifyKZGProof); else z = challenge, y = p(z)
@@ -75,7 +75,7 @@ static int verify_front(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm4
     c->launches += 2;
     if (blobs) {
         c->mark(KZGB200_KC_FR);
-        k_fiat_shamir<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_blobs, (const uint8_t *)d_cm, (uint32_t *)c->zbuf.p, m);
+        k_fiat_shamir<<<(unsigned)((m + 31) / 32), 32, 0, c->stream>>>((const uint8_t *)d_blobs, (const uint8_t *)d_cm, (uint32_t *)c->zbuf.p, m);
         k_eval_quotient<<<(unsigned)m, KZG_NTT_THREADS, 0, c->stream>>>((const uint8_t *)d_blobs, (const uint32_t *)c->zbuf.p, c->roots, d_status,
                                                                          nullptr, nullptr, (uint32_t *)c->ybuf.p, inv4096);
         c->launches += 2;
@@ -272,8 +272,8 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     if ((rc = c->v_aff2.ensure(std::max<size_t>(N, 1) * sizeof(G1Aff)))) return rc;
     if ((rc = c->v_T.ensure(std::max<size_t>(N, 1) * sizeof(G1)))) return rc;
     if ((rc = c->v_fr.ensure(std::max<size_t>(N, 1) * sizeof(Fr)))) return rc;
-    if ((rc = c->v_S.ensure(nb * 128 * sizeof(G1)))) return rc;
-    if ((rc = c->v_W.ensure(nb * 128 * sizeof(G1)))) return rc;
+    if ((rc = c->v_S.ensure(nb * sizeof(G1)))) return rc;
+    if ((rc = c->v_W.ensure(nb * sizeof(G1)))) return rc;
     if ((rc = c->v_partial.ensure(std::max<size_t>(n_items, 1) * 64 * sizeof(Fr)))) return rc;
     if ((rc = c->scalars.ensure(nb * 64 * 32))) return rc;
     if ((rc = c->sums.ensure(nb * sizeof(G1)))) return rc;

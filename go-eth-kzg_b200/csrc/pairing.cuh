@@ -83,7 +83,37 @@ static __device__ __noinline__ void fp12_mul(Fp12 *r, const Fp12 *a, const Fp12 
     fp6_add(&r->c0, &t0, &t1v);
     r->c1 = m;
 }
-__device__ __forceinline__ void fp12_sqr(Fp12 *r, const Fp12 *a) { Fp12 t = *a; fp12_mul(r, &t, &t); }
+// complex squaring: (c0 + c1 w)^2 = (c0 + c1)(c0 + v c1) - t - v t  +  2 t w,  t = c0 c1   (2 Fp6 products)
+static __device__ __noinline__ void fp12_sqr(Fp12 *r, const Fp12 *a) {
+    Fp6 t, s0, s1, m, tv;
+    fp6_mul(&t, &a->c0, &a->c1);
+    fp6_add(&s0, &a->c0, &a->c1);
+    fp6_mul_v(&s1, &a->c1);
+    fp6_add(&s1, &s1, &a->c0);
+    fp6_mul(&m, &s0, &s1);
+    fp6_mul_v(&tv, &t);
+    fp6_sub(&m, &m, &t);
+    fp6_sub(&r->c0, &m, &tv);
+    fp6_add(&r->c1, &t, &t);
+}
+// g * (a0 + a1 v) for g in Fp6 (6 Fp2 products)
+static __device__ __noinline__ void fp6_mul_by_01(Fp6 *r, const Fp6 *g, Fp2 a0, Fp2 a1) {
+    Fp2 r0 = fp2_add(fp2_mul(g->c0, a0), fp2_mul_xi(fp2_mul(g->c2, a1)));
+    Fp2 r1 = fp2_add(fp2_mul(g->c0, a1), fp2_mul(g->c1, a0));
+    Fp2 r2 = fp2_add(fp2_mul(g->c1, a1), fp2_mul(g->c2, a0));
+    r->c0 = r0; r->c1 = r1; r->c2 = r2;
+}
+// f *= l for the sparse line l = (a0 + a1 v) + (v) w:
+//   f l = (f0 L0 + v^2 f1) + (v f0 + f1 L0) w,   L0 = a0 + a1 v        (12 Fp2 products)
+static __device__ __noinline__ void fp12_mul_by_line(Fp12 *f, Fp2 a0, Fp2 a1) {
+    Fp6 x, y, t, u;
+    fp6_mul_by_01(&x, &f->c0, a0, a1);
+    fp6_mul_by_01(&y, &f->c1, a0, a1);
+    fp6_mul_v(&t, &f->c1); fp6_mul_v(&u, &t);          // v^2 f1
+    Fp6 vf0; fp6_mul_v(&vf0, &f->c0);
+    fp6_add(&f->c0, &x, &u);
+    fp6_add(&f->c1, &vf0, &y);
+}
 __device__ __forceinline__ void fp12_conj(Fp12 *r, const Fp12 *a) { r->c0 = a->c0; fp6_neg(&r->c1, &a->c1); }
 __device__ __forceinline__ void fp12_one(Fp12 *r) {
     r->c0.c0 = fp2_one(); r->c0.c1 = fp2_zero(); r->c0.c2 = fp2_zero();
@@ -125,12 +155,38 @@ __device__ __forceinline__ void fp12_frobenius(Fp12 *r, const Fp12 *a, const Fp2
 
 #define KZG_BLS_X_ABS 0xd201000000010000ULL
 
+// Granger-Scott squaring for elements of the cyclotomic subgroup (everything after the easy part of
+// the final exponentiation).  View Fp12 = Fp4[w]/(w^3 - s), Fp4 = Fp2[s]/(s^2 - xi), s = v w:
+//   a = A0 + A1 w + A2 w^2,  A0 = g0 + h1 s,  A1 = h0 + g2 s,  A2 = g1 + h2 s
+//   a^2 = (3 A0^2 - 2 conj A0) + (3 s A2^2 + 2 conj A1) w + (3 A1^2 - 2 conj A2) w^2
+// 9 Fp2 squarings = 18 Fp products (validated against the generic square in the oracle:
+// ko_dbg_cyclotomic_sqr_check).
+__device__ __forceinline__ void fp4_sqr(Fp2 &rx, Fp2 &ry, const Fp2 &x, const Fp2 &y) {
+    Fp2 xx = fp2_sqr(x), yy = fp2_sqr(y);
+    rx = fp2_add(xx, fp2_mul_xi(yy));
+    ry = fp2_sub(fp2_sub(fp2_sqr(fp2_add(x, y)), xx), yy);
+}
+__device__ __forceinline__ Fp2 fp2_triple(const Fp2 &z) { return fp2_add(fp2_dbl(z), z); }
+static __device__ __noinline__ void fp12_cyc_sqr(Fp12 *r, const Fp12 *a) {
+    Fp2 x0 = a->c0.c0, y0 = a->c1.c1, x1 = a->c1.c0, y1 = a->c0.c2, x2 = a->c0.c1, y2 = a->c1.c2;
+    Fp2 t0x, t0y, t1x, t1y, t2x, t2y;
+    fp4_sqr(t0x, t0y, x0, y0);
+    fp4_sqr(t1x, t1y, x1, y1);
+    fp4_sqr(t2x, t2y, x2, y2);
+    r->c0.c0 = fp2_sub(fp2_triple(t0x), fp2_dbl(x0));
+    r->c1.c1 = fp2_add(fp2_triple(t0y), fp2_dbl(y0));
+    r->c1.c0 = fp2_add(fp2_triple(fp2_mul_xi(t2y)), fp2_dbl(x1));
+    r->c0.c2 = fp2_sub(fp2_triple(t2x), fp2_dbl(y1));
+    r->c0.c1 = fp2_sub(fp2_triple(t1x), fp2_dbl(x2));
+    r->c1.c2 = fp2_add(fp2_triple(t1y), fp2_dbl(y2));
+}
+
 // f^|x| then conjugate (x < 0); valid in the cyclotomic subgroup where inverse == conjugate
 static __device__ __noinline__ void fp12_pow_x(Fp12 *r, const Fp12 *a) {
     Fp12 acc = *a;
 #pragma unroll 1
     for (int bit = 62; bit >= 0; --bit) {
-        fp12_sqr(&acc, &acc);
+        fp12_cyc_sqr(&acc, &acc);
         if ((KZG_BLS_X_ABS >> bit) & 1) { Fp12 t = acc; fp12_mul(&acc, &t, a); }
     }
     fp12_conj(r, &acc);
@@ -157,7 +213,7 @@ static __device__ __noinline__ void final_exp(Fp12 *r, const Fp12 *f0, const Fp2
     fp12_frobenius(&t, &b, g); fp12_frobenius(&bp2, &t, g);
     fp12_conj(&bc, &b);
     fp12_mul(&t, &u, &bp2); fp12_mul(&c, &t, &bc);                        // ^(x^2+p^2-1)
-    fp12_sqr(&t, &f); fp12_mul(&u, &t, &f);                               // f^3
+    fp12_cyc_sqr(&t, &f); fp12_mul(&u, &t, &f);                           // f^3
     fp12_mul(r, &c, &u);
 }
 
@@ -174,8 +230,6 @@ static __device__ __noinline__ void miller2(Fp12 *f, const G1Aff *P0, const G2Li
     }
     fp12_one(f);
     int li = 0;
-    Fp12 l;
-    l.c0.c2 = fp2_zero(); l.c1.c0 = fp2_zero(); l.c1.c1 = fp2_one(); l.c1.c2 = fp2_zero();
 #pragma unroll 1
     for (int bit = 62; bit >= 0; --bit) {
         fp12_sqr(f, f);
@@ -185,10 +239,7 @@ static __device__ __noinline__ void miller2(Fp12 *f, const G1Aff *P0, const G2Li
 #pragma unroll 1
             for (int i = 0; i < 2; ++i) {
                 if (!use[i]) continue;
-                l.c0.c0 = fp2_mul_fp(Ls[i]->A[li], py[i]);
-                l.c0.c1 = fp2_mul_fp(Ls[i]->B[li], px[i]);
-                Fp12 t = *f;
-                fp12_mul(f, &t, &l);
+                fp12_mul_by_line(f, fp2_mul_fp(Ls[i]->A[li], py[i]), fp2_mul_fp(Ls[i]->B[li], px[i]));
             }
         }
     }

@@ -270,22 +270,37 @@ static __global__ void k_cell_interp_reduce(const Fr *__restrict__ partial, cons
     Fr p = fr_from_mont(tot);
     for (int q = 0; q < 8; ++q) interp[((size_t)b * 64 + j) * 8 + q] = p.v[q];
 }
-// column sums: thread (batch b, column c): S = sum of T over the batch's cells with cell index c
-// (CSR from the host), W = [h_c^64] S = [w_128^brp7(c)] S
+// column sums: thread (batch b, column c): S_c = sum of T over the batch's cells with cell index c
+// (CSR from the host), W_c = [h_c^64] S_c = [w_128^brp7(c)] S_c; then the block adds them up:
+// sumS[b] = sum_c S_c = sum_k r_k pi_k,  sumW[b] = sum_c W_c = sum_k r_k h_k^64 pi_k   (kzg_verify.go:32,73-83)
 static __global__ void __launch_bounds__(128) k_cell_columns(const G1 *__restrict__ T, const uint32_t *__restrict__ order, const uint64_t *__restrict__ col_off,
-                                                      const int8_t *__restrict__ digits, G1 *__restrict__ S, G1 *__restrict__ Wt) {
+                                                      const int8_t *__restrict__ digits, G1 *__restrict__ sumS, G1 *__restrict__ sumW) {
+    __shared__ G1 sm[128];
     const size_t b = blockIdx.x;
     const int cidx = threadIdx.x;
     const uint64_t lo = col_off[b * 128 + cidx], hi = col_off[b * 128 + cidx + 1];
     G1 acc = G1::infinity();
     for (uint64_t q = lo; q < hi; ++q) g1_add(acc, T[order[q]]);
-    S[b * 128 + cidx] = acc;
+    sm[cidx] = acc;
+    __syncthreads();
+    for (int st = 64; st > 0; st >>= 1) {
+        if (cidx < st) g1_add_ool(&sm[cidx], &sm[cidx + st]);
+        __syncthreads();
+    }
+    if (cidx == 0) sumS[b] = sm[0];
+    __syncthreads();
     int t = (int)(__brev((unsigned)cidx) >> 25);
     if (t) g1_mul_twiddle(&acc, digits + (size_t)t * 2 * KZG_GLV_DIGITS);
-    Wt[b * 128 + cidx] = acc;
+    sm[cidx] = acc;
+    __syncthreads();
+    for (int st = 64; st > 0; st >>= 1) {
+        if (cidx < st) g1_add_ool(&sm[cidx], &sm[cidx + st]);
+        __syncthreads();
+    }
+    if (cidx == 0) sumW[b] = sm[0];
 }
 // per batch: final combination + pairing.  rows: CSR of the batch's cells grouped by unique commitment.
-static __global__ void __launch_bounds__(32) k_cell_finish(const G1 *__restrict__ S, const G1 *__restrict__ Wt, const G1 *__restrict__ interp_commit,
+static __global__ void __launch_bounds__(32) k_cell_finish(const G1 *__restrict__ S /*sumS[b]*/, const G1 *__restrict__ Wt /*sumW[b]*/, const G1 *__restrict__ interp_commit,
                                                     const G1Aff *__restrict__ uniq_commit, const uint64_t *__restrict__ row_off,
                                                     const uint64_t *__restrict__ batch_row_off, const uint32_t *__restrict__ row_cells,
                                                     const Fr *__restrict__ rpow, const PairingConsts *__restrict__ pc,
@@ -293,8 +308,7 @@ static __global__ void __launch_bounds__(32) k_cell_finish(const G1 *__restrict_
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_batches) return;
     if (batch_status[b] != ST_OK) { result[b] = batch_status[b]; return; }
-    G1 sumS = G1::infinity(), sumW = G1::infinity();
-    for (int cidx = 0; cidx < 128; ++cidx) { g1_add(sumS, S[b * 128 + cidx]); g1_add(sumW, Wt[b * 128 + cidx]); }
+    G1 sumS = S[b], sumW = Wt[b];
     G1 comms = G1::infinity();
     for (uint64_t row = batch_row_off[b]; row < batch_row_off[b + 1]; ++row) {
         Fr wsum = Fr::zero();

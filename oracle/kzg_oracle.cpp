@@ -721,3 +721,35 @@ extern "C" int ko_dbg_dump_pairing(const uint8_t *g2_96, uint8_t *out) {
     for (int s = 0; s < 4; ++s) { vals[s].c0.to_bytes_be(out + s * 96); vals[s].c1.to_bytes_be(out + s * 96 + 48); }
     return li;
 }
+
+// debug: Granger-Scott cyclotomic squaring vs generic squaring on an element of the cyclotomic
+// subgroup (used to validate the formula the CUDA pairing uses).  Returns 1 if equal.
+extern "C" int ko_dbg_cyclotomic_sqr_check(uint64_t seed) {
+    init_all();
+    auto rnd = [&]() { seed = seed * 6364136223846793005ULL + 1442695040888963407ULL; return Fp::from_u64(seed >> 11) * Fp::from_u64(seed | 1); };
+    Fp12 a;
+    Fp2 *c[6] = {&a.c0.c0, &a.c0.c1, &a.c0.c2, &a.c1.c0, &a.c1.c1, &a.c1.c2};
+    for (auto p : c) { p->c0 = rnd(); p->c1 = rnd(); }
+    // easy part -> cyclotomic subgroup
+    Fp12 f = a.conj() * a.inv();
+    f = frobenius(frobenius(f)) * f;
+    Fp12 ref = f.sqr();
+    // Fp4 view: A0 = g0 + h1 s, A1 = h0 + g2 s, A2 = g1 + h2 s   (s = v w, s^2 = xi)
+    Fp2 x0 = f.c0.c0, y0 = f.c1.c1, x1 = f.c1.c0, y1 = f.c0.c2, x2 = f.c0.c1, y2 = f.c1.c2;
+    auto sq4 = [](const Fp2 &x, const Fp2 &y, Fp2 &rx, Fp2 &ry) {   // (x + y s)^2
+        Fp2 xx = x.sqr(), yy = y.sqr();
+        rx = xx + yy.mul_xi();
+        ry = (x + y).sqr() - xx - yy;
+    };
+    Fp2 t0x, t0y, t1x, t1y, t2x, t2y;
+    sq4(x0, y0, t0x, t0y); sq4(x1, y1, t1x, t1y); sq4(x2, y2, t2x, t2y);
+    auto three = [](const Fp2 &z) { return z.dbl() + z; };
+    // A0' = 3 A0^2 - 2 conj(A0);  A1' = 3 s A2^2 + 2 conj(A1);  A2' = 3 A1^2 - 2 conj(A2)
+    Fp2 n0x = three(t0x) - x0.dbl(), n0y = three(t0y) + y0.dbl();
+    Fp2 sx = t2y.mul_xi(), sy = t2x;                 // s * (t2x + t2y s) = xi t2y + t2x s
+    Fp2 n1x = three(sx) + x1.dbl(), n1y = three(sy) - y1.dbl();
+    Fp2 n2x = three(t1x) - x2.dbl(), n2y = three(t1y) + y2.dbl();
+    Fp12 r;
+    r.c0.c0 = n0x; r.c1.c1 = n0y; r.c1.c0 = n1x; r.c0.c2 = n1y; r.c0.c1 = n2x; r.c1.c2 = n2y;
+    return r == ref ? 1 : 0;
+}
