@@ -138,7 +138,7 @@ WORKLOAD_NAME = {"cells_proofs": "EIP-7594 ComputeCellsAndKZGProofs (FK20, 128 c
                  "verify_blob_batch": "EIP-4844 VerifyBlobKZGProofBatch, one RLC verdict over 4096 blobs per GPU",
                  "recover": "EIP-7594 RecoverCellsAndComputeKZGProofs, 64 of 128 cells (random pattern), 1024 blobs per GPU",
                  "verify_cells": "EIP-7594 VerifyCellKZGProofBatch, independent 128-cell batches, 128 x B cells per GPU"}
-DEFAULT_B = {"cells_proofs": 1024, "commit": 4096, "blob_proof": 4096, "verify_blob_batch": 4096, "recover": 1024, "verify_cells": 1024}
+DEFAULT_B = {"cells_proofs": 1024, "commit": 4096, "blob_proof": 4096, "verify_blob_batch": 4096, "recover": 1024, "verify_cells": 4096}
 # canonical IMAD per unit
 CANONICAL_W.update({"blob_proof": 560e6, "verify_blob_batch": 8.2e6, "recover": 2701e6, "verify_cells": 1.79e6})
 
