@@ -108,7 +108,7 @@ static __global__ void __launch_bounds__(64) k_fk20_rows(const Fr *__restrict__ 
 
 // ---- G1 side -----------------------------------------------------------------------------
 // P = [w_128^t] P with the precomputed GLV digits dig[2][KZG_GLV_DIGITS] (top window first)
-static __device__ __noinline__ void g1_mul_twiddle(G1 *pp, const int8_t *__restrict__ dig) {
+template <class M_> static __device__ __noinline__ void g1_mul_twiddle_t(G1 *pp, const int8_t *__restrict__ dig) {
     G1 P = *pp;
     if (P.is_inf()) return;
     G1J base = jac_from_xyzz(P);
@@ -129,7 +129,7 @@ static __device__ __noinline__ void g1_mul_twiddle(G1 *pp, const int8_t *__restr
     for (int w = 0; w < KZG_GLV_DIGITS; ++w) {
         if (w) {
 #pragma unroll 1
-            for (int i = 0; i < 4; ++i) jac_dbl(acc);
+            for (int i = 0; i < 4; ++i) jac_dbl<M_>(acc);
         }
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
@@ -138,15 +138,16 @@ static __device__ __noinline__ void g1_mul_twiddle(G1 *pp, const int8_t *__restr
             G1JT t = tab[(d < 0 ? -d : d) - 1];
             if (h) t.X = fp_mul_ni(t.X, beta);
             if (d < 0) t.Y = Fp::neg(t.Y);
-            jac_add(acc, t);
+            jac_add<M_>(acc, t);
         }
     }
     *pp = jac_to_xyzz(acc);
 }
 
+static __device__ __forceinline__ void g1_mul_twiddle(G1 *pp, const int8_t *__restrict__ dig) { g1_mul_twiddle_t<MulCall>(pp, dig); }
 // radix-2 stages of a size-128 G1 FFT on points in shared memory, 64 threads.
 //   DIT: bit-reversed in -> natural out.  DIF: natural in -> bit-reversed out.
-template <bool DIT, bool INVERSE>
+template <bool DIT, bool INVERSE, class M_ = MulCall>
 __device__ __forceinline__ void g1_fft128_smem(G1 *pts, const int8_t *__restrict__ digits, int tid) {
 #pragma unroll 1
     for (int s = 0; s < 7; ++s) {
@@ -163,14 +164,14 @@ __device__ __forceinline__ void g1_fft128_smem(G1 *pts, const int8_t *__restrict
         const int8_t *dg = digits + (size_t)t * 2 * KZG_GLV_DIGITS;
         G1 x = pts[i0], y = pts[i1];
         if (DIT) {
-            if (t) g1_mul_twiddle(&y, dg);
+            if (t) g1_mul_twiddle_t<M_>(&y, dg);
             G1 s0 = x; g1_add(s0, y);
             y.neg_inplace(); g1_add(x, y);
             pts[i0] = s0; pts[i1] = x;
         } else {
             G1 s0 = x; g1_add(s0, y);
             y.neg_inplace(); g1_add(x, y);
-            if (t) g1_mul_twiddle(&x, dg);
+            if (t) g1_mul_twiddle_t<M_>(&x, dg);
             pts[i0] = s0; pts[i1] = x;
         }
         __syncthreads();

@@ -143,34 +143,34 @@ static __device__ __noinline__ void g1_add_ool(G1 *a, const G1 *b) { g1_add<MulC
 struct G1J { Fp X, Y, Z; };
 struct G1JT { Fp X, Y, Z, ZZ, ZZZ; };
 
-__device__ __forceinline__ void jac_dbl(G1J &p) {          // dbl-2009-l, a = 0; no-op on infinity (Z = 0 stays 0)
-    Fp A = fp_sqr_ni(p.X), B = fp_sqr_ni(p.Y), C = fp_sqr_ni(B);
+template <class M_ = MulCall> __device__ __forceinline__ void jac_dbl(G1J &p) {          // dbl-2009-l, a = 0; no-op on infinity (Z = 0 stays 0)
+    Fp A = M_::sqr(p.X), B = M_::sqr(p.Y), C = M_::sqr(B);
     Fp t = Fp::add(p.X, B);
-    Fp D = Fp::dbl(Fp::sub(Fp::sub(fp_sqr_ni(t), A), C));
+    Fp D = Fp::dbl(Fp::sub(Fp::sub(M_::sqr(t), A), C));
     Fp E = Fp::add(Fp::dbl(A), A);
-    Fp F = fp_sqr_ni(E);
-    Fp Z3 = Fp::dbl(fp_mul_ni(p.Y, p.Z));
+    Fp F = M_::sqr(E);
+    Fp Z3 = Fp::dbl(M_::mul(p.Y, p.Z));
     p.X = Fp::sub(F, Fp::dbl(D));
     Fp C8 = Fp::dbl(Fp::dbl(Fp::dbl(C)));
-    p.Y = Fp::sub(fp_mul_ni(E, Fp::sub(D, p.X)), C8);
+    p.Y = Fp::sub(M_::mul(E, Fp::sub(D, p.X)), C8);
     p.Z = Z3;
 }
-__device__ __forceinline__ void jac_add(G1J &a, const G1JT &b) {   // b is never the point at infinity
+template <class M_ = MulCall> __device__ __forceinline__ void jac_add(G1J &a, const G1JT &b) {   // b is never the point at infinity
     if (a.Z.is_zero()) { a.X = b.X; a.Y = b.Y; a.Z = b.Z; return; }
-    Fp Z1Z1 = fp_sqr_ni(a.Z);
-    Fp U1 = fp_mul_ni(a.X, b.ZZ), U2 = fp_mul_ni(b.X, Z1Z1);
-    Fp S1 = fp_mul_ni(a.Y, b.ZZZ), S2 = fp_mul_ni(fp_mul_ni(b.Y, a.Z), Z1Z1);
+    Fp Z1Z1 = M_::sqr(a.Z);
+    Fp U1 = M_::mul(a.X, b.ZZ), U2 = M_::mul(b.X, Z1Z1);
+    Fp S1 = M_::mul(a.Y, b.ZZZ), S2 = M_::mul(M_::mul(b.Y, a.Z), Z1Z1);
     Fp H = Fp::sub(U2, U1), r = Fp::sub(S2, S1);
     if (H.is_zero()) {
-        if (r.is_zero()) { a.X = b.X; a.Y = b.Y; a.Z = b.Z; jac_dbl(a); }
+        if (r.is_zero()) { a.X = b.X; a.Y = b.Y; a.Z = b.Z; jac_dbl<M_>(a); }
         else a.Z = Fp::zero();
         return;
     }
-    Fp HH = fp_sqr_ni(H), HHH = fp_mul_ni(H, HH), V = fp_mul_ni(U1, HH);
-    Fp X3 = Fp::sub(Fp::sub(fp_sqr_ni(r), HHH), Fp::dbl(V));
-    a.Y = Fp::sub(fp_mul_ni(r, Fp::sub(V, X3)), fp_mul_ni(S1, HHH));
+    Fp HH = M_::sqr(H), HHH = M_::mul(H, HH), V = M_::mul(U1, HH);
+    Fp X3 = Fp::sub(Fp::sub(M_::sqr(r), HHH), Fp::dbl(V));
+    a.Y = Fp::sub(M_::mul(r, Fp::sub(V, X3)), M_::mul(S1, HHH));
     a.X = X3;
-    a.Z = fp_mul_ni(fp_mul_ni(a.Z, b.Z), H);
+    a.Z = M_::mul(M_::mul(a.Z, b.Z), H);
 }
 __device__ __forceinline__ G1JT jac_cache(const G1J &p) {
     G1JT t; t.X = p.X; t.Y = p.Y; t.Z = p.Z; t.ZZ = fp_sqr_ni(p.Z); t.ZZZ = fp_mul_ni(t.ZZ, p.Z);
