@@ -86,6 +86,31 @@ template <class P> struct Mont {
         for (int i = 0; i < N; ++i) r[i] = borrow ? r[i] : t[i];
     }
 
+    // Montgomery reduction of a 2N-limb value (< p * 2^(32N)) with reduction-only rows
+    static __device__ __forceinline__ Mont reduce_wide(const uint32_t *T) {
+        uint32_t even[N], odd[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) even[i] = T[i];
+#pragma unroll
+        for (int r = 0; r < N; r += 2) {
+            redc_row(even, odd, r == 0);
+            redc_row(odd, even, false);
+        }
+        even[0] = ptx_add_cc(even[0], odd[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; ++i) even[i] = ptx_addc_cc(even[i], odd[i + 1]);
+        even[N - 1] = ptx_addc(even[N - 1], 0);
+        even[0] = ptx_add_cc(even[0], T[N]);
+#pragma unroll
+        for (int i = 1; i < N - 1; ++i) even[i] = ptx_addc_cc(even[i], T[N + i]);
+        even[N - 1] = ptx_addc(even[N - 1], T[2 * N - 1]);
+        final_sub(even);
+        Mont r;
+#pragma unroll
+        for (int i = 0; i < N; ++i) r.v[i] = even[i];
+        return r;
+    }
+
     // ---- field ops ------------------------------------------------------------------------
     static __device__ __forceinline__ Mont mul(const Mont &a, const Mont &b) {
         uint32_t even[N], odd[N];
@@ -170,31 +195,7 @@ template <class P> struct Mont {
             T[2 * i] = ptx_madc_lo_cc(a.v[i], a.v[i], T[2 * i]);
             T[2 * i + 1] = ptx_madc_hi_cc(a.v[i], a.v[i], T[2 * i + 1]);
         }
-        // reduction-only rows on the low half
-        const uint32_t *MOD = P::mod();
-        uint32_t even[N], odd[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) even[i] = T[i];
-#pragma unroll
-        for (int r = 0; r < N; r += 2) {
-            redc_row(even, odd, r == 0);
-            redc_row(odd, even, false);
-        }
-        even[0] = ptx_add_cc(even[0], odd[1]);
-#pragma unroll
-        for (int i = 1; i < N - 1; ++i) even[i] = ptx_addc_cc(even[i], odd[i + 1]);
-        even[N - 1] = ptx_addc(even[N - 1], 0);
-        // + high half
-        even[0] = ptx_add_cc(even[0], T[N]);
-#pragma unroll
-        for (int i = 1; i < N - 1; ++i) even[i] = ptx_addc_cc(even[i], T[N + i]);
-        even[N - 1] = ptx_addc(even[N - 1], T[2 * N - 1]);
-        final_sub(even);
-        (void)MOD;
-        Mont r;
-#pragma unroll
-        for (int i = 0; i < N; ++i) r.v[i] = even[i];
-        return r;
+        return reduce_wide(T);
     }
     // one reduction-only row: (even + 2^32 odd) <- ((even + 2^32 odd) + m*p) / 2^32, roles swapped by the caller
     static __device__ __forceinline__ void redc_row(uint32_t *even, uint32_t *odd, bool first) {
