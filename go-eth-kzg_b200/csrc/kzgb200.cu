@@ -37,17 +37,45 @@ static __global__ void k_blob_to_scalars(const uint8_t *__restrict__ blobs, uint
     o[1] = make_uint4(l[4], l[5], l[6], l[7]);
 }
 
-// XYZZ sums -> 48-byte compressed points; items with a non-OK status get zero bytes
+// XYZZ sums -> 48-byte compressed points; items with a non-OK status get zero bytes.
+// Each thread normalises FIN_BATCH consecutive points with one shared inversion (Montgomery's
+// trick over the ZZZ coordinates), so the Fermat inversion is amortised 8x.
+#define KZG_FIN_BATCH 8
 static __global__ void k_finalize_g1(const G1 *__restrict__ in, uint8_t *__restrict__ out48, const int32_t *__restrict__ status, size_t n, int per_status) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint8_t *o = out48 + i * 48;
-    if (status && status[i / per_status] != ST_OK) {
-        uint32_t *w = reinterpret_cast<uint32_t *>(o);
-        for (int k = 0; k < 12; ++k) w[k] = 0;
-        return;
+    size_t base = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * KZG_FIN_BATCH;
+    if (base >= n) return;
+    int cnt = (int)min((size_t)KZG_FIN_BATCH, n - base);
+    Fp pre[KZG_FIN_BATCH];
+    bool live[KZG_FIN_BATCH];
+    Fp run = Fp::one();
+    for (int k = 0; k < cnt; ++k) {
+        size_t i = base + k;
+        Fp zzz = in[i].ZZZ;
+        live[k] = !(status && status[i / per_status] != ST_OK) && !in[i].ZZ.is_zero();
+        pre[k] = run;
+        if (live[k]) run = fp_mul_ni(run, zzz);
     }
-    g1_compress(o, g1_to_affine(in[i]));
+    Fp inv = fp_inv(run);
+    for (int k = cnt - 1; k >= 0; --k) {
+        size_t i = base + k;
+        uint8_t *o = out48 + i * 48;
+        if (status && status[i / per_status] != ST_OK) {
+            uint32_t *w = reinterpret_cast<uint32_t *>(o);
+            for (int q = 0; q < 12; ++q) w[q] = 0;
+            continue;
+        }
+        G1Aff a;
+        if (!live[k]) { a.x = Fp::zero(); a.y = Fp::zero(); }        // point at infinity
+        else {
+            G1 p = in[i];
+            Fp i3 = fp_mul_ni(inv, pre[k]);                            // 1 / ZZZ_i
+            inv = fp_mul_ni(inv, p.ZZZ);
+            Fp i2 = fp_mul_ni(fp_sqr_ni(i3), fp_sqr_ni(p.ZZ));         // 1 / ZZ_i
+            a.x = fp_mul_ni(p.X, i2);
+            a.y = fp_mul_ni(p.Y, i3);
+        }
+        g1_compress(o, a);
+    }
 }
 
 // zero the y outputs of failed items
@@ -354,7 +382,7 @@ int kzgb200_blob_to_kzg_commitment(kzgb200_ctx *c, const uint8_t *blobs, size_t 
         k_msm_fixed<<<dim3(1, (unsigned)m), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->commit_tab, N_BLOB, 1, TPB,
                                                                                   d_status, (G1 *)c->sums.p);
         c->mark(KZGB200_KC_FINALIZE);
-        k_finalize_g1<<<(unsigned)((m + 63) / 64), 64, 0, c->stream>>>((const G1 *)c->sums.p, d_out, d_status, m, 1);
+        k_finalize_g1<<<(unsigned)((m + 64 * KZG_FIN_BATCH - 1) / (64 * KZG_FIN_BATCH)), 64, 0, c->stream>>>((const G1 *)c->sums.p, d_out, d_status, m, 1);
         c->launches += 3;
         c->mark(-1);
         CU(cudaGetLastError());
@@ -414,7 +442,7 @@ static int open_common(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *z32,
         k_msm_fixed<<<dim3(1, (unsigned)m), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->commit_tab, N_BLOB, 1, TPB,
                                                                                   d_status, (G1 *)c->sums.p);
         c->mark(KZGB200_KC_FINALIZE);
-        k_finalize_g1<<<gb, 64, 0, c->stream>>>((const G1 *)c->sums.p, d_out, d_status, m, 1);
+        k_finalize_g1<<<(unsigned)((m + 64 * KZG_FIN_BATCH - 1) / (64 * KZG_FIN_BATCH)), 64, 0, c->stream>>>((const G1 *)c->sums.p, d_out, d_status, m, 1);
         if (d_y) { k_zero_failed<<<gb, 64, 0, c->stream>>>(d_y, d_status, m, 32); c->launches += 1; }
         c->launches += 3;
         c->mark(-1);
@@ -454,7 +482,7 @@ static void launch_fk20_proofs(kzgb200_ctx *c, cudaStream_t st, size_t m, const 
     k_fk20_g1fft<4><<<(unsigned)m, 64, 0, st>>>(sums, pxyzz, d_status, c->glv_digits);
     size_t np = m * 128;
     if (marks) c->mark(KZGB200_KC_FINALIZE);
-    k_finalize_g1<<<(unsigned)((np + 63) / 64), 64, 0, st>>>(pxyzz, d_proofs, d_status, np, 128);
+    k_finalize_g1<<<(unsigned)((np + 64 * KZG_FIN_BATCH - 1) / (64 * KZG_FIN_BATCH)), 64, 0, st>>>(pxyzz, d_proofs, d_status, np, 128);
     c->launches += 4;
 }
 
