@@ -67,7 +67,7 @@ struct DevBuf {
 struct kzgb200_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_piece[8] = {nullptr};
     std::mutex mu;
     // setup
     G1Aff *g1_monomial = nullptr;      // natural order

@@ -211,6 +211,7 @@ void kzgb200_ctx_free(kzgb200_ctx *c) {
     c->v_W.release(); c->v_partial.release(); c->v_in2.release(); c->v_in3.release(); c->v_st2.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_piece) if (e) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -230,6 +231,7 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
+    for (cudaEvent_t &e : c->ev_piece) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->g2_bytes.assign(g2, g2 + n_g2 * 96);
 
     int cw = opts && opts->commit_window ? opts->commit_window : 0;
@@ -349,6 +351,7 @@ int kzgb200_last_kernel_ms(kzgb200_ctx *c, double *out) {
 // SRS -> compress.  Processed in chunks of CHUNK blobs.
 // -------------------------------------------------------------------------------------------
 static const size_t COMMIT_CHUNK = 4096;
+#define KZG_H2D_PIECES 4
 
 int kzgb200_blob_to_kzg_commitment(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint8_t *out48, int32_t *status) {
     if (!c || (n && (!blobs || !out48 || !status))) return set_err(KZGB200_ERR_ARGS, "null argument");
@@ -368,22 +371,33 @@ int kzgb200_blob_to_kzg_commitment(kzgb200_ctx *c, const uint8_t *blobs, size_t 
     for (size_t off = 0; off < n; off += chunk) {
         size_t m = std::min(chunk, n - off);
         const uint8_t *d_blobs = blobs + off * KZGB200_BYTES_PER_BLOB;
-        if (!in_dev) {
-            CU(cudaMemcpyAsync(c->in_bytes.p, d_blobs, m * KZGB200_BYTES_PER_BLOB, cudaMemcpyHostToDevice, c->stream));
-            d_blobs = (const uint8_t *)c->in_bytes.p;
-        }
         int32_t *d_status = st_dev ? status + off : (int32_t *)c->status.p;
         uint8_t *d_out = out_dev ? out48 + off * 48 : (uint8_t *)c->out_bytes.p;
-        c->mark(KZGB200_KC_FR);
         CU(cudaMemsetAsync(d_status, 0, m * sizeof(int32_t), c->stream));
-        size_t ns = m * N_BLOB;
-        k_blob_to_scalars<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(d_blobs, (uint32_t *)c->scalars.p, d_status, ns, N_BLOB);
-        c->mark(KZGB200_KC_MSM);
-        k_msm_fixed<<<dim3(1, (unsigned)m), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->commit_tab, N_BLOB, 1, TPB,
-                                                                                  d_status, (G1 *)c->sums.p);
-        c->mark(KZGB200_KC_FINALIZE);
-        k_finalize_g1<<<(unsigned)((m + 64 * KZG_FIN_BATCH - 1) / (64 * KZG_FIN_BATCH)), 64, 0, c->stream>>>((const G1 *)c->sums.p, d_out, d_status, m, 1);
-        c->launches += 3;
+        // host input: the H2D runs on the copy stream in up to 4 pieces and each piece's kernels start
+        // as soon as its bytes have landed; device input: one launch over the whole chunk
+        const size_t pieces = in_dev ? 1 : std::min<size_t>(KZG_H2D_PIECES, (m + 255) / 256);
+        const size_t per = (m + pieces - 1) / pieces;
+        for (size_t pc = 0, po = 0; po < m; ++pc, po += per) {
+            size_t pm = std::min(per, m - po);
+            const uint8_t *pb = d_blobs + po * KZGB200_BYTES_PER_BLOB;
+            if (!in_dev) {
+                uint8_t *dst = (uint8_t *)c->in_bytes.p + po * KZGB200_BYTES_PER_BLOB;
+                CU(cudaMemcpyAsync(dst, pb, pm * KZGB200_BYTES_PER_BLOB, cudaMemcpyHostToDevice, c->copy_stream));
+                CU(cudaEventRecord(c->ev_piece[pc], c->copy_stream));
+                CU(cudaStreamWaitEvent(c->stream, c->ev_piece[pc], 0));
+                pb = dst;
+            }
+            c->mark(KZGB200_KC_FR);
+            size_t ns = pm * N_BLOB;
+            k_blob_to_scalars<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(pb, (uint32_t *)c->scalars.p + po * N_BLOB * 8, d_status + po, ns, N_BLOB);
+            c->mark(KZGB200_KC_MSM);
+            k_msm_fixed<<<dim3(1, (unsigned)pm), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p + po * N_BLOB * 8, c->commit_tab, N_BLOB, 1, TPB,
+                                                                                       d_status + po, (G1 *)c->sums.p + po);
+            c->mark(KZGB200_KC_FINALIZE);
+            k_finalize_g1<<<(unsigned)((pm + 64 * KZG_FIN_BATCH - 1) / (64 * KZG_FIN_BATCH)), 64, 0, c->stream>>>((const G1 *)c->sums.p + po, d_out + po * 48, d_status + po, pm, 1);
+            c->launches += 3;
+        }
         c->mark(-1);
         CU(cudaGetLastError());
         if (!out_dev) CU(cudaMemcpyAsync(out48 + off * 48, d_out, m * 48, cudaMemcpyDeviceToHost, c->stream));
@@ -510,19 +524,29 @@ static int cells_and_proofs(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint
     for (size_t off = 0; off < n; off += chunk) {
         size_t m = std::min(chunk, n - off);
         const uint8_t *d_blobs = blobs + off * KZGB200_BYTES_PER_BLOB;
-        if (!in_dev) {
-            CU(cudaMemcpyAsync(c->in_bytes.p, d_blobs, m * KZGB200_BYTES_PER_BLOB, cudaMemcpyHostToDevice, c->stream));
-            d_blobs = (const uint8_t *)c->in_bytes.p;
-        }
         int32_t *d_status = st_dev ? status + off : (int32_t *)c->status.p;
         uint8_t *d_cells = cells_dev ? out_cells + off * 262144 : (uint8_t *)c->cells.p;
         uint8_t *d_proofs = !out_proofs ? nullptr : proofs_dev ? out_proofs + off * 6144 : (uint8_t *)c->out_bytes.p;
+        // host input: H2D in pieces on the copy stream, the per-blob Fr kernels of a piece start when
+        // its bytes have landed.  The cells are final after k_coset_fft_cells: their D2H (the bulk of
+        // the output bytes) also runs on the copy stream, underneath the FK20 kernels.
+        const size_t pieces = in_dev ? 1 : std::min<size_t>(KZG_H2D_PIECES, (m + 63) / 64);
+        const size_t per = (m + pieces - 1) / pieces;
         c->mark(KZGB200_KC_FR);
-        k_blob_ifft<<<(unsigned)m, KZG_NTT_THREADS, 4096 * 32, c->stream>>>(d_blobs, (Fr *)c->coeffs.p, d_status, c->roots, inv4096);
-        k_coset_fft_cells<<<(unsigned)m, KZG_NTT_THREADS, 4096 * 32, c->stream>>>((const Fr *)c->coeffs.p, d_blobs, d_cells, d_status, c->roots);
-        c->launches += 2;
-        // the cells are final after the second kernel: their D2H (the bulk of the output bytes) runs on
-        // the copy stream underneath the FK20 kernels
+        for (size_t pc = 0, po = 0; po < m; ++pc, po += per) {
+            size_t pm = std::min(per, m - po);
+            const uint8_t *pb = d_blobs + po * KZGB200_BYTES_PER_BLOB;
+            if (!in_dev) {
+                uint8_t *dst = (uint8_t *)c->in_bytes.p + po * KZGB200_BYTES_PER_BLOB;
+                CU(cudaMemcpyAsync(dst, pb, pm * KZGB200_BYTES_PER_BLOB, cudaMemcpyHostToDevice, c->copy_stream));
+                CU(cudaEventRecord(c->ev_piece[pc], c->copy_stream));
+                CU(cudaStreamWaitEvent(c->stream, c->ev_piece[pc], 0));
+                pb = dst;
+            }
+            k_blob_ifft<<<(unsigned)pm, KZG_NTT_THREADS, 4096 * 32, c->stream>>>(pb, (Fr *)c->coeffs.p + po * N_BLOB, d_status + po, c->roots, inv4096);
+            k_coset_fft_cells<<<(unsigned)pm, KZG_NTT_THREADS, 4096 * 32, c->stream>>>((const Fr *)c->coeffs.p + po * N_BLOB, pb, d_cells + po * 262144, d_status + po, c->roots);
+            c->launches += 2;
+        }
         if (!cells_dev) {
             CU(cudaEventRecord(c->ev0, c->stream));
             CU(cudaStreamWaitEvent(c->copy_stream, c->ev0, 0));
