@@ -167,17 +167,16 @@ template <int MODE> static __global__ void k_imad_peak(uint32_t *out, int iters,
 }  // namespace kzg
 
 static int build_table(kzgb200_ctx *c, const G1Aff *pts, int npts, int window, MsmTable &tab) {
-    tab.npts = npts; tab.c = window; tab.W = (256 + window - 1) / window; tab.H = 1 << (window - 1);
+    tab.plan(npts, window);
     size_t n_bases = (size_t)npts * tab.W;
     G1 *bases = nullptr; G1Aff *bases_aff = nullptr;
     CU(cudaMalloc(&bases, n_bases * sizeof(G1)));
     CU(cudaMalloc(&bases_aff, n_bases * sizeof(G1Aff)));
     CU(cudaMalloc(&tab.entries, tab.bytes()));
-    k_table_bases<<<(npts + 63) / 64, 64, 0, c->stream>>>(pts, npts, tab.c, tab.W, bases);
+    k_table_bases<<<(npts + 63) / 64, 64, 0, c->stream>>>(pts, tab, bases);
     k_to_affine<<<(unsigned)((n_bases + 127) / 128), 128, 0, c->stream>>>(bases, bases_aff, n_bases);
-    size_t chunks = (tab.H + KZG_TABLE_CHUNK - 1) / KZG_TABLE_CHUNK;
-    size_t threads = n_bases * chunks;
-    k_table_fill<<<(unsigned)((threads + 63) / 64), 64, 0, c->stream>>>(bases_aff, n_bases, tab.H, tab.entries);
+    size_t threads = (size_t)npts * (tab.row_entries / KZG_TABLE_CHUNK);
+    k_table_fill<<<(unsigned)((threads + 63) / 64), 64, 0, c->stream>>>(bases_aff, tab);
     c->launches += 3;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
@@ -236,7 +235,7 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
 
     int cw = opts && opts->commit_window ? opts->commit_window : 0;
     if (!cw) { const char *e = getenv("KZGB200_COMMIT_WINDOW"); cw = e ? atoi(e) : 13; }
-    if (cw < 4 || cw > 15) return set_err(KZGB200_ERR_ARGS, "commit_window must be in 4..15");
+    if (cw < 7 || cw > 15) return set_err(KZGB200_ERR_ARGS, "commit_window must be in 7..15");
 
     uint8_t *d_in = nullptr; int32_t *d_bad = nullptr;
     CU(cudaMalloc(&d_in, 2 * N_BLOB * 48));
@@ -280,7 +279,7 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
     // FK20 table (fk20.go:23-52, toeplitz.go:50-93): 64 G1 FFTs of size 128, then the window table
     int fw = opts && opts->fk20_window ? opts->fk20_window : 0;
     if (!fw) { const char *e = getenv("KZGB200_FK20_WINDOW"); fw = e ? atoi(e) : 12; }
-    if (fw < 4 || fw > 15) return set_err(KZGB200_ERR_ARGS, "fk20_window must be in 4..15");
+    if (fw < 7 || fw > 15) return set_err(KZGB200_ERR_ARGS, "fk20_window must be in 7..15");
     G1 *fk_xyzz = nullptr; G1Aff *fk_aff = nullptr;
     CU(cudaMalloc(&fk_xyzz, 8192 * sizeof(G1)));
     CU(cudaMalloc(&fk_aff, 8192 * sizeof(G1Aff)));

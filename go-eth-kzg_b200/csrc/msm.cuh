@@ -8,7 +8,7 @@
 // blobs, so instead of Pippenger buckets (whose per-blob bucket state, 4096 x 192 B, fits no
 // shared memory and costs a 2*2^(c-1)-add reduction per blob) the table stores EVERY signed
 // digit multiple of every window of every base point in affine form:
-//     table[(j*W + k)*H + (d-1)] = d * 2^(c*k) * P_j      d = 1..H,  H = 2^(c-1),  W = ceil(256/c)
+//     table[j*row + rowoff[k] + (d-1)] = d * 2^(bitpos[k]) * P_j      d = 1..2^(bits[k]-1)   (see MsmTable::plan)
 // and an MSM is just n*W mixed additions of gathered table entries plus a log-depth reduction --
 // no buckets, no sorting, no atomics, no doublings.  c = 13 gives 32 GB for the 4096-point base.
 // Entries are 96-byte affine points (3 x 32 B sectors per gather); the gathers are random over
@@ -18,25 +18,46 @@
 
 namespace kzg {
 
+// Window plan: W windows covering exactly 256 bits.  With c the requested (minimum) window size,
+// W = floor(256/c) and the top 256 - W*c windows are one bit wider, which saves the nearly empty
+// extra window of a uniform split (c = 15: 16 x 15 + 1 x 16 bits = 17 windows instead of 18 at the
+// same table size; c = 14: 14 x 14 + 4 x 15 = 18 instead of 19).  Falls back to ceil(256/c)
+// uniform windows when the remainder does not fit.
+#define KZG_MAX_WINDOWS 40
 struct MsmTable {
     G1Aff *entries;     // device
-    int npts, c, W, H;
-    size_t bytes() const { return (size_t)npts * W * H * sizeof(G1Aff); }
+    int npts, c, W;
+    uint32_t row_entries;                 // entries per base point = sum_k 2^(bits[k]-1)
+    uint8_t bits[KZG_MAX_WINDOWS];        // window sizes
+    uint16_t bitpos[KZG_MAX_WINDOWS];     // first bit of window k
+    uint32_t rowoff[KZG_MAX_WINDOWS];     // entry offset of window k inside a point's row
+    size_t bytes() const { return (size_t)npts * row_entries * sizeof(G1Aff); }
+    void plan(int npts_, int c_) {
+        npts = npts_; c = c_;
+        int Wf = 256 / c, rem = 256 - Wf * c;
+        if (rem > Wf) { W = Wf + 1; rem = 0; } else W = Wf;
+        uint32_t off = 0; int pos = 0;
+        for (int k = 0; k < W; ++k) {
+            int b = c + ((rem && k >= W - rem) ? 1 : 0);
+            bits[k] = (uint8_t)b; bitpos[k] = (uint16_t)pos; rowoff[k] = off;
+            off += 1u << (b - 1); pos += b;
+        }
+        row_entries = off;
+    }
 };
 
 // signed-digit recoding state for one scalar (plain little-endian limbs, < 2^255)
 struct DigitStream {
     uint32_t s[8];
     uint32_t carry;
-    int c;
-    __device__ __forceinline__ void init(const uint32_t *limbs, int c_) {
+    __device__ __forceinline__ void init(const uint32_t *limbs) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) s[i] = limbs[i];
-        carry = 0; c = c_;
+        carry = 0;
     }
-    // digit of window k (must be called for k = 0,1,2,... in order); returns signed digit
-    __device__ __forceinline__ int next(int k) {
-        int bit = k * c;
+    // digit of the window [bit, bit+c) (must be called window by window from the bottom); signed digit
+    // in [-(2^(c-1) - 1), 2^(c-1)].  The top window never overflows because bit 255 of a scalar is 0.
+    __device__ __forceinline__ int next(int bit, int c) {
         int wi = bit >> 5, sh = bit & 31;
         // dynamic limb index without local memory: select via unrolled compare
         uint32_t lo = 0, hi = 0;
@@ -87,14 +108,14 @@ static __global__ void __launch_bounds__(128) k_msm_fixed(const uint32_t *__rest
                 const uint4 *q = reinterpret_cast<const uint4 *>(sc + (size_t)j * 8);
                 uint4 a = __ldg(q), b = __ldg(q + 1);
                 uint32_t l[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                ds.init(l, tab.c);
+                ds.init(l);
             }
-            const G1Aff *row = tab.entries + ((size_t)(group * group_pts + j) * tab.W) * tab.H;
+            const G1Aff *row = tab.entries + (size_t)(group * group_pts + j) * tab.row_entries;
             for (int k = 0; k < tab.W; ++k) {
-                int d = ds.next(k);
+                int d = ds.next(tab.bitpos[k], tab.bits[k]);
                 if (d == 0) continue;
                 int mag = d < 0 ? -d : d;
-                G1Aff e = load_aff(row + (size_t)k * tab.H + (mag - 1));
+                G1Aff e = load_aff(row + tab.rowoff[k] + (mag - 1));
                 if (d < 0) e.y = Fp::neg(e.y);
                 g1_add_affine<MulInline>(acc, e);
             }
@@ -112,14 +133,14 @@ static __global__ void __launch_bounds__(128) k_msm_fixed(const uint32_t *__rest
 }
 
 // ---- table construction (context init) ---------------------------------------------------
-// step 1: bases[(j*W + k)] = 2^(c*k) * P_j  in XYZZ
-static __global__ void k_table_bases(const G1Aff *__restrict__ pts, int npts, int c, int W, G1 *__restrict__ bases) {
+// step 1: bases[(j*W + k)] = 2^(bitpos[k]) * P_j  in XYZZ
+static __global__ void k_table_bases(const G1Aff *__restrict__ pts, MsmTable tab, G1 *__restrict__ bases) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= npts) return;
+    if (j >= tab.npts) return;
     G1 q = G1::from_affine(pts[j]);
-    for (int k = 0; k < W; ++k) {
-        bases[(size_t)j * W + k] = q;
-        if (k + 1 < W) for (int i = 0; i < c; ++i) q = g1_dbl(q);
+    for (int k = 0; k < tab.W; ++k) {
+        bases[(size_t)j * tab.W + k] = q;
+        if (k + 1 < tab.W) for (int i = 0; i < tab.bits[k]; ++i) q = g1_dbl(q);
     }
 }
 // XYZZ -> affine, one thread per point (used only at init / for small batches)
@@ -128,25 +149,27 @@ static __global__ void k_to_affine(const G1 *__restrict__ in, G1Aff *__restrict_
     if (i >= n) return;
     out[i] = g1_to_affine(in[i]);
 }
-// step 2: for base b = (j,k) and chunk q of CH digits: entries d = q*CH+1 .. q*CH+CH of d*Q_b,
-// batch-normalised with one inversion per chunk.
+// step 2: one thread per chunk of CH consecutive digits of one (point j, window k): entries
+// d = q*CH+1 .. q*CH+CH of d * 2^(bitpos[k]) * P_j, batch-normalised with one inversion per chunk.
 #define KZG_TABLE_CHUNK 16
-static __global__ void __launch_bounds__(64) k_table_fill(const G1Aff *__restrict__ bases_aff, size_t n_bases, int H, G1Aff *__restrict__ table) {
-    const int chunks = (H + KZG_TABLE_CHUNK - 1) / KZG_TABLE_CHUNK;
+static __global__ void __launch_bounds__(64) k_table_fill(const G1Aff *__restrict__ bases_aff, MsmTable tab) {
+    const uint32_t chunks_per_point = tab.row_entries / KZG_TABLE_CHUNK;     // every window has >= 16 entries (c >= 5)
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= n_bases * chunks) return;
-    size_t b = gid / chunks;
-    int q = (int)(gid % chunks);
-    G1Aff Q = bases_aff[b];
-    G1Aff *dst = table + b * H + (size_t)q * KZG_TABLE_CHUNK;
-    int cnt = min(KZG_TABLE_CHUNK, H - q * KZG_TABLE_CHUNK);
+    if (gid >= (size_t)tab.npts * chunks_per_point) return;
+    size_t j = gid / chunks_per_point;
+    uint32_t e0 = (uint32_t)(gid % chunks_per_point) * KZG_TABLE_CHUNK;      // first entry of this chunk inside the row
+    int k = 0;
+    for (int w = 1; w < tab.W; ++w) if (e0 >= tab.rowoff[w]) k = w;
+    unsigned d0 = e0 - tab.rowoff[k];                                        // digits d0+1 .. d0+CH
+    G1Aff Q = bases_aff[j * tab.W + k];
+    G1Aff *dst = tab.entries + j * tab.row_entries + e0;
+    const int cnt = KZG_TABLE_CHUNK;
     if (Q.is_inf()) {
         for (int i = 0; i < cnt; ++i) dst[i] = Q;
         return;
     }
-    // start = (q*CH) * Q by MSB-first double-and-add
+    // start = d0 * Q by MSB-first double-and-add
     G1 cur = G1::infinity();
-    unsigned d0 = (unsigned)q * KZG_TABLE_CHUNK;
     for (int bit = 31 - __clz(d0 | 1); bit >= 0; --bit) {
         cur = g1_dbl(cur);
         if ((d0 >> bit) & 1) g1_add_affine(cur, Q);
@@ -164,7 +187,7 @@ static __global__ void __launch_bounds__(64) k_table_fill(const G1Aff *__restric
     for (int i = cnt - 1; i >= 0; --i) {
         Fp i3 = fp_mul_ni(inv, pre[i]);          // 1/ZZZ_i
         inv = fp_mul_ni(inv, pts[i].ZZZ);
-        Fp i2 = fp_mul_ni(fp_sqr_ni(i3), fp_mul_ni(pts[i].ZZ, pts[i].ZZ));
+        Fp i2 = fp_mul_ni(fp_sqr_ni(i3), fp_sqr_ni(pts[i].ZZ));
         G1Aff a;
         a.x = fp_mul_ni(pts[i].X, i2);
         a.y = fp_mul_ni(pts[i].Y, i3);

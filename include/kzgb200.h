@@ -61,7 +61,7 @@ typedef struct kzgb200_ctx kzgb200_ctx;
 /* Tunables.  Zero-initialise for defaults. */
 typedef struct kzgb200_opts {
     int device;          /* CUDA device ordinal */
-    int commit_window;   /* bits per fixed-base window for the 4096-point Lagrange MSM (8..15);
+    int commit_window;   /* bits per fixed-base window for the 4096-point Lagrange MSM (7..15); the top 256 mod c windows are one bit wider (MsmTable::plan);
                             table bytes = 4096 * ceil(256/c) * 2^(c-1) * 96.  0 = default */
     int fk20_window;     /* same for the 8192-point FK20 table (twice the bytes).  0 = default */
     int reserved[5];
