@@ -349,13 +349,17 @@ def main():
         c_used, W_used = (tab["commit_window"], tab["commit_windows_per_scalar"]) if uses_commit else (tab["fk20_window"], tab["fk20_windows_per_scalar"])
         npts = 4096 if uses_commit else 8192
         # dominant kernel k_msm_fixed; executed work per blob: npts*W mixed additions of 10 Fp muls
-        msm_imad = npts * W_used * 10 * IMAD_FP_MUL
+        # a mixed addition is 8 Fp mul (588 IMAD each) + 2 Fp sqr; the dedicated squaring executes
+        # 222 wide products + 12 lo = 456 IMAD-equivalents, so executed work is 5616 per addition
+        # (SURVEY's nominal 5880 counts a squaring as a multiplication)
+        IMAD_MIXED_ADD = 8 * IMAD_FP_MUL + 2 * 456
+        msm_imad = npts * W_used * IMAD_MIXED_ADD
         msm_ms = kms.get("msm", 0.0) / args.steps
         achieved = msm_imad * B / (msm_ms * 1e-3) if msm_ms else None
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
         roof.update({"kernel": "k_msm_fixed", "achieved": achieved / 1e12 if achieved else None, "frac": achieved / peak if achieved else None,
                      "frac_of_wide_multiply_rate": achieved / (2 * peaks["mad_wide"]) if achieved else None,
-                     "work_model": "executed: %d pts x %d windows x 10 Fp-mul x 588 IMAD = %.0f M IMAD/blob in this kernel" % (npts, W_used, msm_imad / 1e6),
+                     "work_model": "executed: %d pts x %d windows x (8 mul x 588 + 2 sqr x 456) IMAD = %.0f M IMAD/blob in this kernel (nominal at 588 per sqr: %.0f M)" % (npts, W_used, msm_imad / 1e6, npts * W_used * 10 * IMAD_FP_MUL / 1e6),
                      "hbm_table_gather": {"achieved": npts * W_used * 96.0 * B / (msm_ms * 1e-3) / 1e9 if msm_ms else None, "unit": "GB/s", "peak": hbm_peak}})
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("cells_proofs" if uses_fk20 else "commit")
