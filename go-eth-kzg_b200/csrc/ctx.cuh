@@ -81,7 +81,7 @@ struct kzgb200_ctx {
     PairingConsts *pairing = nullptr;       // Frobenius constants + line tables of G2, [s]G2, [s^64]G2
     MsmTable mono64_tab{};                  // digit table of monomial G1[0..63] (kzg_multi/srs.go:143-149)
     // scratch
-    DevBuf in_bytes, scalars, status, sums, out_bytes, coeffs, cells, proofs_xyzz, in_small, in_small2, zbuf, ybuf;
+    DevBuf in_bytes, scalars, status, sums, out_bytes, coeffs, cells, proofs_xyzz, fft_work, in_small, in_small2, zbuf, ybuf;
     DevBuf rec_a, rec_b, rec_meta, rec_zev, rec_czinv;
     DevBuf v_aff1, v_aff2, v_T, v_fr, v_meta, v_S, v_W, v_partial, v_in2, v_in3, v_st2;
     double init_ms = 0, last_device_ms = 0;

@@ -1,0 +1,213 @@
+// Batched size-128 G1 FFTs for FK20, one kernel launch per radix-2 stage over the whole batch.
+//
+// Replaces the two group FFTs of internal/kzg_multi/fk20/fk20.go:76-124 (-> toeplitz.go:113-125,
+// internal/domain/fft.go:39-83: IFFT of the 128 MSM sums, keep 64, zero-pad, FFT).
+//
+// Work decomposition: thread (butterfly b, blob n) of stage s.  All threads of a block share the
+// butterfly, so the twiddle w^t -- a compile-time constant of the protocol -- is block-uniform and
+// its scalar multiplication is a fixed op list in constant memory ("double k times, add +-T[i]"),
+// with no per-lane digit scanning and no divergence.  Blocks whose twiddle is 1 only do the two
+// additions; they are numbered last so they fill the tail of the launch.  The working set
+// (128 Jacobian points per blob, 18 KB) lives in global memory and is L2-resident for a chunk
+// of 1024 blobs; every stage reads and writes it once.
+//
+// [w^t]P (jac_mul_prog): GLV split w^t = k1 + k2*lambda, both halves in width-5 NAF (~42 additions
+// and ~128 doublings).  The table of odd multiples P, 3P, .. 15P is built on the curve isomorphic
+// to E in which 2P is affine (mixed additions, 8M+3S), rescaled to one common Z and then used as
+// an AFFINE table on that isomorphic curve (a = 0 formulas do not involve b), so the main loop
+// also runs on mixed additions.  The result is mapped back by Z *= Z_common * Z_2P.
+#pragma once
+#include "g1.cuh"
+
+namespace kzg {
+
+#define KZG_G1FFT_TPB 64
+__device__ __constant__ uint16_t TW_PROG[128][KZG_TW_PROG_LEN];   // uploaded from H_TW_PROG (constants.inc)
+
+// 16-byte vector moves of field elements / points (all records are 16-byte aligned)
+__device__ __forceinline__ Fp ld_fp(const Fp *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = q[0], b = q[1], c = q[2];
+    Fp r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    r.v[8] = c.x; r.v[9] = c.y; r.v[10] = c.z; r.v[11] = c.w;
+    return r;
+}
+__device__ __forceinline__ void st_fp(Fp *p, const Fp &r) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+    q[2] = make_uint4(r.v[8], r.v[9], r.v[10], r.v[11]);
+}
+__device__ __forceinline__ G1J ld_jac(const G1J *p) { G1J r; r.X = ld_fp(&p->X); r.Y = ld_fp(&p->Y); r.Z = ld_fp(&p->Z); return r; }
+__device__ __forceinline__ void st_jac(G1J *p, const G1J &r) { st_fp(&p->X, r.X); st_fp(&p->Y, r.Y); st_fp(&p->Z, r.Z); }
+
+// a += (x2, y2), Jacobian + affine, 8M + 3S.  a must not be the point at infinity.
+template <class M_ = MulCall> __device__ __forceinline__ void jac_madd(G1J &a, const Fp &x2, const Fp &y2) {
+    Fp Z1Z1 = M_::sqr(a.Z);
+    Fp U2 = M_::mul(x2, Z1Z1), S2 = M_::mul(M_::mul(y2, a.Z), Z1Z1);
+    Fp H = Fp::sub(U2, a.X), r = Fp::sub(S2, a.Y);
+    if (H.is_zero()) {
+        if (r.is_zero()) { a.X = x2; a.Y = y2; a.Z = Fp::one(); jac_dbl<M_>(a); }
+        else a.Z = Fp::zero();
+        return;
+    }
+    Fp HH = M_::sqr(H), HHH = M_::mul(H, HH), V = M_::mul(a.X, HH);
+    Fp X3 = Fp::sub(Fp::sub(M_::sqr(r), HHH), Fp::dbl(V));
+    a.Y = Fp::sub(M_::mul(r, Fp::sub(V, X3)), M_::mul(a.Y, HHH));
+    a.X = X3;
+    a.Z = M_::mul(a.Z, H);
+}
+
+// a += b, both Jacobian (add-2007-bl shape, 11M + 5S), every degenerate case handled
+template <class M_ = MulCall> __device__ __forceinline__ void jac_add_full(G1J &a, const G1J &b) {
+    if (b.Z.is_zero()) return;
+    if (a.Z.is_zero()) { a = b; return; }
+    Fp Z1Z1 = M_::sqr(a.Z), Z2Z2 = M_::sqr(b.Z);
+    Fp U1 = M_::mul(a.X, Z2Z2), U2 = M_::mul(b.X, Z1Z1);
+    Fp S1 = M_::mul(M_::mul(a.Y, b.Z), Z2Z2), S2 = M_::mul(M_::mul(b.Y, a.Z), Z1Z1);
+    Fp H = Fp::sub(U2, U1), r = Fp::sub(S2, S1);
+    if (H.is_zero()) {
+        if (r.is_zero()) jac_dbl<M_>(a);
+        else a.Z = Fp::zero();
+        return;
+    }
+    Fp HH = M_::sqr(H), HHH = M_::mul(H, HH), V = M_::mul(U1, HH);
+    Fp X3 = Fp::sub(Fp::sub(M_::sqr(r), HHH), Fp::dbl(V));
+    a.Y = Fp::sub(M_::mul(r, Fp::sub(V, X3)), M_::mul(S1, HHH));
+    a.X = X3;
+    a.Z = M_::mul(M_::mul(a.Z, b.Z), H);
+}
+static __device__ __noinline__ void jac_add_ool(G1J *a, const G1J *b) { jac_add_full<MulCall>(*a, *b); }
+
+// *pp = [w_128^t] *pp, t block-uniform in 1..127.  Infinity in -> infinity out (Z = 0 propagates
+// through Z_2P).  Scripts/check_tw_prog.py is the big-integer model of this routine.
+static __device__ __noinline__ void jac_mul_prog(G1J *pp, int t) {
+    typedef MulCall M_;
+    Fp tx[8], ty[8], tbx[8], zr[8];
+    Fp ZC;                                     // Z_common * Z_2P
+    {
+        G1J P = *pp;
+        G1J D = P;
+        jac_dbl<M_>(D);
+        Fp C2 = M_::sqr(D.Z), C3 = M_::mul(C2, D.Z);
+        G1J T; T.X = M_::mul(P.X, C2); T.Y = M_::mul(P.Y, C3); T.Z = P.Z;      // P on the curve where 2P = (D.X, D.Y) is affine
+        tx[0] = T.X; ty[0] = T.Y;
+#pragma unroll 1
+        for (int k = 1; k < 8; ++k) {          // T_k = T_{k-1} + 2P, raw mixed addition; zr[k] = Z_k / Z_{k-1}
+            Fp Z1Z1 = M_::sqr(T.Z);
+            Fp U2 = M_::mul(D.X, Z1Z1), S2 = M_::mul(M_::mul(D.Y, T.Z), Z1Z1);
+            Fp H = Fp::sub(U2, T.X), r = Fp::sub(S2, T.Y);
+            Fp HH = M_::sqr(H), HHH = M_::mul(H, HH), V = M_::mul(T.X, HH);
+            Fp X3 = Fp::sub(Fp::sub(M_::sqr(r), HHH), Fp::dbl(V));
+            T.Y = Fp::sub(M_::mul(r, Fp::sub(V, X3)), M_::mul(T.Y, HHH));
+            T.X = X3;
+            T.Z = M_::mul(T.Z, H);
+            tx[k] = T.X; ty[k] = T.Y; zr[k] = H;
+        }
+        ZC = M_::mul(T.Z, D.Z);
+    }
+    {
+        Fp beta;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) beta.v[i] = FP_BETA[i];
+        tbx[7] = M_::mul(tx[7], beta);
+        Fp s = zr[7];                          // s = Z_7 / Z_k
+#pragma unroll 1
+        for (int k = 6; k >= 0; --k) {
+            Fp s2 = M_::sqr(s);
+            Fp x = M_::mul(tx[k], s2);
+            tx[k] = x;
+            tbx[k] = M_::mul(x, beta);
+            ty[k] = M_::mul(ty[k], M_::mul(s2, s));
+            if (k) s = M_::mul(s, zr[k]);
+        }
+    }
+    const uint16_t *prog = TW_PROG[t];
+    const int n_ops = prog[0] & 255, trailing = prog[0] >> 8;
+    G1J acc;
+    {
+        uint32_t op = prog[1];
+        int idx = (op >> 8) & 7;
+        acc.X = (op & 0x1000u) ? tbx[idx] : tx[idx];
+        acc.Y = (op & 0x0800u) ? Fp::neg(ty[idx]) : ty[idx];
+        acc.Z = Fp::one();
+    }
+#pragma unroll 1
+    for (int k = 2; k <= n_ops; ++k) {
+        uint32_t op = prog[k];
+#pragma unroll 1
+        for (int d = op & 255; d > 0; --d) jac_dbl<M_>(acc);
+        int idx = (op >> 8) & 7;
+        Fp ex = (op & 0x1000u) ? tbx[idx] : tx[idx];
+        Fp ey = ty[idx];
+        if (op & 0x0800u) ey = Fp::neg(ey);
+        jac_madd<M_>(acc, ex, ey);
+    }
+#pragma unroll 1
+    for (int d = trailing; d > 0; --d) jac_dbl<M_>(acc);
+    acc.Z = M_::mul(acc.Z, ZC);
+    *pp = acc;
+}
+
+// butterfly number of the y-th block of a stage: non-trivial twiddles first
+__device__ __forceinline__ int g1fft_butterfly(int y, int log_half) {
+    const int half = 1 << log_half;
+    if (half == 1) return y;
+    const int heavy = 64 - (64 >> log_half);
+    if (y < heavy) { int g = y / (half - 1), j = y - g * (half - 1) + 1; return (g << log_half) + j; }
+    return (y - heavy) << log_half;
+}
+
+// One radix-2 stage over all blobs.  grid = (ceil(blobs / TPB), 64), block = TPB.
+//   DIT (bit-reversed in, natural out):  y *= w; (x, y) <- (x + y, x - y)
+//   DIF (natural in, bit-reversed out):  (x, y) <- (x + y, (x - y) * w)
+// SRC_XYZZ: the stage reads the MSM sums (XYZZ) instead of the working set.  DST_XYZZ: it writes
+// XYZZ points for k_finalize_g1.  ONLY_SUM: x - y is not needed (inverse transform, last stage,
+// upper half discarded: toeplitz.go:124).  UPPER_ZERO: y is the zero padding (fk20.go:82-85).
+template <bool DIT, bool INVERSE, bool SRC_XYZZ, bool DST_XYZZ, bool ONLY_SUM, bool UPPER_ZERO>
+static __global__ void __launch_bounds__(KZG_G1FFT_TPB) k_g1fft_stage(const G1 *__restrict__ src_xyzz, G1J *__restrict__ work, G1 *__restrict__ dst_xyzz,
+                                                                      const int32_t *__restrict__ status, int nblobs, int log_half) {
+    const int blob = blockIdx.x * KZG_G1FFT_TPB + threadIdx.x;
+    if (blob >= nblobs || status[blob] != ST_OK) return;
+    const int bf = g1fft_butterfly(blockIdx.y, log_half);
+    const int half = 1 << log_half, j = bf & (half - 1);
+    const int i0 = ((bf >> log_half) << (log_half + 1)) + j, i1 = i0 + half;
+    int t = j * (64 >> log_half);
+    if (INVERSE) t = (128 - t) & 127;
+    G1J *w0 = work + (size_t)blob * 128 + i0, *w1 = work + (size_t)blob * 128 + i1;
+    G1J x, y;
+    if (!UPPER_ZERO) {
+        if (SRC_XYZZ) { G1 q = src_xyzz[(size_t)blob * 128 + i1]; y = jac_from_xyzz(q); }
+        else y = ld_jac(w1);
+    }
+    if (DIT) {
+        if (t) jac_mul_prog(&y, t);
+        if (SRC_XYZZ) { G1 q = src_xyzz[(size_t)blob * 128 + i0]; x = jac_from_xyzz(q); }
+        else x = ld_jac(w0);
+        G1J s = x;
+        jac_add_ool(&s, &y);
+        if (!ONLY_SUM) { y.Y = Fp::neg(y.Y); jac_add_ool(&x, &y); }
+        y = x; x = s;
+    } else {
+        if (SRC_XYZZ) { G1 q = src_xyzz[(size_t)blob * 128 + i0]; x = jac_from_xyzz(q); }
+        else x = ld_jac(w0);
+        if (UPPER_ZERO) y = x;
+        else {
+            G1J s = x;
+            jac_add_ool(&s, &y);
+            y.Y = Fp::neg(y.Y); jac_add_ool(&x, &y);
+            y = x; x = s;
+        }
+        if (t) jac_mul_prog(&y, t);
+    }
+    if (DST_XYZZ) {
+        dst_xyzz[(size_t)blob * 128 + i0] = jac_to_xyzz(x);
+        dst_xyzz[(size_t)blob * 128 + i1] = jac_to_xyzz(y);
+    } else {
+        st_jac(w0, x);
+        if (!ONLY_SUM) st_jac(w1, y);
+    }
+}
+
+}  // namespace kzg

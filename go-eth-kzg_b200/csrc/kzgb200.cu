@@ -5,6 +5,7 @@
 // One context = one GPU.  All per-call scratch lives in a grow-only device arena owned by the
 // context; inputs are processed in chunks so the arena stays bounded regardless of batch size.
 #include "ctx.cuh"
+#include "g1fft.cuh"
 
 std::string &kzgb200_err_slot() { static thread_local std::string s; return s; }
 
@@ -202,7 +203,7 @@ void kzgb200_ctx_free(kzgb200_ctx *c) {
     cudaFree(c->g1_monomial); cudaFree(c->g1_lagrange_brp); cudaFree(c->commit_tab.entries);
     cudaFree(c->fk20_tab.entries); cudaFree(c->roots); cudaFree(c->glv_digits);
     c->in_bytes.release(); c->scalars.release(); c->status.release(); c->sums.release(); c->out_bytes.release();
-    c->coeffs.release(); c->cells.release(); c->proofs_xyzz.release();
+    c->coeffs.release(); c->cells.release(); c->proofs_xyzz.release(); c->fft_work.release();
     c->in_small.release(); c->in_small2.release(); c->zbuf.release(); c->ybuf.release();
     c->rec_a.release(); c->rec_b.release(); c->rec_meta.release(); c->rec_zev.release(); c->rec_czinv.release();
     cudaFree(c->pow7); cudaFree(c->ipow7); cudaFree(c->pairing); cudaFree(c->mono64_tab.entries);
@@ -261,6 +262,7 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
     CU(cudaMalloc(&c->roots, ROOTS_N * sizeof(Fr)));
     CU(cudaMalloc(&c->glv_digits, sizeof(H_GLV_TW)));
     CU(cudaMemcpyAsync(c->glv_digits, H_GLV_TW, sizeof(H_GLV_TW), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyToSymbolAsync(TW_PROG, H_TW_PROG, sizeof(H_TW_PROG), 0, cudaMemcpyHostToDevice, c->stream));
     Fr gen; memcpy(gen.v, H_FR_W8192, sizeof gen.v);
     k_init_roots<<<ROOTS_N / 128, 128, 0, c->stream>>>(c->roots, gen);
     CU(cudaMalloc(&c->pow7, 8192 * sizeof(Fr)));
@@ -492,11 +494,23 @@ static void launch_fk20_proofs(kzgb200_ctx *c, cudaStream_t st, size_t m, const 
     if (marks) c->mark(KZGB200_KC_MSM);
     k_msm_fixed<<<dim3(128 / (TPB / L), (unsigned)m), TPB, TPB * sizeof(G1), st>>>(scalars, c->fk20_tab, 64, 128, L, d_status, sums);
     if (marks) c->mark(KZGB200_KC_G1FFT);
-    k_fk20_g1fft<4><<<(unsigned)m, 64, 0, st>>>(sums, pxyzz, d_status, c->glv_digits);
+    // sums (bit-reversed) --IFFT--> h, keep 64 (toeplitz.go:124), zero-pad (fk20.go:82-85) --FFT--> proofs (bit-reversed);
+    // one launch per radix-2 stage over the whole chunk, working set in c->fft_work
+    {
+        G1J *work = (G1J *)c->fft_work.p;
+        const dim3 grid((unsigned)((m + KZG_G1FFT_TPB - 1) / KZG_G1FFT_TPB), 64);
+        const int nb = (int)m;
+        k_g1fft_stage<true, true, true, false, false, false><<<grid, KZG_G1FFT_TPB, 0, st>>>(sums, work, nullptr, d_status, nb, 0);
+        for (int lh = 1; lh < 6; ++lh) k_g1fft_stage<true, true, false, false, false, false><<<grid, KZG_G1FFT_TPB, 0, st>>>(nullptr, work, nullptr, d_status, nb, lh);
+        k_g1fft_stage<true, true, false, false, true, false><<<grid, KZG_G1FFT_TPB, 0, st>>>(nullptr, work, nullptr, d_status, nb, 6);
+        k_g1fft_stage<false, false, false, false, false, true><<<grid, KZG_G1FFT_TPB, 0, st>>>(nullptr, work, nullptr, d_status, nb, 6);
+        for (int lh = 5; lh >= 1; --lh) k_g1fft_stage<false, false, false, false, false, false><<<grid, KZG_G1FFT_TPB, 0, st>>>(nullptr, work, nullptr, d_status, nb, lh);
+        k_g1fft_stage<false, false, false, true, false, false><<<grid, KZG_G1FFT_TPB, 0, st>>>(nullptr, work, pxyzz, d_status, nb, 0);
+    }
     size_t np = m * 128;
     if (marks) c->mark(KZGB200_KC_FINALIZE);
     k_finalize_g1<<<(unsigned)((np + 64 * KZG_FIN_BATCH - 1) / (64 * KZG_FIN_BATCH)), 64, 0, st>>>(pxyzz, d_proofs, d_status, np, 128);
-    c->launches += 4;
+    c->launches += 17;
 }
 
 static int cells_and_proofs(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, uint8_t *out_proofs, int32_t *status) {
@@ -517,6 +531,7 @@ static int cells_and_proofs(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint
         if ((rc = c->scalars.ensure(chunk * 8192 * 32))) return rc;
         if ((rc = c->sums.ensure(chunk * 128 * sizeof(G1)))) return rc;
         if ((rc = c->proofs_xyzz.ensure(chunk * 128 * sizeof(G1)))) return rc;
+        if ((rc = c->fft_work.ensure(chunk * 128 * sizeof(G1J)))) return rc;
         if (!proofs_dev && (rc = c->out_bytes.ensure(chunk * 128 * 48))) return rc;
     }
     Fr inv4096; memcpy(inv4096.v, H_FR_INV4096, sizeof inv4096.v);
@@ -621,6 +636,7 @@ int kzgb200_recover_cells_and_kzg_proofs(kzgb200_ctx *c, const uint64_t *cell_id
         if ((rc = c->scalars.ensure(chunk * 8192 * 32))) return rc;
         if ((rc = c->sums.ensure(chunk * 128 * sizeof(G1)))) return rc;
         if ((rc = c->proofs_xyzz.ensure(chunk * 128 * sizeof(G1)))) return rc;
+        if ((rc = c->fft_work.ensure(chunk * 128 * sizeof(G1J)))) return rc;
         if (!proofs_dev && (rc = c->out_bytes.ensure(chunk * 128 * 48))) return rc;
     }
     Fr inv8192; memcpy(inv8192.v, H_FR_INV8192, sizeof inv8192.v);
