@@ -12,13 +12,13 @@
 //        == cells 64..127; cells 0..63 are the blob itself                           [k_coset_fft_cells]
 //   64 circulant rows --DIF forward FFT-128--> scalars at brp positions q            [k_fk20_rows]
 //   FK20 table stored with rows in the same brp order q (built by a DIF G1 FFT)      [k_g1_fft128_dif]
-//   u'[q] = MSM_64(row q) --DIT inverse G1 FFT--> h natural; keep 64; pad            [k_fk20_g1fft]
+//   u'[q] = MSM_64(row q) --DIT inverse G1 FFT--> h natural; keep 64; pad            [k_g1fft_stage, g1fft.cuh]
 //        --DIF forward G1 FFT--> proofs in brp order (= fk20.go:88-90 BitReverse)
 // The 1/128 of the inverse G1 FFT is folded into the Fr scalars (the map is linear).
 //
-// Twiddle multiplications [w^t]P use the GLV endomorphism (w^t = k1 + k2*lambda, |ki| < 2^128)
-// with precomputed signed base-16 digits: 128 doublings + <= 64 additions instead of the
-// reference's 255-bit double-and-add.
+// The per-blob G1 FFTs of the proving path live in g1fft.cuh (one launch per stage over the batch).
+// The shared-memory FFT below (per-lane GLV digits, signed base-16, 128 doublings + <= 64 additions
+// per twiddle) is kept for context creation (FK20 table rows) and the cell verifier.
 #pragma once
 #include "ntt.cuh"
 #include "constants.inc"
@@ -188,23 +188,6 @@ static __global__ void __launch_bounds__(64) k_fk20_table_fft(const G1Aff *__res
     __syncthreads();
     g1_fft128_smem<false, false>(pts, digits, tid);
     for (int q = tid; q < 128; q += 64) fk_pts[(size_t)q * 64 + i] = pts[q];
-}
-
-// per blob: u' (brp) --IFFT--> h --truncate/pad--> --FFT--> proofs (brp).  grid = blobs, block = 64
-template <int MINB> static __global__ void __launch_bounds__(64, MINB) k_fk20_g1fft(const G1 *__restrict__ u, G1 *__restrict__ proofs, const int32_t *__restrict__ status,
-                                                   const int8_t *__restrict__ digits) {
-    __shared__ G1 pts[128];
-    const int blob = blockIdx.x, tid = threadIdx.x;
-    if (status[blob] != ST_OK) return;
-    const G1 *src = u + (size_t)blob * 128;
-    pts[tid] = src[tid]; pts[tid + 64] = src[tid + 64];
-    __syncthreads();
-    g1_fft128_smem<true, true>(pts, digits, tid);
-    pts[tid + 64] = G1::infinity();          // keep the first half (toeplitz.go:124), pad (fk20.go:82-85)
-    __syncthreads();
-    g1_fft128_smem<false, false>(pts, digits, tid);
-    G1 *dst = proofs + (size_t)blob * 128;
-    dst[tid] = pts[tid]; dst[tid + 64] = pts[tid + 64];
 }
 
 }  // namespace kzg

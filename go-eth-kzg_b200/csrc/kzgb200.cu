@@ -210,6 +210,9 @@ void kzgb200_ctx_free(kzgb200_ctx *c) {
     c->v_aff1.release(); c->v_aff2.release(); c->v_T.release(); c->v_fr.release(); c->v_meta.release(); c->v_S.release();
     c->v_W.release(); c->v_partial.release(); c->v_in2.release(); c->v_in3.release(); c->v_st2.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (cudaStream_t q : c->fft_streams) if (q) cudaStreamDestroy(q);
+    for (cudaEvent_t e : c->ev_join) if (e) cudaEventDestroy(e);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_piece) if (e) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -232,6 +235,10 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
     for (cudaEvent_t &e : c->ev_piece) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (cudaStream_t &q : c->fft_streams) CU(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : c->ev_join) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    if (const char *e = getenv("KZGB200_G1FFT_SPLIT")) c->g1fft_split = (size_t)std::min(std::max(atoi(e), 1), KZG_G1FFT_MAX_SPLIT);
     c->g2_bytes.assign(g2, g2 + n_g2 * 96);
 
     int cw = opts && opts->commit_window ? opts->commit_window : 0;
@@ -495,22 +502,36 @@ static void launch_fk20_proofs(kzgb200_ctx *c, cudaStream_t st, size_t m, const 
     k_msm_fixed<<<dim3(128 / (TPB / L), (unsigned)m), TPB, TPB * sizeof(G1), st>>>(scalars, c->fk20_tab, 64, 128, L, d_status, sums);
     if (marks) c->mark(KZGB200_KC_G1FFT);
     // sums (bit-reversed) --IFFT--> h, keep 64 (toeplitz.go:124), zero-pad (fk20.go:82-85) --FFT--> proofs (bit-reversed);
-    // one launch per radix-2 stage over the whole chunk, working set in c->fft_work
+    // one launch per radix-2 stage, working set in c->fft_work.  The chunk is cut into independent
+    // sub-batches on separate streams so that the draining tail of one stage launch (a block is one
+    // ~130-doubling scalar multiplication) is filled by another sub-batch's blocks.
     {
-        G1J *work = (G1J *)c->fft_work.p;
-        const dim3 grid((unsigned)((m + KZG_G1FFT_TPB - 1) / KZG_G1FFT_TPB), 64);
-        const int nb = (int)m;
-        k_g1fft_stage<true, true, true, false, false, false><<<grid, KZG_G1FFT_TPB, 0, st>>>(sums, work, nullptr, d_status, nb, 0);
-        for (int lh = 1; lh < 6; ++lh) k_g1fft_stage<true, true, false, false, false, false><<<grid, KZG_G1FFT_TPB, 0, st>>>(nullptr, work, nullptr, d_status, nb, lh);
-        k_g1fft_stage<true, true, false, false, true, false><<<grid, KZG_G1FFT_TPB, 0, st>>>(nullptr, work, nullptr, d_status, nb, 6);
-        k_g1fft_stage<false, false, false, false, false, true><<<grid, KZG_G1FFT_TPB, 0, st>>>(nullptr, work, nullptr, d_status, nb, 6);
-        for (int lh = 5; lh >= 1; --lh) k_g1fft_stage<false, false, false, false, false, false><<<grid, KZG_G1FFT_TPB, 0, st>>>(nullptr, work, nullptr, d_status, nb, lh);
-        k_g1fft_stage<false, false, false, true, false, false><<<grid, KZG_G1FFT_TPB, 0, st>>>(nullptr, work, pxyzz, d_status, nb, 0);
+        const size_t nsplit = std::max<size_t>(1, std::min<size_t>(c->g1fft_split, (m + 127) / 128));
+        const size_t per = (m + nsplit - 1) / nsplit;
+        if (nsplit > 1) cudaEventRecord(c->ev_fork, st);
+        for (size_t k = 0, off = 0; off < m; ++k, off += per) {
+            const int nb = (int)std::min(per, m - off);
+            cudaStream_t s = k == 0 ? st : c->fft_streams[k - 1];
+            if (k) cudaStreamWaitEvent(s, c->ev_fork, 0);
+            const G1 *src = sums + off * 128;
+            G1J *work = (G1J *)c->fft_work.p + off * 128;
+            G1 *dst = pxyzz + off * 128;
+            const int32_t *stt = d_status + off;
+            const dim3 grid((unsigned)((nb + KZG_G1FFT_TPB - 1) / KZG_G1FFT_TPB), 64);
+            k_g1fft_stage<true, true, true, false, false, false><<<grid, KZG_G1FFT_TPB, 0, s>>>(src, work, nullptr, stt, nb, 0);
+            for (int lh = 1; lh < 6; ++lh) k_g1fft_stage<true, true, false, false, false, false><<<grid, KZG_G1FFT_TPB, 0, s>>>(nullptr, work, nullptr, stt, nb, lh);
+            k_g1fft_stage<true, true, false, false, true, false><<<grid, KZG_G1FFT_TPB, 0, s>>>(nullptr, work, nullptr, stt, nb, 6);
+            k_g1fft_stage<false, false, false, false, false, true><<<grid, KZG_G1FFT_TPB, 0, s>>>(nullptr, work, nullptr, stt, nb, 6);
+            for (int lh = 5; lh >= 1; --lh) k_g1fft_stage<false, false, false, false, false, false><<<grid, KZG_G1FFT_TPB, 0, s>>>(nullptr, work, nullptr, stt, nb, lh);
+            k_g1fft_stage<false, false, false, true, false, false><<<grid, KZG_G1FFT_TPB, 0, s>>>(nullptr, work, dst, stt, nb, 0);
+            c->launches += 14;
+            if (k) { cudaEventRecord(c->ev_join[k - 1], s); cudaStreamWaitEvent(st, c->ev_join[k - 1], 0); }
+        }
     }
     size_t np = m * 128;
     if (marks) c->mark(KZGB200_KC_FINALIZE);
     k_finalize_g1<<<(unsigned)((np + 64 * KZG_FIN_BATCH - 1) / (64 * KZG_FIN_BATCH)), 64, 0, st>>>(pxyzz, d_proofs, d_status, np, 128);
-    c->launches += 17;
+    c->launches += 3;
 }
 
 static int cells_and_proofs(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, uint8_t *out_proofs, int32_t *status) {
