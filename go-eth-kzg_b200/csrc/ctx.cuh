@@ -88,6 +88,7 @@ struct kzgb200_ctx {
     DevBuf in_bytes, scalars, status, sums, out_bytes, coeffs, cells, proofs_xyzz, fft_work, in_small, in_small2, zbuf, ybuf;
     DevBuf rec_a, rec_b, rec_meta, rec_zev, rec_czinv;
     DevBuf v_aff1, v_aff2, v_T, v_fr, v_meta, v_S, v_W, v_partial, v_in2, v_in3, v_st2;
+    DevBuf vm_digits, vm_scratch, vm_ws, vm_wsb, v_pa, v_pb;
     double init_ms = 0, last_device_ms = 0;
     uint64_t launches = 0;
     // per-kernel-class device timing of the last call (CUDA events on `stream`)
@@ -134,3 +135,15 @@ static inline int stage_in(kzgb200_ctx *c, const void *user, size_t bytes, DevBu
     return 0;
 }
 
+// ---- launch wrappers of kzgb200_vmsm.cu (verification throughput kernels, full optimisation) ----
+int vm_g1_check(cudaStream_t st, const uint8_t *in48, G1Aff *out, int32_t *status, size_t n, int per_status, int subgroup);
+int vm_cell_coeff_digits(cudaStream_t st, const Fr &seed, const uint32_t *batch_of, const uint64_t *batch_start, const uint64_t *cell_idx,
+                         const Fr *roots, Fr *rpow, int8_t *digits, size_t n);
+size_t vm_scratch_bytes(size_t n_items, int nw);
+int vm_msm_windows(cudaStream_t st, const G1Aff *points, const int8_t *digits, int TW, int w_lo, int nw,
+                   const uint64_t *item_start, const uint64_t *item_end, size_t n_items, const uint64_t *batch_item_off, size_t nb,
+                   G1 *scratch, G1 *WS, G1 *WSb);
+int vm_combine(cudaStream_t st, const G1 *WSb, int TW, int w0, int nw, G1 *out, size_t nb);
+// result[i] = pre_status[i] if that is an error (pre_status may be null or alias result), else OK / VERIFY_FAILED for
+// e(A_i, Q[qa]) e(B_i, Q[qb]) == 1, Q = {G2, [s]G2, [s^64]G2}
+int vm_pairing_check(cudaStream_t st, const PairingConsts *pc, const G1 *A, int qa, const G1 *B, int qb, const int32_t *pre_status, int32_t *result, size_t n);

@@ -84,7 +84,11 @@ template <class M_ = MulCall> __device__ __forceinline__ G1 g1_dbl(const G1 &p) 
     r.ZZZ = M_::mul(W, p.ZZZ);
     return r;
 }
-static __device__ __noinline__ void g1_dbl_cold(G1 *r, const G1 *p) { *r = g1_dbl<MulCall>(*p); }
+// Value semantics on purpose: g1_dbl_cold is reached from inside other out-of-line functions, and a
+// pointer to a register-resident point handed down two levels of cloned callees has been seen to be
+// read as a global address by nvcc 12.9 code (compute-sanitizer: invalid __global__ read at a
+// local-window address, in g1_add_ool -> g1_dbl_cold).
+static __device__ __noinline__ G1 g1_dbl_cold(G1 p) { return g1_dbl<MulCall>(p); }
 
 // acc += (x2,y2)   (madd-2008-s); b must not be the infinity encoding unless checked by caller
 template <class M_ = MulCall> __device__ __forceinline__ void g1_add_affine(G1 &acc, const G1Aff &b) {
@@ -120,7 +124,7 @@ template <class M_ = MulCall> __device__ __forceinline__ void g1_add(G1 &a, cons
     Fp Pd = Fp::sub(U2, U1);
     Fp R = Fp::sub(S2, S1);
     if (Pd.is_zero()) {
-        if (R.is_zero()) { G1 t; g1_dbl_cold(&t, &a); a = t; }
+        if (R.is_zero()) a = g1_dbl_cold(a);
         else a = G1::infinity();
         return;
     }
@@ -133,8 +137,10 @@ template <class M_ = MulCall> __device__ __forceinline__ void g1_add(G1 &a, cons
     a.ZZ = M_::mul(M_::mul(a.ZZ, b.ZZ), PP);
     a.ZZZ = M_::mul(M_::mul(a.ZZZ, b.ZZZ), PPP);
 }
-// out-of-line full add for cold / code-size-sensitive call sites
+// out-of-line full add for cold / code-size-sensitive call sites: g1_add_ool for operands in
+// shared or global memory, g1_add_v (value semantics) for register-resident operands
 static __device__ __noinline__ void g1_add_ool(G1 *a, const G1 *b) { g1_add<MulCall>(*a, *b); }
+static __device__ __noinline__ G1 g1_add_v(G1 a, G1 b) { g1_add<MulCall>(a, b); return a; }
 
 // ---- Jacobian coordinates for doubling-heavy code (scalar multiplications, subgroup check) ----
 // Twiddle multiplications run in Jacobian coordinates (x = X/Z^2, y = Y/Z^3): a doubling is

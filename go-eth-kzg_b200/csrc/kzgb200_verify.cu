@@ -18,12 +18,12 @@ static __global__ void k_dbg_g1_mul(const uint8_t *p48, const uint8_t *s32, uint
     g1_mul_scalar(&r, &P, k);
     g1_compress(out48 + i * 48, g1_to_affine(r));
 }
-static __global__ void k_dbg_pairing(const PairingConsts *pc, const uint8_t *a48, const int *qa, const uint8_t *b48, const int *qb, int *out, int n) {
+static __global__ void k_dbg_decode_pair(const uint8_t *a48, const uint8_t *b48, G1 *A, G1 *B, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     G1Aff a, b;
     g1_decompress(a, a48 + i * 48); g1_decompress(b, b48 + i * 48);
-    out[i] = pairing_check2(pc, &a, qa[i], &b, qb[i]) ? 1 : 0;
+    A[i] = G1::from_affine(a); B[i] = G1::from_affine(b);
 }
 static __global__ void k_dbg_dump_pairing(const PairingConsts *pc, uint32_t *out) {
     // gamma[1] (24 limbs, plain), then q[0].A[0], q[0].B[0], q[0].A[67] (24 limbs each)
@@ -70,8 +70,8 @@ static int verify_front(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm4
         k_scalars_from_be<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_z, (uint32_t *)c->zbuf.p, d_status, m);
         c->launches += 2;
     }
-    k_g1_check<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_cm, (G1Aff *)c->v_aff1.p, d_status, m, 1, 1);
-    k_g1_check<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_pf, (G1Aff *)c->v_aff2.p, d_status, m, 1, 1);
+    if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_cm, (G1Aff *)c->v_aff1.p, d_status, m, 1, 1))) return rc;
+    if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_pf, (G1Aff *)c->v_aff2.p, d_status, m, 1, 1))) return rc;
     c->launches += 2;
     if (blobs) {
         c->mark(KZGB200_KC_FR);
@@ -94,15 +94,18 @@ static int verify_independent(kzgb200_ctx *c, const uint8_t *blobs, const uint8_
     const size_t chunk = std::min(n, VERIFY_CHUNK);
     int rc;
     if ((rc = c->status.ensure(chunk * sizeof(int32_t)))) return rc;
+    if ((rc = c->v_S.ensure(chunk * sizeof(G1)))) return rc;
+    if ((rc = c->v_W.ensure(chunk * sizeof(G1)))) return rc;
     for (size_t off = 0; off < n; off += chunk) {
         size_t m = std::min(chunk, n - off);
         int32_t *d_status = st_dev ? status + off : (int32_t *)c->status.p;
         if ((rc = verify_front(c, blobs ? blobs + off * KZGB200_BYTES_PER_BLOB : nullptr, cm48 + off * 48, z32 ? z32 + off * 32 : nullptr,
                                y32 ? y32 + off * 32 : nullptr, pf48 + off * 48, m, d_status))) return rc;
         c->mark(KZGB200_KC_VERIFY);
-        k_verify_single<<<(unsigned)((m + 63) / 64), 64, 0, c->stream>>>((const G1Aff *)c->v_aff1.p, (const G1Aff *)c->v_aff2.p, (const uint32_t *)c->zbuf.p,
-                                                                          (const uint32_t *)c->ybuf.p, c->g1_monomial, c->pairing, d_status, m);
-        c->launches += 1;
+        k_verify_single_prep<<<(unsigned)((m + 63) / 64), 64, 0, c->stream>>>((const G1Aff *)c->v_aff1.p, (const G1Aff *)c->v_aff2.p, (const uint32_t *)c->zbuf.p,
+                                                                               (const uint32_t *)c->ybuf.p, c->g1_monomial, d_status, (G1 *)c->v_S.p, (G1 *)c->v_W.p, m);
+        if ((rc = vm_pairing_check(c->stream, c->pairing, (const G1 *)c->v_S.p, 0, (const G1 *)c->v_W.p, 1, d_status, d_status, m))) return rc;   // e(-A, G2) e(pi, [s]G2) == 1
+        c->launches += 2;
         c->mark(-1);
         CU(cudaGetLastError());
         if (!st_dev) CU(cudaMemcpyAsync(status + off, d_status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -143,6 +146,8 @@ int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *blobs, co
     if ((rc = c->v_T.ensure(3 * n * sizeof(G1)))) return rc;
     if ((rc = c->v_fr.ensure(n * sizeof(Fr)))) return rc;
     if ((rc = c->v_st2.ensure(sizeof(int32_t)))) return rc;
+    if ((rc = c->v_S.ensure(sizeof(G1)))) return rc;
+    if ((rc = c->v_W.ensure(sizeof(G1)))) return rc;
     // the per-blob front end runs in chunks (bounded staging), all writing into full-size arrays
     if ((rc = c->v_aff1.ensure(n * sizeof(G1Aff)))) return rc;
     if ((rc = c->v_aff2.ensure(n * sizeof(G1Aff)))) return rc;
@@ -174,8 +179,9 @@ int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *blobs, co
     c->mark(KZGB200_KC_VERIFY);
     k_rlc_terms<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>((const G1Aff *)c->v_aff1.p, (const G1Aff *)c->v_aff2.p, (const uint32_t *)c->zbuf.p,
                                                                   (const uint32_t *)c->ybuf.p, r_dev, n == 1 ? 1 : 0, (const int32_t *)c->status.p, (G1 *)c->v_T.p, (Fr *)c->v_fr.p, n);
-    k_rlc_finish<<<1, 128, 0, c->stream>>>((const G1 *)c->v_T.p, (const Fr *)c->v_fr.p, n, c->g1_monomial, c->pairing, (int32_t *)c->v_st2.p);
-    c->launches += 2;
+    k_rlc_prep<<<1, 128, 0, c->stream>>>((const G1 *)c->v_T.p, (const Fr *)c->v_fr.p, n, c->g1_monomial, (G1 *)c->v_S.p, (G1 *)c->v_W.p);
+    if ((rc = vm_pairing_check(c->stream, c->pairing, (const G1 *)c->v_S.p, 0, (const G1 *)c->v_W.p, 1, nullptr, (int32_t *)c->v_st2.p, 1))) return rc;
+    c->launches += 3;
     c->mark(-1);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(result, c->v_st2.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -206,11 +212,11 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
         h_cm = h_cm_copy.data();
     }
     std::vector<int32_t> h_bstatus(nb, KZGB200_OK);
-    std::vector<uint32_t> batch_of(N), order(N), row_cells(N);
-    std::vector<uint64_t> batch_start(nb), col_off(nb * 128 + 1, 0), batch_row_off(nb + 1, 0), row_off(1, 0), item_start, item_end, batch_item_off(nb + 1, 0);
+    std::vector<uint32_t> batch_of(N), row_cells(N);
+    std::vector<uint64_t> batch_start(nb), batch_row_off(nb + 1, 0), row_off(1, 0), item_start, item_end, batch_item_off(nb + 1, 0);
     std::vector<uint8_t> uniq_bytes;
     const uint64_t ITEM = 512;
-    size_t ord_pos = 0, rc_pos = 0;
+    size_t rc_pos = 0;
     for (size_t b = 0; b < nb; ++b) {
         uint64_t lo = batch_offsets[b], hi = batch_offsets[b + 1];
         if (hi < lo || hi > N) return set_err(KZGB200_ERR_ARGS, "batch_offsets not monotone / out of range");
@@ -218,7 +224,6 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
         // de-duplicate on raw bytes, first-seen order (api_eip7594.go:238-265)
         std::unordered_map<std::string, uint32_t> seen;
         std::vector<std::vector<uint32_t>> rows;
-        std::vector<std::vector<uint32_t>> cols(128);
         for (uint64_t k = lo; k < hi; ++k) {
             batch_of[k] = (uint32_t)b;
             std::string key((const char *)h_cm + k * 48, 48);
@@ -228,18 +233,12 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
             else row = it->second;
             rows[row].push_back((uint32_t)k);
             if (cell_indices[k] >= 128) h_bstatus[b] = KZGB200_BAD_CELL_INDEX;      // api_eip7594.go:184-188
-            else cols[cell_indices[k]].push_back((uint32_t)k);
-        }
-        for (int cidx = 0; cidx < 128; ++cidx) {
-            for (uint32_t k : cols[cidx]) order[ord_pos++] = k;
-            col_off[b * 128 + cidx + 1] = ord_pos;
         }
         for (auto &rw : rows) { for (uint32_t k : rw) row_cells[rc_pos++] = k; row_off.push_back(rc_pos); }
         batch_row_off[b + 1] = row_off.size() - 1;
         for (uint64_t s = lo; s < hi; s += ITEM) { item_start.push_back(s); item_end.push_back(std::min(hi, s + ITEM)); }
         batch_item_off[b + 1] = item_start.size();
     }
-    // cells with an out-of-range index were skipped in `order`; col_off stays consistent because ord_pos only counts placed cells
     const size_t U = row_off.size() - 1, n_items = item_start.size();
     Fr seed_dev; random_scalar_plain(c, seed_dev.v);   // PRF seed of this call's 128-bit coefficients
     std::vector<uint32_t> row_batch(U);
@@ -254,7 +253,7 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     // meta arena layout
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) & ~(size_t)255; return at; };
-    size_t o_idx = take(N * 8), o_batch_of = take(N * 4), o_bstart = take(nb * 8), o_order = take(N * 4), o_col = take((nb * 128 + 1) * 8);
+    size_t o_idx = take(N * 8), o_batch_of = take(N * 4), o_bstart = take(nb * 8);
     size_t o_rowc = take(N * 4), o_rowoff = take((U + 1) * 8), o_browoff = take((nb + 1) * 8), o_is = take(n_items * 8), o_ie = take(n_items * 8);
     size_t o_bio = take((nb + 1) * 8), o_bst = take(nb * 4), o_cst = take(std::max<size_t>(N, 1) * 4), o_ust = take(std::max<size_t>(U, 1) * 4);
     size_t o_rowb = take(std::max<size_t>(U, 1) * 4), o_res = take(nb * 4);
@@ -262,7 +261,7 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     char *M = (char *)c->v_meta.p;
     auto up = [&](size_t at, const void *src, size_t bytes) { return bytes ? cudaMemcpyAsync(M + at, src, bytes, cudaMemcpyHostToDevice, c->stream) : cudaSuccess; };
     CU(up(o_idx, cell_indices, N * 8)); CU(up(o_batch_of, batch_of.data(), N * 4)); CU(up(o_bstart, batch_start.data(), nb * 8));
-    CU(up(o_order, order.data(), N * 4)); CU(up(o_col, col_off.data(), (nb * 128 + 1) * 8)); CU(up(o_rowc, row_cells.data(), N * 4));
+    CU(up(o_rowc, row_cells.data(), N * 4));
     CU(up(o_rowoff, row_off.data(), (U + 1) * 8)); CU(up(o_browoff, batch_row_off.data(), (nb + 1) * 8));
     CU(up(o_is, item_start.data(), n_items * 8)); CU(up(o_ie, item_end.data(), n_items * 8)); CU(up(o_bio, batch_item_off.data(), (nb + 1) * 8));
     CU(up(o_bst, h_bstatus.data(), nb * 4)); CU(up(o_rowb, row_batch.data(), U * 4));
@@ -270,38 +269,47 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     CU(cudaMemsetAsync(M + o_ust, 0, std::max<size_t>(U, 1) * 4, c->stream));
     if ((rc = c->v_aff1.ensure(std::max<size_t>(U, 1) * sizeof(G1Aff)))) return rc;
     if ((rc = c->v_aff2.ensure(std::max<size_t>(N, 1) * sizeof(G1Aff)))) return rc;
-    if ((rc = c->v_T.ensure(std::max<size_t>(N, 1) * sizeof(G1)))) return rc;
     if ((rc = c->v_fr.ensure(std::max<size_t>(N, 1) * sizeof(Fr)))) return rc;
+    if ((rc = c->vm_digits.ensure(std::max<size_t>(N, 1) * KZG_CELL_TW))) return rc;
+    if ((rc = c->vm_scratch.ensure(std::max<size_t>(vm_scratch_bytes(n_items, KZG_CELL_TW), 256)))) return rc;
+    if ((rc = c->vm_ws.ensure(std::max<size_t>(n_items, 1) * KZG_CELL_TW * sizeof(G1)))) return rc;
+    if ((rc = c->vm_wsb.ensure(nb * KZG_CELL_TW * sizeof(G1)))) return rc;
     if ((rc = c->v_S.ensure(nb * sizeof(G1)))) return rc;
     if ((rc = c->v_W.ensure(nb * sizeof(G1)))) return rc;
+    if ((rc = c->v_pa.ensure(nb * sizeof(G1)))) return rc;
+    if ((rc = c->v_pb.ensure(nb * sizeof(G1)))) return rc;
     if ((rc = c->v_partial.ensure(std::max<size_t>(n_items, 1) * 64 * sizeof(Fr)))) return rc;
     if ((rc = c->scalars.ensure(nb * 64 * 32))) return rc;
     if ((rc = c->sums.ensure(nb * sizeof(G1)))) return rc;
     Fr inv64; memcpy(inv64.v, H_FR_INV64, sizeof inv64.v);
     int32_t *d_cst = (int32_t *)(M + o_cst), *d_ust = (int32_t *)(M + o_ust), *d_bst = (int32_t *)(M + o_bst), *d_res = (int32_t *)(M + o_res);
     c->mark(KZGB200_KC_VERIFY);
-    if (U) k_g1_check<<<(unsigned)((U + 63) / 64), 64, 0, c->stream>>>((const uint8_t *)c->in_small2.p, (G1Aff *)c->v_aff1.p, d_ust, U, 1, 1);
+    if ((rc = vm_g1_check(c->stream, (const uint8_t *)c->in_small2.p, (G1Aff *)c->v_aff1.p, d_ust, U, 1, 1))) return rc;
     if (N) {
-        unsigned gN = (unsigned)((N + 63) / 64);
-        k_g1_check<<<gN, 64, 0, c->stream>>>((const uint8_t *)d_proofs, (G1Aff *)c->v_aff2.p, d_cst, N, 1, 1);
-        k_cell_coeffs<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(seed_dev, (const uint32_t *)(M + o_batch_of), (const uint64_t *)(M + o_bstart), (Fr *)c->v_fr.p, N);
-        k_cell_proof_terms<<<gN, 64, 0, c->stream>>>((const G1Aff *)c->v_aff2.p, (const Fr *)c->v_fr.p, d_cst, (G1 *)c->v_T.p, N);
+        if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_proofs, (G1Aff *)c->v_aff2.p, d_cst, N, 1, 1))) return rc;
+        if ((rc = vm_cell_coeff_digits(c->stream, seed_dev, (const uint32_t *)(M + o_batch_of), (const uint64_t *)(M + o_bstart), (const uint64_t *)(M + o_idx),
+                                       c->roots, (Fr *)c->v_fr.p, (int8_t *)c->vm_digits.p, N))) return rc;
         c->mark(KZGB200_KC_FR);
         k_cell_interp<<<(unsigned)n_items, 256, 0, c->stream>>>((const uint8_t *)d_cells, (const uint64_t *)(M + o_idx), (const Fr *)c->v_fr.p, (const uint64_t *)(M + o_is),
                                                                 (const uint64_t *)(M + o_ie), c->roots, inv64, d_cst, (Fr *)c->v_partial.p);
-        c->launches += 4;
+        c->launches += 3;
     }
     k_cell_interp_reduce<<<(unsigned)nb, 64, 0, c->stream>>>((const Fr *)c->v_partial.p, (const uint64_t *)(M + o_bio), (uint32_t *)c->scalars.p);
     c->mark(KZGB200_KC_MSM);
     k_msm_fixed<<<dim3(1, (unsigned)nb), 32, 32 * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p);
     c->mark(KZGB200_KC_VERIFY);
-    k_cell_columns<<<(unsigned)nb, 128, 0, c->stream>>>((const G1 *)c->v_T.p, (const uint32_t *)(M + o_order), (const uint64_t *)(M + o_col), c->glv_digits, (G1 *)c->v_S.p, (G1 *)c->v_W.p);
+    // sumS[b] = sum_k r_k pi_k (windows 0..31), sumW[b] = sum_k r_k h_k^64 pi_k (windows 32..95)   (kzg_verify.go:32,73-83)
+    if ((rc = vm_msm_windows(c->stream, (const G1Aff *)c->v_aff2.p, (const int8_t *)c->vm_digits.p, KZG_CELL_TW, 0, KZG_CELL_TW, (const uint64_t *)(M + o_is),
+                             (const uint64_t *)(M + o_ie), n_items, (const uint64_t *)(M + o_bio), nb, (G1 *)c->vm_scratch.p, (G1 *)c->vm_ws.p, (G1 *)c->vm_wsb.p))) return rc;
+    if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_CELL_TW, 0, 32, (G1 *)c->v_S.p, nb))) return rc;
+    if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_CELL_TW, 32, 64, (G1 *)c->v_W.p, nb))) return rc;
     if (N) k_merge_status<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(d_cst, (const uint32_t *)(M + o_batch_of), d_bst, N);
     if (U) k_merge_status<<<(unsigned)((U + 127) / 128), 128, 0, c->stream>>>(d_ust, (const uint32_t *)(M + o_rowb), d_bst, U);
-    k_cell_finish<<<(unsigned)((nb + 31) / 32), 32, 0, c->stream>>>((const G1 *)c->v_S.p, (const G1 *)c->v_W.p, (const G1 *)c->sums.p, (const G1Aff *)c->v_aff1.p,
-                                                                     (const uint64_t *)(M + o_rowoff), (const uint64_t *)(M + o_browoff), (const uint32_t *)(M + o_rowc),
-                                                                     (const Fr *)c->v_fr.p, c->pairing, d_bst, d_res, nb);
-    c->launches += 6;
+    k_cell_prep<<<(unsigned)((nb + 31) / 32), 32, 0, c->stream>>>((const G1 *)c->v_S.p, (const G1 *)c->v_W.p, (const G1 *)c->sums.p, (const G1Aff *)c->v_aff1.p,
+                                                                   (const uint64_t *)(M + o_rowoff), (const uint64_t *)(M + o_browoff), (const uint32_t *)(M + o_rowc),
+                                                                   (const Fr *)c->v_fr.p, d_bst, (G1 *)c->v_pa.p, (G1 *)c->v_pb.p, nb);
+    if ((rc = vm_pairing_check(c->stream, c->pairing, (const G1 *)c->v_pa.p, 2, (const G1 *)c->v_pb.p, 0, d_bst, d_res, nb))) return rc;
+    c->launches += 10;
     c->mark(-1);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(results, d_res, nb * 4, res_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
@@ -321,15 +329,20 @@ int kzgb200_dbg_g1_mul(const uint8_t *p48, const uint8_t *s32, uint8_t *out48, i
     return 0;
 }
 int kzgb200_dbg_pairing(kzgb200_ctx *c, const uint8_t *a48, const int *qa, const uint8_t *b48, const int *qb, int *out, int n) {
-    uint8_t *da, *db; int *dqa, *dqb, *dout;
+    uint8_t *da, *db; int32_t *dout; G1 *dA, *dB;
     CU(cudaSetDevice(c->device));
-    CU(cudaMalloc(&da, n * 48)); CU(cudaMalloc(&db, n * 48)); CU(cudaMalloc(&dqa, n * 4)); CU(cudaMalloc(&dqb, n * 4)); CU(cudaMalloc(&dout, n * 4));
+    CU(cudaMalloc(&da, n * 48)); CU(cudaMalloc(&db, n * 48)); CU(cudaMalloc(&dout, n * 4)); CU(cudaMalloc(&dA, n * sizeof(G1))); CU(cudaMalloc(&dB, n * sizeof(G1)));
     CU(cudaMemcpy(da, a48, n * 48, cudaMemcpyHostToDevice)); CU(cudaMemcpy(db, b48, n * 48, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dqa, qa, n * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(dqb, qb, n * 4, cudaMemcpyHostToDevice));
-    k_dbg_pairing<<<(n + 31) / 32, 32>>>(c->pairing, da, dqa, db, dqb, dout, n);
+    k_dbg_decode_pair<<<(n + 31) / 32, 32>>>(da, db, dA, dB, n);
     CU(cudaGetLastError());
-    CU(cudaMemcpy(out, dout, n * 4, cudaMemcpyDeviceToHost));
-    cudaFree(da); cudaFree(db); cudaFree(dqa); cudaFree(dqb); cudaFree(dout);
+    CU(cudaDeviceSynchronize());
+    int rc = 0;
+    for (int i = 0; i < n && !rc; ++i) rc = vm_pairing_check(nullptr, c->pairing, dA + i, qa[i], dB + i, qb[i], nullptr, dout + i, 1);   // selectors are per launch
+    if (rc) return rc;
+    std::vector<int32_t> st(n);
+    CU(cudaMemcpy(st.data(), dout, n * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) out[i] = st[i] == KZGB200_OK ? 1 : 0;
+    cudaFree(da); cudaFree(db); cudaFree(dout); cudaFree(dA); cudaFree(dB);
     return 0;
 }
 int kzgb200_dbg_dump_pairing(kzgb200_ctx *c, uint32_t *out96) {

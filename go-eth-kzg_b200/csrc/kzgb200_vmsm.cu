@@ -1,0 +1,54 @@
+// libkzgb200.so -- throughput kernels of the verification paths, compiled at full optimisation
+// (kzgb200_verify.cu, the host side of the verifiers, is built with -Xptxas -O1; see build.py).
+// Only launch wrappers are exported to the other translation units.
+#include "ctx.cuh"
+#include "vmsm.cuh"
+#include "pairing_lanes.cuh"
+
+#define CUL(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return set_err(KZGB200_ERR_CUDA, #call, e_); } while (0)
+
+int vm_g1_check(cudaStream_t st, const uint8_t *in48, G1Aff *out, int32_t *status, size_t n, int per_status, int subgroup) {
+    if (!n) return 0;
+    k_g1_check<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(in48, out, status, n, per_status, subgroup);
+    CUL(cudaGetLastError());
+    return 0;
+}
+
+int vm_cell_coeff_digits(cudaStream_t st, const Fr &seed, const uint32_t *batch_of, const uint64_t *batch_start, const uint64_t *cell_idx,
+                         const Fr *roots, Fr *rpow, int8_t *digits, size_t n) {
+    if (!n) return 0;
+    k_cell_coeff_digits<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seed, batch_of, batch_start, cell_idx, roots, rpow, digits, n);
+    CUL(cudaGetLastError());
+    return 0;
+}
+
+size_t vm_scratch_bytes(size_t n_items, int nw) { return n_items * (size_t)nw * KZG_VM_BUCKETS * sizeof(G1); }
+
+// per verdict b and window w (nw windows starting at digit column w_lo): WSb[b][w] = window sum
+int vm_msm_windows(cudaStream_t st, const G1Aff *points, const int8_t *digits, int TW, int w_lo, int nw,
+                   const uint64_t *item_start, const uint64_t *item_end, size_t n_items, const uint64_t *batch_item_off, size_t nb,
+                   G1 *scratch, G1 *WS, G1 *WSb) {
+    if (n_items) {
+        k_vmsm_buckets<<<(unsigned)n_items, nw, 0, st>>>(points, digits, TW, w_lo, item_start, item_end, scratch);
+        const size_t n_tasks = n_items * (size_t)nw;
+        k_vmsm_bucket_reduce<<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(scratch, WS, n_tasks);
+    }
+    if (nb) k_vmsm_item_reduce<<<(unsigned)nb, nw, 0, st>>>(WS, batch_item_off, WSb);
+    CUL(cudaGetLastError());
+    return 0;
+}
+
+int vm_combine(cudaStream_t st, const G1 *WSb, int TW, int w0, int nw, G1 *out, size_t nb) {
+    if (!nb) return 0;
+    k_vmsm_combine<<<(unsigned)((nb + 31) / 32), 32, 0, st>>>(WSb, TW, w0, nw, out, nb);
+    CUL(cudaGetLastError());
+    return 0;
+}
+
+int vm_pairing_check(cudaStream_t st, const PairingConsts *pc, const G1 *A, int qa, const G1 *B, int qb, const int32_t *pre_status, int32_t *result, size_t n) {
+    if (!n) return 0;
+    const unsigned per_block = 128 / KZG_PL_GROUP;
+    k_pairing_lanes<<<(unsigned)((n + per_block - 1) / per_block), 128, 0, st>>>(pc, A, qa, B, qb, pre_status, result, n);
+    CUL(cudaGetLastError());
+    return 0;
+}

@@ -11,6 +11,7 @@
 #include "pairing.cuh"
 #include "recover.cuh"
 #include "fk20.cuh"
+#include "vmsm.cuh"
 
 namespace kzg {
 
@@ -50,31 +51,6 @@ __device__ __forceinline__ void g1_mul_scalar(G1 *out, const G1 *pp, const uint3
     G1 r = g1_mul_scalar_v(*pp, ks, nwin);
     *out = r;
 }
-// 128-bit pseudo-random coefficient: first 16 bytes of SHA-256(seed32 || a || b).  The seed is fresh
-// host randomness per API call, so the coefficients are unpredictable to whoever chose the inputs
-// (the reference uses powers of one random r, internal/kzg/kzg_verify.go:136-141; any coefficients
-// that are independent of the inputs give the same soundness bound).
-__device__ __forceinline__ void prf128(uint32_t *out4, const uint32_t *seed8, unsigned long long a, unsigned long long b) {
-    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
-    uint32_t w[16];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = seed8[i];
-    w[8] = (uint32_t)(a >> 32); w[9] = (uint32_t)a; w[10] = (uint32_t)(b >> 32); w[11] = (uint32_t)b;
-    w[12] = 0x80000000u; w[13] = 0; w[14] = 0; w[15] = 48 * 8;
-    sha256_block(h, w);
-    out4[0] = h[0]; out4[1] = h[1]; out4[2] = h[2]; out4[3] = h[3] | 1u;   // never zero
-}
-
-__device__ __forceinline__ Fr fr_to_mont(const uint32_t *plain) {
-    Fr x, r2;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { x.v[i] = plain[i]; r2.v[i] = FR_R2[i]; }
-    return fr_mul_ni(x, r2);
-}
-__device__ __forceinline__ Fr fr_from_mont(const Fr &a) {
-    Fr o = Fr::zero(); o.v[0] = 1;
-    return fr_mul_ni(a, o);
-}
 // base^e for a small exponent e
 static __device__ __noinline__ Fr fr_pow_u64(Fr base, unsigned long long e) {
     Fr r = Fr::one();
@@ -88,12 +64,14 @@ static __device__ __noinline__ Fr fr_pow_u64(Fr base, unsigned long long e) {
 
 // ---- n independent single-proof checks (kzg_verify.go:35-100 rewritten to fixed G2) ------------
 // status[i] must hold OK or an earlier decode error; z/y are plain limbs.
-static __global__ void __launch_bounds__(64) k_verify_single(const G1Aff *__restrict__ commitments, const G1Aff *__restrict__ proofs,
-                                                      const uint32_t *__restrict__ z, const uint32_t *__restrict__ y,
-                                                      const G1Aff *__restrict__ g1_gen, const PairingConsts *__restrict__ pc,
-                                                      int32_t *__restrict__ status, size_t n) {
+// PA[i] = -(C - [y]G + [z]pi), PB[i] = pi; the check e(PA, G2) e(PB, [s]G2) == 1 runs in k_pairing_lanes.
+static __global__ void __launch_bounds__(64) k_verify_single_prep(const G1Aff *__restrict__ commitments, const G1Aff *__restrict__ proofs,
+                                                           const uint32_t *__restrict__ z, const uint32_t *__restrict__ y,
+                                                           const G1Aff *__restrict__ g1_gen, const int32_t *__restrict__ status,
+                                                           G1 *__restrict__ PA, G1 *__restrict__ PB, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || status[i] != ST_OK) return;
+    if (i >= n) return;
+    if (status[i] != ST_OK) { PA[i] = G1::infinity(); PB[i] = G1::infinity(); return; }
     G1 G = G1::from_affine(*g1_gen), Pi = G1::from_affine(proofs[i]), A = G1::from_affine(commitments[i]);
     G1 yG, zPi;
     g1_mul_scalar(&yG, &G, y + i * 8);
@@ -102,8 +80,7 @@ static __global__ void __launch_bounds__(64) k_verify_single(const G1Aff *__rest
     g1_add(A, yG);
     g1_add(A, zPi);                       // C - [y]G + [z]pi
     A.neg_inplace();
-    G1Aff a = g1_to_affine(A), p = proofs[i];
-    status[i] = pairing_check2(pc, &a, 0, &p, 1) ? ST_OK : ST_VERIFY_FAILED;   // e(-A, G2) e(pi, [s]G2) == 1
+    PA[i] = A; PB[i] = Pi;
 }
 
 // ---- EIP-4844 RLC batch (kzg_verify.go:111-231) -------------------------------------------------
@@ -126,9 +103,9 @@ static __global__ void __launch_bounds__(64) k_rlc_terms(const G1Aff *__restrict
     g1_mul_scalar(&t, &C, rip.v, 32); T[n + i] = t;
     g1_mul_scalar(&t, &Pi, rzp.v, 64); T[2 * n + i] = t;
 }
-// one block: sums, final combination and the pairing check
-static __global__ void __launch_bounds__(128) k_rlc_finish(const G1 *__restrict__ T, const Fr *__restrict__ fy, size_t n,
-                                                    const G1Aff *__restrict__ g1_gen, const PairingConsts *__restrict__ pc, int32_t *__restrict__ result) {
+// one block: sums and final combination; PA[0], PB[0] feed k_pairing_lanes (qa = 0, qb = 1)
+static __global__ void __launch_bounds__(128) k_rlc_prep(const G1 *__restrict__ T, const Fr *__restrict__ fy, size_t n,
+                                                  const G1Aff *__restrict__ g1_gen, G1 *__restrict__ PA, G1 *__restrict__ PB) {
     __shared__ G1 sm[128];
     __shared__ uint32_t sf[8 * 128];
     const int tid = threadIdx.x;
@@ -163,39 +140,15 @@ static __global__ void __launch_bounds__(128) k_rlc_finish(const G1 *__restrict_
     g1_add(A, sums[2]);                   // sum r^i C_i - [sum r^i y_i]G + sum r^i z_i pi_i
     G1 B = sums[0];
     B.neg_inplace();
-    G1Aff a = g1_to_affine(A), b = g1_to_affine(B);
-    *result = pairing_check2(pc, &a, 0, &b, 1) ? ST_OK : ST_VERIFY_FAILED;     // e(A, G2) e(-sum r^i pi_i, [s]G2) == 1
+    PA[0] = A; PB[0] = B;                 // e(A, G2) e(-sum r^i pi_i, [s]G2) == 1
 }
 
 // ---- EIP-7594 cell batch (kzg_multi/kzg_verify.go:16-105) ---------------------------------------
-// rpow[cell] = 128-bit coefficient PRF(seed, batch, position in batch), Montgomery form
-static __global__ void k_cell_coeffs(Fr seed, const uint32_t *__restrict__ batch_of, const uint64_t *__restrict__ batch_start,
-                                     Fr *__restrict__ rpow, size_t n) {
-    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    uint32_t b = batch_of[k];
-    Fr p = Fr::zero();
-    prf128(p.v, seed.v, b, k - batch_start[b]);
-    rpow[k] = fr_to_mont(p.v);
-}
 // batch_status[group_of[i]] = max(., status[i])  (any error in a batch makes the batch an error)
 static __global__ void k_merge_status(const int32_t *__restrict__ status, const uint32_t *__restrict__ group_of, int32_t *__restrict__ batch_status, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (status[i] != ST_OK) atomicMax(&batch_status[group_of[i]], status[i]);
-}
-// T[k] = [r^k] proof_k   (proofs already decoded; failed ones contribute nothing)
-static __global__ void __launch_bounds__(64) k_cell_proof_terms(const G1Aff *__restrict__ proofs, const Fr *__restrict__ rpow,
-                                                         const int32_t *__restrict__ status, G1 *__restrict__ T, size_t n) {
-    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    G1 t = G1::infinity();
-    if (status[k] == ST_OK) {
-        Fr rp = fr_from_mont(rpow[k]);          // 128-bit
-        G1 P = G1::from_affine(proofs[k]);
-        g1_mul_scalar(&t, &P, rp.v, 32);
-    }
-    T[k] = t;
 }
 // work item w = (cells [start, end) of ONE batch): partial[w][64] = sum_k r^k * interpolation poly of cell k.
 // One warp per cell, 8 warps per block.  interpolation = CosetIFFT_64(brp(evals)) on the coset
@@ -270,44 +223,15 @@ static __global__ void k_cell_interp_reduce(const Fr *__restrict__ partial, cons
     Fr p = fr_from_mont(tot);
     for (int q = 0; q < 8; ++q) interp[((size_t)b * 64 + j) * 8 + q] = p.v[q];
 }
-// column sums: thread (batch b, column c): S_c = sum of T over the batch's cells with cell index c
-// (CSR from the host), W_c = [h_c^64] S_c = [w_128^brp7(c)] S_c; then the block adds them up:
-// sumS[b] = sum_c S_c = sum_k r_k pi_k,  sumW[b] = sum_c W_c = sum_k r_k h_k^64 pi_k   (kzg_verify.go:32,73-83)
-static __global__ void __launch_bounds__(128) k_cell_columns(const G1 *__restrict__ T, const uint32_t *__restrict__ order, const uint64_t *__restrict__ col_off,
-                                                      const int8_t *__restrict__ digits, G1 *__restrict__ sumS, G1 *__restrict__ sumW) {
-    __shared__ G1 sm[128];
-    const size_t b = blockIdx.x;
-    const int cidx = threadIdx.x;
-    const uint64_t lo = col_off[b * 128 + cidx], hi = col_off[b * 128 + cidx + 1];
-    G1 acc = G1::infinity();
-    for (uint64_t q = lo; q < hi; ++q) g1_add(acc, T[order[q]]);
-    sm[cidx] = acc;
-    __syncthreads();
-    for (int st = 64; st > 0; st >>= 1) {
-        if (cidx < st) g1_add_ool(&sm[cidx], &sm[cidx + st]);
-        __syncthreads();
-    }
-    if (cidx == 0) sumS[b] = sm[0];
-    __syncthreads();
-    int t = (int)(__brev((unsigned)cidx) >> 25);
-    if (t) g1_mul_twiddle(&acc, digits + (size_t)t * 2 * KZG_GLV_DIGITS);
-    sm[cidx] = acc;
-    __syncthreads();
-    for (int st = 64; st > 0; st >>= 1) {
-        if (cidx < st) g1_add_ool(&sm[cidx], &sm[cidx + st]);
-        __syncthreads();
-    }
-    if (cidx == 0) sumW[b] = sm[0];
-}
-// per batch: final combination + pairing.  rows: CSR of the batch's cells grouped by unique commitment.
-static __global__ void __launch_bounds__(32) k_cell_finish(const G1 *__restrict__ S /*sumS[b]*/, const G1 *__restrict__ Wt /*sumW[b]*/, const G1 *__restrict__ interp_commit,
+// per batch: final combination; PA[b], PB[b] feed k_pairing_lanes (qa = 2, qb = 0).  rows: CSR of the batch's cells grouped by unique commitment.
+static __global__ void __launch_bounds__(32) k_cell_prep(const G1 *__restrict__ S /*sumS[b]*/, const G1 *__restrict__ Wt /*sumW[b]*/, const G1 *__restrict__ interp_commit,
                                                     const G1Aff *__restrict__ uniq_commit, const uint64_t *__restrict__ row_off,
                                                     const uint64_t *__restrict__ batch_row_off, const uint32_t *__restrict__ row_cells,
-                                                    const Fr *__restrict__ rpow, const PairingConsts *__restrict__ pc,
-                                                    const int32_t *__restrict__ batch_status, int32_t *__restrict__ result, size_t n_batches) {
+                                                    const Fr *__restrict__ rpow, const int32_t *__restrict__ batch_status,
+                                                    G1 *__restrict__ PA, G1 *__restrict__ PB, size_t n_batches) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_batches) return;
-    if (batch_status[b] != ST_OK) { result[b] = batch_status[b]; return; }
+    if (batch_status[b] != ST_OK) { PA[b] = G1::infinity(); PB[b] = G1::infinity(); return; }
     G1 sumS = S[b], sumW = Wt[b];
     G1 comms = G1::infinity();
     for (uint64_t row = batch_row_off[b]; row < batch_row_off[b + 1]; ++row) {
@@ -323,8 +247,7 @@ static __global__ void __launch_bounds__(32) k_cell_finish(const G1 *__restrict_
     g1_add(comms, I);
     g1_add(comms, sumW);                  // rl = sum w C - [interp] + sum r^k h^64 pi   (kzg_verify.go:85-87)
     comms.neg_inplace();
-    G1Aff a = g1_to_affine(sumS), rl = g1_to_affine(comms);
-    result[b] = pairing_check2(pc, &a, 2, &rl, 0) ? ST_OK : ST_VERIFY_FAILED;   // e(sum r^k pi, [s^64]G2) e(-rl, G2) == 1
+    PA[b] = sumS; PB[b] = comms;          // e(sum r^k pi, [s^64]G2) e(-rl, G2) == 1
 }
 
 }  // namespace kzg
