@@ -136,6 +136,13 @@ static __device__ __noinline__ Fr fr_inv(Fr a) {
     return r;
 }
 
+__device__ __forceinline__ Fr fr_to_mont_limbs(const uint32_t *plain) {
+    Fr x, r2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x.v[i] = plain[i]; r2.v[i] = FR_R2[i]; }
+    return fr_mul_ni(x, r2);
+}
+
 // block-wide inclusive product scan helper over KZG_NTT_THREADS values held in planes sm[8][T]
 // (Hillis-Steele; `dir` +1 = prefix, -1 = suffix).  Returns this thread's inclusive product.
 __device__ __forceinline__ Fr block_scan_mul(uint32_t *sm, Fr v, int tid, int dir) {
@@ -154,92 +161,119 @@ __device__ __forceinline__ Fr block_scan_mul(uint32_t *sm, Fr v, int tid, int di
     return v;
 }
 
-// Open (internal/kzg/kzg_prove.go:14-44) for one blob per CTA.
+// Open (internal/kzg/kzg_prove.go:14-44), one blob per CTA, in three launches so that the single
+// field inversion each blob needs (the batch inversion of the 4096 denominators z - w_i) is done for
+// ALL blobs of the chunk at once, one lane per blob, instead of stalling a whole CTA behind one
+// thread's 380-product Fermat chain:
+//   k_eval_products : den_i = z - w_i; per-thread products; block-wide exclusive prefix x suffix
+//                     products -> cex[blob][thread], total[blob]; in-domain index (domain.go:163-171)
+//   k_fr_inv_batch  : total[blob] <- 1 / total[blob]
+//   k_eval_finish   : per-element inverses, y = (z^n - 1)/n * sum f_i w_i / (z - w_i)
+//                     (domain.go:193-235), quotient (kzg_prove.go:81-180)
+// The blob's scalars are used in PLAIN form: a Montgomery product of a plain and a Montgomery operand
+// is plain, so f_i never needs converting and y / the quotient come out ready to serialise.
 //   in : blob bytes (Lagrange evaluations over the bit-reversed domain), z (plain limbs)
 //   out: y (32 B big-endian and/or plain limbs, optional), quotient scalars as plain limbs
 //        [4096][8] for k_msm_fixed (optional: null = EvaluateLagrangePolynomial only)
-// status[blob] must be pre-set (OK or an earlier error); non-canonical blob sets it here.
-static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_eval_quotient(const uint8_t *__restrict__ blobs, const uint32_t *__restrict__ z_limbs,
-                                                                   const Fr *__restrict__ roots, int32_t *__restrict__ status,
-                                                                   uint32_t *__restrict__ quotient, uint8_t *__restrict__ y_out,
-                                                                   uint32_t *__restrict__ y_limbs, Fr inv_n) {
-    constexpr int T = KZG_NTT_THREADS, PER = 4096 / T;
+// status[blob] must be pre-set (OK or an earlier error); a non-canonical blob sets it in k_eval_finish.
+#define KZG_EVAL_PER (4096 / KZG_NTT_THREADS)
+__device__ __forceinline__ int eval_root_index(int i) { return (int)(__brev((unsigned)i) >> 20) * 2; }   // bit-reversed 4096-domain: w_4096^brp(i) = w_8192^(2 brp(i))
+
+static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_eval_products(const uint32_t *__restrict__ z_limbs, const Fr *__restrict__ roots,
+                                                                   const int32_t *__restrict__ status, Fr *__restrict__ cex,
+                                                                   Fr *__restrict__ total, int32_t *__restrict__ dom_index) {
+    constexpr int T = KZG_NTT_THREADS, PER = KZG_EVAL_PER;
     __shared__ uint32_t sm[8 * T];
     __shared__ int s_index;
-    __shared__ uint32_t s_y[8];
     const int blob = blockIdx.x, tid = threadIdx.x;
     if (status[blob] != ST_OK) return;
     if (tid == 0) s_index = -1;
-    Fr r2;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r2.v[i] = FR_R2[i];
-    Fr z;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) z.v[i] = z_limbs[(size_t)blob * 8 + i];
-    z = fr_mul_ni(z, r2);
+    Fr z = fr_to_mont_limbs(z_limbs + (size_t)blob * 8);
     __syncthreads();
-    // this thread owns elements i = tid*PER + k (contiguous, so the sequential Montgomery trick runs in-thread)
-    Fr f[PER], w[PER], den[PER];
-    int bad = 0;
-    const uint8_t *src = blobs + (size_t)blob * 131072;
+    Fr run = Fr::one();
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
         int i = tid * PER + k;
-        Fr x;
-        load_be32(x.v, src + i * 32);
-        if (!fr_is_canonical(x.v)) bad = 1;
-        f[k] = fr_mul_ni(x, r2);
-        int t = (int)(__brev((unsigned)i) >> 20) * 2;          // bit-reversed 4096-domain: w_4096^brp(i) = w_8192^(2 brp(i))
-        w[k] = ld_fr(roots + t);
-        den[k] = Fr::sub(z, w[k]);
-        if (den[k].is_zero()) { s_index = i; den[k] = Fr::one(); }   // z is in the domain (domain.go:163-171)
+        Fr den = Fr::sub(z, ld_fr(roots + eval_root_index(i)));
+        if (den.is_zero()) { s_index = i; den = Fr::one(); }          // z is in the domain
+        run = k ? fr_mul_ni(run, den) : den;
     }
-    bad = __syncthreads_or(bad);
-    if (bad) { if (tid == 0) status[blob] = ST_NON_CANONICAL_SCALAR; return; }
-    const int index = s_index;
-    // ---- batch inversion of den over the whole block ------------------------------------------
-    Fr pre[PER];
-    Fr run = den[0];
-    pre[0] = Fr::one();
-#pragma unroll
-    for (int k = 1; k < PER; ++k) { pre[k] = run; run = fr_mul_ni(run, den[k]); }
-    Fr inc = block_scan_mul(sm, run, tid, +1);
+    block_scan_mul(sm, run, tid, +1);
     Fr excl_pre = Fr::one();
     if (tid > 0) excl_pre = sm_load<T>(sm, tid - 1);
-    Fr total = sm_load<T>(sm, T - 1);
+    Fr tot = sm_load<T>(sm, T - 1);
     __syncthreads();
     block_scan_mul(sm, run, tid, -1);
     Fr excl_suf = Fr::one();
     if (tid < T - 1) excl_suf = sm_load<T>(sm, tid + 1);
-    __syncthreads();
-    (void)inc;
-    // one Fermat inversion per blob (thread 0), broadcast through shared memory
-    if (tid == 0) { Fr it = fr_inv(total); sm_store<T>(sm, 0, it); }
-    __syncthreads();
-    Fr inv_total = sm_load<T>(sm, 0);
-    __syncthreads();
-    Fr c = fr_mul_ni(fr_mul_ni(inv_total, excl_pre), excl_suf);    // 1 / (product of this thread's PER elements)
+    st_fr(cex + (size_t)blob * T + tid, fr_mul_ni(excl_pre, excl_suf));
+    if (tid == 0) { st_fr(total + blob, tot); dom_index[blob] = s_index; }
+}
+
+static __global__ void k_fr_inv_batch(Fr *__restrict__ v, const int32_t *__restrict__ status, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || status[i] != ST_OK) return;
+    st_fr(v + i, fr_inv(ld_fr(v + i)));
+}
+
+static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_eval_finish(const uint8_t *__restrict__ blobs, const uint32_t *__restrict__ z_limbs,
+                                                                 const Fr *__restrict__ roots, int32_t *__restrict__ status,
+                                                                 const Fr *__restrict__ cex, const Fr *__restrict__ inv_total, const int32_t *__restrict__ dom_index,
+                                                                 uint32_t *__restrict__ quotient, uint8_t *__restrict__ y_out,
+                                                                 uint32_t *__restrict__ y_limbs, Fr inv_n) {
+    constexpr int T = KZG_NTT_THREADS, PER = KZG_EVAL_PER;
+    __shared__ uint32_t sm[8 * T];
+    __shared__ uint32_t s_y[8];
+    const int blob = blockIdx.x, tid = threadIdx.x;
+    if (status[blob] != ST_OK) return;
+    const int index = dom_index[blob];
+    Fr z = fr_to_mont_limbs(z_limbs + (size_t)blob * 8);
+    // inv[k] = 1 / den_k: prefix products inside the thread, then the backward sweep from
+    // c = 1 / (product of this thread's PER elements) = inv_total * (product of everyone else's)
     Fr inv[PER];
+    {
+        Fr run = Fr::one();
 #pragma unroll
-    for (int k = PER - 1; k >= 0; --k) { inv[k] = fr_mul_ni(c, pre[k]); c = fr_mul_ni(c, den[k]); }
-    // ---- evaluation -----------------------------------------------------------------------------
-    Fr y;
-    if (index >= 0) {
-        if (index / PER == tid) {
-#pragma unroll
-            for (int k = 0; k < PER; ++k) if (k == index % PER) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) s_y[q] = f[k].v[q];
-            }
+        for (int k = 0; k < PER; ++k) {
+            int i = tid * PER + k;
+            Fr den = Fr::sub(z, ld_fr(roots + eval_root_index(i)));
+            if (i == index) den = Fr::one();
+            inv[k] = run;
+            run = k ? fr_mul_ni(run, den) : den;
         }
-        __syncthreads();
+        Fr c = fr_mul_ni(ld_fr(inv_total + blob), ld_fr(cex + (size_t)blob * T + tid));
+#pragma unroll
+        for (int k = PER - 1; k >= 0; --k) {
+            int i = tid * PER + k;
+            Fr den = Fr::sub(z, ld_fr(roots + eval_root_index(i)));
+            if (i == index) den = Fr::one();
+            inv[k] = k ? fr_mul_ni(c, inv[k]) : c;
+            if (k) c = fr_mul_ni(c, den);
+        }
+    }
+    // ---- evaluation (f plain, w and inv Montgomery: the products are plain) ----------------------
+    const uint8_t *src = blobs + (size_t)blob * 131072;
+    int bad = 0;
+    Fr acc = Fr::zero();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        int i = tid * PER + k;
+        Fr f;
+        load_be32(f.v, src + i * 32);
+        if (!fr_is_canonical(f.v)) bad = 1;
+        if (i == index) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s_y[q] = f.v[q];
+        }
+        acc = Fr::add(acc, fr_mul_ni(fr_mul_ni(f, ld_fr(roots + eval_root_index(i))), inv[k]));
+    }
+    bad = __syncthreads_or(bad);
+    if (bad) { if (tid == 0) status[blob] = ST_NON_CANONICAL_SCALAR; return; }
+    Fr y;                                                              // plain
+    if (index >= 0) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) y.v[q] = s_y[q];
     } else {
-        Fr acc = Fr::zero();
-#pragma unroll
-        for (int k = 0; k < PER; ++k) acc = Fr::add(acc, fr_mul_ni(fr_mul_ni(f[k], w[k]), inv[k]));
-        // block sum
         sm_store<T>(sm, tid, acc);
         __syncthreads();
         for (int s = T >> 1; s > 0; s >>= 1) {
@@ -253,13 +287,11 @@ static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_eval_quotient(const 
         for (int i = 0; i < 12; ++i) zn = fr_sqr_ni(zn);                 // z^4096
         y = fr_mul_ni(fr_mul_ni(Fr::sub(zn, Fr::one()), inv_n), sum);
     }
-    Fr one_plain = Fr::zero(); one_plain.v[0] = 1;
-    if (tid == 0 && (y_out || y_limbs)) {
-        Fr yp = fr_mul_ni(y, one_plain);
-        if (y_out) store_be32(y_out + (size_t)blob * 32, yp.v);
+    if (tid == 0) {
+        if (y_out) store_be32(y_out + (size_t)blob * 32, y.v);
         if (y_limbs) {
 #pragma unroll
-            for (int q8 = 0; q8 < 8; ++q8) y_limbs[(size_t)blob * 8 + q8] = yp.v[q8];
+            for (int q8 = 0; q8 < 8; ++q8) y_limbs[(size_t)blob * 8 + q8] = y.v[q8];
         }
     }
     if (!quotient) return;      // evaluation only (verify.go:69, 128)
@@ -272,10 +304,12 @@ static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_eval_quotient(const 
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
         int i = tid * PER + k;
-        q[k] = Fr::neg(fr_mul_ni(Fr::sub(f[k], y), inv[k]));
+        Fr f;
+        load_be32(f.v, src + i * 32);
+        q[k] = Fr::neg(fr_mul_ni(Fr::sub(f, y), inv[k]));
         if (index >= 0) {
             if (i == index) q[k] = Fr::zero();
-            else qm_acc = Fr::sub(qm_acc, fr_mul_ni(q[k], w[k]));
+            else qm_acc = Fr::sub(qm_acc, fr_mul_ni(q[k], ld_fr(roots + eval_root_index(i))));
         }
     }
     if (index >= 0) {
@@ -287,7 +321,7 @@ static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_eval_quotient(const 
         }
         Fr tot = sm_load<T>(sm, 0);
         // 1 / w_m = w_8192^(8192 - 2 brp(m))
-        int t = (int)(__brev((unsigned)index) >> 20) * 2;
+        int t = eval_root_index(index);
         Fr inv_wm = ld_fr(roots + ((ROOTS_N - t) & (ROOTS_N - 1)));
         Fr qm = fr_mul_ni(tot, inv_wm);
 #pragma unroll
@@ -296,10 +330,9 @@ static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_eval_quotient(const 
     uint32_t *dst = quotient + (size_t)blob * 4096 * 8;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
-        Fr p = fr_mul_ni(q[k], one_plain);
         uint4 *o = reinterpret_cast<uint4 *>(dst + (size_t)(tid * PER + k) * 8);
-        o[0] = make_uint4(p.v[0], p.v[1], p.v[2], p.v[3]);
-        o[1] = make_uint4(p.v[4], p.v[5], p.v[6], p.v[7]);
+        o[0] = make_uint4(q[k].v[0], q[k].v[1], q[k].v[2], q[k].v[3]);
+        o[1] = make_uint4(q[k].v[4], q[k].v[5], q[k].v[6], q[k].v[7]);
     }
 }
 

@@ -62,7 +62,6 @@ static int verify_front(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm4
     if ((rc = c->zbuf.ensure(m * 32))) return rc;
     if ((rc = c->ybuf.ensure(m * 32))) return rc;
     unsigned gb = (unsigned)((m + 63) / 64);
-    Fr inv4096; memcpy(inv4096.v, H_FR_INV4096, sizeof inv4096.v);
     c->mark(KZGB200_KC_VERIFY);
     CU(cudaMemsetAsync(d_status, 0, m * sizeof(int32_t), c->stream));
     if (!blobs) {
@@ -76,9 +75,8 @@ static int verify_front(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm4
     if (blobs) {
         c->mark(KZGB200_KC_FR);
         k_fiat_shamir<<<(unsigned)((m + 31) / 32), 32, 0, c->stream>>>((const uint8_t *)d_blobs, (const uint8_t *)d_cm, (uint32_t *)c->zbuf.p, m);
-        k_eval_quotient<<<(unsigned)m, KZG_NTT_THREADS, 0, c->stream>>>((const uint8_t *)d_blobs, (const uint32_t *)c->zbuf.p, c->roots, d_status,
-                                                                         nullptr, nullptr, (uint32_t *)c->ybuf.p, inv4096);
-        c->launches += 2;
+        if ((rc = vm_eval_quotient(c, (const uint8_t *)d_blobs, (const uint32_t *)c->zbuf.p, d_status, nullptr, nullptr, (uint32_t *)c->ybuf.p, m))) return rc;
+        c->launches += 1;
     }
     return 0;
 }
@@ -203,38 +201,65 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     if (nb == 0) return KZGB200_OK;
     const bool res_dev = is_device_ptr(results);
     int rc;
+    // ---- device first: the proofs' decode + subgroup check (the longest kernel of the call) needs nothing from
+    // the host bookkeeping below, and the cells' H2D rides the copy stream meanwhile ------------------
+    const void *d_cells = cells, *d_proofs;
+    if ((rc = c->v_cst.ensure(std::max<size_t>(N, 1) * 4))) return rc;
+    if ((rc = c->v_aff2.ensure(std::max<size_t>(N, 1) * sizeof(G1Aff)))) return rc;
+    int32_t *d_cst = (int32_t *)c->v_cst.p;
+    c->mark(KZGB200_KC_VERIFY);
+    if ((rc = stage_in(c, proofs48, N * 48, c->in_small, &d_proofs))) return rc;
+    CU(cudaMemsetAsync(d_cst, 0, std::max<size_t>(N, 1) * 4, c->stream));
+    if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_proofs, (G1Aff *)c->v_aff2.p, d_cst, N, 1, 1))) return rc;
+    if (N && !is_device_ptr(cells)) {
+        if ((rc = c->in_bytes.ensure(N * 2048))) return rc;
+        // (every entry point ends with a stream synchronise under the context lock, so the staging buffer is free)
+        CU(cudaMemcpyAsync(c->in_bytes.p, cells, N * 2048, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(c->ev1, c->copy_stream));
+        d_cells = c->in_bytes.p;
+    }
     // ---- host: commitments for de-duplication -------------------------------------------------
     std::vector<uint8_t> h_cm_copy;
     const uint8_t *h_cm = commitments48;
     if (N && is_device_ptr(commitments48)) {
         h_cm_copy.resize(N * 48);
-        CU(cudaMemcpy(h_cm_copy.data(), commitments48, N * 48, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpyAsync(h_cm_copy.data(), commitments48, N * 48, cudaMemcpyDeviceToHost, c->copy_stream));
+        CU(cudaStreamSynchronize(c->copy_stream));
         h_cm = h_cm_copy.data();
     }
     std::vector<int32_t> h_bstatus(nb, KZGB200_OK);
-    std::vector<uint32_t> batch_of(N), row_cells(N);
+    std::vector<uint32_t> batch_of(N), row_cells(N), row_of(N);
     std::vector<uint64_t> batch_start(nb), batch_row_off(nb + 1, 0), row_off(1, 0), item_start, item_end, batch_item_off(nb + 1, 0);
     std::vector<uint8_t> uniq_bytes;
     const uint64_t ITEM = 512;
-    size_t rc_pos = 0;
+    std::unordered_map<std::string, uint32_t> seen;
+    std::vector<uint32_t> row_count;
     for (size_t b = 0; b < nb; ++b) {
         uint64_t lo = batch_offsets[b], hi = batch_offsets[b + 1];
-        if (hi < lo || hi > N) return set_err(KZGB200_ERR_ARGS, "batch_offsets not monotone / out of range");
+        if (hi < lo || hi > N) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); return set_err(KZGB200_ERR_ARGS, "batch_offsets not monotone / out of range"); }
         batch_start[b] = lo;
-        // de-duplicate on raw bytes, first-seen order (api_eip7594.go:238-265)
-        std::unordered_map<std::string, uint32_t> seen;
-        std::vector<std::vector<uint32_t>> rows;
+        // de-duplicate on raw bytes, first-seen order (api_eip7594.go:238-265).  Runs of equal commitments
+        // (the usual layout: all cells of a blob together) skip the hash lookup.
+        seen.clear(); row_count.clear();
+        uint32_t prev_row = 0;
         for (uint64_t k = lo; k < hi; ++k) {
             batch_of[k] = (uint32_t)b;
-            std::string key((const char *)h_cm + k * 48, 48);
-            auto it = seen.find(key);
             uint32_t row;
-            if (it == seen.end()) { row = (uint32_t)rows.size(); seen.emplace(key, row); rows.emplace_back(); uniq_bytes.insert(uniq_bytes.end(), key.begin(), key.end()); }
-            else row = it->second;
-            rows[row].push_back((uint32_t)k);
+            if (k > lo && memcmp(h_cm + k * 48, h_cm + (k - 1) * 48, 48) == 0) row = prev_row;
+            else {
+                std::string key((const char *)h_cm + k * 48, 48);
+                auto it = seen.find(key);
+                if (it == seen.end()) { row = (uint32_t)row_count.size(); seen.emplace(key, row); row_count.push_back(0); uniq_bytes.insert(uniq_bytes.end(), key.begin(), key.end()); }
+                else row = it->second;
+            }
+            prev_row = row; row_of[k] = row; ++row_count[row];
             if (cell_indices[k] >= 128) h_bstatus[b] = KZGB200_BAD_CELL_INDEX;      // api_eip7594.go:184-188
         }
-        for (auto &rw : rows) { for (uint32_t k : rw) row_cells[rc_pos++] = k; row_off.push_back(rc_pos); }
+        // counting sort of the batch's cells by row
+        const size_t row_base = row_off.size() - 1;
+        for (uint32_t cnt : row_count) row_off.push_back(row_off.back() + cnt);
+        std::vector<uint64_t> fill(row_off.begin() + row_base, row_off.begin() + row_base + row_count.size());
+        for (uint64_t k = lo; k < hi; ++k) row_cells[fill[row_of[k]]++] = (uint32_t)k;
         batch_row_off[b + 1] = row_off.size() - 1;
         for (uint64_t s = lo; s < hi; s += ITEM) { item_start.push_back(s); item_end.push_back(std::min(hi, s + ITEM)); }
         batch_item_off[b + 1] = item_start.size();
@@ -245,9 +270,6 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     for (size_t b = 0; b < nb; ++b) for (uint64_t rw = batch_row_off[b]; rw < batch_row_off[b + 1]; ++rw) row_batch[rw] = (uint32_t)b;
 
     // ---- device buffers ---------------------------------------------------------------------------
-    const void *d_cells, *d_proofs;
-    if ((rc = stage_in(c, cells, N * 2048, c->in_bytes, &d_cells))) return rc;
-    if ((rc = stage_in(c, proofs48, N * 48, c->in_small, &d_proofs))) return rc;
     if ((rc = c->in_small2.ensure(std::max<size_t>(U, 1) * 48))) return rc;
     if (U) CU(cudaMemcpyAsync(c->in_small2.p, uniq_bytes.data(), U * 48, cudaMemcpyHostToDevice, c->stream));
     // meta arena layout
@@ -255,7 +277,7 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) & ~(size_t)255; return at; };
     size_t o_idx = take(N * 8), o_batch_of = take(N * 4), o_bstart = take(nb * 8);
     size_t o_rowc = take(N * 4), o_rowoff = take((U + 1) * 8), o_browoff = take((nb + 1) * 8), o_is = take(n_items * 8), o_ie = take(n_items * 8);
-    size_t o_bio = take((nb + 1) * 8), o_bst = take(nb * 4), o_cst = take(std::max<size_t>(N, 1) * 4), o_ust = take(std::max<size_t>(U, 1) * 4);
+    size_t o_bio = take((nb + 1) * 8), o_bst = take(nb * 4), o_ust = take(std::max<size_t>(U, 1) * 4);
     size_t o_rowb = take(std::max<size_t>(U, 1) * 4), o_res = take(nb * 4);
     if ((rc = c->v_meta.ensure(o))) return rc;
     char *M = (char *)c->v_meta.p;
@@ -265,10 +287,8 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     CU(up(o_rowoff, row_off.data(), (U + 1) * 8)); CU(up(o_browoff, batch_row_off.data(), (nb + 1) * 8));
     CU(up(o_is, item_start.data(), n_items * 8)); CU(up(o_ie, item_end.data(), n_items * 8)); CU(up(o_bio, batch_item_off.data(), (nb + 1) * 8));
     CU(up(o_bst, h_bstatus.data(), nb * 4)); CU(up(o_rowb, row_batch.data(), U * 4));
-    CU(cudaMemsetAsync(M + o_cst, 0, std::max<size_t>(N, 1) * 4, c->stream));
     CU(cudaMemsetAsync(M + o_ust, 0, std::max<size_t>(U, 1) * 4, c->stream));
     if ((rc = c->v_aff1.ensure(std::max<size_t>(U, 1) * sizeof(G1Aff)))) return rc;
-    if ((rc = c->v_aff2.ensure(std::max<size_t>(N, 1) * sizeof(G1Aff)))) return rc;
     if ((rc = c->v_fr.ensure(std::max<size_t>(N, 1) * sizeof(Fr)))) return rc;
     if ((rc = c->vm_digits.ensure(std::max<size_t>(N, 1) * KZG_CELL_TW))) return rc;
     if ((rc = c->vm_scratch.ensure(std::max<size_t>(vm_scratch_bytes(n_items, KZG_CELL_TW), 256)))) return rc;
@@ -282,13 +302,12 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     if ((rc = c->scalars.ensure(nb * 64 * 32))) return rc;
     if ((rc = c->sums.ensure(nb * sizeof(G1)))) return rc;
     Fr inv64; memcpy(inv64.v, H_FR_INV64, sizeof inv64.v);
-    int32_t *d_cst = (int32_t *)(M + o_cst), *d_ust = (int32_t *)(M + o_ust), *d_bst = (int32_t *)(M + o_bst), *d_res = (int32_t *)(M + o_res);
-    c->mark(KZGB200_KC_VERIFY);
+    int32_t *d_ust = (int32_t *)(M + o_ust), *d_bst = (int32_t *)(M + o_bst), *d_res = (int32_t *)(M + o_res);
     if ((rc = vm_g1_check(c->stream, (const uint8_t *)c->in_small2.p, (G1Aff *)c->v_aff1.p, d_ust, U, 1, 1))) return rc;
     if (N) {
-        if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_proofs, (G1Aff *)c->v_aff2.p, d_cst, N, 1, 1))) return rc;
         if ((rc = vm_cell_coeff_digits(c->stream, seed_dev, (const uint32_t *)(M + o_batch_of), (const uint64_t *)(M + o_bstart), (const uint64_t *)(M + o_idx),
                                        c->roots, (Fr *)c->v_fr.p, (int8_t *)c->vm_digits.p, N))) return rc;
+        if (d_cells == c->in_bytes.p) CU(cudaStreamWaitEvent(c->stream, c->ev1, 0));     // the cells have landed
         c->mark(KZGB200_KC_FR);
         k_cell_interp<<<(unsigned)n_items, 256, 0, c->stream>>>((const uint8_t *)d_cells, (const uint64_t *)(M + o_idx), (const Fr *)c->v_fr.p, (const uint64_t *)(M + o_is),
                                                                 (const uint64_t *)(M + o_ie), c->roots, inv64, d_cst, (Fr *)c->v_partial.p);

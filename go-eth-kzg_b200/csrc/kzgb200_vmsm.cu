@@ -52,3 +52,21 @@ int vm_pairing_check(cudaStream_t st, const PairingConsts *pc, const G1 *A, int 
     CUL(cudaGetLastError());
     return 0;
 }
+
+// Open / EvaluateLagrangePolynomial for m blobs on c->stream (three launches, see kzg4844.cuh)
+int vm_eval_quotient(kzgb200_ctx *c, const uint8_t *d_blobs, const uint32_t *z_limbs, int32_t *d_status, uint32_t *quotient, uint8_t *y_out,
+                     uint32_t *y_limbs, size_t m) {
+    if (!m) return 0;
+    int rc;
+    if ((rc = c->ev_cex.ensure(m * KZG_NTT_THREADS * sizeof(Fr)))) return rc;
+    if ((rc = c->ev_total.ensure(m * sizeof(Fr)))) return rc;
+    if ((rc = c->ev_index.ensure(m * sizeof(int32_t)))) return rc;
+    Fr inv4096; memcpy(inv4096.v, H_FR_INV4096, sizeof inv4096.v);
+    k_eval_products<<<(unsigned)m, KZG_NTT_THREADS, 0, c->stream>>>(z_limbs, c->roots, d_status, (Fr *)c->ev_cex.p, (Fr *)c->ev_total.p, (int32_t *)c->ev_index.p);
+    k_fr_inv_batch<<<(unsigned)((m + 31) / 32), 32, 0, c->stream>>>((Fr *)c->ev_total.p, d_status, m);
+    k_eval_finish<<<(unsigned)m, KZG_NTT_THREADS, 0, c->stream>>>(d_blobs, z_limbs, c->roots, d_status, (const Fr *)c->ev_cex.p, (const Fr *)c->ev_total.p,
+                                                                   (const int32_t *)c->ev_index.p, quotient, y_out, y_limbs, inv4096);
+    c->launches += 3;
+    CUL(cudaGetLastError());
+    return 0;
+}
