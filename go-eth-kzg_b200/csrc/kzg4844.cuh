@@ -299,18 +299,21 @@ static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_eval_finish(const ui
     // outside: q_i = (f_i - y)/(w_i - z) = -(f_i - y) * inv_i                    (kzg_prove.go:81-111)
     // on domain (index m): same for i != m (den_m was replaced by 1), and
     //   q_m = sum_{i != m} -q_i * w_i / w_m                                       (kzg_prove.go:118-180)
-    Fr q[PER];
+    uint32_t *dst = quotient + (size_t)blob * 4096 * 8;
     Fr qm_acc = Fr::zero();
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
         int i = tid * PER + k;
         Fr f;
         load_be32(f.v, src + i * 32);
-        q[k] = Fr::neg(fr_mul_ni(Fr::sub(f, y), inv[k]));
+        Fr q = Fr::neg(fr_mul_ni(Fr::sub(f, y), inv[k]));
         if (index >= 0) {
-            if (i == index) q[k] = Fr::zero();
-            else qm_acc = Fr::sub(qm_acc, fr_mul_ni(q[k], ld_fr(roots + eval_root_index(i))));
+            if (i == index) q = Fr::zero();                              // overwritten below
+            else qm_acc = Fr::sub(qm_acc, fr_mul_ni(q, ld_fr(roots + eval_root_index(i))));
         }
+        uint4 *o = reinterpret_cast<uint4 *>(dst + (size_t)i * 8);
+        o[0] = make_uint4(q.v[0], q.v[1], q.v[2], q.v[3]);
+        o[1] = make_uint4(q.v[4], q.v[5], q.v[6], q.v[7]);
     }
     if (index >= 0) {
         sm_store<T>(sm, tid, qm_acc);
@@ -319,20 +322,15 @@ static __global__ void __launch_bounds__(KZG_NTT_THREADS) k_eval_finish(const ui
             if (tid < s) sm_store<T>(sm, tid, Fr::add(sm_load<T>(sm, tid), sm_load<T>(sm, tid + s)));
             __syncthreads();
         }
-        Fr tot = sm_load<T>(sm, 0);
-        // 1 / w_m = w_8192^(8192 - 2 brp(m))
-        int t = eval_root_index(index);
-        Fr inv_wm = ld_fr(roots + ((ROOTS_N - t) & (ROOTS_N - 1)));
-        Fr qm = fr_mul_ni(tot, inv_wm);
-#pragma unroll
-        for (int k = 0; k < PER; ++k) if (tid * PER + k == index) q[k] = qm;
-    }
-    uint32_t *dst = quotient + (size_t)blob * 4096 * 8;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        uint4 *o = reinterpret_cast<uint4 *>(dst + (size_t)(tid * PER + k) * 8);
-        o[0] = make_uint4(q[k].v[0], q[k].v[1], q[k].v[2], q[k].v[3]);
-        o[1] = make_uint4(q[k].v[4], q[k].v[5], q[k].v[6], q[k].v[7]);
+        if (tid == index / PER) {
+            Fr tot = sm_load<T>(sm, 0);
+            // 1 / w_m = w_8192^(8192 - 2 brp(m))
+            int t = eval_root_index(index);
+            Fr qm = fr_mul_ni(tot, ld_fr(roots + ((ROOTS_N - t) & (ROOTS_N - 1))));
+            uint4 *o = reinterpret_cast<uint4 *>(dst + (size_t)index * 8);
+            o[0] = make_uint4(qm.v[0], qm.v[1], qm.v[2], qm.v[3]);
+            o[1] = make_uint4(qm.v[4], qm.v[5], qm.v[6], qm.v[7]);
+        }
     }
 }
 
