@@ -87,8 +87,8 @@ struct kzgb200_ctx {
     // scratch
     DevBuf in_bytes, scalars, status, sums, out_bytes, coeffs, cells, proofs_xyzz, fft_work, in_small, in_small2, zbuf, ybuf;
     DevBuf rec_a, rec_b, rec_meta, rec_zev, rec_czinv;
-    DevBuf v_aff1, v_aff2, v_T, v_fr, v_meta, v_S, v_W, v_partial, v_in2, v_in3, v_st2;
-    DevBuf vm_digits, vm_scratch, vm_ws, vm_wsb, v_pa, v_pb, v_cst, ev_cex, ev_total, ev_index;
+    DevBuf v_aff1, v_aff2, v_fr, v_meta, v_S, v_W, v_partial, v_in2, v_in3, v_st2;
+    DevBuf vm_digits, vm_scratch, vm_ws, vm_wsb, v_pa, v_pb, v_cst, v_st3, ev_cex, ev_total, ev_index;
     double init_ms = 0, last_device_ms = 0;
     uint64_t launches = 0;
     // per-kernel-class device timing of the last call (CUDA events on `stream`)
@@ -143,10 +143,15 @@ size_t vm_scratch_bytes(size_t n_items, int nw);
 int vm_msm_windows(cudaStream_t st, const G1Aff *points, const int8_t *digits, int TW, int w_lo, int nw,
                    const uint64_t *item_start, const uint64_t *item_end, size_t n_items, const uint64_t *batch_item_off, size_t nb,
                    G1 *scratch, G1 *WS, G1 *WSb);
-int vm_combine(cudaStream_t st, const G1 *WSb, int TW, int w0, int nw, G1 *out, size_t nb);
+// out[seg * nb + b] = Horner over windows [32 seg, 32 seg + 32) of WSb[b]
+int vm_combine(cudaStream_t st, const G1 *WSb, int TW, int n_segs, G1 *out, size_t nb);
+int vm_rlc_coeff_digits(cudaStream_t st, const Fr &seed, int unit_coeff, const uint32_t *z, const uint32_t *y, const int32_t *status,
+                        Fr *fy, int8_t *digits, size_t n);
 // result[i] = pre_status[i] if that is an error (pre_status may be null or alias result), else OK / VERIFY_FAILED for
 // e(A_i, Q[qa]) e(B_i, Q[qb]) == 1, Q = {G2, [s]G2, [s^64]G2}
 int vm_pairing_check(cudaStream_t st, const PairingConsts *pc, const G1 *A, int qa, const G1 *B, int qb, const int32_t *pre_status, int32_t *result, size_t n);
-// Open / EvaluateLagrangePolynomial for m blobs on c->stream (k_eval_products, k_fr_inv_batch, k_eval_finish)
-int vm_eval_quotient(kzgb200_ctx *c, const uint8_t *d_blobs, const uint32_t *z_limbs, int32_t *d_status, uint32_t *quotient, uint8_t *y_out,
-                     uint32_t *y_limbs, size_t m);
+// Open / EvaluateLagrangePolynomial for m blobs on stream st (k_eval_products, k_fr_inv_batch, k_eval_finish), using
+// scratch slots [slot, slot + m) of the scratch sized by vm_eval_scratch(total)
+int vm_eval_scratch(kzgb200_ctx *c, size_t total);
+int vm_eval_quotient(kzgb200_ctx *c, cudaStream_t st, size_t slot, const uint8_t *d_blobs, const uint32_t *z_limbs, int32_t *d_status, uint32_t *quotient,
+                     uint8_t *y_out, uint32_t *y_limbs, size_t m);

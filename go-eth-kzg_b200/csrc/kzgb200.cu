@@ -207,9 +207,9 @@ void kzgb200_ctx_free(kzgb200_ctx *c) {
     c->in_small.release(); c->in_small2.release(); c->zbuf.release(); c->ybuf.release();
     c->rec_a.release(); c->rec_b.release(); c->rec_meta.release(); c->rec_zev.release(); c->rec_czinv.release();
     cudaFree(c->pow7); cudaFree(c->ipow7); cudaFree(c->pairing); cudaFree(c->mono64_tab.entries);
-    c->v_aff1.release(); c->v_aff2.release(); c->v_T.release(); c->v_fr.release(); c->v_meta.release(); c->v_S.release();
+    c->v_aff1.release(); c->v_aff2.release(); c->v_fr.release(); c->v_meta.release(); c->v_S.release();
     c->v_W.release(); c->v_partial.release(); c->v_in2.release(); c->v_in3.release(); c->v_st2.release();
-    c->vm_digits.release(); c->vm_scratch.release(); c->vm_ws.release(); c->vm_wsb.release(); c->v_pa.release(); c->v_pb.release(); c->v_cst.release(); c->ev_cex.release(); c->ev_total.release(); c->ev_index.release();
+    c->vm_digits.release(); c->vm_scratch.release(); c->vm_ws.release(); c->vm_wsb.release(); c->v_pa.release(); c->v_pb.release(); c->v_cst.release(); c->v_st3.release(); c->ev_cex.release(); c->ev_total.release(); c->ev_index.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (cudaStream_t q : c->fft_streams) if (q) cudaStreamDestroy(q);
     for (cudaEvent_t e : c->ev_join) if (e) cudaEventDestroy(e);
@@ -458,7 +458,8 @@ static int open_common(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *z32,
             k_fiat_shamir<<<(unsigned)((m + 31) / 32), 32, 0, c->stream>>>((const uint8_t *)d_blobs, (const uint8_t *)d_aux, (uint32_t *)c->zbuf.p, m);
             c->launches += 2;
         }
-        if ((rc = vm_eval_quotient(c, (const uint8_t *)d_blobs, (const uint32_t *)c->zbuf.p, d_status, (uint32_t *)c->scalars.p, d_y, nullptr, m))) return rc;
+        if ((rc = vm_eval_scratch(c, m))) return rc;
+        if ((rc = vm_eval_quotient(c, c->stream, 0, (const uint8_t *)d_blobs, (const uint32_t *)c->zbuf.p, d_status, (uint32_t *)c->scalars.p, d_y, nullptr, m))) return rc;
         c->mark(KZGB200_KC_MSM);
         k_msm_fixed<<<dim3(1, (unsigned)m), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->commit_tab, N_BLOB, 1, TPB,
                                                                                   d_status, (G1 *)c->sums.p);

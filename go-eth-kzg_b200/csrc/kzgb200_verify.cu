@@ -45,37 +45,72 @@ static const size_t VERIFY_CHUNK = 4096;
 
 // shared front end: decode commitments/proofs, obtain z and y (given, or Fiat-Shamir + evaluation)
 //   blobs == nullptr: z32/y32 given (VerifyKZGProof); else z = challenge, y = p(z)
-// leaves: v_aff1 = commitments, v_aff2 = proofs, zbuf = z limbs, ybuf = y limbs, d_status filled
+// writes: out_cm = commitments, out_pf = proofs (affine), zl = z limbs, yl = y limbs, d_status filled.
+// Host blobs travel in pieces on the copy stream; each piece is hashed and evaluated on a side stream of its
+// own as soon as it has landed (the SHA-256 of a blob is one thread's 2050 sequential compressions, so pieces
+// queued on ONE stream would serialise that latency), while the point decoding runs on the main stream.
+#define VERIFY_MAX_PIECES (KZG_G1FFT_MAX_SPLIT - 1)
 static int verify_front(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm48, const uint8_t *z32, const uint8_t *y32, const uint8_t *pf48,
-                        size_t m, int32_t *d_status) {
+                        size_t m, int32_t *d_status, G1Aff *out_cm, G1Aff *out_pf, uint32_t *zl, uint32_t *yl) {
     int rc;
-    const void *d_cm, *d_pf, *d_blobs = nullptr, *d_z = nullptr, *d_y = nullptr;
+    const void *d_cm, *d_pf, *d_z = nullptr, *d_y = nullptr;
     if ((rc = stage_in(c, cm48, m * 48, c->in_small, &d_cm))) return rc;
     if ((rc = stage_in(c, pf48, m * 48, c->in_small2, &d_pf))) return rc;
-    if (blobs) { if ((rc = stage_in(c, blobs, m * KZGB200_BYTES_PER_BLOB, c->in_bytes, &d_blobs))) return rc; }
-    else {
+    const bool blobs_host = blobs && !is_device_ptr(blobs);
+    const size_t piece = ((m + VERIFY_MAX_PIECES - 1) / VERIFY_MAX_PIECES + 31) & ~(size_t)31;
+    const size_t n_pieces = blobs_host ? (m + piece - 1) / piece : 0;
+    if (blobs_host) {
+        if ((rc = c->in_bytes.ensure(m * KZGB200_BYTES_PER_BLOB))) return rc;
+        for (size_t p = 0; p < n_pieces; ++p) {
+            size_t po = p * piece, pm = std::min(piece, m - po);
+            CU(cudaMemcpyAsync((char *)c->in_bytes.p + po * KZGB200_BYTES_PER_BLOB, blobs + po * KZGB200_BYTES_PER_BLOB, pm * KZGB200_BYTES_PER_BLOB,
+                               cudaMemcpyHostToDevice, c->copy_stream));
+            CU(cudaEventRecord(c->ev_piece[p], c->copy_stream));
+        }
+    }
+    if (!blobs) {
         if ((rc = stage_in(c, z32, m * 32, c->v_in2, &d_z))) return rc;
         if ((rc = stage_in(c, y32, m * 32, c->v_in3, &d_y))) return rc;
     }
-    if ((rc = c->v_aff1.ensure(m * sizeof(G1Aff)))) return rc;
-    if ((rc = c->v_aff2.ensure(m * sizeof(G1Aff)))) return rc;
-    if ((rc = c->zbuf.ensure(m * 32))) return rc;
-    if ((rc = c->ybuf.ensure(m * 32))) return rc;
     unsigned gb = (unsigned)((m + 63) / 64);
     c->mark(KZGB200_KC_VERIFY);
     CU(cudaMemsetAsync(d_status, 0, m * sizeof(int32_t), c->stream));
     if (!blobs) {
-        k_scalars_from_be<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_y, (uint32_t *)c->ybuf.p, d_status, m);
-        k_scalars_from_be<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_z, (uint32_t *)c->zbuf.p, d_status, m);
+        k_scalars_from_be<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_y, yl, d_status, m);
+        k_scalars_from_be<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_z, zl, d_status, m);
         c->launches += 2;
     }
-    if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_cm, (G1Aff *)c->v_aff1.p, d_status, m, 1, 1))) return rc;
-    if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_pf, (G1Aff *)c->v_aff2.p, d_status, m, 1, 1))) return rc;
+    if (blobs) { if ((rc = vm_eval_scratch(c, m))) return rc; }
+    int32_t *d_blob_status = nullptr;      // the side streams report into their own array: merged below in the reference's order
+    if (blobs_host) {
+        if ((rc = c->v_st3.ensure(m * sizeof(int32_t)))) return rc;
+        d_blob_status = (int32_t *)c->v_st3.p;
+        CU(cudaMemsetAsync(d_blob_status, 0, m * sizeof(int32_t), c->stream));
+        // side streams start once the commitments are on the device and the status array is cleared
+        CU(cudaEventRecord(c->ev_fork, c->stream));
+        for (size_t p = 0; p < n_pieces; ++p) {
+            size_t po = p * piece, pm = std::min(piece, m - po);
+            cudaStream_t sp = c->fft_streams[p];
+            CU(cudaStreamWaitEvent(sp, c->ev_fork, 0));
+            CU(cudaStreamWaitEvent(sp, c->ev_piece[p], 0));
+            const uint8_t *pb = (const uint8_t *)c->in_bytes.p + po * KZGB200_BYTES_PER_BLOB;
+            k_fiat_shamir<<<(unsigned)((pm + 31) / 32), 32, 0, sp>>>(pb, (const uint8_t *)d_cm + po * 48, zl + po * 8, pm);
+            if ((rc = vm_eval_quotient(c, sp, po, pb, zl + po * 8, d_blob_status + po, nullptr, nullptr, yl + po * 8, pm))) return rc;
+            CU(cudaEventRecord(c->ev_join[p], sp));
+            c->launches += 1;
+        }
+    }
+    if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_cm, out_cm, d_status, m, 1, 1))) return rc;
+    if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_pf, out_pf, d_status, m, 1, 1))) return rc;
     c->launches += 2;
-    if (blobs) {
+    if (blobs_host) {
+        for (size_t p = 0; p < n_pieces; ++p) CU(cudaStreamWaitEvent(c->stream, c->ev_join[p], 0));
+        k_status_merge<<<gb, 64, 0, c->stream>>>(d_status, d_blob_status, m);      // commitment / proof errors come first (verify.go:102-119)
+        c->launches += 1;
+    } else if (blobs) {
         c->mark(KZGB200_KC_FR);
-        k_fiat_shamir<<<(unsigned)((m + 31) / 32), 32, 0, c->stream>>>((const uint8_t *)d_blobs, (const uint8_t *)d_cm, (uint32_t *)c->zbuf.p, m);
-        if ((rc = vm_eval_quotient(c, (const uint8_t *)d_blobs, (const uint32_t *)c->zbuf.p, d_status, nullptr, nullptr, (uint32_t *)c->ybuf.p, m))) return rc;
+        k_fiat_shamir<<<(unsigned)((m + 31) / 32), 32, 0, c->stream>>>(blobs, (const uint8_t *)d_cm, zl, m);
+        if ((rc = vm_eval_quotient(c, c->stream, 0, blobs, zl, d_status, nullptr, nullptr, yl, m))) return rc;
         c->launches += 1;
     }
     return 0;
@@ -92,13 +127,18 @@ static int verify_independent(kzgb200_ctx *c, const uint8_t *blobs, const uint8_
     const size_t chunk = std::min(n, VERIFY_CHUNK);
     int rc;
     if ((rc = c->status.ensure(chunk * sizeof(int32_t)))) return rc;
+    if ((rc = c->v_aff1.ensure(chunk * sizeof(G1Aff)))) return rc;
+    if ((rc = c->v_aff2.ensure(chunk * sizeof(G1Aff)))) return rc;
+    if ((rc = c->zbuf.ensure(chunk * 32))) return rc;
+    if ((rc = c->ybuf.ensure(chunk * 32))) return rc;
     if ((rc = c->v_S.ensure(chunk * sizeof(G1)))) return rc;
     if ((rc = c->v_W.ensure(chunk * sizeof(G1)))) return rc;
     for (size_t off = 0; off < n; off += chunk) {
         size_t m = std::min(chunk, n - off);
         int32_t *d_status = st_dev ? status + off : (int32_t *)c->status.p;
         if ((rc = verify_front(c, blobs ? blobs + off * KZGB200_BYTES_PER_BLOB : nullptr, cm48 + off * 48, z32 ? z32 + off * 32 : nullptr,
-                               y32 ? y32 + off * 32 : nullptr, pf48 + off * 48, m, d_status))) return rc;
+                               y32 ? y32 + off * 32 : nullptr, pf48 + off * 48, m, d_status, (G1Aff *)c->v_aff1.p, (G1Aff *)c->v_aff2.p,
+                               (uint32_t *)c->zbuf.p, (uint32_t *)c->ybuf.p))) return rc;
         c->mark(KZGB200_KC_VERIFY);
         k_verify_single_prep<<<(unsigned)((m + 63) / 64), 64, 0, c->stream>>>((const G1Aff *)c->v_aff1.p, (const G1Aff *)c->v_aff2.p, (const uint32_t *)c->zbuf.p,
                                                                                (const uint32_t *)c->ybuf.p, c->g1_monomial, d_status, (G1 *)c->v_S.p, (G1 *)c->v_W.p, m);
@@ -140,32 +180,41 @@ int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *blobs, co
     *result = KZGB200_OK;
     if (n == 0) return KZGB200_OK;                       // kzg_verify.go:120-122
     int rc;
+    // work items of the bucket MSMs: runs of <= 128 points, first the proofs (verdict slot 0), then the commitments (slot 1)
+    const uint64_t RLC_ITEM = 128;
+    std::vector<uint64_t> item_start, item_end, slot_item_off(3, 0);
+    for (int slot = 0; slot < 2; ++slot) {
+        for (uint64_t s0 = 0; s0 < n; s0 += RLC_ITEM) { item_start.push_back(slot * n + s0); item_end.push_back(slot * n + std::min<uint64_t>(n, s0 + RLC_ITEM)); }
+        slot_item_off[slot + 1] = item_start.size();
+    }
+    const size_t n_items = item_start.size();
     if ((rc = c->status.ensure(n * sizeof(int32_t)))) return rc;
-    if ((rc = c->v_T.ensure(3 * n * sizeof(G1)))) return rc;
     if ((rc = c->v_fr.ensure(n * sizeof(Fr)))) return rc;
     if ((rc = c->v_st2.ensure(sizeof(int32_t)))) return rc;
-    if ((rc = c->v_S.ensure(sizeof(G1)))) return rc;
-    if ((rc = c->v_W.ensure(sizeof(G1)))) return rc;
-    // the per-blob front end runs in chunks (bounded staging), all writing into full-size arrays
-    if ((rc = c->v_aff1.ensure(n * sizeof(G1Aff)))) return rc;
-    if ((rc = c->v_aff2.ensure(n * sizeof(G1Aff)))) return rc;
+    if ((rc = c->v_aff2.ensure(2 * n * sizeof(G1Aff)))) return rc;       // [proofs | commitments]
     if ((rc = c->zbuf.ensure(n * 32))) return rc;
     if ((rc = c->ybuf.ensure(n * 32))) return rc;
-    {
-        // verify_front works on [0, m): run it per chunk with shifted base pointers by temporarily offsetting the buffers
-        const size_t chunk = std::min(n, VERIFY_CHUNK);
-        DevBuf a1 = c->v_aff1, a2 = c->v_aff2, zb = c->zbuf, yb = c->ybuf;
-        for (size_t off = 0; off < n; off += chunk) {
-            size_t m = std::min(chunk, n - off);
-            c->v_aff1.p = (char *)a1.p + off * sizeof(G1Aff); c->v_aff1.cap = a1.cap - off * sizeof(G1Aff);
-            c->v_aff2.p = (char *)a2.p + off * sizeof(G1Aff); c->v_aff2.cap = a2.cap - off * sizeof(G1Aff);
-            c->zbuf.p = (char *)zb.p + off * 32; c->zbuf.cap = zb.cap - off * 32;
-            c->ybuf.p = (char *)yb.p + off * 32; c->ybuf.cap = yb.cap - off * 32;
-            rc = verify_front(c, blobs + off * KZGB200_BYTES_PER_BLOB, cm48 + off * 48, nullptr, nullptr, pf48 + off * 48, m, (int32_t *)c->status.p + off);
-            if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = set_err(KZGB200_ERR_CUDA, "sync");
-            c->v_aff1 = a1; c->v_aff2 = a2; c->zbuf = zb; c->ybuf = yb;
-            if (rc) return rc;
-        }
+    if ((rc = c->vm_digits.ensure(2 * n * KZG_CELL_TW))) return rc;
+    if ((rc = c->vm_scratch.ensure(vm_scratch_bytes(n_items, KZG_CELL_TW)))) return rc;
+    if ((rc = c->vm_ws.ensure(n_items * KZG_CELL_TW * sizeof(G1)))) return rc;
+    if ((rc = c->vm_wsb.ensure(2 * KZG_CELL_TW * sizeof(G1)))) return rc;
+    if ((rc = c->v_S.ensure(KZG_VM_SEGS * 2 * sizeof(G1)))) return rc;
+    if ((rc = c->v_pa.ensure(sizeof(G1)))) return rc;
+    if ((rc = c->v_pb.ensure(sizeof(G1)))) return rc;
+    if ((rc = c->v_meta.ensure((2 * n_items + 3) * 8))) return rc;
+    if ((rc = c->scalars.ensure(64 * 32))) return rc;
+    if ((rc = c->sums.ensure(sizeof(G1)))) return rc;
+    G1Aff *d_pf_aff = (G1Aff *)c->v_aff2.p, *d_cm_aff = d_pf_aff + n;
+    uint64_t *d_is = (uint64_t *)c->v_meta.p, *d_ie = d_is + n_items, *d_sio = d_ie + n_items;
+    CU(cudaMemcpyAsync(d_is, item_start.data(), n_items * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_ie, item_end.data(), n_items * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_sio, slot_item_off.data(), 3 * 8, cudaMemcpyHostToDevice, c->stream));
+    // the per-blob front end runs in chunks (bounded staging), all writing into full-size arrays
+    for (size_t off = 0; off < n; off += VERIFY_CHUNK) {
+        size_t m = std::min(VERIFY_CHUNK, n - off);
+        if ((rc = verify_front(c, blobs + off * KZGB200_BYTES_PER_BLOB, cm48 + off * 48, nullptr, nullptr, pf48 + off * 48, m, (int32_t *)c->status.p + off,
+                               d_cm_aff + off, d_pf_aff + off, (uint32_t *)c->zbuf.p + off * 8, (uint32_t *)c->ybuf.p + off * 8))) return rc;
+        CU(cudaStreamSynchronize(c->stream));
     }
     std::vector<int32_t> h_status(n);
     CU(cudaMemcpyAsync(h_status.data(), c->status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -173,13 +222,18 @@ int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *blobs, co
     for (size_t i = 0; i < n; ++i) if (h_status[i] != KZGB200_OK) { *result = h_status[i]; c->marks_collect(); return KZGB200_OK; }   // first failing element (verify.go:102-119)
     uint32_t seed[8];
     random_scalar_plain(c, seed);
-    Fr r_dev; memcpy(r_dev.v, seed, sizeof seed);      // PRF seed for the 128-bit coefficients; n == 1 uses coefficient 1 (kzg_verify.go:125-127)
+    Fr r_dev; memcpy(r_dev.v, seed, sizeof seed);      // PRF seed for the 127-bit coefficients; n == 1 uses coefficient 1 (kzg_verify.go:125-127)
     c->mark(KZGB200_KC_VERIFY);
-    k_rlc_terms<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>((const G1Aff *)c->v_aff1.p, (const G1Aff *)c->v_aff2.p, (const uint32_t *)c->zbuf.p,
-                                                                  (const uint32_t *)c->ybuf.p, r_dev, n == 1 ? 1 : 0, (const int32_t *)c->status.p, (G1 *)c->v_T.p, (Fr *)c->v_fr.p, n);
-    k_rlc_prep<<<1, 128, 0, c->stream>>>((const G1 *)c->v_T.p, (const Fr *)c->v_fr.p, n, c->g1_monomial, (G1 *)c->v_S.p, (G1 *)c->v_W.p);
-    if ((rc = vm_pairing_check(c->stream, c->pairing, (const G1 *)c->v_S.p, 0, (const G1 *)c->v_W.p, 1, nullptr, (int32_t *)c->v_st2.p, 1))) return rc;
-    c->launches += 3;
+    if ((rc = vm_rlc_coeff_digits(c->stream, r_dev, n == 1 ? 1 : 0, (const uint32_t *)c->zbuf.p, (const uint32_t *)c->ybuf.p, (const int32_t *)c->status.p,
+                                  (Fr *)c->v_fr.p, (int8_t *)c->vm_digits.p, n))) return rc;
+    if ((rc = vm_msm_windows(c->stream, d_pf_aff, (const int8_t *)c->vm_digits.p, KZG_CELL_TW, 0, KZG_CELL_TW, d_is, d_ie, n_items, d_sio, 2,
+                             (G1 *)c->vm_scratch.p, (G1 *)c->vm_ws.p, (G1 *)c->vm_wsb.p))) return rc;
+    if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_CELL_TW, KZG_VM_SEGS, (G1 *)c->v_S.p, 2))) return rc;
+    k_rlc_fsum<<<1, 128, 0, c->stream>>>((const Fr *)c->v_fr.p, n, (uint32_t *)c->scalars.p);
+    k_msm_fixed<<<dim3(1, 1), 32, 32 * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p);   // [sum r_i y_i] G
+    k_rlc_prep<<<1, 32, 0, c->stream>>>((const G1 *)c->v_S.p, (const G1 *)c->sums.p, (G1 *)c->v_pa.p, (G1 *)c->v_pb.p);
+    if ((rc = vm_pairing_check(c->stream, c->pairing, (const G1 *)c->v_pa.p, 0, (const G1 *)c->v_pb.p, 1, nullptr, (int32_t *)c->v_st2.p, 1))) return rc;
+    c->launches += 9;
     c->mark(-1);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(result, c->v_st2.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -294,8 +348,7 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     if ((rc = c->vm_scratch.ensure(std::max<size_t>(vm_scratch_bytes(n_items, KZG_CELL_TW), 256)))) return rc;
     if ((rc = c->vm_ws.ensure(std::max<size_t>(n_items, 1) * KZG_CELL_TW * sizeof(G1)))) return rc;
     if ((rc = c->vm_wsb.ensure(nb * KZG_CELL_TW * sizeof(G1)))) return rc;
-    if ((rc = c->v_S.ensure(nb * sizeof(G1)))) return rc;
-    if ((rc = c->v_W.ensure(nb * sizeof(G1)))) return rc;
+    if ((rc = c->v_S.ensure(KZG_VM_SEGS * nb * sizeof(G1)))) return rc;
     if ((rc = c->v_pa.ensure(nb * sizeof(G1)))) return rc;
     if ((rc = c->v_pb.ensure(nb * sizeof(G1)))) return rc;
     if ((rc = c->v_partial.ensure(std::max<size_t>(n_items, 1) * 64 * sizeof(Fr)))) return rc;
@@ -317,18 +370,17 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     c->mark(KZGB200_KC_MSM);
     k_msm_fixed<<<dim3(1, (unsigned)nb), 32, 32 * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p);
     c->mark(KZGB200_KC_VERIFY);
-    // sumS[b] = sum_k r_k pi_k (windows 0..31), sumW[b] = sum_k r_k h_k^64 pi_k (windows 32..95)   (kzg_verify.go:32,73-83)
+    // v_S[seg][b]: seg 0 = sum_k r_k pi_k, seg 1 + phi2(seg 2) = sum_k r_k h_k^64 pi_k   (kzg_verify.go:32,73-83)
     if ((rc = vm_msm_windows(c->stream, (const G1Aff *)c->v_aff2.p, (const int8_t *)c->vm_digits.p, KZG_CELL_TW, 0, KZG_CELL_TW, (const uint64_t *)(M + o_is),
                              (const uint64_t *)(M + o_ie), n_items, (const uint64_t *)(M + o_bio), nb, (G1 *)c->vm_scratch.p, (G1 *)c->vm_ws.p, (G1 *)c->vm_wsb.p))) return rc;
-    if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_CELL_TW, 0, 32, (G1 *)c->v_S.p, nb))) return rc;
-    if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_CELL_TW, 32, 64, (G1 *)c->v_W.p, nb))) return rc;
+    if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_CELL_TW, KZG_VM_SEGS, (G1 *)c->v_S.p, nb))) return rc;
     if (N) k_merge_status<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(d_cst, (const uint32_t *)(M + o_batch_of), d_bst, N);
     if (U) k_merge_status<<<(unsigned)((U + 127) / 128), 128, 0, c->stream>>>(d_ust, (const uint32_t *)(M + o_rowb), d_bst, U);
-    k_cell_prep<<<(unsigned)((nb + 31) / 32), 32, 0, c->stream>>>((const G1 *)c->v_S.p, (const G1 *)c->v_W.p, (const G1 *)c->sums.p, (const G1Aff *)c->v_aff1.p,
+    k_cell_prep<<<(unsigned)((nb + 31) / 32), 32, 0, c->stream>>>((const G1 *)c->v_S.p, (const G1 *)c->sums.p, (const G1Aff *)c->v_aff1.p,
                                                                    (const uint64_t *)(M + o_rowoff), (const uint64_t *)(M + o_browoff), (const uint32_t *)(M + o_rowc),
                                                                    (const Fr *)c->v_fr.p, d_bst, (G1 *)c->v_pa.p, (G1 *)c->v_pb.p, nb);
     if ((rc = vm_pairing_check(c->stream, c->pairing, (const G1 *)c->v_pa.p, 2, (const G1 *)c->v_pb.p, 0, d_bst, d_res, nb))) return rc;
-    c->launches += 10;
+    c->launches += 10;   // + bucket reduce and item reduce inside vm_msm_windows
     c->mark(-1);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(results, d_res, nb * 4, res_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));

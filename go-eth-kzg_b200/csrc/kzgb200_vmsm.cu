@@ -38,9 +38,17 @@ int vm_msm_windows(cudaStream_t st, const G1Aff *points, const int8_t *digits, i
     return 0;
 }
 
-int vm_combine(cudaStream_t st, const G1 *WSb, int TW, int w0, int nw, G1 *out, size_t nb) {
+int vm_combine(cudaStream_t st, const G1 *WSb, int TW, int n_segs, G1 *out, size_t nb) {
     if (!nb) return 0;
-    k_vmsm_combine<<<(unsigned)((nb + 31) / 32), 32, 0, st>>>(WSb, TW, w0, nw, out, nb);
+    k_vmsm_combine<<<dim3((unsigned)((nb + 31) / 32), n_segs), 32, 0, st>>>(WSb, TW, out, nb);
+    CUL(cudaGetLastError());
+    return 0;
+}
+
+int vm_rlc_coeff_digits(cudaStream_t st, const Fr &seed, int unit_coeff, const uint32_t *z, const uint32_t *y, const int32_t *status,
+                        Fr *fy, int8_t *digits, size_t n) {
+    if (!n) return 0;
+    k_rlc_coeff_digits<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seed, unit_coeff, z, y, status, fy, digits, n);
     CUL(cudaGetLastError());
     return 0;
 }
@@ -53,19 +61,24 @@ int vm_pairing_check(cudaStream_t st, const PairingConsts *pc, const G1 *A, int 
     return 0;
 }
 
-// Open / EvaluateLagrangePolynomial for m blobs on c->stream (three launches, see kzg4844.cuh)
-int vm_eval_quotient(kzgb200_ctx *c, const uint8_t *d_blobs, const uint32_t *z_limbs, int32_t *d_status, uint32_t *quotient, uint8_t *y_out,
-                     uint32_t *y_limbs, size_t m) {
-    if (!m) return 0;
+// Open / EvaluateLagrangePolynomial for m blobs on stream st (three launches, see kzg4844.cuh).
+// vm_eval_scratch sizes the scratch for `total` blobs; a call works on scratch slots [slot, slot + m),
+// so calls on different streams must use disjoint slot ranges.
+int vm_eval_scratch(kzgb200_ctx *c, size_t total) {
     int rc;
-    if ((rc = c->ev_cex.ensure(m * KZG_NTT_THREADS * sizeof(Fr)))) return rc;
-    if ((rc = c->ev_total.ensure(m * sizeof(Fr)))) return rc;
-    if ((rc = c->ev_index.ensure(m * sizeof(int32_t)))) return rc;
+    if ((rc = c->ev_cex.ensure(total * KZG_NTT_THREADS * sizeof(Fr)))) return rc;
+    if ((rc = c->ev_total.ensure(total * sizeof(Fr)))) return rc;
+    return c->ev_index.ensure(total * sizeof(int32_t));
+}
+int vm_eval_quotient(kzgb200_ctx *c, cudaStream_t st, size_t slot, const uint8_t *d_blobs, const uint32_t *z_limbs, int32_t *d_status, uint32_t *quotient,
+                     uint8_t *y_out, uint32_t *y_limbs, size_t m) {
+    if (!m) return 0;
     Fr inv4096; memcpy(inv4096.v, H_FR_INV4096, sizeof inv4096.v);
-    k_eval_products<<<(unsigned)m, KZG_NTT_THREADS, 0, c->stream>>>(z_limbs, c->roots, d_status, (Fr *)c->ev_cex.p, (Fr *)c->ev_total.p, (int32_t *)c->ev_index.p);
-    k_fr_inv_batch<<<(unsigned)((m + 31) / 32), 32, 0, c->stream>>>((Fr *)c->ev_total.p, d_status, m);
-    k_eval_finish<<<(unsigned)m, KZG_NTT_THREADS, 0, c->stream>>>(d_blobs, z_limbs, c->roots, d_status, (const Fr *)c->ev_cex.p, (const Fr *)c->ev_total.p,
-                                                                   (const int32_t *)c->ev_index.p, quotient, y_out, y_limbs, inv4096);
+    Fr *cex = (Fr *)c->ev_cex.p + slot * KZG_NTT_THREADS, *tot = (Fr *)c->ev_total.p + slot;
+    int32_t *idx = (int32_t *)c->ev_index.p + slot;
+    k_eval_products<<<(unsigned)m, KZG_NTT_THREADS, 0, st>>>(z_limbs, c->roots, d_status, cex, tot, idx);
+    k_fr_inv_batch<<<(unsigned)((m + 31) / 32), 32, 0, st>>>(tot, d_status, m);
+    k_eval_finish<<<(unsigned)m, KZG_NTT_THREADS, 0, st>>>(d_blobs, z_limbs, c->roots, d_status, cex, tot, idx, quotient, y_out, y_limbs, inv4096);
     c->launches += 3;
     CUL(cudaGetLastError());
     return 0;

@@ -84,66 +84,49 @@ static __global__ void __launch_bounds__(64) k_verify_single_prep(const G1Aff *_
 }
 
 // ---- EIP-4844 RLC batch (kzg_verify.go:111-231) -------------------------------------------------
-// per item i: 128-bit coefficient r_i = PRF(seed, i); T1 = [r_i]pi_i, T2 = [r_i]C_i, T3 = [r_i z_i]pi_i, fy = r_i y_i
-static __global__ void __launch_bounds__(64) k_rlc_terms(const G1Aff *__restrict__ commitments, const G1Aff *__restrict__ proofs,
-                                                  const uint32_t *__restrict__ z, const uint32_t *__restrict__ y, Fr seed, int unit_coeff,
-                                                  const int32_t *__restrict__ status, G1 *__restrict__ T, Fr *__restrict__ fy, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    G1 inf = G1::infinity();
-    if (status[i] != ST_OK) { T[i] = inf; T[n + i] = inf; T[2 * n + i] = inf; fy[i] = Fr::zero(); return; }
-    Fr rip = Fr::zero();                         // plain 128-bit coefficient r_i
-    if (unit_coeff) rip.v[0] = 1; else prf128(rip.v, seed.v, 0, i);
-    Fr ri = fr_to_mont(rip.v);
-    Fr rz = fr_mul_ni(ri, fr_to_mont(z + i * 8));
-    fy[i] = fr_mul_ni(ri, fr_to_mont(y + i * 8));
-    Fr rzp = fr_from_mont(rz);
-    G1 Pi = G1::from_affine(proofs[i]), C = G1::from_affine(commitments[i]), t;
-    g1_mul_scalar(&t, &Pi, rip.v, 32); T[i] = t;
-    g1_mul_scalar(&t, &C, rip.v, 32); T[n + i] = t;
-    g1_mul_scalar(&t, &Pi, rzp.v, 64); T[2 * n + i] = t;
-}
-// one block: sums and final combination; PA[0], PB[0] feed k_pairing_lanes (qa = 0, qb = 1)
-static __global__ void __launch_bounds__(128) k_rlc_prep(const G1 *__restrict__ T, const Fr *__restrict__ fy, size_t n,
-                                                  const G1Aff *__restrict__ g1_gen, G1 *__restrict__ PA, G1 *__restrict__ PB) {
-    __shared__ G1 sm[128];
+// The three sums  sum r_i pi_i,  sum r_i C_i,  sum r_i z_i pi_i  are bucket MSMs (vmsm.cuh) over the
+// point array [proofs | commitments] with two verdict slots; comb[seg * 2 + slot] are their 32-window
+// segments.  fsum = sum r_i y_i goes through the fixed-base table of the monomial SRS (point 0 = G).
+// one block: scal[0..7] = plain limbs of sum fy[i], scal[8..511] = 0  (a 64-scalar row for k_msm_fixed)
+static __global__ void __launch_bounds__(128) k_rlc_fsum(const Fr *__restrict__ fy, size_t n, uint32_t *__restrict__ scal) {
     __shared__ uint32_t sf[8 * 128];
     const int tid = threadIdx.x;
-    G1 sums[3];
-    for (int s = 0; s < 3; ++s) {
-        G1 acc = G1::infinity();
-        for (size_t i = tid; i < n; i += 128) g1_add(acc, T[s * n + i]);
-        sm[tid] = acc;
-        __syncthreads();
-        for (int st = 64; st > 0; st >>= 1) {
-            if (tid < st) g1_add_ool(&sm[tid], &sm[tid + st]);
-            __syncthreads();
-        }
-        sums[s] = sm[0];
-        __syncthreads();
-    }
     Fr f = Fr::zero();
-    for (size_t i = tid; i < n; i += 128) f = Fr::add(f, fy[i]);
+    for (size_t i = tid; i < n; i += 128) f = Fr::add(f, ld_fr(fy + i));
     sm_store<128>(sf, tid, f);
     __syncthreads();
     for (int st = 64; st > 0; st >>= 1) {
         if (tid < st) sm_store<128>(sf, tid, Fr::add(sm_load<128>(sf, tid), sm_load<128>(sf, tid + st)));
         __syncthreads();
     }
-    if (tid != 0) return;
-    Fr fsum = fr_from_mont(sm_load<128>(sf, 0));
-    G1 G = G1::from_affine(*g1_gen), yG;
-    g1_mul_scalar(&yG, &G, fsum.v);
-    yG.neg_inplace();
-    G1 A = sums[1];
-    g1_add(A, yG);
-    g1_add(A, sums[2]);                   // sum r^i C_i - [sum r^i y_i]G + sum r^i z_i pi_i
-    G1 B = sums[0];
+    for (int i = tid; i < 512; i += 128) scal[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        Fr fsum = fr_from_mont(sm_load<128>(sf, 0));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) scal[q] = fsum.v[q];
+    }
+}
+// PA[0] = sum r_i C_i - [sum r_i y_i]G + sum r_i z_i pi_i,  PB[0] = -sum r_i pi_i;  the check
+// e(PA, G2) e(PB, [s]G2) == 1 runs in k_pairing_lanes (qa = 0, qb = 1)   (kzg_verify.go:160-193)
+static __global__ void k_rlc_prep(const G1 *__restrict__ comb, const G1 *__restrict__ yG, G1 *__restrict__ PA, G1 *__restrict__ PB) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    G1 A = comb[1];                         // seg 0, slot 1: sum r_i C_i
+    G1 t = *yG; t.neg_inplace();
+    g1_add(A, t);
+    g1_add(A, comb[2]);                     // seg 1, slot 0: k1 half of sum r_i z_i pi_i
+    g1_add(A, g1_phi2(comb[4]));            // seg 2, slot 0: k2 half
+    G1 B = comb[0];                         // seg 0, slot 0: sum r_i pi_i
     B.neg_inplace();
-    PA[0] = A; PB[0] = B;                 // e(A, G2) e(-sum r^i pi_i, [s]G2) == 1
+    PA[0] = A; PB[0] = B;
 }
 
 // ---- EIP-7594 cell batch (kzg_multi/kzg_verify.go:16-105) ---------------------------------------
+// status[i] = status[i] if that is an error, else later[i]
+static __global__ void k_status_merge(int32_t *__restrict__ status, const int32_t *__restrict__ later, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && status[i] == ST_OK) status[i] = later[i];
+}
 // batch_status[group_of[i]] = max(., status[i])  (any error in a batch makes the batch an error)
 static __global__ void k_merge_status(const int32_t *__restrict__ status, const uint32_t *__restrict__ group_of, int32_t *__restrict__ batch_status, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -224,7 +207,7 @@ static __global__ void k_cell_interp_reduce(const Fr *__restrict__ partial, cons
     for (int q = 0; q < 8; ++q) interp[((size_t)b * 64 + j) * 8 + q] = p.v[q];
 }
 // per batch: final combination; PA[b], PB[b] feed k_pairing_lanes (qa = 2, qb = 0).  rows: CSR of the batch's cells grouped by unique commitment.
-static __global__ void __launch_bounds__(32) k_cell_prep(const G1 *__restrict__ S /*sumS[b]*/, const G1 *__restrict__ Wt /*sumW[b]*/, const G1 *__restrict__ interp_commit,
+static __global__ void __launch_bounds__(32) k_cell_prep(const G1 *__restrict__ comb /*[seg][batch]: seg 0 = sum r pi, 1 and 2 = GLV halves of sum r h^64 pi*/, const G1 *__restrict__ interp_commit,
                                                     const G1Aff *__restrict__ uniq_commit, const uint64_t *__restrict__ row_off,
                                                     const uint64_t *__restrict__ batch_row_off, const uint32_t *__restrict__ row_cells,
                                                     const Fr *__restrict__ rpow, const int32_t *__restrict__ batch_status,
@@ -232,7 +215,8 @@ static __global__ void __launch_bounds__(32) k_cell_prep(const G1 *__restrict__ 
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_batches) return;
     if (batch_status[b] != ST_OK) { PA[b] = G1::infinity(); PB[b] = G1::infinity(); return; }
-    G1 sumS = S[b], sumW = Wt[b];
+    G1 sumS = comb[b], sumW = comb[n_batches + b];
+    g1_add(sumW, g1_phi2(comb[2 * n_batches + b]));
     G1 comms = G1::infinity();
     for (uint64_t row = batch_row_off[b]; row < batch_row_off[b + 1]; ++row) {
         Fr wsum = Fr::zero();

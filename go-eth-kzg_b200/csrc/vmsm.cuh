@@ -8,7 +8,10 @@
 // (the bases here are the caller's proofs / commitments, so no table can be precomputed).
 //
 // Shape of the work: a 128-cell verdict needs sum_k r_k P_k (127-bit r_k) and sum_k s_k P_k
-// (255-bit s_k) over the SAME 128 points.  Window w of either scalar is an independent task:
+// (255-bit s_k) over the SAME 128 points.  s_k is split with the curve endomorphism,
+// s = k1 - k2 x^2 (mod r), |k1|, |k2| < 2^127, so that sum s_k P_k = sum k1_k P_k + phi2(sum k2_k P_k)
+// with phi2(x, y) = (beta^2 x, y) = [-x^2](x, y): three 32-window sums, and the final Horner chain
+// over the windows is 124 doublings deep instead of 252.  Window w of a scalar is an independent task:
 // 8 buckets (|digit| = 1..8), one mixed addition per point, then the running-sum reduction
 // sum_j j*B_j (16 full additions).  One thread per (item, window) task; every thread of a block
 // walks the same points, so the point loads are L1 broadcasts, and the 96 digit bytes of a point
@@ -19,10 +22,12 @@
 // each point on its own (4 doublings + 15/16 addition per window) -- and no per-point table.
 #pragma once
 #include "kzg4844.cuh"
+#include "fk20.cuh"      // constants.inc: FP_BETA2
 
 namespace kzg {
 
 #define KZG_VM_BUCKETS 8      // signed base-16 digits in [-8, 8]
+#define KZG_BLS_X_ABS_VM 0xd201000000010000ULL
 
 __device__ __forceinline__ Fr fr_to_mont(const uint32_t *plain) {
     Fr x, r2;
@@ -69,6 +74,48 @@ template <int ND> __device__ __forceinline__ void recode16(int8_t *out, const ui
     }
 }
 
+// GLV split of a plain scalar s < r for lambda = -x^2 (x the BLS parameter, r = x^4 - x^2 + 1):
+// s = rem + q X2 with X2 = x^2, brought into the balanced range with the lattice vectors (X2, -1) and
+// (1, X2 - 1) (1 + (X2 - 1) X2 = r).  Since [X2]P = -phi2(P):  [s]P = [rem]P + phi2([-q]P).
+// Outputs sign-magnitude: k1 = rem, k2 = -q, magnitudes <= X2/2 + 1 < 2^127 as four 32-bit limbs.
+__device__ __forceinline__ void glv_split(const uint32_t *s, uint32_t *k1, bool &k1_neg, uint32_t *k2, bool &k2_neg) {
+    typedef unsigned __int128 u128;
+    const unsigned long long X = KZG_BLS_X_ABS_VM;
+    const u128 X2 = (u128)X * X, half = X2 >> 1;
+    unsigned long long n[4] = {((unsigned long long)s[1] << 32) | s[0], ((unsigned long long)s[3] << 32) | s[2],
+                               ((unsigned long long)s[5] << 32) | s[4], ((unsigned long long)s[7] << 32) | s[6]};
+    unsigned long long q1[4], q2[4];
+    u128 r = 0;
+#pragma unroll
+    for (int i = 3; i >= 0; --i) { r = (r << 64) | n[i]; q1[i] = (unsigned long long)(r / X); r = r % X; }
+    const unsigned long long r1 = (unsigned long long)r;
+    r = 0;
+#pragma unroll
+    for (int i = 3; i >= 0; --i) { r = (r << 64) | q1[i]; q2[i] = (unsigned long long)(r / X); r = r % X; }
+    u128 rem = r * X + r1;                       // < X2
+    u128 q = ((u128)q2[1] << 64) | q2[0];        // <= X2 - 1   (q2[2] = q2[3] = 0 because s < r < X2^2)
+    bool rn = false;
+    if (rem > half) { rn = true; rem = X2 - rem; ++q; }
+    bool qn = false;                             // sign of q itself
+    if (q > half) {
+        // (rem, q) -= (1, X2 - 1)
+        if (q > X2 - 1) q = q - (X2 - 1); else { qn = true; q = (X2 - 1) - q; }
+        if (rn) ++rem; else if (rem == 0) { rn = true; rem = 1; } else --rem;
+    }
+    k1[0] = (uint32_t)rem; k1[1] = (uint32_t)(rem >> 32); k1[2] = (uint32_t)(rem >> 64); k1[3] = (uint32_t)(rem >> 96);
+    k2[0] = (uint32_t)q; k2[1] = (uint32_t)(q >> 32); k2[2] = (uint32_t)(q >> 64); k2[3] = (uint32_t)(q >> 96);
+    k1_neg = rn; k2_neg = !qn;                   // k2 = -q
+}
+// digits of a sign-magnitude 127-bit value
+__device__ __forceinline__ void recode16_signed(int8_t *out, const uint32_t *mag4, bool neg) {
+    recode16<32>(out, mag4);
+    if (neg) {
+        uint32_t *w = reinterpret_cast<uint32_t *>(out);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = __vneg4(w[i]);     // four packed int8 digits at a time
+    }
+}
+
 __device__ __forceinline__ G1 load_g1(const G1 *p) {
     const uint4 *q = reinterpret_cast<const uint4 *>(p);
     uint4 t[12];
@@ -96,10 +143,11 @@ __device__ __forceinline__ void store_g1(G1 *p, const G1 &r) {
 }
 
 // ---- coefficients and digits ------------------------------------------------------------------
-#define KZG_CELL_TW 96        // windows per cell: 32 (r_k, 127 bits) + 64 (r_k h_k^64, 255 bits)
+#define KZG_CELL_TW 96        // windows per point: 32 (r_k, 127 bits) + 2 x 32 (GLV halves of the 255-bit scalar)
+#define KZG_VM_SEGS 3         // ... = three 32-window segments
 // per cell k: r_k = PRF(seed, batch, position in batch); rpow[k] = r_k (Montgomery, for the
-// interpolation and the commitment weights); digits[k][0..31] = r_k, digits[k][32..95] =
-// r_k * h_k^64 with h_k^64 = w_128^brp7(cell index)   (kzg_multi/srs.go:60-103, kzg_verify.go:73-83)
+// interpolation and the commitment weights); digits[k][0..31] = r_k, digits[k][32..63], [64..95] =
+// GLV halves of r_k * h_k^64 with h_k^64 = w_128^brp7(cell index)   (kzg_multi/srs.go:60-103, kzg_verify.go:73-83)
 static __global__ void k_cell_coeff_digits(Fr seed, const uint32_t *__restrict__ batch_of, const uint64_t *__restrict__ batch_start,
                                            const uint64_t *__restrict__ cell_idx, const Fr *__restrict__ roots,
                                            Fr *__restrict__ rpow, int8_t *__restrict__ digits, size_t n) {
@@ -115,7 +163,41 @@ static __global__ void k_cell_coeff_digits(Fr seed, const uint32_t *__restrict__
     if (t) s = fr_mul_ni(rm, ld_fr(roots + 64 * t));
     Fr sp = fr_from_mont(s);
     recode16<32>(digits + k * KZG_CELL_TW, p.v);
-    recode16<64>(digits + k * KZG_CELL_TW + 32, sp.v);
+    uint32_t k1[4], k2[4];
+    bool n1, n2;
+    glv_split(sp.v, k1, n1, k2, n2);
+    recode16_signed(digits + k * KZG_CELL_TW + 32, k1, n1);
+    recode16_signed(digits + k * KZG_CELL_TW + 64, k2, n2);
+}
+
+// EIP-4844 batch, rows 0..n-1 (proofs) and n..2n-1 (commitments) of a [2n][96] digit array, per item i:
+// r_i = PRF(seed, 0, i) (or 1 when unit_coeff: a single item is checked as is, kzg_verify.go:125-127);
+// proofs row: [0..31] = r_i, [32..95] = GLV halves of r_i z_i; commitments row: [0..31] = r_i, rest 0;
+// fy[i] = r_i y_i (Montgomery).  z, y: plain limbs.  Items whose status is not OK get all-zero digits.
+static __global__ void k_rlc_coeff_digits(Fr seed, int unit_coeff, const uint32_t *__restrict__ z, const uint32_t *__restrict__ y,
+                                          const int32_t *__restrict__ status, Fr *__restrict__ fy, int8_t *__restrict__ digits, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr p = Fr::zero();
+    if (unit_coeff) p.v[0] = 1; else prf128(p.v, seed.v, 0, i);
+    if (status[i] != ST_OK) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) p.v[q] = 0;
+    }
+    Fr rm = fr_to_mont(p.v);
+    Fr rz = fr_from_mont(fr_mul_ni(rm, fr_to_mont(z + i * 8)));
+    st_fr(fy + i, fr_mul_ni(rm, fr_to_mont(y + i * 8)));
+    int8_t *dp = digits + i * KZG_CELL_TW, *dc = digits + (n + i) * KZG_CELL_TW;
+    recode16<32>(dp, p.v);
+    recode16<32>(dc, p.v);
+    uint32_t k1[4], k2[4];
+    bool n1, n2;
+    glv_split(rz.v, k1, n1, k2, n2);
+    recode16_signed(dp + 32, k1, n1);
+    recode16_signed(dp + 64, k2, n2);
+    uint4 zero = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int q = 2; q < 6; ++q) reinterpret_cast<uint4 *>(dc)[q] = zero;
 }
 
 // ---- bucket accumulation ------------------------------------------------------------------------
@@ -180,21 +262,32 @@ static __global__ void k_vmsm_item_reduce(const G1 *__restrict__ WS, const uint6
     store_g1(WSb + b * nw + w, acc);
 }
 
-// out[b] = sum_{i < nw} 16^i WSb[b][w0 + i]   (Horner from the top window)
-static __global__ void __launch_bounds__(32) k_vmsm_combine(const G1 *__restrict__ WSb, int TW, int w0, int nw, G1 *__restrict__ out, size_t nb) {
+// out[seg * nb + b] = sum_{i < 32} 16^i WSb[b][32 seg + i]   (Horner from the top window), blockIdx.y = seg
+static __global__ void __launch_bounds__(32) k_vmsm_combine(const G1 *__restrict__ WSb, int TW, G1 *__restrict__ out, size_t nb) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
+    const int seg = blockIdx.y;
     G1 acc = G1::infinity();
 #pragma unroll 1
-    for (int i = nw - 1; i >= 0; --i) {
-        if (i != nw - 1) {
+    for (int i = 31; i >= 0; --i) {
+        if (i != 31) {
 #pragma unroll 1
             for (int q = 0; q < 4; ++q) acc = g1_dbl_cold(acc);
         }
-        G1 t = load_g1(WSb + b * TW + w0 + i);
+        G1 t = load_g1(WSb + b * TW + 32 * seg + i);
         g1_add<MulCall>(acc, t);
     }
-    store_g1(out + b, acc);
+    store_g1(out + (size_t)seg * nb + b, acc);
+}
+
+// phi2(P) = [-x^2]P on XYZZ coordinates
+__device__ __forceinline__ G1 g1_phi2(const G1 &p) {
+    Fp b2;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) b2.v[i] = FP_BETA2[i];
+    G1 r = p;
+    r.X = fp_mul_ni(p.X, b2);
+    return r;
 }
 
 }  // namespace kzg

@@ -86,6 +86,27 @@ def test_synthetic_cell_batches(ctx):
     assert r == [0, 0]
 
 
+def test_cell_batch_larger_than_one_work_item(ctx):
+    """one verdict over 5 blobs x 128 cells (640 cells: more than one 512-cell work item of the bucket MSM and
+    of the interpolation), cells of different blobs interleaved so commitment rows are not contiguous"""
+    blobs = [oracle_lib.rand_blob((80 + b) << 20) for b in range(5)]
+    cms = [c for _, c in ctx.blob_to_kzg_commitment_batch(blobs)]
+    full = ctx.compute_cells_and_kzg_proofs_batch(blobs)
+    commitments, idx, cells, proofs = [], [], [], []
+    for i in range(128):
+        for b, (st, cl, pr) in enumerate(full):
+            commitments.append(cms[b]); idx.append(i); cells.append(cl[2048 * i:2048 * (i + 1)]); proofs.append(pr[48 * i:48 * (i + 1)])
+    n = len(cells)
+    assert ctx.verify_cell_kzg_proof_batches(commitments, idx, cells, proofs, [0, n]) == [0]
+    bad = list(proofs); bad[600] = proofs[601]                       # a valid point, wrong proof, in the second work item
+    assert ctx.verify_cell_kzg_proof_batches(commitments, idx, cells, bad, [0, n]) == [1]
+    # same cells split into two verdicts at an odd boundary; the corrupted proof lands in the second
+    assert ctx.verify_cell_kzg_proof_batches(commitments, idx, cells, bad, [0, 517, n]) == [0, 1]
+    # oracle agrees on the accept case
+    o = oracle_lib.get_oracle()
+    assert o.verify_cell_kzg_proof_batch(commitments[:130], idx[:130], cells[:130], proofs[:130]) == 0
+
+
 def test_subgroup_check_matches_oracle(ctx):
     """random x-coordinates: on-curve points outside G1 must be rejected exactly as the oracle's [r]P test does"""
     import ctypes, random
