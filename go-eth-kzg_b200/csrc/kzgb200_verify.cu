@@ -100,15 +100,16 @@ static int verify_front(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm4
             c->launches += 1;
         }
     }
+    c->mark(KZGB200_KC_DECODE);
     if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_cm, out_cm, d_status, m, 1, 1))) return rc;
     if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_pf, out_pf, d_status, m, 1, 1))) return rc;
     c->launches += 2;
+    c->mark(KZGB200_KC_FR);          // with host blobs: the wait for the side streams' hashing / evaluation
     if (blobs_host) {
         for (size_t p = 0; p < n_pieces; ++p) CU(cudaStreamWaitEvent(c->stream, c->ev_join[p], 0));
         k_status_merge<<<gb, 64, 0, c->stream>>>(d_status, d_blob_status, m);      // commitment / proof errors come first (verify.go:102-119)
         c->launches += 1;
     } else if (blobs) {
-        c->mark(KZGB200_KC_FR);
         k_fiat_shamir<<<(unsigned)((m + 31) / 32), 32, 0, c->stream>>>(blobs, (const uint8_t *)d_cm, zl, m);
         if ((rc = vm_eval_quotient(c, c->stream, 0, blobs, zl, d_status, nullptr, nullptr, yl, m))) return rc;
         c->launches += 1;
@@ -142,6 +143,7 @@ static int verify_independent(kzgb200_ctx *c, const uint8_t *blobs, const uint8_
         c->mark(KZGB200_KC_VERIFY);
         k_verify_single_prep<<<(unsigned)((m + 63) / 64), 64, 0, c->stream>>>((const G1Aff *)c->v_aff1.p, (const G1Aff *)c->v_aff2.p, (const uint32_t *)c->zbuf.p,
                                                                                (const uint32_t *)c->ybuf.p, c->g1_monomial, d_status, (G1 *)c->v_S.p, (G1 *)c->v_W.p, m);
+        c->mark(KZGB200_KC_PAIRING);
         if ((rc = vm_pairing_check(c->stream, c->pairing, (const G1 *)c->v_S.p, 0, (const G1 *)c->v_W.p, 1, d_status, d_status, m))) return rc;   // e(-A, G2) e(pi, [s]G2) == 1
         c->launches += 2;
         c->mark(-1);
@@ -226,12 +228,15 @@ int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *blobs, co
     c->mark(KZGB200_KC_VERIFY);
     if ((rc = vm_rlc_coeff_digits(c->stream, r_dev, n == 1 ? 1 : 0, (const uint32_t *)c->zbuf.p, (const uint32_t *)c->ybuf.p, (const int32_t *)c->status.p,
                                   (Fr *)c->v_fr.p, (int8_t *)c->vm_digits.p, n))) return rc;
+    c->mark(KZGB200_KC_VMSM);
     if ((rc = vm_msm_windows(c->stream, d_pf_aff, (const int8_t *)c->vm_digits.p, KZG_CELL_TW, 0, KZG_CELL_TW, d_is, d_ie, n_items, d_sio, 2,
                              (G1 *)c->vm_scratch.p, (G1 *)c->vm_ws.p, (G1 *)c->vm_wsb.p))) return rc;
     if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_CELL_TW, KZG_VM_SEGS, (G1 *)c->v_S.p, 2))) return rc;
+    c->mark(KZGB200_KC_VERIFY);
     k_rlc_fsum<<<1, 128, 0, c->stream>>>((const Fr *)c->v_fr.p, n, (uint32_t *)c->scalars.p);
     k_msm_fixed<<<dim3(1, 1), 32, 32 * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p);   // [sum r_i y_i] G
     k_rlc_prep<<<1, 32, 0, c->stream>>>((const G1 *)c->v_S.p, (const G1 *)c->sums.p, (G1 *)c->v_pa.p, (G1 *)c->v_pb.p);
+    c->mark(KZGB200_KC_PAIRING);
     if ((rc = vm_pairing_check(c->stream, c->pairing, (const G1 *)c->v_pa.p, 0, (const G1 *)c->v_pb.p, 1, nullptr, (int32_t *)c->v_st2.p, 1))) return rc;
     c->launches += 9;
     c->mark(-1);
@@ -261,7 +266,7 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     if ((rc = c->v_cst.ensure(std::max<size_t>(N, 1) * 4))) return rc;
     if ((rc = c->v_aff2.ensure(std::max<size_t>(N, 1) * sizeof(G1Aff)))) return rc;
     int32_t *d_cst = (int32_t *)c->v_cst.p;
-    c->mark(KZGB200_KC_VERIFY);
+    c->mark(KZGB200_KC_DECODE);
     if ((rc = stage_in(c, proofs48, N * 48, c->in_small, &d_proofs))) return rc;
     CU(cudaMemsetAsync(d_cst, 0, std::max<size_t>(N, 1) * 4, c->stream));
     if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_proofs, (G1Aff *)c->v_aff2.p, d_cst, N, 1, 1))) return rc;
@@ -369,16 +374,18 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     k_cell_interp_reduce<<<(unsigned)nb, 64, 0, c->stream>>>((const Fr *)c->v_partial.p, (const uint64_t *)(M + o_bio), (uint32_t *)c->scalars.p);
     c->mark(KZGB200_KC_MSM);
     k_msm_fixed<<<dim3(1, (unsigned)nb), 32, 32 * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p);
-    c->mark(KZGB200_KC_VERIFY);
+    c->mark(KZGB200_KC_VMSM);
     // v_S[seg][b]: seg 0 = sum_k r_k pi_k, seg 1 + phi2(seg 2) = sum_k r_k h_k^64 pi_k   (kzg_verify.go:32,73-83)
     if ((rc = vm_msm_windows(c->stream, (const G1Aff *)c->v_aff2.p, (const int8_t *)c->vm_digits.p, KZG_CELL_TW, 0, KZG_CELL_TW, (const uint64_t *)(M + o_is),
                              (const uint64_t *)(M + o_ie), n_items, (const uint64_t *)(M + o_bio), nb, (G1 *)c->vm_scratch.p, (G1 *)c->vm_ws.p, (G1 *)c->vm_wsb.p))) return rc;
     if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_CELL_TW, KZG_VM_SEGS, (G1 *)c->v_S.p, nb))) return rc;
+    c->mark(KZGB200_KC_VERIFY);
     if (N) k_merge_status<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(d_cst, (const uint32_t *)(M + o_batch_of), d_bst, N);
     if (U) k_merge_status<<<(unsigned)((U + 127) / 128), 128, 0, c->stream>>>(d_ust, (const uint32_t *)(M + o_rowb), d_bst, U);
     k_cell_prep<<<(unsigned)((nb + 31) / 32), 32, 0, c->stream>>>((const G1 *)c->v_S.p, (const G1 *)c->sums.p, (const G1Aff *)c->v_aff1.p,
                                                                    (const uint64_t *)(M + o_rowoff), (const uint64_t *)(M + o_browoff), (const uint32_t *)(M + o_rowc),
                                                                    (const Fr *)c->v_fr.p, d_bst, (G1 *)c->v_pa.p, (G1 *)c->v_pb.p, nb);
+    c->mark(KZGB200_KC_PAIRING);
     if ((rc = vm_pairing_check(c->stream, c->pairing, (const G1 *)c->v_pa.p, 2, (const G1 *)c->v_pb.p, 0, d_bst, d_res, nb))) return rc;
     c->launches += 10;   // + bucket reduce and item reduce inside vm_msm_windows
     c->mark(-1);

@@ -83,3 +83,72 @@ int vm_eval_quotient(kzgb200_ctx *c, cudaStream_t st, size_t slot, const uint8_t
     CUL(cudaGetLastError());
     return 0;
 }
+
+// ---- unit-test hooks (include/kzgb200_debug.h) -----------------------------------------------------
+namespace kzg {
+static __global__ void k_dbg_glv_digits(const uint32_t *__restrict__ s, int8_t *__restrict__ digits, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k1[4], k2[4];
+    bool n1, n2;
+    glv_split(s + i * 8, k1, n1, k2, n2);
+    recode16_signed(digits + i * 64, k1, n1);
+    recode16_signed(digits + i * 64 + 32, k2, n2);
+}
+// digit rows [n][96] for a plain MSM: windows 0..31 unused (zero), 32..95 = GLV halves of s_i
+static __global__ void k_dbg_vmsm_digits(const uint32_t *__restrict__ s, int8_t *__restrict__ digits, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k1[4], k2[4];
+    bool n1, n2;
+    glv_split(s + i * 8, k1, n1, k2, n2);
+    int8_t *d = digits + (size_t)i * KZG_CELL_TW;
+    for (int q = 0; q < 32; ++q) d[q] = 0;
+    recode16_signed(d + 32, k1, n1);
+    recode16_signed(d + 64, k2, n2);
+}
+static __global__ void k_dbg_vmsm_finish(const uint8_t *__restrict__ p48, G1Aff *__restrict__ pts, int n, const G1 *__restrict__ comb, uint8_t *__restrict__ out48, int phase) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (phase == 0) { if (i < n) g1_decompress(pts[i], p48 + (size_t)i * 48); return; }
+    if (i) return;
+    G1 a = comb[1];
+    g1_add(a, g1_phi2(comb[2]));
+    g1_compress(out48, g1_to_affine(a));
+}
+}  // namespace kzg
+
+extern "C" int kzgb200_dbg_glv_digits(const uint32_t *s, int8_t *digits, int n) {
+    uint32_t *ds; int8_t *dd;
+    CUL(cudaMalloc(&ds, (size_t)n * 32)); CUL(cudaMalloc(&dd, (size_t)n * 64));
+    CUL(cudaMemcpy(ds, s, (size_t)n * 32, cudaMemcpyHostToDevice));
+    k_dbg_glv_digits<<<(n + 63) / 64, 64>>>(ds, dd, n);
+    CUL(cudaGetLastError());
+    CUL(cudaMemcpy(digits, dd, (size_t)n * 64, cudaMemcpyDeviceToHost));
+    cudaFree(ds); cudaFree(dd);
+    return 0;
+}
+
+extern "C" int kzgb200_dbg_vmsm(kzgb200_ctx *c, const uint8_t *p48, const uint32_t *s, int n, uint8_t *out48) {
+    if (!c || n <= 0) return set_err(KZGB200_ERR_ARGS, "bad argument");
+    CUL(cudaSetDevice(c->device));
+    const size_t n_items = ((size_t)n + 127) / 128;
+    std::vector<uint64_t> is(n_items), ie(n_items), off = {0, n_items};
+    for (size_t k = 0; k < n_items; ++k) { is[k] = k * 128; ie[k] = std::min<uint64_t>(n, k * 128 + 128); }
+    uint8_t *dp, *dout; uint32_t *ds; int8_t *dd; G1Aff *pts; G1 *scratch, *ws, *wsb, *comb; uint64_t *meta;
+    CUL(cudaMalloc(&dp, (size_t)n * 48)); CUL(cudaMalloc(&ds, (size_t)n * 32)); CUL(cudaMalloc(&dd, (size_t)n * KZG_CELL_TW)); CUL(cudaMalloc(&pts, (size_t)n * sizeof(G1Aff)));
+    CUL(cudaMalloc(&scratch, vm_scratch_bytes(n_items, KZG_CELL_TW))); CUL(cudaMalloc(&ws, n_items * KZG_CELL_TW * sizeof(G1)));
+    CUL(cudaMalloc(&wsb, KZG_CELL_TW * sizeof(G1))); CUL(cudaMalloc(&comb, KZG_VM_SEGS * sizeof(G1))); CUL(cudaMalloc(&meta, (2 * n_items + 2) * 8)); CUL(cudaMalloc(&dout, 48));
+    CUL(cudaMemcpy(dp, p48, (size_t)n * 48, cudaMemcpyHostToDevice)); CUL(cudaMemcpy(ds, s, (size_t)n * 32, cudaMemcpyHostToDevice));
+    CUL(cudaMemcpy(meta, is.data(), n_items * 8, cudaMemcpyHostToDevice)); CUL(cudaMemcpy(meta + n_items, ie.data(), n_items * 8, cudaMemcpyHostToDevice));
+    CUL(cudaMemcpy(meta + 2 * n_items, off.data(), 16, cudaMemcpyHostToDevice));
+    k_dbg_vmsm_finish<<<(n + 63) / 64, 64>>>(dp, pts, n, nullptr, nullptr, 0);
+    k_dbg_vmsm_digits<<<(n + 63) / 64, 64>>>(ds, dd, n);
+    int rc = vm_msm_windows(nullptr, pts, dd, KZG_CELL_TW, 0, KZG_CELL_TW, meta, meta + n_items, n_items, meta + 2 * n_items, 1, scratch, ws, wsb);
+    if (!rc) rc = vm_combine(nullptr, wsb, KZG_CELL_TW, KZG_VM_SEGS, comb, 1);
+    if (rc) return rc;
+    k_dbg_vmsm_finish<<<1, 32>>>(nullptr, nullptr, 0, comb, dout, 1);
+    CUL(cudaGetLastError());
+    CUL(cudaMemcpy(out48, dout, 48, cudaMemcpyDeviceToHost));
+    cudaFree(dp); cudaFree(ds); cudaFree(dd); cudaFree(pts); cudaFree(scratch); cudaFree(ws); cudaFree(wsb); cudaFree(comb); cudaFree(meta); cudaFree(dout);
+    return 0;
+}

@@ -125,7 +125,7 @@ class Context:
     def last_device_ms(self):
         return self.L.kzgb200_last_device_ms(self.ctx)
 
-    KERNEL_CLASSES = ["fr", "msm", "g1fft", "finalize", "verify"]
+    KERNEL_CLASSES = ["fr", "msm", "g1fft", "finalize", "verify", "decode", "vmsm", "pairing"]
 
     def last_kernel_ms(self):
         arr = (ctypes.c_double * 8)()
@@ -356,6 +356,23 @@ class Debug:
         if rc:
             raise KzgError(rc, self.L.kzgb200_last_error().decode())
         return [out.raw[48 * i:48 * i + 48] for i in range(n)]
+
+    def glv_digits(self, scalars):
+        """[(k1_digits[32], k2_digits[32])] of the verifiers' GLV split + signed base-16 recoding"""
+        n = len(scalars)
+        out = (ctypes.c_int8 * (64 * n))()
+        rc = self.L.kzgb200_dbg_glv_digits(self._limbs(scalars, 8), out, n)
+        if rc:
+            raise KzgError(rc, self.L.kzgb200_last_error().decode())
+        return [(list(out[64 * i:64 * i + 32]), list(out[64 * i + 32:64 * i + 64])) for i in range(n)]
+
+    def vmsm(self, ctx, points48, scalars):
+        """sum [s_i] P_i through the verifiers' bucket MSM kernels -> compressed point"""
+        out = ctypes.create_string_buffer(48)
+        rc = self.L.kzgb200_dbg_vmsm(ctx.ctx, b"".join(points48), self._limbs(scalars, 8), len(scalars), out)
+        if rc:
+            raise KzgError(rc, self.L.kzgb200_last_error().decode())
+        return out.raw
 
     def imad_peak(self, device=0, mode=0):
         """instructions*lanes per second for mad.lo (0), mad.hi (1), mad.wide (2)"""

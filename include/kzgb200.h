@@ -145,7 +145,10 @@ enum kzgb200_kernel_class {
     KZGB200_KC_MSM = 1,       /* k_msm_fixed (fixed-base digit-table MSM) */
     KZGB200_KC_G1FFT = 2,     /* G1 FFT-128 pair of the FK20 pipeline */
     KZGB200_KC_FINALIZE = 3,  /* to-affine + compression */
-    KZGB200_KC_VERIFY = 4,    /* decompression, subgroup checks, pairing */
+    KZGB200_KC_VERIFY = 4,    /* verifier glue: coefficient / digit preparation, status merging, final combinations */
+    KZGB200_KC_DECODE = 5,    /* k_g1_check: G1 decompression (sqrt) + subgroup check */
+    KZGB200_KC_VMSM = 6,      /* variable-base bucket MSMs of the RLC verifiers (k_vmsm_*) */
+    KZGB200_KC_PAIRING = 7,   /* k_pairing_lanes */
     KZGB200_N_KERNEL_CLASSES = 8
 };
 int kzgb200_last_kernel_ms(kzgb200_ctx *ctx, double out[KZGB200_N_KERNEL_CLASSES]);

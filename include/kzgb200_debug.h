@@ -20,6 +20,12 @@ struct kzgb200_ctx;
 int kzgb200_dbg_pairing(struct kzgb200_ctx *ctx, const uint8_t *a48, const int *qa, const uint8_t *b48, const int *qb, int *out, int n);
 /* gamma[1], lines[0].A[0], lines[0].B[0], lines[0].A[67] as 4 x (c0,c1) x 12 plain limbs */
 int kzgb200_dbg_dump_pairing(struct kzgb200_ctx *ctx, uint32_t *out96);
+/* GLV split + signed base-16 recoding used by the verifiers' bucket MSMs: for n plain scalars s < r (8 limbs each)
+ * writes 64 digits per scalar, digits[0..31] of k1 and [32..63] of k2 with s = k1 - k2 x^2 (mod r), each in [-8, 8] */
+int kzgb200_dbg_glv_digits(const uint32_t *s, int8_t *digits, int n);
+/* the verifiers' variable-base bucket MSM on its own: out48 = sum_i [s_i] P_i for n compressed points and n plain
+ * 255-bit scalars (one verdict, work items of 128 points), through k_vmsm_buckets / reduce / combine */
+int kzgb200_dbg_vmsm(struct kzgb200_ctx *ctx, const uint8_t *p48, const uint32_t *s, int n, uint8_t *out48);
 /* dependency-free integer multiply-add microbenchmark: device-wide instructions*lanes per second.
  * mode 0: mad.lo.u32 (IMAD), 1: mad.hi.u32 (IMAD.HI), 2: mad.wide.u32 (IMAD.WIDE, 32x32+64) */
 int kzgb200_bench_imad(int device, int mode, double *per_s, double *ms_out);
