@@ -146,7 +146,7 @@ CANONICAL_W.update({"blob_proof": 560e6, "verify_blob_batch": 8.2e6, "recover": 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (default: 5; 25 / 10 for the short verifier steps so the clock sampler sees the timed region)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="cells_proofs", choices=sorted(METRIC))
@@ -156,6 +156,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.steps <= 0:
+        args.steps = {"verify_blob_batch": 25, "verify_cells": 10}.get(args.workload, 5)
     if args.impl == "reference":
         if args.workload not in ("commit", "cells_proofs"):
             print(json.dumps({"impl": "reference", "unavailable": "reference arm implemented for commit and cells_proofs only"}))
@@ -174,6 +176,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line (NCCL_DEBUG=VERSION would add one)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():

@@ -127,6 +127,7 @@ static inline bool is_device_ptr(const void *p) {
 
 // stage a (possibly host) input buffer on the device
 static inline int stage_in(kzgb200_ctx *c, const void *user, size_t bytes, DevBuf &buf, const void **dev) {
+    if (bytes == 0) { *dev = buf.p; return 0; }          // empty input: user may be null
     if (is_device_ptr(user)) { *dev = user; return 0; }
     int rc = buf.ensure(bytes);
     if (rc) return rc;

@@ -84,6 +84,9 @@ def test_synthetic_cell_batches(ctx):
     r = ctx.verify_cell_kzg_proof_batches([commitments[i] for i in sub], [idx[i] for i in sub], [cells[i] for i in sub],
                                           [proofs[i] for i in sub], [0, 0, len(sub)])
     assert r == [0, 0]
+    # nothing at all: one empty verdict (api_eip7594.go:173-175: an empty batch verifies), and no verdicts
+    assert ctx.verify_cell_kzg_proof_batches([], [], [], [], [0, 0]) == [0]
+    assert ctx.verify_cell_kzg_proof_batches([], [], [], [], [0]) == []
 
 
 def test_cell_batch_larger_than_one_work_item(ctx):
