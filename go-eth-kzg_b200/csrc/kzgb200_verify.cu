@@ -46,9 +46,10 @@ static const size_t VERIFY_CHUNK = 4096;
 // shared front end: decode commitments/proofs, obtain z and y (given, or Fiat-Shamir + evaluation)
 //   blobs == nullptr: z32/y32 given (VerifyKZGProof); else z = challenge, y = p(z)
 // writes: out_cm = commitments, out_pf = proofs (affine), zl = z limbs, yl = y limbs, d_status filled.
-// Host blobs travel in pieces on the copy stream; each piece is hashed and evaluated on a side stream of its
-// own as soon as it has landed (the SHA-256 of a blob is one thread's 2050 sequential compressions, so pieces
-// queued on ONE stream would serialise that latency), while the point decoding runs on the main stream.
+// The hashing + evaluation of the blobs runs on side streams while the main stream decodes the points
+// (the SHA-256 of a blob is one thread's 2050 sequential compressions: latency, not throughput).  Host blobs
+// travel in pieces on the copy stream and each piece gets a side stream of its own as soon as it has landed
+// (pieces queued on ONE stream would serialise that latency); device blobs are one piece.
 #define VERIFY_MAX_PIECES (KZG_G1FFT_MAX_SPLIT - 1)
 static int verify_front(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm48, const uint8_t *z32, const uint8_t *y32, const uint8_t *pf48,
                         size_t m, int32_t *d_status, G1Aff *out_cm, G1Aff *out_pf, uint32_t *zl, uint32_t *yl) {
@@ -57,8 +58,8 @@ static int verify_front(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm4
     if ((rc = stage_in(c, cm48, m * 48, c->in_small, &d_cm))) return rc;
     if ((rc = stage_in(c, pf48, m * 48, c->in_small2, &d_pf))) return rc;
     const bool blobs_host = blobs && !is_device_ptr(blobs);
-    const size_t piece = ((m + VERIFY_MAX_PIECES - 1) / VERIFY_MAX_PIECES + 31) & ~(size_t)31;
-    const size_t n_pieces = blobs_host ? (m + piece - 1) / piece : 0;
+    const size_t piece = blobs_host ? ((m + VERIFY_MAX_PIECES - 1) / VERIFY_MAX_PIECES + 31) & ~(size_t)31 : m;
+    const size_t n_pieces = blobs ? (m + piece - 1) / piece : 0;
     if (blobs_host) {
         if ((rc = c->in_bytes.ensure(m * KZGB200_BYTES_PER_BLOB))) return rc;
         for (size_t p = 0; p < n_pieces; ++p) {
@@ -80,20 +81,21 @@ static int verify_front(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm4
         k_scalars_from_be<<<gb, 64, 0, c->stream>>>((const uint8_t *)d_z, zl, d_status, m);
         c->launches += 2;
     }
-    if (blobs) { if ((rc = vm_eval_scratch(c, m))) return rc; }
     int32_t *d_blob_status = nullptr;      // the side streams report into their own array: merged below in the reference's order
-    if (blobs_host) {
+    if (blobs) {
+        if ((rc = vm_eval_scratch(c, m))) return rc;
         if ((rc = c->v_st3.ensure(m * sizeof(int32_t)))) return rc;
         d_blob_status = (int32_t *)c->v_st3.p;
         CU(cudaMemsetAsync(d_blob_status, 0, m * sizeof(int32_t), c->stream));
         // side streams start once the commitments are on the device and the status array is cleared
         CU(cudaEventRecord(c->ev_fork, c->stream));
+        const uint8_t *d_blobs = blobs_host ? (const uint8_t *)c->in_bytes.p : blobs;
         for (size_t p = 0; p < n_pieces; ++p) {
             size_t po = p * piece, pm = std::min(piece, m - po);
             cudaStream_t sp = c->fft_streams[p];
             CU(cudaStreamWaitEvent(sp, c->ev_fork, 0));
-            CU(cudaStreamWaitEvent(sp, c->ev_piece[p], 0));
-            const uint8_t *pb = (const uint8_t *)c->in_bytes.p + po * KZGB200_BYTES_PER_BLOB;
+            if (blobs_host) CU(cudaStreamWaitEvent(sp, c->ev_piece[p], 0));
+            const uint8_t *pb = d_blobs + po * KZGB200_BYTES_PER_BLOB;
             k_fiat_shamir<<<(unsigned)((pm + 31) / 32), 32, 0, sp>>>(pb, (const uint8_t *)d_cm + po * 48, zl + po * 8, pm);
             if ((rc = vm_eval_quotient(c, sp, po, pb, zl + po * 8, d_blob_status + po, nullptr, nullptr, yl + po * 8, pm))) return rc;
             CU(cudaEventRecord(c->ev_join[p], sp));
@@ -104,14 +106,10 @@ static int verify_front(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm4
     if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_cm, out_cm, d_status, m, 1, 1))) return rc;
     if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_pf, out_pf, d_status, m, 1, 1))) return rc;
     c->launches += 2;
-    c->mark(KZGB200_KC_FR);          // with host blobs: the wait for the side streams' hashing / evaluation
-    if (blobs_host) {
+    c->mark(KZGB200_KC_FR);          // what is left of the side streams' hashing / evaluation after the decode
+    if (blobs) {
         for (size_t p = 0; p < n_pieces; ++p) CU(cudaStreamWaitEvent(c->stream, c->ev_join[p], 0));
         k_status_merge<<<gb, 64, 0, c->stream>>>(d_status, d_blob_status, m);      // commitment / proof errors come first (verify.go:102-119)
-        c->launches += 1;
-    } else if (blobs) {
-        k_fiat_shamir<<<(unsigned)((m + 31) / 32), 32, 0, c->stream>>>(blobs, (const uint8_t *)d_cm, zl, m);
-        if ((rc = vm_eval_quotient(c, c->stream, 0, blobs, zl, d_status, nullptr, nullptr, yl, m))) return rc;
         c->launches += 1;
     }
     return 0;
