@@ -248,11 +248,15 @@ static __device__ __noinline__ void miller2(Fp12 *f, const G1Aff *P0, const G2Li
 }
 
 // ---- context init: G2 decompression + line precomputation (one thread per fixed G2 point) --------
-static __device__ __noinline__ bool fp_sqrt_checked(Fp *out, Fp a) {
-    Fp s = fp_pow(a, FP_P1D4, 12);
-    if (!Fp::eq(fp_sqr_ni(s), a)) return false;
-    *out = s;
-    return true;
+// Square roots return VALUES (result + flag): see DESIGN.md section 7 on pointers to registers across
+// out-of-line calls.
+struct FpOpt { Fp v; bool ok; };
+struct Fp2Opt { Fp2 v; bool ok; };
+static __device__ __noinline__ FpOpt fp_sqrt_checked(Fp a) {
+    FpOpt r;
+    r.v = fp_pow(a, FP_P1D4, 12);
+    r.ok = Fp::eq(fp_sqr_ni(r.v), a);
+    return r;
 }
 __device__ __forceinline__ bool fp_lex_largest(const Fp &a) {
     Fp o1 = Fp::zero(); o1.v[0] = 1;
@@ -260,29 +264,31 @@ __device__ __forceinline__ bool fp_lex_largest(const Fp &a) {
     return !Fp::geq_limbs(FP_HALF, p.v);
 }
 // sqrt in Fp2 by the norm method (result verified by squaring)
-static __device__ __noinline__ bool fp2_sqrt(Fp2 *out, const Fp2 *pa) {
-    Fp2 a = *pa;
-    if (fp2_is_zero(a)) { *out = a; return true; }
+static __device__ __noinline__ Fp2Opt fp2_sqrt(Fp2 a) {
+    Fp2Opt out; out.v = a; out.ok = true;
+    if (fp2_is_zero(a)) return out;
+    out.ok = false;
     Fp two = Fp::dbl(Fp::one());
     Fp inv2 = fp_inv(two);
-    Fp s;
     if (a.c1.is_zero()) {
-        if (fp_sqrt_checked(&s, a.c0)) { out->c0 = s; out->c1 = Fp::zero(); return true; }
-        if (fp_sqrt_checked(&s, Fp::neg(a.c0))) { out->c0 = Fp::zero(); out->c1 = s; return true; }
-        return false;
+        FpOpt s = fp_sqrt_checked(a.c0);
+        if (s.ok) { out.v.c0 = s.v; out.v.c1 = Fp::zero(); out.ok = true; return out; }
+        s = fp_sqrt_checked(Fp::neg(a.c0));
+        if (s.ok) { out.v.c0 = Fp::zero(); out.v.c1 = s.v; out.ok = true; }
+        return out;
     }
     Fp n = Fp::add(fp_sqr_ni(a.c0), fp_sqr_ni(a.c1));
-    if (!fp_sqrt_checked(&s, n)) return false;
-    Fp d = fp_mul_ni(Fp::add(a.c0, s), inv2), x0;
-    if (!fp_sqrt_checked(&x0, d)) {
-        d = fp_mul_ni(Fp::sub(a.c0, s), inv2);
-        if (!fp_sqrt_checked(&x0, d)) return false;
+    FpOpt s = fp_sqrt_checked(n);
+    if (!s.ok) return out;
+    FpOpt x0 = fp_sqrt_checked(fp_mul_ni(Fp::add(a.c0, s.v), inv2));
+    if (!x0.ok) {
+        x0 = fp_sqrt_checked(fp_mul_ni(Fp::sub(a.c0, s.v), inv2));
+        if (!x0.ok) return out;
     }
-    Fp x1 = fp_mul_ni(a.c1, fp_inv(Fp::dbl(x0)));
-    Fp2 r; r.c0 = x0; r.c1 = x1;
-    if (!fp2_eq(fp2_sqr(r), a)) return false;
-    *out = r;
-    return true;
+    Fp2 r; r.c0 = x0.v; r.c1 = fp_mul_ni(a.c1, fp_inv(Fp::dbl(x0.v)));
+    if (!fp2_eq(fp2_sqr(r), a)) return out;
+    out.v = r; out.ok = true;
+    return out;
 }
 __device__ __forceinline__ Fp fp_from_be48(const uint8_t *p, bool mask_flags, bool *ok) {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(p);
@@ -324,8 +330,9 @@ static __global__ void k_g2_prepare(const uint8_t *__restrict__ in96, PairingCon
     if (!ok) { atomicMax(bad, (int32_t)ST_BAD_G1_ENCODING); return; }
     Fp four = Fp::dbl(Fp::dbl(Fp::one()));
     Fp2 b2; b2.c0 = four; b2.c1 = four;
-    Fp2 y2 = fp2_add(fp2_mul(fp2_sqr(x), x), b2), y;
-    if (!fp2_sqrt(&y, &y2)) { atomicMax(bad, (int32_t)ST_NOT_ON_CURVE); return; }
+    Fp2Opt ys = fp2_sqrt(fp2_add(fp2_mul(fp2_sqr(x), x), b2));
+    if (!ys.ok) { atomicMax(bad, (int32_t)ST_NOT_ON_CURVE); return; }
+    Fp2 y = ys.v;
     bool largest = y.c1.is_zero() ? fp_lex_largest(y.c0) : fp_lex_largest(y.c1);
     if (largest != (m == 5)) y = fp2_neg(y);
     // affine Miller-loop walk over Q, recording the line coefficients

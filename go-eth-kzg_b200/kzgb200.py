@@ -52,6 +52,7 @@ EXPORTS = [
     "kzgb200_compute_kzg_proof", "kzgb200_compute_blob_kzg_proof", "kzgb200_recover_cells_and_kzg_proofs",
     "kzgb200_verify_kzg_proof", "kzgb200_verify_blob_kzg_proof", "kzgb200_verify_blob_kzg_proof_batch",
     "kzgb200_verify_cell_kzg_proof_batch",
+    "kzgb200_parse_trusted_setup_json", "kzgb200_ctx_new_from_json", "kzgb200_check_trusted_setup",
 ]
 
 
@@ -79,6 +80,29 @@ def load_trusted_setup(path=SETUP):
     return raw[:n], raw[n:2 * n], raw[2 * n:]
 
 
+def parse_trusted_setup_json(text):
+    """JSONTrustedSetup text (trusted_setup.go:23-27) -> (g1_monomial, g1_lagrange, g2_monomial) flat bytes; host only"""
+    L = load_library()
+    raw = text.encode() if isinstance(text, str) else bytes(text)
+    m = ctypes.create_string_buffer(4096 * 48); l = ctypes.create_string_buffer(4096 * 48); g2 = ctypes.create_string_buffer(4096 * 96)
+    n = ctypes.c_size_t()
+    rc = L.kzgb200_parse_trusted_setup_json(raw, ctypes.c_size_t(len(raw)), m, l, g2, ctypes.c_size_t(4096), ctypes.byref(n))
+    if rc != OK:
+        raise KzgError(rc, L.kzgb200_last_error().decode())
+    return m.raw, l.raw, g2.raw[:96 * n.value]
+
+
+def check_trusted_setup(g1_lagrange, g1_monomial, g2_monomial, device=0):
+    """CheckTrustedSetupIsWellFormed (trusted_setup.go:45-83) on the GPU -> (status, index of the first bad point)"""
+    L = load_library()
+    res = ctypes.c_int32(); bad = ctypes.c_size_t()
+    rc = L.kzgb200_check_trusted_setup(device, g1_lagrange, ctypes.c_size_t(len(g1_lagrange) // 48), g1_monomial, ctypes.c_size_t(len(g1_monomial) // 48),
+                                       g2_monomial, ctypes.c_size_t(len(g2_monomial) // 96), ctypes.byref(res), ctypes.byref(bad))
+    if rc != OK:
+        raise KzgError(rc, L.kzgb200_last_error().decode())
+    return res.value, bad.value
+
+
 def _ptr(x):
     """bytes / ctypes buffer / int address -> c_void_p"""
     if isinstance(x, int):
@@ -91,13 +115,18 @@ def _ptr(x):
 class Context:
     """Mirror of goethkzg.Context.  NewContext4096Secure (api.go:53) == Context()."""
 
-    def __init__(self, device=0, commit_window=0, fk20_window=0, setup_path=SETUP):
+    def __init__(self, device=0, commit_window=0, fk20_window=0, setup_path=SETUP, setup_json=None):
+        """setup_json: text of a JSONTrustedSetup (NewContext4096(&parsed), api.go:90); default: the packed mainnet setup"""
         L = load_library()
         self.L = L
-        m, l, g2 = load_trusted_setup(setup_path)
         opts = Opts(device=device, commit_window=commit_window, fk20_window=fk20_window)
         ctx = ctypes.c_void_p()
-        rc = L.kzgb200_ctx_new(m, l, g2, ctypes.c_size_t(len(g2) // 96), ctypes.byref(opts), ctypes.byref(ctx))
+        if setup_json is not None:
+            raw = setup_json.encode() if isinstance(setup_json, str) else bytes(setup_json)
+            rc = L.kzgb200_ctx_new_from_json(raw, ctypes.c_size_t(len(raw)), ctypes.byref(opts), ctypes.byref(ctx))
+        else:
+            m, l, g2 = load_trusted_setup(setup_path)
+            rc = L.kzgb200_ctx_new(m, l, g2, ctypes.c_size_t(len(g2) // 96), ctypes.byref(opts), ctypes.byref(ctx))
         if rc != OK:
             raise KzgError(rc, L.kzgb200_last_error().decode())
         self.ctx = ctx

@@ -74,6 +74,20 @@ typedef struct kzgb200_opts {
 int kzgb200_ctx_new(const uint8_t *g1_monomial, const uint8_t *g1_lagrange, const uint8_t *g2_monomial,
                     size_t n_g2, const kzgb200_opts *opts, kzgb200_ctx **out);
 void kzgb200_ctx_free(kzgb200_ctx *ctx);
+
+/* Trusted-setup ingestion.
+ * kzgb200_parse_trusted_setup_json: the reference's JSONTrustedSetup text (trusted_setup.go:23-27: keys g1_monomial,
+ *   g1_lagrange, g2_monomial; hex strings with optional 0x prefix) -> flat 48/96-byte records in ceremony order.
+ *   g1 buffers: 4096*48 bytes each; g2_monomial: g2_capacity*96 bytes, *n_g2 receives the count.  Host only.
+ * kzgb200_ctx_new_from_json: NewContext4096 (api.go:90-149) on that text.
+ * kzgb200_check_trusted_setup: CheckTrustedSetupIsWellFormed (trusted_setup.go:45-83) as batched kernels: every
+ *   Lagrange G1, monomial G1 and G2 point must decode and lie in the prime-order subgroup.  *result = OK or the
+ *   status of the first failing point in that order; *bad_index (optional) = its index in the concatenation. */
+int kzgb200_parse_trusted_setup_json(const char *json, size_t len, uint8_t *g1_monomial, uint8_t *g1_lagrange,
+                                     uint8_t *g2_monomial, size_t g2_capacity, size_t *n_g2);
+int kzgb200_ctx_new_from_json(const char *json, size_t len, const kzgb200_opts *opts, kzgb200_ctx **out);
+int kzgb200_check_trusted_setup(int device, const uint8_t *g1_lagrange, size_t n_lagrange, const uint8_t *g1_monomial, size_t n_monomial,
+                                const uint8_t *g2_monomial, size_t n_g2, int32_t *result, size_t *bad_index);
 const char *kzgb200_last_error(void);
 
 /* pinned host memory for zero-staging H2D/D2H */

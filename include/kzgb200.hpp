@@ -50,6 +50,11 @@ public:
         int rc = kzgb200_ctx_new(g1_monomial, g1_lagrange, g2_monomial, n_g2, opts, &h_);
         if (rc != KZGB200_OK) throw std::runtime_error(std::string("kzgb200_ctx_new: ") + kzgb200_last_error());
     }
+    // NewContext4096 on the text of a JSONTrustedSetup (trusted_setup.go:23-27, api.go:90)
+    explicit Context(const std::string &setup_json, const kzgb200_opts *opts = nullptr) {
+        int rc = kzgb200_ctx_new_from_json(setup_json.data(), setup_json.size(), opts, &h_);
+        if (rc != KZGB200_OK) throw std::runtime_error(std::string("kzgb200_ctx_new_from_json: ") + kzgb200_last_error());
+    }
     ~Context() { kzgb200_ctx_free(h_); }
     Context(const Context &) = delete;
     Context &operator=(const Context &) = delete;

@@ -26,6 +26,10 @@ int kzgb200_dbg_glv_digits(const uint32_t *s, int8_t *digits, int n);
 /* the verifiers' variable-base bucket MSM on its own: out48 = sum_i [s_i] P_i for n compressed points and n plain
  * 255-bit scalars (one verdict, work items of 128 points), through k_vmsm_buckets / reduce / combine */
 int kzgb200_dbg_vmsm(struct kzgb200_ctx *ctx, const uint8_t *p48, const uint32_t *s, int n, uint8_t *out48);
+/* self-consistency of the device G2 code on one compressed point: bit 0 decodes, 1 on the twist, 2 2Q on the twist,
+ * 3 3Q on the twist, 4 2(2Q) == 3Q + Q, 5 Q + Q (addition's doubling branch) == 2Q, 6 Q + (-Q) == O,
+ * 7 g2_in_subgroup(Q), 8 [r]Q == O by a ladder written out in the test kernel (7 and 8 must agree) */
+int kzgb200_dbg_g2_selftest(const uint8_t *in96, int *mask);
 /* dependency-free integer multiply-add microbenchmark: device-wide instructions*lanes per second.
  * mode 0: mad.lo.u32 (IMAD), 1: mad.hi.u32 (IMAD.HI), 2: mad.wide.u32 (IMAD.WIDE, 32x32+64) */
 int kzgb200_bench_imad(int device, int mode, double *per_s, double *ms_out);

@@ -665,6 +665,21 @@ int ko_g1_decompress(const uint8_t *in48, uint8_t *xy96, int subgroup_check) {
     a.x.to_bytes_be(xy96); a.y.to_bytes_be(xy96 + 48);
     return 0;
 }
+// G2Affine.SetBytes semantics (gnark-crypto, as used by trusted_setup.go:45-83): decode and, if asked, test [r]Q == O
+int ko_g2_decompress(const uint8_t *in96, int subgroup_check) {
+    init_all();
+    if ((in96[0] >> 5) == 6) {          // infinity: every other bit must be clear
+        if (in96[0] & 0x1f) return DEC_BAD_ENCODING;
+        for (int i = 1; i < 96; ++i) if (in96[i]) return DEC_BAD_ENCODING;
+        return DEC_OK;
+    }
+    G2Affine q; int st = g2_decompress(q, in96);
+    if (st) return st;
+    if (subgroup_check) {
+        if (!G2Jac::from_affine(q).mul(FR_MOD, 4).is_inf()) return DEC_NOT_IN_SUBGROUP;      // the definition, as g1_in_subgroup
+    }
+    return DEC_OK;
+}
 // sum_i scalars[i] * points[i]  (compressed points in, compressed point out, BE scalars)
 int ko_g1_msm(const uint8_t *points48, const uint8_t *scalars32, size_t n, uint8_t *out48) {
     init_all();
