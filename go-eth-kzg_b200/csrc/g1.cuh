@@ -9,6 +9,7 @@
 // Cost in Fp multiplications (mul == sqr here): mixed add 10, full add 14, double 9.
 #pragma once
 #include "field.cuh"
+#include "bingcd.cuh"
 
 namespace kzg {
 
@@ -227,7 +228,16 @@ __device__ __constant__ const uint32_t FP_PM2[12] = {0xffffaaa9u, 0xb9feffffu, 0
 // (p+1)/4, for square roots (p = 3 mod 4)
 __device__ __constant__ const uint32_t FP_P1D4[12] = {0xffffeaabu, 0xee7fbfffu, 0xac54ffffu, 0x07aaffffu, 0x3dac3d89u, 0xd9cc34a8u,
                                                       0x3ce144afu, 0xd91dd2e1u, 0x90d2eb35u, 0x92c6e9edu, 0x8e5ff9a6u, 0x0680447au};
-__device__ __forceinline__ Fp fp_inv(const Fp &a) { return fp_pow(a, FP_PM2, 12); }
+// a^-1 (0 -> 0) by the binary GCD of bingcd.cuh: the Montgomery operand aR is inverted as a plain integer,
+// (aR)^-1 = a^-1 R^-1, and one product with R^3 brings it back to a^-1 R.  ~6x fewer instructions than the
+// Fermat chain fp_pow(a, p-2), most of them on the ALU pipe.
+static __device__ __noinline__ Fp fp_inv(Fp a) {
+    Fp t, r3;
+    BinGcd<12>::inverse(t.v, a.v, FP_MOD, FpParams::inv() & 0x7fffffffu);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) r3.v[i] = FP_R3[i];
+    return fp_mul_ni(t, r3);
+}
 
 // XYZZ -> affine (one inversion).  x = X * ZZ^2 / ZZZ^2,  y = Y / ZZZ.
 __device__ __forceinline__ G1Aff g1_to_affine(const G1 &p) {

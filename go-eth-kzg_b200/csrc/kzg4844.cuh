@@ -121,19 +121,13 @@ static __global__ void k_scalars_from_be(const uint8_t *__restrict__ in, uint32_
     for (int k = 0; k < 8; ++k) out[i * 8 + k] = l[k];
 }
 
-// a^-1 in Fr by Fermat (a != 0)
-__device__ __constant__ const uint32_t FR_RM2[8] = {0xffffffffu, 0xfffffffeu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+// a^-1 in Fr (0 -> 0), binary GCD as fp_inv
 static __device__ __noinline__ Fr fr_inv(Fr a) {
-    Fr r = Fr::one();
-    bool started = false;
-#pragma unroll 1
-    for (int i = 254; i >= 0; --i) {
-        if (started) r = fr_sqr_ni(r);
-        if ((FR_RM2[i >> 5] >> (i & 31)) & 1) {
-            if (started) r = fr_mul_ni(r, a); else { r = a; started = true; }
-        }
-    }
-    return r;
+    Fr t, r3;
+    BinGcd<8>::inverse(t.v, a.v, FR_MOD, FrParams::inv() & 0x7fffffffu);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r3.v[i] = FR_R3[i];
+    return fr_mul_ni(t, r3);
 }
 
 __device__ __forceinline__ Fr fr_to_mont_limbs(const uint32_t *plain) {
