@@ -67,6 +67,17 @@ static bool skip_value(Cursor &c) {      // unknown keys: skip a string / array 
 }
 }  // namespace
 
+namespace kzg {
+// canonical check only: status[i / per_item] = NON_CANONICAL if scalar i >= r
+static __global__ void k_blob_to_scalars_any(const uint8_t *__restrict__ in, int32_t *__restrict__ status, size_t n_scalars, size_t per_item) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_scalars) return;
+    uint32_t l[8];
+    load_be32(l, in + i * 32);
+    if (!fr_is_canonical(l)) atomicMax(&status[i / per_item], (int32_t)ST_NON_CANONICAL_SCALAR);
+}
+}  // namespace kzg
+
 extern "C" int kzgb200_parse_trusted_setup_json(const char *json, size_t len, uint8_t *g1_monomial, uint8_t *g1_lagrange,
                                                  uint8_t *g2_monomial, size_t g2_capacity, size_t *n_g2) {
     if (!json || !g1_monomial || !g1_lagrange || !g2_monomial || !n_g2) return set_err(KZGB200_ERR_ARGS, "null argument");
@@ -141,6 +152,51 @@ extern "C" int kzgb200_check_trusted_setup(int device, const uint8_t *g1_lagrang
     CUS(cudaMemcpy(st.data(), d_st, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     cudaFree(d_in); cudaFree(d_st);
     for (size_t i = 0; i < n; ++i) if (st[i] != KZGB200_OK) { *result = st[i]; if (bad_index) *bad_index = i; break; }
+    return KZGB200_OK;
+}
+
+// ---- codec validation entry points ---------------------------------------
+// DeserializeKZGCommitment / DeserializeKZGProof (serialization.go:108-131): status[i] of n compressed G1 points
+// (decode + subgroup check, exactly what every API call applies to its G1 inputs).
+extern "C" int kzgb200_check_g1_points(kzgb200_ctx *c, const uint8_t *points48, size_t n, int32_t *status) {
+    if (!c || (n && (!points48 || !status))) return set_err(KZGB200_ERR_ARGS, "null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUS(cudaSetDevice(c->device));
+    if (!n) return KZGB200_OK;
+    const bool st_dev = is_device_ptr(status);
+    int rc;
+    const void *d_in;
+    if ((rc = stage_in(c, points48, n * 48, c->in_small, &d_in))) return rc;
+    if (!st_dev && (rc = c->status.ensure(n * sizeof(int32_t)))) return rc;
+    int32_t *d_st = st_dev ? status : (int32_t *)c->status.p;
+    CUS(cudaMemsetAsync(d_st, 0, n * sizeof(int32_t), c->stream));
+    k_g1_check<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>((const uint8_t *)d_in, nullptr, d_st, n, 1, 1);
+    c->launches += 1;
+    CUS(cudaGetLastError());
+    if (!st_dev) CUS(cudaMemcpyAsync(status, d_st, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUS(cudaStreamSynchronize(c->stream));
+    return KZGB200_OK;
+}
+// DeserializeScalar / DeserializeBlob (serialization.go:134-159): status[i] = OK or NON_CANONICAL_SCALAR for n items of
+// `scalars_per_item` big-endian 32-byte scalars each (1 for a Scalar, 4096 for a Blob, 64 for a Cell)
+extern "C" int kzgb200_check_scalars(kzgb200_ctx *c, const uint8_t *scalars32, size_t n_items, size_t scalars_per_item, int32_t *status) {
+    if (!c || !scalars_per_item || (n_items && (!scalars32 || !status))) return set_err(KZGB200_ERR_ARGS, "null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUS(cudaSetDevice(c->device));
+    if (!n_items) return KZGB200_OK;
+    const bool st_dev = is_device_ptr(status);
+    const size_t ns = n_items * scalars_per_item;
+    int rc;
+    const void *d_in;
+    if ((rc = stage_in(c, scalars32, ns * 32, c->in_bytes, &d_in))) return rc;
+    if (!st_dev && (rc = c->status.ensure(n_items * sizeof(int32_t)))) return rc;
+    int32_t *d_st = st_dev ? status : (int32_t *)c->status.p;
+    CUS(cudaMemsetAsync(d_st, 0, n_items * sizeof(int32_t), c->stream));
+    k_blob_to_scalars_any<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>((const uint8_t *)d_in, d_st, ns, scalars_per_item);
+    c->launches += 1;
+    CUS(cudaGetLastError());
+    if (!st_dev) CUS(cudaMemcpyAsync(status, d_st, n_items * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUS(cudaStreamSynchronize(c->stream));
     return KZGB200_OK;
 }
 

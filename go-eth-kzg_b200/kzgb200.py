@@ -53,6 +53,7 @@ EXPORTS = [
     "kzgb200_verify_kzg_proof", "kzgb200_verify_blob_kzg_proof", "kzgb200_verify_blob_kzg_proof_batch",
     "kzgb200_verify_cell_kzg_proof_batch",
     "kzgb200_parse_trusted_setup_json", "kzgb200_ctx_new_from_json", "kzgb200_check_trusted_setup",
+    "kzgb200_check_g1_points", "kzgb200_check_scalars",
 ]
 
 
@@ -260,6 +261,20 @@ class Context:
                                                                _ptr(b"".join(cells)) if N else None, _ptr(b"".join(proofs)) if N else None,
                                                                ctypes.c_size_t(N), offs, ctypes.c_size_t(nb), res))
         return list(res[:nb])
+
+    def check_g1_points(self, points48):
+        """DeserializeKZGCommitment / DeserializeKZGProof (serialization.go:108-131) validity -> list of statuses"""
+        n = len(points48)
+        st = (ctypes.c_int32 * max(n, 1))()
+        self._check(self.L.kzgb200_check_g1_points(self.ctx, _ptr(b"".join(points48)) if n else None, ctypes.c_size_t(n), st))
+        return list(st[:n])
+
+    def check_scalars(self, items, scalars_per_item=1):
+        """DeserializeScalar / DeserializeBlob (serialization.go:134-159) validity -> list of statuses"""
+        n = len(items)
+        st = (ctypes.c_int32 * max(n, 1))()
+        self._check(self.L.kzgb200_check_scalars(self.ctx, _ptr(b"".join(items)) if n else None, ctypes.c_size_t(n), ctypes.c_size_t(scalars_per_item), st))
+        return list(st[:n])
 
     # ---- single-item methods, named after the reference's Context methods --------------------
     def blob_to_kzg_commitment(self, blob):

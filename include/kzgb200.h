@@ -141,6 +141,13 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *ctx, const uint8_t *commitm
                                         const uint8_t *cells, const uint8_t *proofs48, size_t n_cells,
                                         const uint64_t *batch_offsets, size_t n_batches, int32_t *results);
 
+/* Codec validation without a computation attached (the exported deserialisers of serialization.go:108-159, which in
+ * the reference return gnark types): status[i] of n compressed G1 points (DeserializeKZGCommitment / DeserializeKZGProof:
+ * decode + subgroup check), and of n_items groups of scalars_per_item big-endian scalars (DeserializeScalar: 1,
+ * DeserializeBlob: 4096, a cell: 64; NON_CANONICAL_SCALAR if any scalar of the group is >= r). */
+int kzgb200_check_g1_points(kzgb200_ctx *ctx, const uint8_t *points48, size_t n, int32_t *status);
+int kzgb200_check_scalars(kzgb200_ctx *ctx, const uint8_t *scalars32, size_t n_items, size_t scalars_per_item, int32_t *status);
+
 /* Introspection for benches / DESIGN.md numbers */
 typedef struct kzgb200_info {
     int device;

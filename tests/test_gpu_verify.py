@@ -134,3 +134,25 @@ def test_subgroup_check_matches_oracle(ctx):
         if e != 0:
             assert g == e
     assert any(e == 5 for e in exp) and any(e == 4 for e in exp) and any(e == 0 for e in exp)
+
+
+def test_codec_validation_entry_points(ctx):
+    """kzgb200_check_g1_points / kzgb200_check_scalars against the oracle's decoder and Python integers"""
+    import ctypes, random
+    rng = random.Random(31)
+    P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    m = oracle_lib.load_setup()[0]
+    pts = [m[48 * i:48 * i + 48] for i in range(6)] + [bytes([0xc0]) + bytes(47), bytes(48), bytes([0xc0]) + bytes(46) + b"\x01"]
+    for _ in range(16):
+        b = bytearray(rng.randrange(P).to_bytes(48, "big")); b[0] |= 0x80 | (0x20 if rng.random() < 0.5 else 0)
+        pts.append(bytes(b))
+    L = oracle_lib.lib()
+    exp = [L.ko_g1_decompress(p, ctypes.create_string_buffer(96), 1) for p in pts]
+    assert ctx.check_g1_points(pts) == exp and {0, 3, 4, 5} <= set(exp)
+    assert ctx.check_g1_points([]) == []
+    sc = [0, 1, R - 1, R, R + 1, 2**256 - 1, 2**255] + [rng.randrange(2**256) for _ in range(50)]
+    assert ctx.check_scalars([v.to_bytes(32, "big") for v in sc]) == [0 if v < R else 2 for v in sc]
+    blob_ok = oracle_lib.rand_blob(9 << 20)
+    bad = bytearray(blob_ok); bad[32 * 4095:32 * 4096] = R.to_bytes(32, "big")
+    assert ctx.check_scalars([blob_ok, bytes(bad), blob_ok], 4096) == [0, 2, 0]
