@@ -131,16 +131,18 @@ def run_reference(args):
 
 METRIC = {"cells_proofs": "ComputeCellsAndKZGProofs blobs/s", "commit": "BlobToKZGCommitment blobs/s",
           "blob_proof": "ComputeBlobKZGProof blobs/s", "verify_blob_batch": "VerifyBlobKZGProofBatch blobs/s",
-          "recover": "RecoverCellsAndComputeKZGProofs blobs/s", "verify_cells": "VerifyCellKZGProofBatch cells/s"}
+          "recover": "RecoverCellsAndComputeKZGProofs blobs/s", "verify_cells": "VerifyCellKZGProofBatch cells/s",
+          "verify_cells_one_batch": "VerifyCellKZGProofBatch cells/s"}
 WORKLOAD_NAME = {"cells_proofs": "EIP-7594 ComputeCellsAndKZGProofs (FK20, 128 cells x 64 Fr), 1024 random blobs per GPU",
                  "commit": "EIP-4844 BlobToKZGCommitment, 4096 random blobs per GPU",
                  "blob_proof": "EIP-4844 ComputeBlobKZGProof, 4096 random blobs per GPU",
                  "verify_blob_batch": "EIP-4844 VerifyBlobKZGProofBatch, one RLC verdict over 4096 blobs per GPU",
                  "recover": "EIP-7594 RecoverCellsAndComputeKZGProofs, 64 of 128 cells (random pattern), 1024 blobs per GPU",
-                 "verify_cells": "EIP-7594 VerifyCellKZGProofBatch, independent 128-cell batches, 128 x B cells per GPU"}
-DEFAULT_B = {"cells_proofs": 1024, "commit": 4096, "blob_proof": 4096, "verify_blob_batch": 4096, "recover": 1024, "verify_cells": 4096}
+                 "verify_cells": "EIP-7594 VerifyCellKZGProofBatch, independent 128-cell batches, 128 x B cells per GPU",
+                 "verify_cells_one_batch": "EIP-7594 VerifyCellKZGProofBatch, ONE verdict over all 128 x B cells per GPU (SURVEY 8d secondary shape)"}
+DEFAULT_B = {"cells_proofs": 1024, "commit": 4096, "blob_proof": 4096, "verify_blob_batch": 4096, "recover": 1024, "verify_cells": 4096, "verify_cells_one_batch": 4096}
 # canonical IMAD per unit
-CANONICAL_W.update({"blob_proof": 560e6, "verify_blob_batch": 8.2e6, "recover": 2701e6, "verify_cells": 1.79e6})
+CANONICAL_W.update({"blob_proof": 560e6, "verify_blob_batch": 8.2e6, "recover": 2701e6, "verify_cells": 1.79e6, "verify_cells_one_batch": 1.27e6})
 
 
 def main():
@@ -157,7 +159,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.steps <= 0:
-        args.steps = {"verify_blob_batch": 25, "verify_cells": 10}.get(args.workload, 5)
+        args.steps = {"verify_blob_batch": 25, "verify_cells": 10, "verify_cells_one_batch": 10}.get(args.workload, 5)
     if args.impl == "reference":
         if args.workload not in ("commit", "cells_proofs"):
             print(json.dumps({"impl": "reference", "unavailable": "reference arm implemented for commit and cells_proofs only"}))
@@ -282,18 +284,21 @@ def main():
                 N = 128 * B
                 d_cm = d_cm1.view(B, 1, 48).expand(B, 128, 48).contiguous().view(-1)
                 h_cm = d_cm.cpu().pin_memory(); h_cells.copy_(d_cells); h_pr.copy_(d_pr)
-                idx = np.tile(np.arange(128, dtype=np.uint64), B); offs = (np.arange(B + 1, dtype=np.uint64) * 128)
-                d_res = torch.empty(B, dtype=torch.int32, device="cuda"); h_res = pinned(B, torch.int32)
+                one = wl == "verify_cells_one_batch"
+                idx = np.tile(np.arange(128, dtype=np.uint64), B)
+                offs = np.array([0, N], dtype=np.uint64) if one else (np.arange(B + 1, dtype=np.uint64) * 128)
+                nv = 1 if one else B
+                d_res = torch.empty(nv, dtype=torch.int32, device="cuda"); h_res = pinned(nv, torch.int32)
                 ip = idx.ctypes.data_as(ctypes.c_void_p); op_ = offs.ctypes.data_as(ctypes.c_void_p)
                 def step(dev):
                     cm, ce, pr, rs = (d_cm, d_cells, d_pr, d_res) if dev else (h_cm, h_cells, h_pr, h_res)
-                    ctx._check(L.kzgb200_verify_cell_kzg_proof_batch(ctx.ctx, P(cm), ip, P(ce), P(pr), SZ(N), op_, SZ(B), P(rs)))
+                    ctx._check(L.kzgb200_verify_cell_kzg_proof_batch(ctx.ctx, P(cm), ip, P(ce), P(pr), SZ(N), op_, SZ(nv), P(rs)))
                 units_per_step = N
-                h2d, d2h = N * (48 + 2048 + 48), 4 * B
+                h2d, d2h = N * (48 + 2048 + 48), 4 * nv
                 def same():
                     ok = int(d_res.abs().sum().item()) == 0 and int(h_res.abs().sum().item()) == 0
                     badc = d_cells.clone(); badc[5 * 2048 + 40] ^= 1                                   # corrupt one cell of batch 0
-                    ctx._check(L.kzgb200_verify_cell_kzg_proof_batch(ctx.ctx, P(d_cm), ip, P(badc), P(d_pr), SZ(N), op_, SZ(B), P(d_res)))
+                    ctx._check(L.kzgb200_verify_cell_kzg_proof_batch(ctx.ctx, P(d_cm), ip, P(badc), P(d_pr), SZ(N), op_, SZ(nv), P(d_res)))
                     r = d_res.cpu()
                     return ok and int(r[0]) == 1 and int(r[1:].abs().sum()) == 0
 
@@ -332,7 +337,7 @@ def main():
         dist.destroy_process_group()
     if rank != 0:
         return
-    unit = "cells/s" if wl == "verify_cells" else "blobs/s"
+    unit = "cells/s" if wl.startswith("verify_cells") else "blobs/s"
     total_units = units_per_step * world * args.steps
     value = total_units / wall
     tab = info0
@@ -380,8 +385,9 @@ def main():
         SQR = 456
         DECODE = (384 * SQR + 100 * IMAD_FP_MUL) + 126 * (2 * IMAD_FP_MUL + 5 * SQR) + 10 * (11 * IMAD_FP_MUL + 3 * SQR) + 4 * IMAD_FP_MUL
         VMSM = 96 * 15 / 16 * (8 * IMAD_FP_MUL + 2 * SQR)
-        pts_decode = {"verify_cells": units_per_step + B, "verify_blob_batch": 2 * B}[wl]      # proofs + unique commitments / proofs + commitments
-        pts_vmsm = {"verify_cells": units_per_step, "verify_blob_batch": 2 * B * (64 / 96)}[wl]  # commitments carry 32 of 96 windows
+        pts_decode = {"verify_cells": units_per_step + B, "verify_cells_one_batch": units_per_step + B, "verify_blob_batch": 2 * B}[wl]      # proofs + unique commitments / proofs + commitments
+        # bucket-MSM points in units of 96 four-bit windows: commitments of the 4844 batch carry 32 of 96; the one-verdict cell path uses 16 eight-bit windows
+        pts_vmsm = {"verify_cells": units_per_step, "verify_cells_one_batch": units_per_step * (16 / (96 * 15 / 16)), "verify_blob_batch": 2 * B * (64 / 96)}[wl]
         per = {k: v / args.steps for k, v in kms.items() if v}
         models = {"decode": ("k_g1_check", pts_decode * DECODE), "vmsm": ("k_vmsm_buckets (+ reduce, combine)", pts_vmsm * VMSM)}
         top = max((k for k in per if k in models), key=lambda k: per[k], default=None)

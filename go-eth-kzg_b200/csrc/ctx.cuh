@@ -88,7 +88,7 @@ struct kzgb200_ctx {
     DevBuf in_bytes, scalars, status, sums, out_bytes, coeffs, cells, proofs_xyzz, fft_work, in_small, in_small2, zbuf, ybuf;
     DevBuf rec_a, rec_b, rec_meta, rec_zev, rec_czinv;
     DevBuf v_aff1, v_aff2, v_fr, v_meta, v_S, v_W, v_partial, v_in2, v_in3, v_st2;
-    DevBuf vm_digits, vm_scratch, vm_ws, vm_wsb, v_pa, v_pb, v_cst, v_st3, ev_cex, ev_total, ev_index;
+    DevBuf vm_digits, vm_digits256, vm_colsum, vm_rowdig, vm_commsum, vm_scratch, vm_ws, vm_wsb, v_pa, v_pb, v_cst, v_st3, ev_cex, ev_total, ev_index;
     double init_ms = 0, last_device_ms = 0;
     uint64_t launches = 0;
     // per-kernel-class device timing of the last call (CUDA events on `stream`)
@@ -139,13 +139,15 @@ static inline int stage_in(kzgb200_ctx *c, const void *user, size_t bytes, DevBu
 // ---- launch wrappers of kzgb200_vmsm.cu (verification throughput kernels, full optimisation) ----
 int vm_g1_check(cudaStream_t st, const uint8_t *in48, G1Aff *out, int32_t *status, size_t n, int per_status, int subgroup);
 int vm_cell_coeff_digits(cudaStream_t st, const Fr &seed, const uint32_t *batch_of, const uint64_t *batch_start, const uint64_t *cell_idx,
-                         const Fr *roots, Fr *rpow, int8_t *digits, size_t n);
-size_t vm_scratch_bytes(size_t n_items, int nw);
-int vm_msm_windows(cudaStream_t st, const G1Aff *points, const int8_t *digits, int TW, int w_lo, int nw,
+                         const Fr *roots, Fr *rpow, int8_t *digits, int8_t *digits256, size_t n);
+size_t vm_scratch_bytes(size_t n_items, int nw, int nbuckets);
+int vm_msm_windows(cudaStream_t st, const G1Aff *points, const int8_t *digits, int TW, int w_lo, int nw, const uint32_t *order, int nbuckets,
                    const uint64_t *item_start, const uint64_t *item_end, size_t n_items, const uint64_t *batch_item_off, size_t nb,
                    G1 *scratch, G1 *WS, G1 *WSb);
-// out[seg * nb + b] = Horner over windows [32 seg, 32 seg + 32) of WSb[b]
-int vm_combine(cudaStream_t st, const G1 *WSb, int TW, int n_segs, G1 *out, size_t nb);
+// out[seg * nb + b] = Horner over windows [nw seg, nw seg + nw) of WSb[b], dbl doublings between windows
+int vm_combine(cudaStream_t st, const G1 *WSb, int TW, int nw, int dbl, int n_segs, G1 *out, size_t nb);
+int vm_row_weight_digits(cudaStream_t st, const Fr *rpow, const uint64_t *row_off, const uint32_t *row_cells, int8_t *digits, size_t n_rows);
+int vm_cell_columns_large(cudaStream_t st, const G1 *colsum, const uint32_t *large_ids, size_t n_large, const int8_t *glv_tw_digits, G1 *comb, size_t nb);
 int vm_rlc_coeff_digits(cudaStream_t st, const Fr &seed, int unit_coeff, const uint32_t *z, const uint32_t *y, const int32_t *status,
                         Fr *fy, int8_t *digits, size_t n);
 // result[i] = pre_status[i] if that is an error (pre_status may be null or alias result), else OK / VERIFY_FAILED for

@@ -209,7 +209,7 @@ void kzgb200_ctx_free(kzgb200_ctx *c) {
     cudaFree(c->pow7); cudaFree(c->ipow7); cudaFree(c->pairing); cudaFree(c->mono64_tab.entries);
     c->v_aff1.release(); c->v_aff2.release(); c->v_fr.release(); c->v_meta.release(); c->v_S.release();
     c->v_W.release(); c->v_partial.release(); c->v_in2.release(); c->v_in3.release(); c->v_st2.release();
-    c->vm_digits.release(); c->vm_scratch.release(); c->vm_ws.release(); c->vm_wsb.release(); c->v_pa.release(); c->v_pb.release(); c->v_cst.release(); c->v_st3.release(); c->ev_cex.release(); c->ev_total.release(); c->ev_index.release();
+    c->vm_digits.release(); c->vm_digits256.release(); c->vm_colsum.release(); c->vm_rowdig.release(); c->vm_commsum.release(); c->vm_scratch.release(); c->vm_ws.release(); c->vm_wsb.release(); c->v_pa.release(); c->v_pb.release(); c->v_cst.release(); c->v_st3.release(); c->ev_cex.release(); c->ev_total.release(); c->ev_index.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (cudaStream_t q : c->fft_streams) if (q) cudaStreamDestroy(q);
     for (cudaEvent_t e : c->ev_join) if (e) cudaEventDestroy(e);

@@ -195,7 +195,7 @@ int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *blobs, co
     if ((rc = c->zbuf.ensure(n * 32))) return rc;
     if ((rc = c->ybuf.ensure(n * 32))) return rc;
     if ((rc = c->vm_digits.ensure(2 * n * KZG_CELL_TW))) return rc;
-    if ((rc = c->vm_scratch.ensure(vm_scratch_bytes(n_items, KZG_CELL_TW)))) return rc;
+    if ((rc = c->vm_scratch.ensure(vm_scratch_bytes(n_items, KZG_CELL_TW, KZG_VM_BUCKETS)))) return rc;
     if ((rc = c->vm_ws.ensure(n_items * KZG_CELL_TW * sizeof(G1)))) return rc;
     if ((rc = c->vm_wsb.ensure(2 * KZG_CELL_TW * sizeof(G1)))) return rc;
     if ((rc = c->v_S.ensure(KZG_VM_SEGS * 2 * sizeof(G1)))) return rc;
@@ -227,9 +227,9 @@ int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *blobs, co
     if ((rc = vm_rlc_coeff_digits(c->stream, r_dev, n == 1 ? 1 : 0, (const uint32_t *)c->zbuf.p, (const uint32_t *)c->ybuf.p, (const int32_t *)c->status.p,
                                   (Fr *)c->v_fr.p, (int8_t *)c->vm_digits.p, n))) return rc;
     c->mark(KZGB200_KC_VMSM);
-    if ((rc = vm_msm_windows(c->stream, d_pf_aff, (const int8_t *)c->vm_digits.p, KZG_CELL_TW, 0, KZG_CELL_TW, d_is, d_ie, n_items, d_sio, 2,
+    if ((rc = vm_msm_windows(c->stream, d_pf_aff, (const int8_t *)c->vm_digits.p, KZG_CELL_TW, 0, KZG_CELL_TW, nullptr, KZG_VM_BUCKETS, d_is, d_ie, n_items, d_sio, 2,
                              (G1 *)c->vm_scratch.p, (G1 *)c->vm_ws.p, (G1 *)c->vm_wsb.p))) return rc;
-    if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_CELL_TW, KZG_VM_SEGS, (G1 *)c->v_S.p, 2))) return rc;
+    if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_CELL_TW, 32, 4, KZG_VM_SEGS, (G1 *)c->v_S.p, 2))) return rc;
     c->mark(KZGB200_KC_VERIFY);
     k_rlc_fsum<<<1, 128, 0, c->stream>>>((const Fr *)c->v_fr.p, n, (uint32_t *)c->scalars.p);
     k_msm_fixed<<<dim3(1, 1), 32, 32 * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p);   // [sum r_i y_i] G
@@ -289,6 +289,13 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     std::vector<uint64_t> batch_start(nb), batch_row_off(nb + 1, 0), row_off(1, 0), item_start, item_end, batch_item_off(nb + 1, 0);
     std::vector<uint8_t> uniq_bytes;
     const uint64_t ITEM = 512;
+    // bucket-MSM work items: verdicts below KZG_LARGE_BATCH cells use 4-bit windows over contiguous runs (vs_*: the same runs
+    // as the interpolation's when no verdict is large); larger verdicts are grouped by cell index (column) and use 8-bit
+    // windows over the coefficients only -- the column twiddle h^64 is applied to the 128 column sums (l_*)
+    std::vector<uint64_t> vs_item_start, vs_item_end, vs_batch_item_off(nb + 1, 0), l_item_start, l_item_end, l_slot_item_off(1, 0);
+    std::vector<uint32_t> l_order, large_ids;
+    std::vector<uint64_t> r_item_start, r_item_end, r_slot_item_off(1, 0);      // runs of unique commitments (rows) of each large verdict
+    std::vector<int32_t> large_of(nb, -1);
     std::unordered_map<std::string, uint32_t> seen;
     std::vector<uint32_t> row_count;
     for (size_t b = 0; b < nb; ++b) {
@@ -320,8 +327,30 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
         batch_row_off[b + 1] = row_off.size() - 1;
         for (uint64_t s = lo; s < hi; s += ITEM) { item_start.push_back(s); item_end.push_back(std::min(hi, s + ITEM)); }
         batch_item_off[b + 1] = item_start.size();
+        if (hi - lo >= KZG_LARGE_BATCH) {
+            large_of[b] = (int32_t)large_ids.size();
+            large_ids.push_back((uint32_t)b);
+            for (uint64_t s = batch_row_off[b]; s < batch_row_off[b + 1]; s += KZG_ROW_ITEM) { r_item_start.push_back(s); r_item_end.push_back(std::min<uint64_t>(batch_row_off[b + 1], s + KZG_ROW_ITEM)); }
+            r_slot_item_off.push_back(r_item_start.size());
+            uint64_t cnt[129] = {0};
+            for (uint64_t k = lo; k < hi; ++k) ++cnt[(cell_indices[k] & 127) + 1];
+            const uint64_t base = l_order.size();
+            for (int q = 0; q < 128; ++q) cnt[q + 1] += cnt[q];
+            l_order.resize(base + (hi - lo));
+            uint64_t fillc[128];
+            for (int q = 0; q < 128; ++q) fillc[q] = base + cnt[q];
+            for (uint64_t k = lo; k < hi; ++k) l_order[fillc[cell_indices[k] & 127]++] = (uint32_t)k;
+            for (int q = 0; q < 128; ++q) {
+                for (uint64_t s = base + cnt[q]; s < base + cnt[q + 1]; s += ITEM) { l_item_start.push_back(s); l_item_end.push_back(std::min(base + cnt[q + 1], s + ITEM)); }
+                l_slot_item_off.push_back(l_item_start.size());
+            }
+        } else {
+            for (uint64_t s = lo; s < hi; s += ITEM) { vs_item_start.push_back(s); vs_item_end.push_back(std::min(hi, s + ITEM)); }
+        }
+        vs_batch_item_off[b + 1] = vs_item_start.size();
     }
     const size_t U = row_off.size() - 1, n_items = item_start.size();
+    const size_t n_large = large_ids.size(), n_vs = vs_item_start.size(), n_li = l_item_start.size(), n_slots = n_large * 128, n_ri = r_item_start.size();
     Fr seed_dev; random_scalar_plain(c, seed_dev.v);   // PRF seed of this call's 128-bit coefficients
     std::vector<uint32_t> row_batch(U);
     for (size_t b = 0; b < nb; ++b) for (uint64_t rw = batch_row_off[b]; rw < batch_row_off[b + 1]; ++rw) row_batch[rw] = (uint32_t)b;
@@ -336,6 +365,13 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     size_t o_rowc = take(N * 4), o_rowoff = take((U + 1) * 8), o_browoff = take((nb + 1) * 8), o_is = take(n_items * 8), o_ie = take(n_items * 8);
     size_t o_bio = take((nb + 1) * 8), o_bst = take(nb * 4), o_ust = take(std::max<size_t>(U, 1) * 4);
     size_t o_rowb = take(std::max<size_t>(U, 1) * 4), o_res = take(nb * 4);
+    // without large verdicts the bucket MSM shares the interpolation's work items
+    size_t o_vis = o_is, o_vie = o_ie, o_vbio = o_bio, o_lis = 0, o_lie = 0, o_lsio = 0, o_lord = 0, o_lids = 0, o_ris = 0, o_rie = 0, o_rsio = 0, o_lof = 0;
+    if (n_large) {
+        o_vis = take(n_vs * 8); o_vie = take(n_vs * 8); o_vbio = take((nb + 1) * 8);
+        o_lis = take(n_li * 8); o_lie = take(n_li * 8); o_lsio = take((n_slots + 1) * 8); o_lord = take(l_order.size() * 4); o_lids = take(n_large * 4);
+        o_ris = take(n_ri * 8); o_rie = take(n_ri * 8); o_rsio = take((n_large + 1) * 8); o_lof = take(nb * 4);
+    }
     if ((rc = c->v_meta.ensure(o))) return rc;
     char *M = (char *)c->v_meta.p;
     auto up = [&](size_t at, const void *src, size_t bytes) { return bytes ? cudaMemcpyAsync(M + at, src, bytes, cudaMemcpyHostToDevice, c->stream) : cudaSuccess; };
@@ -344,13 +380,27 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     CU(up(o_rowoff, row_off.data(), (U + 1) * 8)); CU(up(o_browoff, batch_row_off.data(), (nb + 1) * 8));
     CU(up(o_is, item_start.data(), n_items * 8)); CU(up(o_ie, item_end.data(), n_items * 8)); CU(up(o_bio, batch_item_off.data(), (nb + 1) * 8));
     CU(up(o_bst, h_bstatus.data(), nb * 4)); CU(up(o_rowb, row_batch.data(), U * 4));
+    if (n_large) {
+        CU(up(o_vis, vs_item_start.data(), n_vs * 8)); CU(up(o_vie, vs_item_end.data(), n_vs * 8)); CU(up(o_vbio, vs_batch_item_off.data(), (nb + 1) * 8));
+        CU(up(o_lis, l_item_start.data(), n_li * 8)); CU(up(o_lie, l_item_end.data(), n_li * 8)); CU(up(o_lsio, l_slot_item_off.data(), (n_slots + 1) * 8));
+        CU(up(o_lord, l_order.data(), l_order.size() * 4)); CU(up(o_lids, large_ids.data(), n_large * 4));
+        CU(up(o_ris, r_item_start.data(), n_ri * 8)); CU(up(o_rie, r_item_end.data(), n_ri * 8)); CU(up(o_rsio, r_slot_item_off.data(), (n_large + 1) * 8));
+        CU(up(o_lof, large_of.data(), nb * 4));
+    }
     CU(cudaMemsetAsync(M + o_ust, 0, std::max<size_t>(U, 1) * 4, c->stream));
     if ((rc = c->v_aff1.ensure(std::max<size_t>(U, 1) * sizeof(G1Aff)))) return rc;
     if ((rc = c->v_fr.ensure(std::max<size_t>(N, 1) * sizeof(Fr)))) return rc;
     if ((rc = c->vm_digits.ensure(std::max<size_t>(N, 1) * KZG_CELL_TW))) return rc;
-    if ((rc = c->vm_scratch.ensure(std::max<size_t>(vm_scratch_bytes(n_items, KZG_CELL_TW), 256)))) return rc;
-    if ((rc = c->vm_ws.ensure(std::max<size_t>(n_items, 1) * KZG_CELL_TW * sizeof(G1)))) return rc;
-    if ((rc = c->vm_wsb.ensure(nb * KZG_CELL_TW * sizeof(G1)))) return rc;
+    const size_t n_vm_items = n_large ? n_vs : n_items;
+    if ((rc = c->vm_scratch.ensure(std::max<size_t>(std::max(std::max(vm_scratch_bytes(n_vm_items, KZG_CELL_TW, KZG_VM_BUCKETS), vm_scratch_bytes(n_li, KZG_LARGE_TW, KZG_LARGE_BUCKETS)), vm_scratch_bytes(n_ri, KZG_ROW_TW, KZG_VM_BUCKETS)), 256)))) return rc;
+    if ((rc = c->vm_ws.ensure(std::max<size_t>(std::max(std::max(n_vm_items * KZG_CELL_TW, n_li * KZG_LARGE_TW), n_ri * KZG_ROW_TW), 1) * sizeof(G1)))) return rc;
+    if ((rc = c->vm_wsb.ensure(std::max(std::max(nb * KZG_CELL_TW, n_slots * KZG_LARGE_TW), n_large * KZG_ROW_TW) * sizeof(G1)))) return rc;
+    if (n_large) {
+        if ((rc = c->vm_digits256.ensure(N * KZG_LARGE_TW))) return rc;
+        if ((rc = c->vm_colsum.ensure(n_slots * sizeof(G1)))) return rc;
+        if ((rc = c->vm_rowdig.ensure(std::max<size_t>(U, 1) * KZG_ROW_TW))) return rc;
+        if ((rc = c->vm_commsum.ensure(n_large * sizeof(G1)))) return rc;
+    }
     if ((rc = c->v_S.ensure(KZG_VM_SEGS * nb * sizeof(G1)))) return rc;
     if ((rc = c->v_pa.ensure(nb * sizeof(G1)))) return rc;
     if ((rc = c->v_pb.ensure(nb * sizeof(G1)))) return rc;
@@ -362,7 +412,7 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     if ((rc = vm_g1_check(c->stream, (const uint8_t *)c->in_small2.p, (G1Aff *)c->v_aff1.p, d_ust, U, 1, 1))) return rc;
     if (N) {
         if ((rc = vm_cell_coeff_digits(c->stream, seed_dev, (const uint32_t *)(M + o_batch_of), (const uint64_t *)(M + o_bstart), (const uint64_t *)(M + o_idx),
-                                       c->roots, (Fr *)c->v_fr.p, (int8_t *)c->vm_digits.p, N))) return rc;
+                                       c->roots, (Fr *)c->v_fr.p, (int8_t *)c->vm_digits.p, n_large ? (int8_t *)c->vm_digits256.p : nullptr, N))) return rc;
         if (d_cells == c->in_bytes.p) CU(cudaStreamWaitEvent(c->stream, c->ev1, 0));     // the cells have landed
         c->mark(KZGB200_KC_FR);
         k_cell_interp<<<(unsigned)n_items, 256, 0, c->stream>>>((const uint8_t *)d_cells, (const uint64_t *)(M + o_idx), (const Fr *)c->v_fr.p, (const uint64_t *)(M + o_is),
@@ -374,15 +424,31 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     k_msm_fixed<<<dim3(1, (unsigned)nb), 32, 32 * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p);
     c->mark(KZGB200_KC_VMSM);
     // v_S[seg][b]: seg 0 = sum_k r_k pi_k, seg 1 + phi2(seg 2) = sum_k r_k h_k^64 pi_k   (kzg_verify.go:32,73-83)
-    if ((rc = vm_msm_windows(c->stream, (const G1Aff *)c->v_aff2.p, (const int8_t *)c->vm_digits.p, KZG_CELL_TW, 0, KZG_CELL_TW, (const uint64_t *)(M + o_is),
-                             (const uint64_t *)(M + o_ie), n_items, (const uint64_t *)(M + o_bio), nb, (G1 *)c->vm_scratch.p, (G1 *)c->vm_ws.p, (G1 *)c->vm_wsb.p))) return rc;
-    if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_CELL_TW, KZG_VM_SEGS, (G1 *)c->v_S.p, nb))) return rc;
+    if ((rc = vm_msm_windows(c->stream, (const G1Aff *)c->v_aff2.p, (const int8_t *)c->vm_digits.p, KZG_CELL_TW, 0, KZG_CELL_TW, nullptr, KZG_VM_BUCKETS,
+                             (const uint64_t *)(M + o_vis), (const uint64_t *)(M + o_vie), n_vm_items, (const uint64_t *)(M + o_vbio), nb,
+                             (G1 *)c->vm_scratch.p, (G1 *)c->vm_ws.p, (G1 *)c->vm_wsb.p))) return rc;
+    if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_CELL_TW, 32, 4, KZG_VM_SEGS, (G1 *)c->v_S.p, nb))) return rc;
+    if (n_large) {
+        // large verdicts: per (verdict, column) bucket MSM of the coefficients with 8-bit windows, then the column twiddles
+        if ((rc = vm_msm_windows(c->stream, (const G1Aff *)c->v_aff2.p, (const int8_t *)c->vm_digits256.p, KZG_LARGE_TW, 0, KZG_LARGE_TW, (const uint32_t *)(M + o_lord),
+                                 KZG_LARGE_BUCKETS, (const uint64_t *)(M + o_lis), (const uint64_t *)(M + o_lie), n_li, (const uint64_t *)(M + o_lsio), n_slots,
+                                 (G1 *)c->vm_scratch.p, (G1 *)c->vm_ws.p, (G1 *)c->vm_wsb.p))) return rc;
+        if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_LARGE_TW, KZG_LARGE_TW, 8, 1, (G1 *)c->vm_colsum.p, n_slots))) return rc;
+        if ((rc = vm_cell_columns_large(c->stream, (const G1 *)c->vm_colsum.p, (const uint32_t *)(M + o_lids), n_large, c->glv_digits, (G1 *)c->v_S.p, nb))) return rc;
+        // sum of w_row C_row over the large verdicts' unique commitments: one more bucket MSM, 40 four-bit windows over short runs
+        if ((rc = vm_row_weight_digits(c->stream, (const Fr *)c->v_fr.p, (const uint64_t *)(M + o_rowoff), (const uint32_t *)(M + o_rowc), (int8_t *)c->vm_rowdig.p, U))) return rc;
+        if ((rc = vm_msm_windows(c->stream, (const G1Aff *)c->v_aff1.p, (const int8_t *)c->vm_rowdig.p, KZG_ROW_TW, 0, KZG_ROW_TW, nullptr, KZG_VM_BUCKETS,
+                                 (const uint64_t *)(M + o_ris), (const uint64_t *)(M + o_rie), n_ri, (const uint64_t *)(M + o_rsio), n_large,
+                                 (G1 *)c->vm_scratch.p, (G1 *)c->vm_ws.p, (G1 *)c->vm_wsb.p))) return rc;
+        if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_ROW_TW, KZG_ROW_TW, 4, 1, (G1 *)c->vm_commsum.p, n_large))) return rc;
+        c->launches += 11;
+    }
     c->mark(KZGB200_KC_VERIFY);
     if (N) k_merge_status<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(d_cst, (const uint32_t *)(M + o_batch_of), d_bst, N);
     if (U) k_merge_status<<<(unsigned)((U + 127) / 128), 128, 0, c->stream>>>(d_ust, (const uint32_t *)(M + o_rowb), d_bst, U);
     k_cell_prep<<<(unsigned)((nb + 31) / 32), 32, 0, c->stream>>>((const G1 *)c->v_S.p, (const G1 *)c->sums.p, (const G1Aff *)c->v_aff1.p,
                                                                    (const uint64_t *)(M + o_rowoff), (const uint64_t *)(M + o_browoff), (const uint32_t *)(M + o_rowc),
-                                                                   (const Fr *)c->v_fr.p, d_bst, (G1 *)c->v_pa.p, (G1 *)c->v_pb.p, nb);
+                                                                   (const Fr *)c->v_fr.p, d_bst, n_large ? (const int32_t *)(M + o_lof) : nullptr, (const G1 *)c->vm_commsum.p, (G1 *)c->v_pa.p, (G1 *)c->v_pb.p, nb);
     c->mark(KZGB200_KC_PAIRING);
     if ((rc = vm_pairing_check(c->stream, c->pairing, (const G1 *)c->v_pa.p, 2, (const G1 *)c->v_pb.p, 0, d_bst, d_res, nb))) return rc;
     c->launches += 10;   // + bucket reduce and item reduce inside vm_msm_windows

@@ -15,32 +15,52 @@ int vm_g1_check(cudaStream_t st, const uint8_t *in48, G1Aff *out, int32_t *statu
 }
 
 int vm_cell_coeff_digits(cudaStream_t st, const Fr &seed, const uint32_t *batch_of, const uint64_t *batch_start, const uint64_t *cell_idx,
-                         const Fr *roots, Fr *rpow, int8_t *digits, size_t n) {
+                         const Fr *roots, Fr *rpow, int8_t *digits, int8_t *digits256, size_t n) {
     if (!n) return 0;
-    k_cell_coeff_digits<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seed, batch_of, batch_start, cell_idx, roots, rpow, digits, n);
+    k_cell_coeff_digits<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seed, batch_of, batch_start, cell_idx, roots, rpow, digits, digits256, n);
     CUL(cudaGetLastError());
     return 0;
 }
 
-size_t vm_scratch_bytes(size_t n_items, int nw) { return n_items * (size_t)nw * KZG_VM_BUCKETS * sizeof(G1); }
+size_t vm_scratch_bytes(size_t n_items, int nw, int nbuckets) { return n_items * (size_t)nw * nbuckets * sizeof(G1); }
 
-// per verdict b and window w (nw windows starting at digit column w_lo): WSb[b][w] = window sum
-int vm_msm_windows(cudaStream_t st, const G1Aff *points, const int8_t *digits, int TW, int w_lo, int nw,
+// per verdict b and window w (nw windows starting at digit column w_lo): WSb[b][w] = window sum.  nbuckets = 8 (signed 4-bit
+// digits) or 128 (signed 8-bit digits); order (optional): item positions index this list of point indices.
+int vm_msm_windows(cudaStream_t st, const G1Aff *points, const int8_t *digits, int TW, int w_lo, int nw, const uint32_t *order, int nbuckets,
                    const uint64_t *item_start, const uint64_t *item_end, size_t n_items, const uint64_t *batch_item_off, size_t nb,
                    G1 *scratch, G1 *WS, G1 *WSb) {
     if (n_items) {
-        k_vmsm_buckets<<<(unsigned)n_items, nw, 0, st>>>(points, digits, TW, w_lo, item_start, item_end, scratch);
         const size_t n_tasks = n_items * (size_t)nw;
-        k_vmsm_bucket_reduce<<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(scratch, WS, n_tasks);
+        if (nbuckets == KZG_LARGE_BUCKETS) {
+            k_vmsm_buckets<KZG_LARGE_BUCKETS><<<(unsigned)n_items, nw, 0, st>>>(points, digits, TW, w_lo, order, item_start, item_end, scratch);
+            k_vmsm_bucket_reduce<KZG_LARGE_BUCKETS><<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(scratch, WS, n_tasks);
+        } else {
+            k_vmsm_buckets<KZG_VM_BUCKETS><<<(unsigned)n_items, nw, 0, st>>>(points, digits, TW, w_lo, order, item_start, item_end, scratch);
+            k_vmsm_bucket_reduce<KZG_VM_BUCKETS><<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(scratch, WS, n_tasks);
+        }
     }
     if (nb) k_vmsm_item_reduce<<<(unsigned)nb, nw, 0, st>>>(WS, batch_item_off, WSb);
     CUL(cudaGetLastError());
     return 0;
 }
 
-int vm_combine(cudaStream_t st, const G1 *WSb, int TW, int n_segs, G1 *out, size_t nb) {
+int vm_combine(cudaStream_t st, const G1 *WSb, int TW, int nw, int dbl, int n_segs, G1 *out, size_t nb) {
     if (!nb) return 0;
-    k_vmsm_combine<<<dim3((unsigned)((nb + 31) / 32), n_segs), 32, 0, st>>>(WSb, TW, out, nb);
+    k_vmsm_combine<<<dim3((unsigned)((nb + 31) / 32), n_segs), 32, 0, st>>>(WSb, TW, nw, dbl, out, nb);
+    CUL(cudaGetLastError());
+    return 0;
+}
+
+int vm_row_weight_digits(cudaStream_t st, const Fr *rpow, const uint64_t *row_off, const uint32_t *row_cells, int8_t *digits, size_t n_rows) {
+    if (!n_rows) return 0;
+    k_row_weight_digits<<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(rpow, row_off, row_cells, digits, n_rows);
+    CUL(cudaGetLastError());
+    return 0;
+}
+
+int vm_cell_columns_large(cudaStream_t st, const G1 *colsum, const uint32_t *large_ids, size_t n_large, const int8_t *glv_tw_digits, G1 *comb, size_t nb) {
+    if (!n_large) return 0;
+    k_cell_columns_large<<<(unsigned)n_large, 128, 0, st>>>(colsum, large_ids, glv_tw_digits, comb, nb);
     CUL(cudaGetLastError());
     return 0;
 }
@@ -136,15 +156,15 @@ extern "C" int kzgb200_dbg_vmsm(kzgb200_ctx *c, const uint8_t *p48, const uint32
     for (size_t k = 0; k < n_items; ++k) { is[k] = k * 128; ie[k] = std::min<uint64_t>(n, k * 128 + 128); }
     uint8_t *dp, *dout; uint32_t *ds; int8_t *dd; G1Aff *pts; G1 *scratch, *ws, *wsb, *comb; uint64_t *meta;
     CUL(cudaMalloc(&dp, (size_t)n * 48)); CUL(cudaMalloc(&ds, (size_t)n * 32)); CUL(cudaMalloc(&dd, (size_t)n * KZG_CELL_TW)); CUL(cudaMalloc(&pts, (size_t)n * sizeof(G1Aff)));
-    CUL(cudaMalloc(&scratch, vm_scratch_bytes(n_items, KZG_CELL_TW))); CUL(cudaMalloc(&ws, n_items * KZG_CELL_TW * sizeof(G1)));
+    CUL(cudaMalloc(&scratch, vm_scratch_bytes(n_items, KZG_CELL_TW, KZG_VM_BUCKETS))); CUL(cudaMalloc(&ws, n_items * KZG_CELL_TW * sizeof(G1)));
     CUL(cudaMalloc(&wsb, KZG_CELL_TW * sizeof(G1))); CUL(cudaMalloc(&comb, KZG_VM_SEGS * sizeof(G1))); CUL(cudaMalloc(&meta, (2 * n_items + 2) * 8)); CUL(cudaMalloc(&dout, 48));
     CUL(cudaMemcpy(dp, p48, (size_t)n * 48, cudaMemcpyHostToDevice)); CUL(cudaMemcpy(ds, s, (size_t)n * 32, cudaMemcpyHostToDevice));
     CUL(cudaMemcpy(meta, is.data(), n_items * 8, cudaMemcpyHostToDevice)); CUL(cudaMemcpy(meta + n_items, ie.data(), n_items * 8, cudaMemcpyHostToDevice));
     CUL(cudaMemcpy(meta + 2 * n_items, off.data(), 16, cudaMemcpyHostToDevice));
     k_dbg_vmsm_finish<<<(n + 63) / 64, 64>>>(dp, pts, n, nullptr, nullptr, 0);
     k_dbg_vmsm_digits<<<(n + 63) / 64, 64>>>(ds, dd, n);
-    int rc = vm_msm_windows(nullptr, pts, dd, KZG_CELL_TW, 0, KZG_CELL_TW, meta, meta + n_items, n_items, meta + 2 * n_items, 1, scratch, ws, wsb);
-    if (!rc) rc = vm_combine(nullptr, wsb, KZG_CELL_TW, KZG_VM_SEGS, comb, 1);
+    int rc = vm_msm_windows(nullptr, pts, dd, KZG_CELL_TW, 0, KZG_CELL_TW, nullptr, KZG_VM_BUCKETS, meta, meta + n_items, n_items, meta + 2 * n_items, 1, scratch, ws, wsb);
+    if (!rc) rc = vm_combine(nullptr, wsb, KZG_CELL_TW, 32, 4, KZG_VM_SEGS, comb, 1);
     if (rc) return rc;
     k_dbg_vmsm_finish<<<1, 32>>>(nullptr, nullptr, 0, comb, dout, 1);
     CUL(cudaGetLastError());

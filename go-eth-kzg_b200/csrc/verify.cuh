@@ -211,6 +211,7 @@ static __global__ void __launch_bounds__(32) k_cell_prep(const G1 *__restrict__ 
                                                     const G1Aff *__restrict__ uniq_commit, const uint64_t *__restrict__ row_off,
                                                     const uint64_t *__restrict__ batch_row_off, const uint32_t *__restrict__ row_cells,
                                                     const Fr *__restrict__ rpow, const int32_t *__restrict__ batch_status,
+                                                    const int32_t *__restrict__ large_of /*may be null*/, const G1 *__restrict__ comm_large,
                                                     G1 *__restrict__ PA, G1 *__restrict__ PB, size_t n_batches) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_batches) return;
@@ -218,7 +219,9 @@ static __global__ void __launch_bounds__(32) k_cell_prep(const G1 *__restrict__ 
     G1 sumS = comb[b], sumW = comb[n_batches + b];
     g1_add(sumW, g1_phi2(comb[2 * n_batches + b]));
     G1 comms = G1::infinity();
-    for (uint64_t row = batch_row_off[b]; row < batch_row_off[b + 1]; ++row) {
+    const int lb = large_of ? large_of[b] : -1;
+    if (lb >= 0) comms = comm_large[lb];          // large verdict: sum of w_row C_row came from a bucket MSM over its commitments
+    else for (uint64_t row = batch_row_off[b]; row < batch_row_off[b + 1]; ++row) {
         Fr wsum = Fr::zero();
         for (uint64_t q = row_off[row]; q < row_off[row + 1]; ++q) wsum = Fr::add(wsum, rpow[row_cells[q]]);
         Fr wp = fr_from_mont(wsum);

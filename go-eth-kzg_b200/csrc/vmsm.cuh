@@ -40,11 +40,12 @@ __device__ __forceinline__ Fr fr_from_mont(const Fr &a) {
     return fr_mul_ni(a, o);
 }
 
-// 127-bit pseudo-random coefficient: first 16 bytes of SHA-256(seed32 || a || b), top bit cleared,
+// 126-bit pseudo-random coefficient: first 16 bytes of SHA-256(seed32 || a || b), top two bits cleared
+// (so that both the base-16 and the base-256 signed recodings below absorb their last carry),
 // forced odd (never zero).  The seed is fresh host randomness per API call, so the coefficients are
 // unpredictable to whoever chose the inputs (the reference uses powers of one random r,
 // internal/kzg/kzg_verify.go:136-141; any coefficients that are independent of the inputs give the
-// same soundness bound, here 2^-126).
+// same soundness bound, here 2^-125).
 __device__ __forceinline__ void prf128(uint32_t *out4, const uint32_t *seed8, unsigned long long a, unsigned long long b) {
     uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
     uint32_t w[16];
@@ -53,7 +54,7 @@ __device__ __forceinline__ void prf128(uint32_t *out4, const uint32_t *seed8, un
     w[8] = (uint32_t)(a >> 32); w[9] = (uint32_t)a; w[10] = (uint32_t)(b >> 32); w[11] = (uint32_t)b;
     w[12] = 0x80000000u; w[13] = 0; w[14] = 0; w[15] = 48 * 8;
     sha256_block(h, w);
-    out4[0] = h[0] | 1u; out4[1] = h[1]; out4[2] = h[2]; out4[3] = h[3] & 0x7fffffffu;
+    out4[0] = h[0] | 1u; out4[1] = h[1]; out4[2] = h[2]; out4[3] = h[3] & 0x3fffffffu;
 }
 
 // signed base-16 recoding of a plain little-endian value < 2^(4*ND - 1): ND digits in [-8, 8],
@@ -69,6 +70,23 @@ template <int ND> __device__ __forceinline__ void recode16(int8_t *out, const ui
             carry = raw > 8u ? 1u : 0u;
             uint32_t d = (raw - (carry << 4)) & 0xffu;
             packed |= d << (8 * q);
+        }
+        *reinterpret_cast<uint32_t *>(out + i) = packed;
+    }
+}
+
+// signed base-256 recoding of a value < 2^(8 ND - 1): ND digits in [-128, 127] (a digit of -128 means bucket 128,
+// negated); used for verdicts with thousands of points, where 8-bit windows pay
+template <int ND> __device__ __forceinline__ void recode256(int8_t *out, const uint32_t *limbs) {
+    uint32_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < ND; i += 4) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t raw = ((limbs[i >> 2] >> (8 * q)) & 255u) + carry;
+            carry = raw >= 128u ? 1u : 0u;
+            packed |= (raw & 0xffu) << (8 * q);            // raw - 256 carry, as a byte
         }
         *reinterpret_cast<uint32_t *>(out + i) = packed;
     }
@@ -145,12 +163,17 @@ __device__ __forceinline__ void store_g1(G1 *p, const G1 &r) {
 // ---- coefficients and digits ------------------------------------------------------------------
 #define KZG_CELL_TW 96        // windows per point: 32 (r_k, 127 bits) + 2 x 32 (GLV halves of the 255-bit scalar)
 #define KZG_VM_SEGS 3         // ... = three 32-window segments
+#define KZG_LARGE_TW 16       // verdicts with >= KZG_LARGE_BATCH cells: 16 signed 8-bit windows of r_k, 128 buckets
+#define KZG_LARGE_BUCKETS 128
+#define KZG_ROW_TW 40         // commitment weights of a large verdict: sums of < 2^32 coefficients of 126 bits (< 2^159), 40 signed 4-bit windows
+#define KZG_ROW_ITEM 64       // ... in short runs: there are few commitments, parallelism matters more than the reduction's cost
+#define KZG_LARGE_BATCH 4096
 // per cell k: r_k = PRF(seed, batch, position in batch); rpow[k] = r_k (Montgomery, for the
 // interpolation and the commitment weights); digits[k][0..31] = r_k, digits[k][32..63], [64..95] =
 // GLV halves of r_k * h_k^64 with h_k^64 = w_128^brp7(cell index)   (kzg_multi/srs.go:60-103, kzg_verify.go:73-83)
 static __global__ void k_cell_coeff_digits(Fr seed, const uint32_t *__restrict__ batch_of, const uint64_t *__restrict__ batch_start,
                                            const uint64_t *__restrict__ cell_idx, const Fr *__restrict__ roots,
-                                           Fr *__restrict__ rpow, int8_t *__restrict__ digits, size_t n) {
+                                           Fr *__restrict__ rpow, int8_t *__restrict__ digits, int8_t *__restrict__ digits256, size_t n) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     uint32_t b = batch_of[k];
@@ -163,6 +186,7 @@ static __global__ void k_cell_coeff_digits(Fr seed, const uint32_t *__restrict__
     if (t) s = fr_mul_ni(rm, ld_fr(roots + 64 * t));
     Fr sp = fr_from_mont(s);
     recode16<32>(digits + k * KZG_CELL_TW, p.v);
+    if (digits256) recode256<KZG_LARGE_TW>(digits256 + k * KZG_LARGE_TW, p.v);     // large verdicts: r_k only, the column twiddle is applied to column sums
     uint32_t k1[4], k2[4];
     bool n1, n2;
     glv_split(sp.v, k1, n1, k2, n2);
@@ -204,16 +228,17 @@ static __global__ void k_rlc_coeff_digits(Fr seed, int unit_coeff, const uint32_
 // block = one item (a run of points of ONE verdict), thread = one window.  digits: [point][TW].
 // w_lo: only windows [w_lo, w_lo + blockDim.x) of each digit row are used (so a second point set can
 // share a digit array).  Leaves the buckets of task item * nw + thread in scratch.
+template <int NB>
 static __global__ void __launch_bounds__(128) k_vmsm_buckets(const G1Aff *__restrict__ points, const int8_t *__restrict__ digits, int TW, int w_lo,
-                                                      const uint64_t *__restrict__ item_start, const uint64_t *__restrict__ item_end,
-                                                      G1 *__restrict__ scratch) {
+                                                      const uint32_t *__restrict__ order, const uint64_t *__restrict__ item_start,
+                                                      const uint64_t *__restrict__ item_end, G1 *__restrict__ scratch) {
     const int w = threadIdx.x, nw = blockDim.x;
     const size_t task = (size_t)blockIdx.x * nw + w;
-    G1 *B = scratch + task * KZG_VM_BUCKETS;
+    G1 *B = scratch + task * NB;
     {
         uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int j = 0; j < KZG_VM_BUCKETS; ++j) {
+#pragma unroll 1
+        for (int j = 0; j < NB; ++j) {
             uint4 *q = reinterpret_cast<uint4 *>(B + j);
 #pragma unroll
             for (int i = 6; i < 12; ++i) q[i] = z;          // ZZ = ZZZ = 0: infinity
@@ -221,13 +246,17 @@ static __global__ void __launch_bounds__(128) k_vmsm_buckets(const G1Aff *__rest
     }
     const uint64_t s = item_start[blockIdx.x], e = item_end[blockIdx.x];
     const int8_t *dg = digits + w_lo + w;
-    int d_next = s < e ? (int)dg[s * TW] : 0;
+    // with `order`, positions [s, e) index the order array (points of one verdict and column gathered from all over the batch)
+    size_t pt_next = s < e ? (order ? order[s] : s) : 0;
+    int d_next = s < e ? (int)dg[pt_next * TW] : 0;
     for (uint64_t k = s; k < e; ++k) {
-        int d = d_next;
-        if (k + 1 < e) d_next = (int)dg[(k + 1) * TW];
-        if (d == 0) continue;
-        G1Aff P = load_aff(points + k);
+        const int d0 = d_next;
+        const size_t pt = pt_next;
+        if (k + 1 < e) { pt_next = order ? order[k + 1] : k + 1; d_next = (int)dg[pt_next * TW]; }
+        if (d0 == 0) continue;
+        G1Aff P = load_aff(points + pt);
         if (P.is_inf()) continue;
+        int d = d0;
         if (d < 0) { P.y = Fp::neg(P.y); d = -d; }
         G1 acc = load_g1(B + (d - 1));
         g1_add_affine<MulInline>(acc, P);
@@ -236,13 +265,14 @@ static __global__ void __launch_bounds__(128) k_vmsm_buckets(const G1Aff *__rest
 }
 // WS[task] = sum_j j * B_j by running sums (a kernel of its own: its two extra accumulators would
 // otherwise set the register count, and with it the occupancy, of the accumulation loop)
+template <int NB>
 static __global__ void __launch_bounds__(128) k_vmsm_bucket_reduce(const G1 *__restrict__ scratch, G1 *__restrict__ WS, size_t n_tasks) {
     const size_t task = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (task >= n_tasks) return;
-    const G1 *B = scratch + task * KZG_VM_BUCKETS;
+    const G1 *B = scratch + task * NB;
     G1 run = G1::infinity(), tot = G1::infinity();
 #pragma unroll 1
-    for (int j = KZG_VM_BUCKETS - 1; j >= 0; --j) {
+    for (int j = NB - 1; j >= 0; --j) {
         G1 b = load_g1(B + j);
         g1_add<MulCall>(run, b);
         g1_add<MulCall>(tot, run);
@@ -262,19 +292,19 @@ static __global__ void k_vmsm_item_reduce(const G1 *__restrict__ WS, const uint6
     store_g1(WSb + b * nw + w, acc);
 }
 
-// out[seg * nb + b] = sum_{i < 32} 16^i WSb[b][32 seg + i]   (Horner from the top window), blockIdx.y = seg
-static __global__ void __launch_bounds__(32) k_vmsm_combine(const G1 *__restrict__ WSb, int TW, G1 *__restrict__ out, size_t nb) {
+// out[seg * nb + b] = sum_{i < nw} 2^(dbl i) WSb[b][nw seg + i]   (Horner from the top window), blockIdx.y = seg
+static __global__ void __launch_bounds__(32) k_vmsm_combine(const G1 *__restrict__ WSb, int TW, int nw, int dbl, G1 *__restrict__ out, size_t nb) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     const int seg = blockIdx.y;
     G1 acc = G1::infinity();
 #pragma unroll 1
-    for (int i = 31; i >= 0; --i) {
-        if (i != 31) {
+    for (int i = nw - 1; i >= 0; --i) {
+        if (i != nw - 1) {
 #pragma unroll 1
-            for (int q = 0; q < 4; ++q) acc = g1_dbl_cold(acc);
+            for (int q = 0; q < dbl; ++q) acc = g1_dbl_cold(acc);
         }
-        G1 t = load_g1(WSb + b * TW + 32 * seg + i);
+        G1 t = load_g1(WSb + b * TW + nw * seg + i);
         g1_add<MulCall>(acc, t);
     }
     store_g1(out + (size_t)seg * nb + b, acc);
@@ -288,6 +318,47 @@ __device__ __forceinline__ G1 g1_phi2(const G1 &p) {
     G1 r = p;
     r.X = fp_mul_ni(p.X, b2);
     return r;
+}
+
+// weights of the unique commitments (rows): w_row = sum of r_k over the row's cells (kzg_verify.go:37-45), as 40 signed
+// base-16 digits for the bucket MSM over the commitments of a large verdict
+static __global__ void k_row_weight_digits(const Fr *__restrict__ rpow, const uint64_t *__restrict__ row_off, const uint32_t *__restrict__ row_cells,
+                                           int8_t *__restrict__ digits, size_t n_rows) {
+    size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    Fr w = Fr::zero();
+    for (uint64_t q = row_off[row]; q < row_off[row + 1]; ++q) w = Fr::add(w, ld_fr(rpow + row_cells[q]));
+    Fr wp = fr_from_mont(w);
+    recode16<KZG_ROW_TW>(digits + row * KZG_ROW_TW, wp.v);
+}
+
+// Large verdicts (>= KZG_LARGE_BATCH cells): colsum[lb * 128 + c] = sum of r_k pi_k over the verdict's cells with cell
+// index c.  S = sum_c colsum, W = sum_c [h_c^64] colsum = sum_c [w_128^brp7(c)] colsum (kzg_verify.go:32,73-83:
+// the reference multiplies every proof by r^k h_k^64; grouping by column needs 128 twiddle multiplications per verdict).
+// comb[0][b] = S, comb[1][b] = W, comb[2][b] = O for b = large_ids[lb].
+static __global__ void __launch_bounds__(128) k_cell_columns_large(const G1 *__restrict__ colsum, const uint32_t *__restrict__ large_ids,
+                                                            const int8_t *__restrict__ glv_tw_digits, G1 *__restrict__ comb, size_t nb) {
+    __shared__ G1 sm[128];
+    const size_t lb = blockIdx.x, b = large_ids[lb];
+    const int cidx = threadIdx.x;
+    G1 acc = load_g1(colsum + lb * 128 + cidx);
+    sm[cidx] = acc;
+    __syncthreads();
+    for (int st = 64; st > 0; st >>= 1) {
+        if (cidx < st) g1_add_ool(&sm[cidx], &sm[cidx + st]);
+        __syncthreads();
+    }
+    if (cidx == 0) { comb[b] = sm[0]; comb[2 * nb + b] = G1::infinity(); }
+    __syncthreads();
+    int t = (int)(__brev((unsigned)cidx) >> 25);
+    if (t) g1_mul_twiddle(&acc, glv_tw_digits + (size_t)t * 2 * KZG_GLV_DIGITS);
+    sm[cidx] = acc;
+    __syncthreads();
+    for (int st = 64; st > 0; st >>= 1) {
+        if (cidx < st) g1_add_ool(&sm[cidx], &sm[cidx + st]);
+        __syncthreads();
+    }
+    if (cidx == 0) comb[nb + b] = sm[0];
 }
 
 }  // namespace kzg

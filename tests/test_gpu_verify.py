@@ -110,6 +110,36 @@ def test_cell_batch_larger_than_one_work_item(ctx):
     assert o.verify_cell_kzg_proof_batch(commitments[:130], idx[:130], cells[:130], proofs[:130]) == 0
 
 
+def test_large_verdict_uses_column_grouping(ctx):
+    """a verdict with >= 4096 cells takes the 8-bit-window, grouped-by-column path (vmsm.cuh: k_cell_columns_large); it
+    must agree with the small-verdict path on accept and reject, alone and mixed with small verdicts in one call"""
+    nblob = 33
+    blobs = [oracle_lib.rand_blob((200 + b) << 20) for b in range(nblob)]
+    cms = [c for _, c in ctx.blob_to_kzg_commitment_batch(blobs)]
+    full = ctx.compute_cells_and_kzg_proofs_batch(blobs)
+    commitments, idx, cells, proofs = [], [], [], []
+    for b, (st, cl, pr) in enumerate(full):
+        for i in range(128):
+            commitments.append(cms[b]); idx.append(i); cells.append(cl[2048 * i:2048 * (i + 1)]); proofs.append(pr[48 * i:48 * (i + 1)])
+    n = len(cells)                                                   # 4224 cells
+    assert ctx.verify_cell_kzg_proof_batches(commitments, idx, cells, proofs, [0, n]) == [0]
+    # a large verdict (first 32 blobs = 4096 cells) followed by a small one (last blob) and an empty one
+    assert ctx.verify_cell_kzg_proof_batches(commitments, idx, cells, proofs, [0, 4096, n, n]) == [0, 0, 0]
+    bad = list(proofs); bad[1234] = proofs[1235]
+    assert ctx.verify_cell_kzg_proof_batches(commitments, idx, cells, bad, [0, 4096, n]) == [1, 0]
+    badc = list(cells); badc[4100] = cells[4101]
+    assert ctx.verify_cell_kzg_proof_batches(commitments, idx, badc, proofs, [0, 4096, n]) == [0, 1]
+    assert ctx.verify_cell_kzg_proof_batches(commitments, idx, badc, proofs, [0, n]) == [1]
+    # wrong cell index on a correct cell/proof pair: the column twiddle must notice
+    widx = list(idx); widx[77], widx[78] = widx[78], widx[77]
+    assert ctx.verify_cell_kzg_proof_batches(commitments, widx, cells, proofs, [0, n]) == [1]
+    # shuffled order inside the verdict (columns gathered from all over the batch) still verifies
+    import random
+    perm = list(range(n)); random.Random(5).shuffle(perm)
+    assert ctx.verify_cell_kzg_proof_batches([commitments[i] for i in perm], [idx[i] for i in perm], [cells[i] for i in perm],
+                                             [proofs[i] for i in perm], [0, n]) == [0]
+
+
 def test_subgroup_check_matches_oracle(ctx):
     """random x-coordinates: on-curve points outside G1 must be rejected exactly as the oracle's [r]P test does"""
     import ctypes, random
