@@ -60,6 +60,18 @@ public:
     Context &operator=(const Context &) = delete;
     kzgb200_ctx *handle() const { return h_; }
 
+    // CheckTrustedSetupIsWellFormed (trusted_setup.go:45-83) on flat records: Ok, or the first failing point's error
+    static Error CheckTrustedSetupIsWellFormed(const uint8_t *g1_lagrange, size_t n_lagrange, const uint8_t *g1_monomial, size_t n_monomial,
+                                               const uint8_t *g2_monomial, size_t n_g2, int device = 0) {
+        int32_t res = 0;
+        int rc = kzgb200_check_trusted_setup(device, g1_lagrange, n_lagrange, g1_monomial, n_monomial, g2_monomial, n_g2, &res, nullptr);
+        return rc != KZGB200_OK ? Error(rc) : Error(res);
+    }
+    // DeserializeKZGCommitment / DeserializeKZGProof (serialization.go:108-131), validity only
+    Error CheckG1Point(const uint8_t *point48) const { int32_t st = 0; int rc = kzgb200_check_g1_points(h_, point48, 1, &st); return both(rc, st); }
+    // DeserializeBlob (serialization.go:134-146), validity only
+    Error CheckBlob(const uint8_t *blob) const { int32_t st = 0; int rc = kzgb200_check_scalars(h_, blob, 1, 4096, &st); return both(rc, st); }
+
     // ---- EIP-4844 -------------------------------------------------------------------------------
     Error BlobToKZGCommitment(const uint8_t *blob, uint8_t *out48) const { int32_t st = 0; int rc = kzgb200_blob_to_kzg_commitment(h_, blob, 1, out48, &st); return both(rc, st); }
     Error ComputeBlobKZGProof(const uint8_t *blob, const uint8_t *commitment48, uint8_t *out48) const {

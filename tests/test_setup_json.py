@@ -108,3 +108,32 @@ def test_check_trusted_setup_is_well_formed():
     # a bad G2 point is reported after clean G1 bases, with its index in the concatenation
     first_bad = next(p for p, e in zip(pts, exp) if e == 5)
     assert kzgb200.check_trusted_setup(l, m, g2[:96 * 3] + first_bad + g2[96 * 4:]) == (5, 8192 + 3)
+
+
+def test_json_parser_never_crashes_on_garbage():
+    """the parser reads untrusted text: truncations, byte flips and random insertions must end in a clean error or a
+    well-formed result, never in a crash (the process surviving this loop is the assertion)"""
+    import kzgb200
+    rng = random.Random(77)
+    m, l, g2 = oracle_lib.load_setup()
+    # a small but structurally complete document keeps the loop fast: the parser insists on 4096 points, so every
+    # mutation of this text must be rejected cleanly; full-size mutations are tried a few times
+    small = json.dumps({"g1_monomial": ["0x" + m[:48].hex()] * 3, "g1_lagrange": ["0x" + l[:48].hex()] * 3, "g2_monomial": ["0x" + g2[:96].hex()]})
+    full = setup_json_text()
+    alphabet = b'{}[]",:\\0xX19afAF \n\t\x00\xff'
+    for trial in range(600):
+        base = full if trial % 100 == 0 else small
+        b = bytearray(base.encode())
+        for _ in range(rng.randrange(1, 6)):
+            op, pos = rng.randrange(4), rng.randrange(len(b))
+            if op == 0: b[pos] = rng.choice(alphabet)
+            elif op == 1: del b[pos:pos + rng.randrange(1, 40)]
+            elif op == 2: b[pos:pos] = bytes(rng.choice(alphabet) for _ in range(rng.randrange(1, 8)))
+            else: b = b[:pos]
+            if not b:
+                break
+        try:
+            out = kzgb200.parse_trusted_setup_json(bytes(b))
+            assert len(out[0]) == 4096 * 48 and len(out[1]) == 4096 * 48 and len(out[2]) % 96 == 0
+        except kzgb200.KzgError as e:
+            assert e.code in (11, 12)
