@@ -166,6 +166,11 @@ def main():
             return
         return run_reference(args)
 
+    # stdout carries exactly ONE JSON line: everything libraries print to fd 1 (e.g. "NCCL version ..." with NCCL_DEBUG
+    # set on the box) is sent to stderr, and the result line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import kzgb200
@@ -178,7 +183,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line (NCCL_DEBUG=VERSION would add one)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -413,7 +417,8 @@ def main():
     }
     if not args.no_cpu_baseline and wl in ("commit", "cells_proofs"):
         line["cpu_baseline"] = cpu_baseline(wl)[0]
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
