@@ -24,7 +24,8 @@ def needs_build():
     return any(os.path.getmtime(f) > t for f in _deps())
 
 
-# per-file extra flags.  kzgb200_verify.cu: ptxas -O1 (see the header of that file)
+# per-file extra flags.  kzgb200_verify.cu (host side of the verifiers + latency-bound preparation kernels): ptxas -O1
+# as a guard against a miscompilation met there (header of that file)
 PER_FILE = {"kzgb200_verify.cu": os.environ.get("KZGB200_VERIFY_FLAGS", "-Xptxas -O1").split()}
 
 

@@ -1,6 +1,7 @@
 // Shared host-side definitions of libkzgb200.so: error plumbing, the context object, staging helpers.
-// Included by both translation units (kzgb200.cu: setup + proving paths at full optimisation;
-// kzgb200_verify.cu: verification paths, built with -Xptxas -O1 -- see build.py for why).
+// Included by every translation unit: kzgb200.cu (setup + proving paths), kzgb200_verify.cu (host side of the
+// verifiers, built with -Xptxas -O1 -- see build.py for why), kzgb200_vmsm.cu (verifier throughput kernels, launch
+// wrappers declared at the bottom of this file), kzgb200_setup.cu (trusted-setup ingestion, codec validation).
 #pragma once
 #include "../../include/kzgb200.h"
 #include "../../include/kzgb200_debug.h"

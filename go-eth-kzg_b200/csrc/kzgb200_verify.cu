@@ -1,10 +1,11 @@
 // libkzgb200.so -- verification entry points of the C ABI (include/kzgb200.h).
 //
-// Separate translation unit because it is compiled with `-Xptxas -O1`: at ptxas' default level
-// nvcc 12.9 miscompiles k_verify_single (the caller of the scalar multiplication mixes a stale
-// register into the reloaded point; caught by the reference's verify_kzg_proof vectors, gone at
-// -O1, PTX identical).  These kernels are latency-bound one-thread-per-check code, so the lower
-// optimisation level costs nothing measurable; the throughput kernels stay in kzgb200.cu.
+// Host side of the verifiers (staging, bookkeeping, launch order) plus their small preparation kernels
+// (verify.cuh).  This translation unit is compiled with `-Xptxas -O1`: at ptxas' default level nvcc 12.9
+// miscompiled the first version of k_verify_single; the guard is kept because
+// everything launched from here directly is latency-bound one-thread-per-item code.  The throughput
+// kernels of the verifiers (point decoding, bucket MSMs, the 8-lane pairing, the evaluation kernels)
+// live in kzgb200_vmsm.cu at full optimisation and are reached through the vm_* launch wrappers.
 #include "ctx.cuh"
 #include "verify.cuh"
 
@@ -222,7 +223,7 @@ int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *blobs, co
     for (size_t i = 0; i < n; ++i) if (h_status[i] != KZGB200_OK) { *result = h_status[i]; c->marks_collect(); return KZGB200_OK; }   // first failing element (verify.go:102-119)
     uint32_t seed[8];
     random_scalar_plain(c, seed);
-    Fr r_dev; memcpy(r_dev.v, seed, sizeof seed);      // PRF seed for the 127-bit coefficients; n == 1 uses coefficient 1 (kzg_verify.go:125-127)
+    Fr r_dev; memcpy(r_dev.v, seed, sizeof seed);      // PRF seed for the 126-bit coefficients; n == 1 uses coefficient 1 (kzg_verify.go:125-127)
     c->mark(KZGB200_KC_VERIFY);
     if ((rc = vm_rlc_coeff_digits(c->stream, r_dev, n == 1 ? 1 : 0, (const uint32_t *)c->zbuf.p, (const uint32_t *)c->ybuf.p, (const int32_t *)c->status.p,
                                   (Fr *)c->v_fr.p, (int8_t *)c->vm_digits.p, n))) return rc;

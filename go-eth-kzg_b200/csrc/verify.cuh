@@ -226,7 +226,7 @@ static __global__ void __launch_bounds__(32) k_cell_prep(const G1 *__restrict__ 
         for (uint64_t q = row_off[row]; q < row_off[row + 1]; ++q) wsum = Fr::add(wsum, rpow[row_cells[q]]);
         Fr wp = fr_from_mont(wsum);
         G1 C = G1::from_affine(uniq_commit[row]), t;
-        int top = 0;                              // the weight is a sum of 127-bit coefficients: ~134 bits for 128 cells
+        int top = 0;                              // the weight is a sum of 126-bit coefficients: ~134 bits for 128 cells
 #pragma unroll
         for (int q = 0; q < 8; ++q) if (wp.v[q]) top = q;
         g1_mul_scalar(&t, &C, wp.v, 8 * (top + 1));

@@ -7,7 +7,7 @@
 //   internal/kzg/kzg_verify.go:150,179,225 sum r^i proof_i, sum r^i z_i proof_i, sum r^i C_i
 // (the bases here are the caller's proofs / commitments, so no table can be precomputed).
 //
-// Shape of the work: a 128-cell verdict needs sum_k r_k P_k (127-bit r_k) and sum_k s_k P_k
+// Shape of the work: a 128-cell verdict needs sum_k r_k P_k (126-bit r_k) and sum_k s_k P_k
 // (255-bit s_k) over the SAME 128 points.  s_k is split with the curve endomorphism,
 // s = k1 - k2 x^2 (mod r), |k1|, |k2| < 2^127, so that sum s_k P_k = sum k1_k P_k + phi2(sum k2_k P_k)
 // with phi2(x, y) = (beta^2 x, y) = [-x^2](x, y): three 32-window sums, and the final Horner chain
@@ -20,6 +20,8 @@
 // word-interleaved layout turns every divergent bucket access into 32 separate cache lines).
 // Cost per point and window: 10 Fp products, against ~13 for a windowed scalar multiplication of
 // each point on its own (4 doublings + 15/16 addition per window) -- and no per-point table.
+// Verdicts with thousands of cells take a second shape (KZG_LARGE_BATCH): cells grouped by cell index,
+// 8-bit windows over the coefficients only, the column twiddle applied to 128 column sums.
 #pragma once
 #include "kzg4844.cuh"
 #include "fk20.cuh"      // constants.inc: FP_BETA2
@@ -161,7 +163,7 @@ __device__ __forceinline__ void store_g1(G1 *p, const G1 &r) {
 }
 
 // ---- coefficients and digits ------------------------------------------------------------------
-#define KZG_CELL_TW 96        // windows per point: 32 (r_k, 127 bits) + 2 x 32 (GLV halves of the 255-bit scalar)
+#define KZG_CELL_TW 96        // windows per point: 32 (r_k, 126 bits) + 2 x 32 (GLV halves of the 255-bit scalar)
 #define KZG_VM_SEGS 3         // ... = three 32-window segments
 #define KZG_LARGE_TW 16       // verdicts with >= KZG_LARGE_BATCH cells: 16 signed 8-bit windows of r_k, 128 buckets
 #define KZG_LARGE_BUCKETS 128
