@@ -30,13 +30,13 @@ template <int N> struct BinGcd {
         const uint64_t a0 = (uint64_t)(f0 < 0 ? -f0 : f0), a1 = (uint64_t)(f1 < 0 ? -f1 : f1);   // <= 2^31
         uint32_t p[N + 2], q[N + 2];
         uint64_t c = 0;
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int i = 0; i < N; ++i) { c += (uint64_t)x0[i] * a0; p[i] = (uint32_t)c; c >>= 32; }
         p[N] = (uint32_t)c; p[N + 1] = 0;
         c = 0;
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int i = 0; i < N; ++i) { c += (uint64_t)x1[i] * a1; q[i] = (uint32_t)c; c >>= 32; }
@@ -44,7 +44,7 @@ template <int N> struct BinGcd {
         // r = (+-p) + (+-q): conditional negation by xor/carry, all in (N+2)-limb two's complement
         const uint32_t m0 = f0 < 0 ? 0xffffffffu : 0u, m1 = f1 < 0 ? 0xffffffffu : 0u;
         uint64_t cp = m0 & 1u, cq = m1 & 1u, cs = 0;
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int i = 0; i < N + 2; ++i) {
@@ -59,11 +59,11 @@ template <int N> struct BinGcd {
         const uint32_t msk = neg ? 0xffffffffu : 0u;
         uint32_t t[N + 2];
         uint64_t c = msk & 1u;
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int i = 0; i < N + 2; ++i) { c += (uint64_t)(r[i] ^ msk); t[i] = (uint32_t)c; c >>= 32; }
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int i = 0; i < N; ++i) x[i] = (t[i] >> 31) | (t[i + 1] << 1);
@@ -75,13 +75,13 @@ template <int N> struct BinGcd {
         neg_mod(un, u, m); neg_mod(vn, v, m);
         const uint64_t a0 = (uint64_t)(f0 < 0 ? -f0 : f0), a1 = (uint64_t)(f1 < 0 ? -f1 : f1);
         uint32_t x0[N], x1[N];                                          // element-wise selects keep everything in registers
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int i = 0; i < N; ++i) { x0[i] = f0 < 0 ? un[i] : u[i]; x1[i] = f1 < 0 ? vn[i] : v[i]; }
         uint32_t t[N + 2];
         uint64_t c = 0;
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int i = 0; i < N; ++i) {                                   // t = x0 a0 + x1 a1  (< 2 m 2^31)
@@ -94,14 +94,14 @@ template <int N> struct BinGcd {
         // make t divisible by 2^31: add k m with k = t * (-1/m) mod 2^31
         const uint64_t k = (uint64_t)((t[0] * m_ninv31) & 0x7fffffffu);
         c = 0;
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int i = 0; i < N; ++i) { c += (uint64_t)m[i] * k + t[i]; t[i] = (uint32_t)c; c >>= 32; }
         c += t[N]; t[N] = (uint32_t)c; c >>= 32;
         t[N + 1] += (uint32_t)c;
         uint32_t w[N + 1];
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int i = 0; i < N + 1; ++i) w[i] = (t[i] >> 31) | (t[i + 1] << 1);        // < 3 m
@@ -109,7 +109,7 @@ template <int N> struct BinGcd {
         for (int rep = 0; rep < 2; ++rep) {
             uint32_t d[N + 1];
             uint64_t br = 0;
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
             for (int i = 0; i < N + 1; ++i) {
@@ -117,13 +117,13 @@ template <int N> struct BinGcd {
                 d[i] = (uint32_t)s; br = (s >> 32) & 1u;
             }
             if (!br) {
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
                 for (int i = 0; i < N + 1; ++i) w[i] = d[i];
             }
         }
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int i = 0; i < N; ++i) out[i] = w[i];
@@ -131,12 +131,12 @@ template <int N> struct BinGcd {
     static KZG_HD void neg_mod(uint32_t *r, const uint32_t *x, const uint32_t *m) {     // m - x, and 0 -> 0
         uint32_t nz = 0;
         uint64_t br = 0;
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int i = 0; i < N; ++i) { nz |= x[i]; uint64_t s = (uint64_t)m[i] - x[i] - br; r[i] = (uint32_t)s; br = (s >> 32) & 1u; }
         if (!nz) {
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
             for (int i = 0; i < N; ++i) r[i] = 0;
@@ -144,7 +144,7 @@ template <int N> struct BinGcd {
     }
     static KZG_HD int bitlen(const uint32_t *x) {
         int n = 0;
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int i = 0; i < N; ++i) if (x[i]) {
@@ -160,7 +160,7 @@ template <int N> struct BinGcd {
     static KZG_HD uint64_t bits64(const uint32_t *x, int pos) {
         const int w = pos >> 5, s = pos & 31;
         uint32_t l0 = 0, l1 = 0, l2 = 0;
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int i = 0; i < N; ++i) { if (i == w) l0 = x[i]; if (i == w + 1) l1 = x[i]; if (i == w + 2) l2 = x[i]; }
@@ -171,7 +171,7 @@ template <int N> struct BinGcd {
     // out = y^-1 mod m.  m_ninv31 = -m^-1 mod 2^31.  Returns the number of outer rounds used.
     static KZG_HD int inverse(uint32_t *out, const uint32_t *y, const uint32_t *m, uint32_t m_ninv31) {
         uint32_t a[N], b[N], u[N], v[N];
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int i = 0; i < N; ++i) { a[i] = y[i]; b[i] = m[i]; u[i] = 0; v[i] = 0; }
@@ -179,7 +179,7 @@ template <int N> struct BinGcd {
         int rounds = 0;
         for (; rounds < 2 * (32 * N + 30) / 31 + 2; ++rounds) {
             uint32_t nz = 0;
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
             for (int i = 0; i < N; ++i) nz |= a[i];
@@ -214,13 +214,13 @@ template <int N> struct BinGcd {
             uint32_t nu[N], nv[N];
             lin2_mod(nu, u, f0, v, g0, m, m_ninv31);
             lin2_mod(nv, u, f1, v, g1, m, m_ninv31);
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
             for (int i = 0; i < N; ++i) { u[i] = nu[i]; v[i] = nv[i]; }
         }
         // a == 0, b == gcd == 1: v y == 1 (mod m)
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int i = 0; i < N; ++i) out[i] = v[i];

@@ -442,7 +442,7 @@ static int open_common(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *z32,
     const int TPB = 128;
     for (size_t off = 0; off < n; off += chunk) {
         size_t m = std::min(chunk, n - off);
-        const void *d_aux;
+        const void *d_aux = nullptr;
         // host blobs travel in geometrically growing pieces on the copy stream (see kzgb200_blob_to_kzg_commitment): every
         // piece runs the whole chain hash -> evaluation -> quotient -> MSM as soon as it has landed.  The hash + evaluation of a
         // piece (latency-bound: one thread per SHA-256) runs on a side stream, under the previous piece's MSM.

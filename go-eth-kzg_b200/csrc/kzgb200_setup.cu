@@ -165,7 +165,7 @@ extern "C" int kzgb200_check_g1_points(kzgb200_ctx *c, const uint8_t *points48, 
     if (!n) return KZGB200_OK;
     const bool st_dev = is_device_ptr(status);
     int rc;
-    const void *d_in;
+    const void *d_in = nullptr;
     if ((rc = stage_in(c, points48, n * 48, c->in_small, &d_in))) return rc;
     if (!st_dev && (rc = c->status.ensure(n * sizeof(int32_t)))) return rc;
     int32_t *d_st = st_dev ? status : (int32_t *)c->status.p;
@@ -187,7 +187,7 @@ extern "C" int kzgb200_check_scalars(kzgb200_ctx *c, const uint8_t *scalars32, s
     const bool st_dev = is_device_ptr(status);
     const size_t ns = n_items * scalars_per_item;
     int rc;
-    const void *d_in;
+    const void *d_in = nullptr;
     if ((rc = stage_in(c, scalars32, ns * 32, c->in_bytes, &d_in))) return rc;
     if (!st_dev && (rc = c->status.ensure(n_items * sizeof(int32_t)))) return rc;
     int32_t *d_st = st_dev ? status : (int32_t *)c->status.p;

@@ -261,7 +261,7 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     int rc;
     // ---- device first: the proofs' decode + subgroup check (the longest kernel of the call) needs nothing from
     // the host bookkeeping below, and the cells' H2D rides the copy stream meanwhile ------------------
-    const void *d_cells = cells, *d_proofs;
+    const void *d_cells = cells, *d_proofs = nullptr;
     if ((rc = c->v_cst.ensure(std::max<size_t>(N, 1) * 4))) return rc;
     if ((rc = c->v_aff2.ensure(std::max<size_t>(N, 1) * sizeof(G1Aff)))) return rc;
     int32_t *d_cst = (int32_t *)c->v_cst.p;
