@@ -8,6 +8,7 @@
 // live in kzgb200_vmsm.cu at full optimisation and are reached through the vm_* launch wrappers.
 #include "ctx.cuh"
 #include "verify.cuh"
+#include "cell_plan.hpp"
 
 namespace kzg {
 static __global__ void k_dbg_g1_mul(const uint8_t *p48, const uint8_t *s32, uint8_t *out48, int n) {
@@ -285,76 +286,22 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
         CU(cudaStreamSynchronize(c->copy_stream));
         h_cm = h_cm_copy.data();
     }
-    std::vector<int32_t> h_bstatus(nb, KZGB200_OK);
-    std::vector<uint32_t> batch_of(N), row_cells(N), row_of(N);
-    std::vector<uint64_t> batch_start(nb), batch_row_off(nb + 1, 0), row_off(1, 0), item_start, item_end, batch_item_off(nb + 1, 0);
-    std::vector<uint8_t> uniq_bytes;
+    // (pure host code in cell_plan.hpp; the GPU is already decoding the proofs meanwhile)
     const uint64_t ITEM = 512;
-    // bucket-MSM work items: verdicts below KZG_LARGE_BATCH cells use 4-bit windows over contiguous runs (vs_*: the same runs
-    // as the interpolation's when no verdict is large); larger verdicts are grouped by cell index (column) and use 8-bit
-    // windows over the coefficients only -- the column twiddle h^64 is applied to the 128 column sums (l_*)
-    std::vector<uint64_t> vs_item_start, vs_item_end, vs_batch_item_off(nb + 1, 0), l_item_start, l_item_end, l_slot_item_off(1, 0);
-    std::vector<uint32_t> l_order, large_ids;
-    std::vector<uint64_t> r_item_start, r_item_end, r_slot_item_off(1, 0);      // runs of unique commitments (rows) of each large verdict
-    std::vector<int32_t> large_of(nb, -1);
-    std::unordered_map<std::string, uint32_t> seen;
-    std::vector<uint32_t> row_count;
-    for (size_t b = 0; b < nb; ++b) {
-        uint64_t lo = batch_offsets[b], hi = batch_offsets[b + 1];
-        if (hi < lo || hi > N) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); return set_err(KZGB200_ERR_ARGS, "batch_offsets not monotone / out of range"); }
-        batch_start[b] = lo;
-        // de-duplicate on raw bytes, first-seen order (api_eip7594.go:238-265).  Runs of equal commitments
-        // (the usual layout: all cells of a blob together) skip the hash lookup.
-        seen.clear(); row_count.clear();
-        uint32_t prev_row = 0;
-        for (uint64_t k = lo; k < hi; ++k) {
-            batch_of[k] = (uint32_t)b;
-            uint32_t row;
-            if (k > lo && memcmp(h_cm + k * 48, h_cm + (k - 1) * 48, 48) == 0) row = prev_row;
-            else {
-                std::string key((const char *)h_cm + k * 48, 48);
-                auto it = seen.find(key);
-                if (it == seen.end()) { row = (uint32_t)row_count.size(); seen.emplace(key, row); row_count.push_back(0); uniq_bytes.insert(uniq_bytes.end(), key.begin(), key.end()); }
-                else row = it->second;
-            }
-            prev_row = row; row_of[k] = row; ++row_count[row];
-            if (cell_indices[k] >= 128) h_bstatus[b] = KZGB200_BAD_CELL_INDEX;      // api_eip7594.go:184-188
-        }
-        // counting sort of the batch's cells by row
-        const size_t row_base = row_off.size() - 1;
-        for (uint32_t cnt : row_count) row_off.push_back(row_off.back() + cnt);
-        std::vector<uint64_t> fill(row_off.begin() + row_base, row_off.begin() + row_base + row_count.size());
-        for (uint64_t k = lo; k < hi; ++k) row_cells[fill[row_of[k]]++] = (uint32_t)k;
-        batch_row_off[b + 1] = row_off.size() - 1;
-        for (uint64_t s = lo; s < hi; s += ITEM) { item_start.push_back(s); item_end.push_back(std::min(hi, s + ITEM)); }
-        batch_item_off[b + 1] = item_start.size();
-        if (hi - lo >= KZG_LARGE_BATCH) {
-            large_of[b] = (int32_t)large_ids.size();
-            large_ids.push_back((uint32_t)b);
-            for (uint64_t s = batch_row_off[b]; s < batch_row_off[b + 1]; s += KZG_ROW_ITEM) { r_item_start.push_back(s); r_item_end.push_back(std::min<uint64_t>(batch_row_off[b + 1], s + KZG_ROW_ITEM)); }
-            r_slot_item_off.push_back(r_item_start.size());
-            uint64_t cnt[129] = {0};
-            for (uint64_t k = lo; k < hi; ++k) ++cnt[(cell_indices[k] & 127) + 1];
-            const uint64_t base = l_order.size();
-            for (int q = 0; q < 128; ++q) cnt[q + 1] += cnt[q];
-            l_order.resize(base + (hi - lo));
-            uint64_t fillc[128];
-            for (int q = 0; q < 128; ++q) fillc[q] = base + cnt[q];
-            for (uint64_t k = lo; k < hi; ++k) l_order[fillc[cell_indices[k] & 127]++] = (uint32_t)k;
-            for (int q = 0; q < 128; ++q) {
-                for (uint64_t s = base + cnt[q]; s < base + cnt[q + 1]; s += ITEM) { l_item_start.push_back(s); l_item_end.push_back(std::min(base + cnt[q + 1], s + ITEM)); }
-                l_slot_item_off.push_back(l_item_start.size());
-            }
-        } else {
-            for (uint64_t s = lo; s < hi; s += ITEM) { vs_item_start.push_back(s); vs_item_end.push_back(std::min(hi, s + ITEM)); }
-        }
-        vs_batch_item_off[b + 1] = vs_item_start.size();
+    CellPlan P;
+    if (!plan_cell_batches(h_cm, cell_indices, N, batch_offsets, nb, ITEM, KZG_LARGE_BATCH, KZG_ROW_ITEM, KZGB200_BAD_CELL_INDEX, P)) {
+        cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream);
+        return set_err(KZGB200_ERR_ARGS, "batch_offsets not monotone / out of range");
     }
+    auto &h_bstatus = P.bstatus; auto &batch_of = P.batch_of; auto &row_cells = P.row_cells; auto &batch_start = P.batch_start;
+    auto &batch_row_off = P.batch_row_off; auto &row_off = P.row_off; auto &item_start = P.item_start; auto &item_end = P.item_end;
+    auto &batch_item_off = P.batch_item_off; auto &uniq_bytes = P.uniq_bytes; auto &vs_item_start = P.vs_item_start; auto &vs_item_end = P.vs_item_end;
+    auto &vs_batch_item_off = P.vs_batch_item_off; auto &l_item_start = P.l_item_start; auto &l_item_end = P.l_item_end; auto &l_slot_item_off = P.l_slot_item_off;
+    auto &l_order = P.l_order; auto &large_ids = P.large_ids; auto &r_item_start = P.r_item_start; auto &r_item_end = P.r_item_end;
+    auto &r_slot_item_off = P.r_slot_item_off; auto &large_of = P.large_of; auto &row_batch = P.row_batch;
     const size_t U = row_off.size() - 1, n_items = item_start.size();
     const size_t n_large = large_ids.size(), n_vs = vs_item_start.size(), n_li = l_item_start.size(), n_slots = n_large * 128, n_ri = r_item_start.size();
-    Fr seed_dev; random_scalar_plain(c, seed_dev.v);   // PRF seed of this call's 128-bit coefficients
-    std::vector<uint32_t> row_batch(U);
-    for (size_t b = 0; b < nb; ++b) for (uint64_t rw = batch_row_off[b]; rw < batch_row_off[b + 1]; ++rw) row_batch[rw] = (uint32_t)b;
+    Fr seed_dev; random_scalar_plain(c, seed_dev.v);   // PRF seed of this call's 126-bit coefficients
 
     // ---- device buffers ---------------------------------------------------------------------------
     if ((rc = c->in_small2.ensure(std::max<size_t>(U, 1) * 48))) return rc;
@@ -459,6 +406,29 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitmen
     CU(cudaStreamSynchronize(c->stream));
     c->marks_collect();
     return KZGB200_OK;
+}
+
+// unit-test hook (host only, no GPU): the plan of plan_cell_batches as JSON text (thread-local buffer), or NULL on malformed offsets
+const char *kzgb200_dbg_plan_cell_batches_json(const uint8_t *commitments48, const uint64_t *cell_indices, size_t N, const uint64_t *batch_offsets, size_t nb,
+                                               uint64_t item, uint64_t large, uint64_t row_item) {
+    static thread_local std::string out;
+    CellPlan P;
+    if (!plan_cell_batches(commitments48, cell_indices, N, batch_offsets, nb, item, large, row_item, KZGB200_BAD_CELL_INDEX, P)) return nullptr;
+    out.clear();
+    auto arr = [&](const char *name, auto &v, bool last = false) {
+        out += "\""; out += name; out += "\": [";
+        for (size_t i = 0; i < v.size(); ++i) { if (i) out += ","; out += std::to_string((long long)v[i]); }
+        out += last ? "]" : "],";
+    };
+    out += "{";
+    arr("bstatus", P.bstatus); arr("batch_start", P.batch_start); arr("batch_row_off", P.batch_row_off); arr("batch_item_off", P.batch_item_off);
+    arr("large_of", P.large_of); arr("batch_of", P.batch_of); arr("uniq_bytes", P.uniq_bytes); arr("row_off", P.row_off); arr("row_cells", P.row_cells);
+    arr("row_batch", P.row_batch); arr("item_start", P.item_start); arr("item_end", P.item_end); arr("vs_item_start", P.vs_item_start);
+    arr("vs_item_end", P.vs_item_end); arr("vs_batch_item_off", P.vs_batch_item_off); arr("large_ids", P.large_ids); arr("l_order", P.l_order);
+    arr("l_item_start", P.l_item_start); arr("l_item_end", P.l_item_end); arr("l_slot_item_off", P.l_slot_item_off); arr("r_item_start", P.r_item_start);
+    arr("r_item_end", P.r_item_end); arr("r_slot_item_off", P.r_slot_item_off, true);
+    out += "}";
+    return out.c_str();
 }
 
 int kzgb200_dbg_g1_mul(const uint8_t *p48, const uint8_t *s32, uint8_t *out48, int n) {

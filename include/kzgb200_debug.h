@@ -30,6 +30,11 @@ int kzgb200_dbg_vmsm(struct kzgb200_ctx *ctx, const uint8_t *p48, const uint32_t
  * 3 3Q on the twist, 4 2(2Q) == 3Q + Q, 5 Q + Q (addition's doubling branch) == 2Q, 6 Q + (-Q) == O,
  * 7 g2_in_subgroup(Q), 8 [r]Q == O by a ladder written out in the test kernel (7 and 8 must agree) */
 int kzgb200_dbg_g2_selftest(const uint8_t *in96, int *mask);
+/* host bookkeeping of VerifyCellKZGProofBatch (csrc/cell_plan.hpp; no GPU involved): per-verdict de-duplication of the
+ * commitments, grouping of cells by unique commitment, range check of the cell indices and the kernels' work-item
+ * lists, as JSON text in a thread-local buffer; NULL if batch_offsets is not monotone / out of range */
+const char *kzgb200_dbg_plan_cell_batches_json(const uint8_t *commitments48, const uint64_t *cell_indices, size_t n_cells,
+                                               const uint64_t *batch_offsets, size_t n_batches, uint64_t item, uint64_t large, uint64_t row_item);
 /* dependency-free integer multiply-add microbenchmark: device-wide instructions*lanes per second.
  * mode 0: mad.lo.u32 (IMAD), 1: mad.hi.u32 (IMAD.HI), 2: mad.wide.u32 (IMAD.WIDE, 32x32+64) */
 int kzgb200_bench_imad(int device, int mode, double *per_s, double *ms_out);
