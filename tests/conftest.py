@@ -9,3 +9,16 @@ sys.path.insert(0, os.path.join(ROOT, "go-eth-kzg_b200"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+def pytest_sessionstart(session):
+    """The built artefacts are git-ignored: in a fresh checkout build them before the first test needs them (nvcc
+    cross-compiles without a GPU; a no-op when they are up to date).  The oracle builds itself on first use (oracle_lib)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("kzgb200_build", os.path.join(ROOT, "go-eth-kzg_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    try:
+        mod.build()
+    except Exception as e:          # tests that need the library will say so themselves
+        print("[conftest] libkzgb200.so build failed:", e, file=sys.stderr)
