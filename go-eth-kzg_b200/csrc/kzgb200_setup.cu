@@ -29,11 +29,12 @@ static bool parse_hex_string(Cursor &c, std::vector<uint8_t> &out) {
     }
     return true;
 }
-// array of hex strings, each exactly `width` bytes, appended to out
+// array of hex strings, each exactly `width` bytes, REPLACING the contents of out: a key that appears twice keeps
+// its last value, as Go's encoding/json does for JSONTrustedSetup (trusted_setup.go:23-27)
 static bool parse_point_array(Cursor &c, size_t width, std::vector<uint8_t> &out, size_t &count) {
     skip_ws(c);
     if (c.p >= c.end || *c.p != '[') return false;
-    ++c.p; count = 0;
+    ++c.p; count = 0; out.clear();
     skip_ws(c);
     if (c.p < c.end && *c.p == ']') { ++c.p; return true; }
     std::vector<uint8_t> one;
@@ -113,8 +114,9 @@ extern "C" int kzgb200_parse_trusted_setup_json(const char *json, size_t len, ui
     if (!have_m || !have_l || !have_g) return set_err(KZGB200_ERR_SETUP, "trusted setup JSON: g1_monomial, g1_lagrange and g2_monomial are required");
     if (nm != (size_t)N_BLOB || nl != (size_t)N_BLOB) return set_err(KZGB200_ERR_SETUP, "trusted setup JSON: need exactly 4096 G1 points in each basis (trusted_setup.go:23-27)");
     if (ng > g2_capacity) return set_err(KZGB200_ERR_ARGS, "g2_monomial buffer too small");
-    memcpy(g1_monomial, m.data(), m.size()); memcpy(g1_lagrange, l.data(), l.size());
-    if (ng) memcpy(g2_monomial, g2.data(), g2.size());
+    if (m.size() != (size_t)N_BLOB * 48 || l.size() != (size_t)N_BLOB * 48 || g2.size() != ng * 96) return set_err(KZGB200_ERR_SETUP, "trusted setup JSON: inconsistent point count");
+    memcpy(g1_monomial, m.data(), (size_t)N_BLOB * 48); memcpy(g1_lagrange, l.data(), (size_t)N_BLOB * 48);
+    if (ng) memcpy(g2_monomial, g2.data(), ng * 96);
     *n_g2 = ng;
     return KZGB200_OK;
 }

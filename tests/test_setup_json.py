@@ -35,6 +35,20 @@ def test_json_parser_round_trip_and_errors():
         with pytest.raises(kzgb200.KzgError) as e:
             kzgb200.parse_trusted_setup_json(json.dumps(d))
         assert e.value.code == 12                                                                                   # KZGB200_ERR_SETUP
+    # a key that appears twice: the last value wins (encoding/json) and nothing is written past the 4096-point buffers
+    # (the parser used to append, so two copies of a key overflowed the caller's buffer)
+    text = setup_json_text()
+    dup = json.loads(text)
+    junk = ["0x" + bytes([i % 251] * 48).hex() for i in range(4096)]
+    for key in ("g1_monomial", "g1_lagrange"):
+        doubled = '{"%s": %s, %s' % (key, json.dumps(junk), text.lstrip()[1:])
+        assert kzgb200.parse_trusted_setup_json(doubled) == (m, l, g2)
+    doubled = '{"g2_monomial": %s, %s' % (json.dumps(dup["g2_monomial"] * 3), text.lstrip()[1:])
+    assert kzgb200.parse_trusted_setup_json(doubled) == (m, l, g2)
+    short_last = text.rstrip()[:-1] + ', "g1_monomial": %s}' % json.dumps(junk[:100])            # last copy has 100 points -> rejected
+    with pytest.raises(kzgb200.KzgError) as e:
+        kzgb200.parse_trusted_setup_json(short_last)
+    assert e.value.code == 12
     for text in ("", "[]", "{", '{"g1_monomial": [', setup_json_text()[:-3]):
         with pytest.raises(kzgb200.KzgError):
             kzgb200.parse_trusted_setup_json(text)
