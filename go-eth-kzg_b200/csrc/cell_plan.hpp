@@ -32,7 +32,9 @@ struct CellPlan {
     std::vector<uint64_t> r_item_start, r_item_end, r_slot_item_off;     // runs of rows of each large verdict
 };
 
-// false: batch_offsets not monotone / out of range
+// false: batch_offsets not monotone / out of range / not covering exactly [0, N) (batch_offsets[0] == 0 and
+// batch_offsets[nb] == N are required: a cell outside every verdict would still be decoded and its errors folded
+// into verdict 0 -- ADVICE r1)
 static inline bool plan_cell_batches(const uint8_t *h_cm, const uint64_t *cell_indices, size_t N, const uint64_t *batch_offsets, size_t nb,
                                      uint64_t item, uint64_t large, uint64_t row_item, int32_t st_bad_cell_index, CellPlan &P) {
     P = CellPlan();
@@ -41,6 +43,7 @@ static inline bool plan_cell_batches(const uint8_t *h_cm, const uint64_t *cell_i
     P.vs_batch_item_off.assign(nb + 1, 0); P.l_slot_item_off.assign(1, 0); P.r_slot_item_off.assign(1, 0);
     std::vector<uint32_t> row_of(N), row_count;
     std::unordered_map<std::string, uint32_t> seen;
+    if (nb == 0 ? N != 0 : (batch_offsets[0] != 0 || batch_offsets[nb] != N)) return false;
     for (size_t b = 0; b < nb; ++b) {
         const uint64_t lo = batch_offsets[b], hi = batch_offsets[b + 1];
         if (hi < lo || hi > N) return false;

@@ -1,4 +1,11 @@
-// Shared host-side definitions of libkzgb200.so: error plumbing, the context object, staging helpers.
+// Shared host-side definitions of libkzgb200.so: error plumbing, the LANE object, staging helpers.
+//
+// A lane (kzg_lane) is one execution slot on one GPU: its own stream set, event pool and grow-only scratch arena,
+// plus pointers to the read-only tables of its GPU (owned by the first lane created there, shared by its clones).
+// The public context (kzgb200_ctx, kzgb200_api.cu) is a set of lanes per GPU; it hands every call -- or every
+// device's share of a call -- to a free lane, so a context is usable from many host threads at once and over
+// several GPUs.  The lane_* functions below are the single-GPU implementations of the entry points of
+// include/kzgb200.h; they are not locked: the pool guarantees a lane runs one call at a time.
 // Included by every translation unit: kzgb200.cu (setup + proving paths), kzgb200_verify.cu (host side of the
 // verifiers, built with -Xptxas -O1 -- see build.py for why), kzgb200_vmsm.cu (verifier throughput kernels, launch
 // wrappers declared at the bottom of this file), kzgb200_setup.cu (trusted-setup ingestion, codec validation).
@@ -65,15 +72,22 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// device temporaries of context creation: freed on every exit path (they leaked on the error returns)
+struct InitTemps {
+    std::vector<void *> ptrs;
+    template <class T> void track(T *p) { ptrs.push_back((void *)p); }
+    ~InitTemps() { for (void *p : ptrs) if (p) cudaFree(p); }
+};
+
 #define KZG_G1FFT_MAX_SPLIT 8
-struct kzgb200_ctx {
+struct kzg_lane {
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_piece[8] = {nullptr};
     cudaStream_t fft_streams[KZG_G1FFT_MAX_SPLIT - 1] = {nullptr};   // sub-batches of the staged G1 FFT (launch_fk20_proofs)
     cudaEvent_t ev_fork = nullptr, ev_join[KZG_G1FFT_MAX_SPLIT - 1] = {nullptr};
     size_t g1fft_split = 8;             // measured: 1 -> 40.9 ms, 2 -> 34.6, 4 -> 33.5, 8 -> 33.1 (KZGB200_G1FFT_SPLIT overrides)
-    std::mutex mu;
+    bool owns_tables = true;            // false for clones: setup pointers below belong to the GPU's first lane
     // setup
     G1Aff *g1_monomial = nullptr;      // natural order
     G1Aff *g1_lagrange_brp = nullptr;  // bit-reversed order (api.go:131)
@@ -86,6 +100,7 @@ struct kzgb200_ctx {
     PairingConsts *pairing = nullptr;       // Frobenius constants + line tables of G2, [s]G2, [s^64]G2
     MsmTable mono64_tab{};                  // digit table of monomial G1[0..63] (kzg_multi/srs.go:143-149)
     // scratch
+    DevBuf msm_partial;
     DevBuf in_bytes, scalars, status, sums, out_bytes, coeffs, cells, proofs_xyzz, fft_work, in_small, in_small2, zbuf, ybuf;
     DevBuf rec_a, rec_b, rec_meta, rec_zev, rec_czinv;
     DevBuf v_aff1, v_aff2, v_fr, v_meta, v_S, v_W, v_partial, v_in2, v_in3, v_st2;
@@ -127,7 +142,7 @@ static inline bool is_device_ptr(const void *p) {
 }
 
 // stage a (possibly host) input buffer on the device
-static inline int stage_in(kzgb200_ctx *c, const void *user, size_t bytes, DevBuf &buf, const void **dev) {
+static inline int stage_in(kzg_lane *c, const void *user, size_t bytes, DevBuf &buf, const void **dev) {
     if (bytes == 0) { *dev = buf.p; return 0; }          // empty input: user may be null
     if (is_device_ptr(user)) { *dev = user; return 0; }
     int rc = buf.ensure(bytes);
@@ -135,6 +150,30 @@ static inline int stage_in(kzgb200_ctx *c, const void *user, size_t bytes, DevBu
     CU(cudaMemcpyAsync(buf.p, user, bytes, cudaMemcpyHostToDevice, c->stream));
     *dev = buf.p;
     return 0;
+}
+
+// ---- per-lane implementations of the C ABI (kzgb200.cu, kzgb200_verify.cu, kzgb200_setup.cu) ----
+extern "C" {
+int lane_ctx_new(const uint8_t *g1_monomial, const uint8_t *g1_lagrange, const uint8_t *g2_monomial, size_t n_g2, const kzgb200_opts *opts, int device, kzg_lane **out);
+int lane_clone(kzg_lane *first, kzg_lane **out);      // another lane on the same GPU sharing `first`'s tables
+void lane_ctx_free(kzg_lane *c);
+int lane_blob_to_kzg_commitment(kzg_lane *c, const uint8_t *blobs, size_t n, uint8_t *out48, int32_t *status);
+int lane_compute_blob_kzg_proof(kzg_lane *c, const uint8_t *blobs, const uint8_t *commitments48, size_t n, uint8_t *out48, int32_t *status);
+int lane_compute_kzg_proof(kzg_lane *c, const uint8_t *blobs, const uint8_t *z32, size_t n, uint8_t *out_proof48, uint8_t *out_y32, int32_t *status);
+int lane_verify_kzg_proof(kzg_lane *c, const uint8_t *commitments48, const uint8_t *z32, const uint8_t *y32, const uint8_t *proofs48, size_t n, int32_t *status);
+int lane_verify_blob_kzg_proof(kzg_lane *c, const uint8_t *blobs, const uint8_t *commitments48, const uint8_t *proofs48, size_t n, int32_t *status);
+int lane_verify_blob_kzg_proof_batch(kzg_lane *c, const uint8_t *blobs, const uint8_t *commitments48, const uint8_t *proofs48, size_t n, int32_t *result);
+int lane_compute_cells(kzg_lane *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, int32_t *status);
+int lane_compute_cells_and_kzg_proofs(kzg_lane *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, uint8_t *out_proofs, int32_t *status);
+int lane_recover_cells_and_kzg_proofs(kzg_lane *c, const uint64_t *cell_ids, const uint64_t *counts, const uint8_t *cells, size_t n,
+                                      uint8_t *out_cells, uint8_t *out_proofs, int32_t *status);
+int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, const uint64_t *cell_indices, const uint8_t *cells, const uint8_t *proofs48,
+                                     size_t n_cells, const uint64_t *batch_offsets, size_t n_batches, int32_t *results);
+int lane_check_g1_points(kzg_lane *c, const uint8_t *points48, size_t n, int32_t *status);
+int lane_check_scalars(kzg_lane *c, const uint8_t *scalars32, size_t n_items, size_t scalars_per_item, int32_t *status);
+int lane_dbg_pairing(kzg_lane *c, const uint8_t *a48, const int *qa, const uint8_t *b48, const int *qb, int *out, int n);
+int lane_dbg_dump_pairing(kzg_lane *c, uint32_t *out96);
+int lane_dbg_vmsm(kzg_lane *c, const uint8_t *p48, const uint32_t *s, int n, uint8_t *out48);
 }
 
 // ---- launch wrappers of kzgb200_vmsm.cu (verification throughput kernels, full optimisation) ----
@@ -156,6 +195,6 @@ int vm_rlc_coeff_digits(cudaStream_t st, const Fr &seed, int unit_coeff, const u
 int vm_pairing_check(cudaStream_t st, const PairingConsts *pc, const G1 *A, int qa, const G1 *B, int qb, const int32_t *pre_status, int32_t *result, size_t n);
 // Open / EvaluateLagrangePolynomial for m blobs on stream st (k_eval_products, k_fr_inv_batch, k_eval_finish), using
 // scratch slots [slot, slot + m) of the scratch sized by vm_eval_scratch(total)
-int vm_eval_scratch(kzgb200_ctx *c, size_t total);
-int vm_eval_quotient(kzgb200_ctx *c, cudaStream_t st, size_t slot, const uint8_t *d_blobs, const uint32_t *z_limbs, int32_t *d_status, uint32_t *quotient,
+int vm_eval_scratch(kzg_lane *c, size_t total);
+int vm_eval_quotient(kzg_lane *c, cudaStream_t st, size_t slot, const uint8_t *d_blobs, const uint32_t *z_limbs, int32_t *d_status, uint32_t *quotient,
                      uint8_t *y_out, uint32_t *y_limbs, size_t m);

@@ -165,14 +165,30 @@ template <int MODE> static __global__ void k_imad_peak(uint32_t *out, int iters,
     }
 }
 
+// isolated chains of the library's own field operations: the practical ceiling of a kernel made of nothing but Fp products
+// (the pipe probe of profiles/r02_pipe_probe.md, kept in the library so bench.py measures it live on the box it runs on)
+template <bool SQR> static __global__ void __launch_bounds__(128) k_fp_chain(uint32_t *out, int iters, uint32_t seed) {
+    Fp x, y;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { x.v[k] = seed * (2 * k + 3) + threadIdx.x + blockIdx.x * 977u; y.v[k] = seed * (2 * k + 5) ^ (threadIdx.x * 2654435761u); }
+    x.v[11] &= 0x0fffffffu; y.v[11] &= 0x0fffffffu;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) x = SQR ? Fp::sqr(x) : Fp::mul(x, y);
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) r ^= x.v[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 }  // namespace kzg
 
-static int build_table(kzgb200_ctx *c, const G1Aff *pts, int npts, int window, MsmTable &tab) {
+static int build_table(kzg_lane *c, const G1Aff *pts, int npts, int window, MsmTable &tab) {
     tab.plan(npts, window);
     size_t n_bases = (size_t)npts * tab.W;
     G1 *bases = nullptr; G1Aff *bases_aff = nullptr;
-    CU(cudaMalloc(&bases, n_bases * sizeof(G1)));
-    CU(cudaMalloc(&bases_aff, n_bases * sizeof(G1Aff)));
+    InitTemps temps;
+    CU(cudaMalloc(&bases, n_bases * sizeof(G1))); temps.track(bases);
+    CU(cudaMalloc(&bases_aff, n_bases * sizeof(G1Aff))); temps.track(bases_aff);
     CU(cudaMalloc(&tab.entries, tab.bytes()));
     k_table_bases<<<(npts + 63) / 64, 64, 0, c->stream>>>(pts, tab, bases);
     k_to_affine<<<(unsigned)((n_bases + 127) / 128), 128, 0, c->stream>>>(bases, bases_aff, n_bases);
@@ -181,7 +197,6 @@ static int build_table(kzgb200_ctx *c, const G1Aff *pts, int npts, int window, M
     c->launches += 3;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(bases); cudaFree(bases_aff);
     return 0;
 }
 
@@ -196,17 +211,20 @@ void *kzgb200_host_alloc(size_t bytes) {
 }
 void kzgb200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
-void kzgb200_ctx_free(kzgb200_ctx *c) {
+void lane_ctx_free(kzg_lane *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->g1_monomial); cudaFree(c->g1_lagrange_brp); cudaFree(c->commit_tab.entries);
-    cudaFree(c->fk20_tab.entries); cudaFree(c->roots); cudaFree(c->glv_digits);
+    if (c->owns_tables) {
+        cudaFree(c->g1_monomial); cudaFree(c->g1_lagrange_brp); cudaFree(c->commit_tab.entries);
+        cudaFree(c->fk20_tab.entries); cudaFree(c->roots); cudaFree(c->glv_digits);
+        cudaFree(c->pow7); cudaFree(c->ipow7); cudaFree(c->pairing); cudaFree(c->mono64_tab.entries);
+    }
+    c->msm_partial.release();
     c->in_bytes.release(); c->scalars.release(); c->status.release(); c->sums.release(); c->out_bytes.release();
     c->coeffs.release(); c->cells.release(); c->proofs_xyzz.release(); c->fft_work.release();
     c->in_small.release(); c->in_small2.release(); c->zbuf.release(); c->ybuf.release();
     c->rec_a.release(); c->rec_b.release(); c->rec_meta.release(); c->rec_zev.release(); c->rec_czinv.release();
-    cudaFree(c->pow7); cudaFree(c->ipow7); cudaFree(c->pairing); cudaFree(c->mono64_tab.entries);
     c->v_aff1.release(); c->v_aff2.release(); c->v_fr.release(); c->v_meta.release(); c->v_S.release();
     c->v_W.release(); c->v_partial.release(); c->v_in2.release(); c->v_in3.release(); c->v_st2.release();
     c->vm_digits.release(); c->vm_digits256.release(); c->vm_colsum.release(); c->vm_rowdig.release(); c->vm_commsum.release(); c->vm_scratch.release(); c->vm_ws.release(); c->vm_wsb.release(); c->v_pa.release(); c->v_pb.release(); c->v_cst.release(); c->v_st3.release(); c->ev_cex.release(); c->ev_total.release(); c->ev_index.release();
@@ -222,10 +240,11 @@ void kzgb200_ctx_free(kzgb200_ctx *c) {
     delete c;
 }
 
-static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, const uint8_t *g2, size_t n_g2, const kzgb200_opts *opts) {
+// streams, events and per-device kernel attributes of a lane on `device`
+static int lane_streams_init(kzg_lane *c, int device) {
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
-    c->device = opts ? opts->device : 0;
+    c->device = device;
     if (c->device < 0 || c->device >= ndev) return set_err(KZGB200_ERR_CUDA, "no such CUDA device");
     CU(cudaSetDevice(c->device));
     cudaDeviceProp prop;
@@ -240,6 +259,13 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
     for (cudaEvent_t &e : c->ev_join) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     if (const char *e = getenv("KZGB200_G1FFT_SPLIT")) c->g1fft_split = (size_t)std::min(std::max(atoi(e), 1), KZG_G1FFT_MAX_SPLIT);
+    return 0;
+}
+
+static int ctx_init(kzg_lane *c, const uint8_t *g1m, const uint8_t *g1l, const uint8_t *g2, size_t n_g2, const kzgb200_opts *opts, int device) {
+    int rc0 = lane_streams_init(c, device);
+    if (rc0) return rc0;
+    InitTemps temps;
     c->g2_bytes.assign(g2, g2 + n_g2 * 96);
 
     int cw = opts && opts->commit_window ? opts->commit_window : 0;
@@ -247,8 +273,8 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
     if (cw < 7 || cw > 15) return set_err(KZGB200_ERR_ARGS, "commit_window must be in 7..15");
 
     uint8_t *d_in = nullptr; int32_t *d_bad = nullptr;
-    CU(cudaMalloc(&d_in, 2 * N_BLOB * 48));
-    CU(cudaMalloc(&d_bad, sizeof(int32_t)));
+    CU(cudaMalloc(&d_in, 2 * N_BLOB * 48)); temps.track(d_in);
+    CU(cudaMalloc(&d_bad, sizeof(int32_t))); temps.track(d_bad);
     CU(cudaMalloc(&c->g1_monomial, N_BLOB * sizeof(G1Aff)));
     CU(cudaMalloc(&c->g1_lagrange_brp, N_BLOB * sizeof(G1Aff)));
     CU(cudaMemsetAsync(d_bad, 0, sizeof(int32_t), c->stream));
@@ -260,7 +286,6 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
     int32_t bad = 0;
     CU(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(d_in); cudaFree(d_bad);
     if (bad) return set_err(KZGB200_ERR_SETUP, "trusted setup: G1 point failed to decode");
 
     int rc = build_table(c, c->g1_lagrange_brp, N_BLOB, cw, c->commit_tab);
@@ -291,14 +316,13 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
     if (!fw) { const char *e = getenv("KZGB200_FK20_WINDOW"); fw = e ? atoi(e) : 12; }
     if (fw < 7 || fw > 15) return set_err(KZGB200_ERR_ARGS, "fk20_window must be in 7..15");
     G1 *fk_xyzz = nullptr; G1Aff *fk_aff = nullptr;
-    CU(cudaMalloc(&fk_xyzz, 8192 * sizeof(G1)));
-    CU(cudaMalloc(&fk_aff, 8192 * sizeof(G1Aff)));
+    CU(cudaMalloc(&fk_xyzz, 8192 * sizeof(G1))); temps.track(fk_xyzz);
+    CU(cudaMalloc(&fk_aff, 8192 * sizeof(G1Aff))); temps.track(fk_aff);
     k_fk20_table_fft<<<64, 64, 0, c->stream>>>(c->g1_monomial, fk_xyzz, c->glv_digits);
     k_to_affine<<<8192 / 128, 128, 0, c->stream>>>(fk_xyzz, fk_aff, 8192);
     c->launches += 3;
     CU(cudaGetLastError());
     rc = build_table(c, fk_aff, 8192, fw, c->fk20_tab);
-    cudaFree(fk_xyzz); cudaFree(fk_aff);
     if (rc) return rc;
 
     // verification constants: G2 line tables (GPU, one thread per point) and the 64-point monomial table
@@ -306,7 +330,8 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
         uint8_t h_g2[3 * 96];
         memcpy(h_g2, g2, 96); memcpy(h_g2 + 96, g2 + 96, 96); memcpy(h_g2 + 192, g2 + 64 * 96, 96);
         uint8_t *d_g2 = nullptr; int32_t *d_bad2 = nullptr;
-        CU(cudaMalloc(&d_g2, sizeof h_g2)); CU(cudaMalloc(&d_bad2, 4));
+        CU(cudaMalloc(&d_g2, sizeof h_g2)); temps.track(d_g2);
+        CU(cudaMalloc(&d_bad2, 4)); temps.track(d_bad2);
         CU(cudaMalloc(&c->pairing, sizeof(PairingConsts)));
         CU(cudaMemsetAsync(d_bad2, 0, 4, c->stream));
         CU(cudaMemcpyAsync(d_g2, h_g2, sizeof h_g2, cudaMemcpyHostToDevice, c->stream));
@@ -315,7 +340,6 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
         int32_t bad2 = 0;
         CU(cudaMemcpyAsync(&bad2, d_bad2, 4, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
-        cudaFree(d_g2); cudaFree(d_bad2);
         if (bad2) return set_err(KZGB200_ERR_SETUP, "trusted setup: G2 point failed to decode");
     }
     rc = build_table(c, c->g1_monomial, 64, 15, c->mono64_tab);      // 64 points only: 1.8 GB buys 17 instead of 26 windows per scalar
@@ -323,21 +347,36 @@ static int ctx_init(kzgb200_ctx *c, const uint8_t *g1m, const uint8_t *g1l, cons
     return 0;
 }
 
-int kzgb200_ctx_new(const uint8_t *g1_monomial, const uint8_t *g1_lagrange, const uint8_t *g2_monomial, size_t n_g2,
-                    const kzgb200_opts *opts, kzgb200_ctx **out) {
+int lane_ctx_new(const uint8_t *g1_monomial, const uint8_t *g1_lagrange, const uint8_t *g2_monomial, size_t n_g2,
+                 const kzgb200_opts *opts, int device, kzg_lane **out) {
     if (!g1_monomial || !g1_lagrange || !g2_monomial || !out) return set_err(KZGB200_ERR_ARGS, "null argument");
     *out = nullptr;
     if (n_g2 < 65) return set_err(KZGB200_ERR_SETUP, "need at least 65 G2 points (api.go:93,115; kzg_multi/kzg_verify.go:92)");
     auto t0 = std::chrono::steady_clock::now();
-    kzgb200_ctx *c = new kzgb200_ctx();
-    int rc = ctx_init(c, g1_monomial, g1_lagrange, g2_monomial, n_g2, opts);
-    if (rc) { kzgb200_ctx_free(c); return rc; }
+    kzg_lane *c = new kzg_lane();
+    int rc = ctx_init(c, g1_monomial, g1_lagrange, g2_monomial, n_g2, opts, device);
+    if (rc) { lane_ctx_free(c); return rc; }
     c->init_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     *out = c;
     return KZGB200_OK;
 }
 
-int kzgb200_get_info(kzgb200_ctx *c, kzgb200_info *o) {
+int lane_clone(kzg_lane *f, kzg_lane **out) {
+    if (!f || !out) return set_err(KZGB200_ERR_ARGS, "null argument");
+    *out = nullptr;
+    kzg_lane *c = new kzg_lane();
+    c->owns_tables = false;
+    int rc = lane_streams_init(c, f->device);
+    if (rc) { lane_ctx_free(c); return rc; }
+    c->g1_monomial = f->g1_monomial; c->g1_lagrange_brp = f->g1_lagrange_brp; c->g2_bytes = f->g2_bytes;
+    c->commit_tab = f->commit_tab; c->fk20_tab = f->fk20_tab; c->mono64_tab = f->mono64_tab;
+    c->roots = f->roots; c->glv_digits = f->glv_digits; c->pow7 = f->pow7; c->ipow7 = f->ipow7; c->pairing = f->pairing;
+    c->g1fft_split = f->g1fft_split;
+    *out = c;
+    return KZGB200_OK;
+}
+
+int lane_get_info(kzg_lane *c, kzgb200_info *o) {
     if (!c || !o) return set_err(KZGB200_ERR_ARGS, "null argument");
     memset(o, 0, sizeof *o);
     o->device = c->device; o->sm_count = c->sm_count;
@@ -348,23 +387,36 @@ int kzgb200_get_info(kzgb200_ctx *c, kzgb200_info *o) {
     o->init_ms = c->init_ms; o->kernel_launches = c->launches;
     return KZGB200_OK;
 }
-double kzgb200_last_device_ms(kzgb200_ctx *c) { return c ? c->last_device_ms : 0.0; }
-int kzgb200_last_kernel_ms(kzgb200_ctx *c, double *out) {
-    if (!c || !out) return set_err(KZGB200_ERR_ARGS, "null argument");
-    for (int i = 0; i < KZGB200_N_KERNEL_CLASSES; ++i) out[i] = c->class_ms[i];
-    return KZGB200_OK;
-}
 
 // -------------------------------------------------------------------------------------------
 // BlobToKZGCommitment (prove.go:13-34): DeserializeBlob -> MSM against the bit-reversed Lagrange
 // SRS -> compress.  Processed in chunks of CHUNK blobs.
 // -------------------------------------------------------------------------------------------
 static const size_t COMMIT_CHUNK = 4096;
+
+// The 4096-point MSM of m blobs.  One CTA per blob fills the GPU only from about three CTAs per SM upwards; below that
+// (the reference's own calling pattern is ONE blob per call, prove.go:13-34) every blob's points are cut into S ranges,
+// one CTA each, and a second small kernel adds the S partial sums: 4096 x W gathered additions spread over S x 128
+// threads instead of 128, i.e. W + 7 + log2(S) dependent additions per thread instead of 32 W + 7.
+static int launch_commit_msm(kzg_lane *c, cudaStream_t st, const uint32_t *scalars, size_t m, const int32_t *d_status, G1 *sums) {
+    const int TPB = 128;
+    unsigned S = 1;
+    while (S < 32 && (size_t)S * m < (size_t)3 * c->sm_count) S <<= 1;
+    if (S == 1) {
+        k_msm_fixed<<<dim3(1, (unsigned)m), TPB, TPB * sizeof(G1), st>>>(scalars, c->commit_tab, N_BLOB, 1, TPB, d_status, sums);
+        return 0;
+    }
+    int rc = c->msm_partial.ensure(m * S * sizeof(G1));
+    if (rc) return rc;
+    k_msm_fixed<<<dim3(S, (unsigned)m), TPB, TPB * sizeof(G1), st>>>(scalars, c->commit_tab, N_BLOB / S, S, TPB, d_status, (G1 *)c->msm_partial.p);
+    k_sum_groups<<<(unsigned)m, 32, 32 * sizeof(G1), st>>>((const G1 *)c->msm_partial.p, S, d_status, sums);
+    c->launches += 1;
+    return 0;
+}
 #define KZG_H2D_PIECES 4
 
-int kzgb200_blob_to_kzg_commitment(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint8_t *out48, int32_t *status) {
+int lane_blob_to_kzg_commitment(kzg_lane *c, const uint8_t *blobs, size_t n, uint8_t *out48, int32_t *status) {
     if (!c || (n && (!blobs || !out48 || !status))) return set_err(KZGB200_ERR_ARGS, "null argument");
-    std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     c->timing_reset();
     const bool in_dev = n && is_device_ptr(blobs), out_dev = n && is_device_ptr(out48), st_dev = n && is_device_ptr(status);
@@ -404,8 +456,7 @@ int kzgb200_blob_to_kzg_commitment(kzgb200_ctx *c, const uint8_t *blobs, size_t 
             size_t ns = pm * N_BLOB;
             k_blob_to_scalars<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(pb, (uint32_t *)c->scalars.p + po * N_BLOB * 8, d_status + po, ns, N_BLOB);
             c->mark(KZGB200_KC_MSM);
-            k_msm_fixed<<<dim3(1, (unsigned)pm), TPB, TPB * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p + po * N_BLOB * 8, c->commit_tab, N_BLOB, 1, TPB,
-                                                                                       d_status + po, (G1 *)c->sums.p + po);
+            if ((rc = launch_commit_msm(c, c->stream, (const uint32_t *)c->scalars.p + po * N_BLOB * 8, pm, d_status + po, (G1 *)c->sums.p + po))) return rc;
             c->mark(KZGB200_KC_FINALIZE);
             k_finalize_g1<<<(unsigned)((pm + 64 * KZG_FIN_BATCH - 1) / (64 * KZG_FIN_BATCH)), 64, 0, c->stream>>>((const G1 *)c->sums.p + po, d_out + po * 48, d_status + po, pm, 1);
             c->launches += 3;
@@ -423,10 +474,9 @@ int kzgb200_blob_to_kzg_commitment(kzgb200_ctx *c, const uint8_t *blobs, size_t 
 // -------------------------------------------------------------------------------------------
 // ComputeKZGProof (prove.go:85-111) and ComputeBlobKZGProof (prove.go:46-77)
 // -------------------------------------------------------------------------------------------
-static int open_common(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *z32, const uint8_t *commitments, size_t n,
+static int open_common(kzg_lane *c, const uint8_t *blobs, const uint8_t *z32, const uint8_t *commitments, size_t n,
                        uint8_t *out_proof, uint8_t *out_y, int32_t *status) {
     if (!c || (n && (!blobs || !out_proof || !status || (!z32 && !commitments)))) return set_err(KZGB200_ERR_ARGS, "null argument");
-    std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     c->timing_reset();
     if (n == 0) return KZGB200_OK;
@@ -443,7 +493,7 @@ static int open_common(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *z32,
     for (size_t off = 0; off < n; off += chunk) {
         size_t m = std::min(chunk, n - off);
         const void *d_aux = nullptr;
-        // host blobs travel in geometrically growing pieces on the copy stream (see kzgb200_blob_to_kzg_commitment): every
+        // host blobs travel in geometrically growing pieces on the copy stream (see lane_blob_to_kzg_commitment): every
         // piece runs the whole chain hash -> evaluation -> quotient -> MSM as soon as it has landed.  The hash + evaluation of a
         // piece (latency-bound: one thread per SHA-256) runs on a side stream, under the previous piece's MSM.
         const bool in_dev = is_device_ptr(blobs);
@@ -489,7 +539,7 @@ static int open_common(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *z32,
             if ((rc = vm_eval_quotient(c, sp, po, pb, zl, d_status + po, ql, d_y ? d_y + po * 32 : nullptr, nullptr, pm))) return rc;
             if (split) { CU(cudaEventRecord(c->ev_join[pc], sp)); CU(cudaStreamWaitEvent(c->stream, c->ev_join[pc], 0)); }
             c->mark(KZGB200_KC_MSM);
-            k_msm_fixed<<<dim3(1, (unsigned)pm), TPB, TPB * sizeof(G1), c->stream>>>(ql, c->commit_tab, N_BLOB, 1, TPB, d_status + po, (G1 *)c->sums.p + po);
+            if ((rc = launch_commit_msm(c, c->stream, ql, pm, d_status + po, (G1 *)c->sums.p + po))) return rc;
             c->mark(KZGB200_KC_FINALIZE);
             k_finalize_g1<<<(unsigned)((pm + 64 * KZG_FIN_BATCH - 1) / (64 * KZG_FIN_BATCH)), 64, 0, c->stream>>>((const G1 *)c->sums.p + po, d_out + po * 48, d_status + po, pm, 1);
             if (d_y) { k_zero_failed<<<gb, 64, 0, c->stream>>>(d_y + po * 32, d_status + po, pm, 32); c->launches += 1; }
@@ -506,11 +556,11 @@ static int open_common(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *z32,
     return KZGB200_OK;
 }
 
-int kzgb200_compute_kzg_proof(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *z32, size_t n, uint8_t *out_proof48, uint8_t *out_y32, int32_t *status) {
+int lane_compute_kzg_proof(kzg_lane *c, const uint8_t *blobs, const uint8_t *z32, size_t n, uint8_t *out_proof48, uint8_t *out_y32, int32_t *status) {
     if (n && (!z32 || !out_y32)) return set_err(KZGB200_ERR_ARGS, "null argument");
     return open_common(c, blobs, z32, nullptr, n, out_proof48, out_y32, status);
 }
-int kzgb200_compute_blob_kzg_proof(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *commitments48, size_t n, uint8_t *out48, int32_t *status) {
+int lane_compute_blob_kzg_proof(kzg_lane *c, const uint8_t *blobs, const uint8_t *commitments48, size_t n, uint8_t *out48, int32_t *status) {
     if (n && !commitments48) return set_err(KZGB200_ERR_ARGS, "null argument");
     return open_common(c, blobs, nullptr, commitments48, n, out48, nullptr, status);
 }
@@ -521,11 +571,15 @@ int kzgb200_compute_blob_kzg_proof(kzgb200_ctx *c, const uint8_t *blobs, const u
 static const size_t CELLS_CHUNK = 1024;
 
 // coefficients (c->coeffs) -> 128 compressed proofs per blob (fk20.go:76-124); buffers must be sized by the caller
-static void launch_fk20_proofs(kzgb200_ctx *c, cudaStream_t st, size_t m, const Fr *coeffs, uint32_t *scalars, G1 *sums, G1 *pxyzz,
+static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr *coeffs, uint32_t *scalars, G1 *sums, G1 *pxyzz,
                                const int32_t *d_status, uint8_t *d_proofs, bool marks) {
     Fr inv128p; memcpy(inv128p.v, H_FR_INV128_PLAIN, sizeof inv128p.v);
     k_fk20_rows<<<dim3(64, (unsigned)m), 64, 0, st>>>(coeffs, scalars, d_status, c->roots, inv128p);
-    const int TPB = 128, L = 8;
+    // lanes per 64-point group: 8 for full batches (8 points x W windows per lane, short reduction tree); small batches
+    // spread each group over up to 64 lanes so that a single blob occupies 64 CTAs instead of 8
+    const int TPB = 128;
+    int L = 8;
+    while (L < 64 && (size_t)L * m < (size_t)2 * c->sm_count) L <<= 1;
     if (marks) c->mark(KZGB200_KC_MSM);
     k_msm_fixed<<<dim3(128 / (TPB / L), (unsigned)m), TPB, TPB * sizeof(G1), st>>>(scalars, c->fk20_tab, 64, 128, L, d_status, sums);
     if (marks) c->mark(KZGB200_KC_G1FFT);
@@ -562,9 +616,8 @@ static void launch_fk20_proofs(kzgb200_ctx *c, cudaStream_t st, size_t m, const 
     c->launches += 3;
 }
 
-static int cells_and_proofs(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, uint8_t *out_proofs, int32_t *status) {
+static int cells_and_proofs(kzg_lane *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, uint8_t *out_proofs, int32_t *status) {
     if (!c || (n && (!blobs || !out_cells || !status))) return set_err(KZGB200_ERR_ARGS, "null argument");
-    std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     c->timing_reset();
     if (n == 0) return KZGB200_OK;
@@ -628,10 +681,10 @@ static int cells_and_proofs(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint
     return KZGB200_OK;
 }
 
-int kzgb200_compute_cells(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, int32_t *status) {
+int lane_compute_cells(kzg_lane *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, int32_t *status) {
     return cells_and_proofs(c, blobs, n, out_cells, nullptr, status);
 }
-int kzgb200_compute_cells_and_kzg_proofs(kzgb200_ctx *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, uint8_t *out_proofs, int32_t *status) {
+int lane_compute_cells_and_kzg_proofs(kzg_lane *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, uint8_t *out_proofs, int32_t *status) {
     if (n && !out_proofs) return set_err(KZGB200_ERR_ARGS, "null argument");
     return cells_and_proofs(c, blobs, n, out_cells, out_proofs, status);
 }
@@ -642,11 +695,10 @@ int kzgb200_compute_cells_and_kzg_proofs(kzgb200_ctx *c, const uint8_t *blobs, s
 // -------------------------------------------------------------------------------------------
 static const size_t RECOVER_CHUNK = 1024;
 
-int kzgb200_recover_cells_and_kzg_proofs(kzgb200_ctx *c, const uint64_t *cell_ids, const uint64_t *counts, const uint8_t *cells, size_t n,
+int lane_recover_cells_and_kzg_proofs(kzg_lane *c, const uint64_t *cell_ids, const uint64_t *counts, const uint8_t *cells, size_t n,
                                          uint8_t *out_cells, uint8_t *out_proofs, int32_t *status) {
     if (!c || (n && (!counts || !out_cells || !status))) return set_err(KZGB200_ERR_ARGS, "null argument");
     if (n && (is_device_ptr(cell_ids) || is_device_ptr(counts))) return set_err(KZGB200_ERR_ARGS, "cell_ids/counts must be host pointers");
-    std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     c->timing_reset();
     if (n == 0) return KZGB200_OK;
@@ -772,6 +824,7 @@ int kzgb200_bench_imad(int device, int mode, double *imad_per_s, double *ms_out)
     CU(cudaSetDevice(device));
     cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
     int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    if (mode >= 3) { threads = 128; iters = 512; }
     uint32_t *d; CU(cudaMalloc(&d, (size_t)blocks * threads * 4));
     cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     double best = 1e30;
@@ -779,13 +832,15 @@ int kzgb200_bench_imad(int device, int mode, double *imad_per_s, double *ms_out)
         CU(cudaEventRecord(e0));
         if (mode == 0) k_imad_peak<0><<<blocks, threads>>>(d, iters, 17u + rep);
         else if (mode == 1) k_imad_peak<1><<<blocks, threads>>>(d, iters, 17u + rep);
-        else k_imad_peak<2><<<blocks, threads>>>(d, iters, 17u + rep);
+        else if (mode == 2) k_imad_peak<2><<<blocks, threads>>>(d, iters, 17u + rep);
+        else if (mode == 3) k_fp_chain<false><<<blocks, threads>>>(d, iters, 17u + rep);
+        else k_fp_chain<true><<<blocks, threads>>>(d, iters, 17u + rep);
         CU(cudaEventRecord(e1));
         CU(cudaEventSynchronize(e1));
         float ms; CU(cudaEventElapsedTime(&ms, e0, e1));
         if (rep > 0 && ms < best) best = ms;
     }
-    double ops = (double)blocks * threads * iters * 8.0 * 8.0;   // 8 unrolled x 8 mads
+    double ops = (double)blocks * threads * iters * (mode >= 3 ? 1.0 : 8.0 * 8.0);   // 8 unrolled x 8 mads; modes 3 / 4: field operations
     *imad_per_s = ops / (best * 1e-3);
     if (ms_out) *ms_out = best;
     cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -160,9 +160,8 @@ extern "C" int kzgb200_check_trusted_setup(int device, const uint8_t *g1_lagrang
 // ---- codec validation entry points ---------------------------------------
 // DeserializeKZGCommitment / DeserializeKZGProof (serialization.go:108-131): status[i] of n compressed G1 points
 // (decode + subgroup check, exactly what every API call applies to its G1 inputs).
-extern "C" int kzgb200_check_g1_points(kzgb200_ctx *c, const uint8_t *points48, size_t n, int32_t *status) {
+extern "C" int lane_check_g1_points(kzg_lane *c, const uint8_t *points48, size_t n, int32_t *status) {
     if (!c || (n && (!points48 || !status))) return set_err(KZGB200_ERR_ARGS, "null argument");
-    std::lock_guard<std::mutex> lk(c->mu);
     CUS(cudaSetDevice(c->device));
     if (!n) return KZGB200_OK;
     const bool st_dev = is_device_ptr(status);
@@ -181,9 +180,8 @@ extern "C" int kzgb200_check_g1_points(kzgb200_ctx *c, const uint8_t *points48, 
 }
 // DeserializeScalar / DeserializeBlob (serialization.go:134-159): status[i] = OK or NON_CANONICAL_SCALAR for n items of
 // `scalars_per_item` big-endian 32-byte scalars each (1 for a Scalar, 4096 for a Blob, 64 for a Cell)
-extern "C" int kzgb200_check_scalars(kzgb200_ctx *c, const uint8_t *scalars32, size_t n_items, size_t scalars_per_item, int32_t *status) {
+extern "C" int lane_check_scalars(kzg_lane *c, const uint8_t *scalars32, size_t n_items, size_t scalars_per_item, int32_t *status) {
     if (!c || !scalars_per_item || (n_items && (!scalars32 || !status))) return set_err(KZGB200_ERR_ARGS, "null argument");
-    std::lock_guard<std::mutex> lk(c->mu);
     CUS(cudaSetDevice(c->device));
     if (!n_items) return KZGB200_OK;
     const bool st_dev = is_device_ptr(status);

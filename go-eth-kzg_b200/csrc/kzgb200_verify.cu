@@ -53,7 +53,7 @@ static const size_t VERIFY_CHUNK = 4096;
 // travel in pieces on the copy stream and each piece gets a side stream of its own as soon as it has landed
 // (pieces queued on ONE stream would serialise that latency); device blobs are one piece.
 #define VERIFY_MAX_PIECES (KZG_G1FFT_MAX_SPLIT - 1)
-static int verify_front(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm48, const uint8_t *z32, const uint8_t *y32, const uint8_t *pf48,
+static int verify_front(kzg_lane *c, const uint8_t *blobs, const uint8_t *cm48, const uint8_t *z32, const uint8_t *y32, const uint8_t *pf48,
                         size_t m, int32_t *d_status, G1Aff *out_cm, G1Aff *out_pf, uint32_t *zl, uint32_t *yl) {
     int rc;
     const void *d_cm, *d_pf, *d_z = nullptr, *d_y = nullptr;
@@ -117,10 +117,9 @@ static int verify_front(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm4
     return 0;
 }
 
-static int verify_independent(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm48, const uint8_t *z32, const uint8_t *y32,
+static int verify_independent(kzg_lane *c, const uint8_t *blobs, const uint8_t *cm48, const uint8_t *z32, const uint8_t *y32,
                               const uint8_t *pf48, size_t n, int32_t *status) {
     if (!c || (n && (!cm48 || !pf48 || !status || (!blobs && (!z32 || !y32))))) return set_err(KZGB200_ERR_ARGS, "null argument");
-    std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     c->timing_reset();
     if (n == 0) return KZGB200_OK;
@@ -155,16 +154,16 @@ static int verify_independent(kzgb200_ctx *c, const uint8_t *blobs, const uint8_
     return KZGB200_OK;
 }
 
-int kzgb200_verify_kzg_proof(kzgb200_ctx *c, const uint8_t *commitments48, const uint8_t *z32, const uint8_t *y32, const uint8_t *proofs48, size_t n, int32_t *status) {
+int lane_verify_kzg_proof(kzg_lane *c, const uint8_t *commitments48, const uint8_t *z32, const uint8_t *y32, const uint8_t *proofs48, size_t n, int32_t *status) {
     if (n && (!z32 || !y32)) return set_err(KZGB200_ERR_ARGS, "null argument");
     return verify_independent(c, nullptr, commitments48, z32, y32, proofs48, n, status);
 }
-int kzgb200_verify_blob_kzg_proof(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *commitments48, const uint8_t *proofs48, size_t n, int32_t *status) {
+int lane_verify_blob_kzg_proof(kzg_lane *c, const uint8_t *blobs, const uint8_t *commitments48, const uint8_t *proofs48, size_t n, int32_t *status) {
     if (n && !blobs) return set_err(KZGB200_ERR_ARGS, "null argument");
     return verify_independent(c, blobs, commitments48, nullptr, nullptr, proofs48, n, status);
 }
 
-static void random_scalar_plain(kzgb200_ctx *c, uint32_t *limbs) {   // 248 random bits from the OS entropy source (std::random_device -> /dev/urandom)
+static void random_scalar_plain(kzg_lane *c, uint32_t *limbs) {   // 248 random bits from the OS entropy source (std::random_device -> /dev/urandom)
     (void)c;
     std::random_device rd;
     for (int i = 0; i < 8; ++i) limbs[i] = rd();
@@ -173,10 +172,9 @@ static void random_scalar_plain(kzgb200_ctx *c, uint32_t *limbs) {   // 248 rand
 }
 
 // VerifyBlobKZGProofBatch (verify.go:88-145 + internal/kzg/kzg_verify.go:111-202): one verdict
-int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *blobs, const uint8_t *cm48, const uint8_t *pf48, size_t n, int32_t *result) {
+int lane_verify_blob_kzg_proof_batch(kzg_lane *c, const uint8_t *blobs, const uint8_t *cm48, const uint8_t *pf48, size_t n, int32_t *result) {
     if (!c || !result || (n && (!blobs || !cm48 || !pf48))) return set_err(KZGB200_ERR_ARGS, "null argument");
     if (is_device_ptr(result)) return set_err(KZGB200_ERR_ARGS, "result must be a host pointer");
-    std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     c->timing_reset();
     *result = KZGB200_OK;
@@ -249,12 +247,11 @@ int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *blobs, co
 
 // VerifyCellKZGProofBatch (api_eip7594.go:163-265 + internal/kzg_multi/kzg_verify.go:16-105)
 // cell_indices and batch_offsets (n_batches+1 entries) are read on the host.
-int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *c, const uint8_t *commitments48, const uint64_t *cell_indices, const uint8_t *cells,
+int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, const uint64_t *cell_indices, const uint8_t *cells,
                                         const uint8_t *proofs48, size_t N, const uint64_t *batch_offsets, size_t nb, int32_t *results) {
     if (!c || (nb && (!batch_offsets || !results)) || (N && (!commitments48 || !cell_indices || !cells || !proofs48)))
         return set_err(KZGB200_ERR_ARGS, "null argument");
     if (N && (is_device_ptr(cell_indices) || is_device_ptr(batch_offsets))) return set_err(KZGB200_ERR_ARGS, "cell_indices/batch_offsets must be host pointers");
-    std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     c->timing_reset();
     if (nb == 0) return KZGB200_OK;
@@ -441,7 +438,7 @@ int kzgb200_dbg_g1_mul(const uint8_t *p48, const uint8_t *s32, uint8_t *out48, i
     cudaFree(dp); cudaFree(ds); cudaFree(dout);
     return 0;
 }
-int kzgb200_dbg_pairing(kzgb200_ctx *c, const uint8_t *a48, const int *qa, const uint8_t *b48, const int *qb, int *out, int n) {
+int lane_dbg_pairing(kzg_lane *c, const uint8_t *a48, const int *qa, const uint8_t *b48, const int *qb, int *out, int n) {
     uint8_t *da, *db; int32_t *dout; G1 *dA, *dB;
     CU(cudaSetDevice(c->device));
     CU(cudaMalloc(&da, n * 48)); CU(cudaMalloc(&db, n * 48)); CU(cudaMalloc(&dout, n * 4)); CU(cudaMalloc(&dA, n * sizeof(G1))); CU(cudaMalloc(&dB, n * sizeof(G1)));
@@ -458,7 +455,7 @@ int kzgb200_dbg_pairing(kzgb200_ctx *c, const uint8_t *a48, const int *qa, const
     cudaFree(da); cudaFree(db); cudaFree(dout); cudaFree(dA); cudaFree(dB);
     return 0;
 }
-int kzgb200_dbg_dump_pairing(kzgb200_ctx *c, uint32_t *out96) {
+int lane_dbg_dump_pairing(kzg_lane *c, uint32_t *out96) {
     uint32_t *d;
     CU(cudaSetDevice(c->device));
     CU(cudaMalloc(&d, 96 * 4));

@@ -84,13 +84,13 @@ int vm_pairing_check(cudaStream_t st, const PairingConsts *pc, const G1 *A, int 
 // Open / EvaluateLagrangePolynomial for m blobs on stream st (three launches, see kzg4844.cuh).
 // vm_eval_scratch sizes the scratch for `total` blobs; a call works on scratch slots [slot, slot + m),
 // so calls on different streams must use disjoint slot ranges.
-int vm_eval_scratch(kzgb200_ctx *c, size_t total) {
+int vm_eval_scratch(kzg_lane *c, size_t total) {
     int rc;
     if ((rc = c->ev_cex.ensure(total * KZG_NTT_THREADS * sizeof(Fr)))) return rc;
     if ((rc = c->ev_total.ensure(total * sizeof(Fr)))) return rc;
     return c->ev_index.ensure(total * sizeof(int32_t));
 }
-int vm_eval_quotient(kzgb200_ctx *c, cudaStream_t st, size_t slot, const uint8_t *d_blobs, const uint32_t *z_limbs, int32_t *d_status, uint32_t *quotient,
+int vm_eval_quotient(kzg_lane *c, cudaStream_t st, size_t slot, const uint8_t *d_blobs, const uint32_t *z_limbs, int32_t *d_status, uint32_t *quotient,
                      uint8_t *y_out, uint32_t *y_limbs, size_t m) {
     if (!m) return 0;
     Fr inv4096; memcpy(inv4096.v, H_FR_INV4096, sizeof inv4096.v);
@@ -148,7 +148,7 @@ extern "C" int kzgb200_dbg_glv_digits(const uint32_t *s, int8_t *digits, int n) 
     return 0;
 }
 
-extern "C" int kzgb200_dbg_vmsm(kzgb200_ctx *c, const uint8_t *p48, const uint32_t *s, int n, uint8_t *out48) {
+extern "C" int lane_dbg_vmsm(kzg_lane *c, const uint8_t *p48, const uint32_t *s, int n, uint8_t *out48) {
     if (!c || n <= 0) return set_err(KZGB200_ERR_ARGS, "bad argument");
     CUL(cudaSetDevice(c->device));
     const size_t n_items = ((size_t)n + 127) / 128;

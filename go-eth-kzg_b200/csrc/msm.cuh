@@ -132,6 +132,20 @@ static __global__ void __launch_bounds__(128) k_msm_fixed(const uint32_t *__rest
     if (lane == 0 && group < n_groups) out[(size_t)blob * n_groups + group] = sm[t];
 }
 
+// out[blob] = sum of the S (<= 32, power of two) partial sums of a blob: one warp per blob, tree through shared memory
+static __global__ void __launch_bounds__(32) k_sum_groups(const G1 *__restrict__ partial, int S, const int32_t *__restrict__ status, G1 *__restrict__ out) {
+    const int blob = blockIdx.x, t = threadIdx.x;
+    if (status && status[blob] != ST_OK) return;
+    G1 *sm = reinterpret_cast<G1 *>(msm_smem);
+    sm[t] = t < S ? partial[(size_t)blob * S + t] : G1::infinity();
+    __syncwarp();
+    for (int s = S >> 1; s > 0; s >>= 1) {
+        if (t < s) g1_add_ool(&sm[t], &sm[t + s]);
+        __syncwarp();
+    }
+    if (t == 0) out[blob] = sm[0];
+}
+
 // ---- table construction (context init) ---------------------------------------------------
 // step 1: bases[(j*W + k)] = 2^(bitpos[k]) * P_j  in XYZZ
 static __global__ void k_table_bases(const G1Aff *__restrict__ pts, MsmTable tab, G1 *__restrict__ bases) {

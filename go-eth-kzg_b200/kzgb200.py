@@ -32,7 +32,8 @@ class KzgError(RuntimeError):
 
 class Opts(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int), ("commit_window", ctypes.c_int), ("fk20_window", ctypes.c_int),
-                ("reserved", ctypes.c_int * 5)]
+                ("n_devices", ctypes.c_int), ("devices", ctypes.POINTER(ctypes.c_int)), ("lanes", ctypes.c_int),
+                ("reserved", ctypes.c_int * 1)]
 
 
 class Info(ctypes.Structure):
@@ -40,7 +41,8 @@ class Info(ctypes.Structure):
                 ("commit_window", ctypes.c_int), ("commit_windows_per_scalar", ctypes.c_int),
                 ("fk20_window", ctypes.c_int), ("fk20_windows_per_scalar", ctypes.c_int),
                 ("commit_table_bytes", ctypes.c_uint64), ("fk20_table_bytes", ctypes.c_uint64),
-                ("init_ms", ctypes.c_double), ("kernel_launches", ctypes.c_uint64)]
+                ("init_ms", ctypes.c_double), ("kernel_launches", ctypes.c_uint64),
+                ("n_devices", ctypes.c_int), ("lanes_per_device", ctypes.c_int)]
 
 
 _lib = None
@@ -116,17 +118,25 @@ def _ptr(x):
 class Context:
     """Mirror of goethkzg.Context.  NewContext4096Secure (api.go:53) == Context()."""
 
-    def __init__(self, device=0, commit_window=0, fk20_window=0, setup_path=SETUP, setup_json=None):
-        """setup_json: text of a JSONTrustedSetup (NewContext4096(&parsed), api.go:90); default: the packed mainnet setup"""
+    def __init__(self, device=0, commit_window=0, fk20_window=0, setup_path=SETUP, setup_json=None, devices=None, lanes=0, setup=None):
+        """setup_json: text of a JSONTrustedSetup (NewContext4096(&parsed), api.go:90); setup: (g1_monomial, g1_lagrange,
+        g2_monomial) flat bytes; default: the packed mainnet setup.  devices: list of CUDA ordinals, or "all" (one replica of
+        the tables per GPU, batched host-buffer calls are sharded over them); lanes: concurrent calls per GPU (0 = default)."""
         L = load_library()
         self.L = L
-        opts = Opts(device=device, commit_window=commit_window, fk20_window=fk20_window)
+        opts = Opts(device=device, commit_window=commit_window, fk20_window=fk20_window, lanes=lanes)
+        if devices == "all":
+            opts.n_devices = -1
+        elif devices:
+            self._devs = (ctypes.c_int * len(devices))(*devices)
+            opts.n_devices = len(devices)
+            opts.devices = ctypes.cast(self._devs, ctypes.POINTER(ctypes.c_int))
         ctx = ctypes.c_void_p()
         if setup_json is not None:
             raw = setup_json.encode() if isinstance(setup_json, str) else bytes(setup_json)
             rc = L.kzgb200_ctx_new_from_json(raw, ctypes.c_size_t(len(raw)), ctypes.byref(opts), ctypes.byref(ctx))
         else:
-            m, l, g2 = load_trusted_setup(setup_path)
+            m, l, g2 = setup if setup is not None else load_trusted_setup(setup_path)
             rc = L.kzgb200_ctx_new(m, l, g2, ctypes.c_size_t(len(g2) // 96), ctypes.byref(opts), ctypes.byref(ctx))
         if rc != OK:
             raise KzgError(rc, L.kzgb200_last_error().decode())

@@ -15,9 +15,10 @@
  *    outcomes are written to status[i] (int32_t), see enum kzgb200_status.  A per-item failure
  *    leaves that item's outputs zeroed.  The library never aborts and never falls back to the
  *    CPU: without a usable CUDA device kzgb200_ctx_new fails with KZGB200_ERR_CUDA.
- *  - A context is immutable after creation and may be used from several host threads
- *    (calls serialise on an internal lock per context; api.go:17-28 documents the same
- *    "create once, share" usage).
+ *  - A context is immutable after creation and may be used from several host threads at once
+ *    (api.go:17-28 documents the same "create once, share" usage; verify.go:159-166 calls a method from
+ *    N goroutines): every GPU of the context has kzgb200_opts.lanes execution lanes, a call takes a free one
+ *    (small calls rotate over the GPUs), callers beyond that wait.
  */
 #ifndef KZGB200_H
 #define KZGB200_H
@@ -58,13 +59,21 @@ enum kzgb200_status {
 
 typedef struct kzgb200_ctx kzgb200_ctx;
 
-/* Tunables.  Zero-initialise for defaults. */
+/* Tunables.  Zero-initialise for defaults (one GPU: device 0). */
 typedef struct kzgb200_opts {
-    int device;          /* CUDA device ordinal */
+    int device;          /* CUDA device ordinal, used when n_devices == 0 */
     int commit_window;   /* bits per fixed-base window for the 4096-point Lagrange MSM (7..15); the top 256 mod c windows are one bit wider (MsmTable::plan);
                             table bytes = 4096 * ceil(256/c) * 2^(c-1) * 96.  0 = default */
     int fk20_window;     /* same for the 8192-point FK20 table (twice the bytes).  0 = default */
-    int reserved[5];
+    int n_devices;       /* 0: the single GPU `device`.  k > 0: the GPUs devices[0..k).  -1: every visible GPU.
+                            Each GPU holds a full replica of the tables; a batched call on HOST buffers is cut into
+                            contiguous ranges, one per GPU, copied and computed concurrently, results written to disjoint slices of
+                            the caller's buffers; the RLC verifiers run one sub-verdict per GPU and AND them (verify.go:152-169 is
+                            the reference's own fan-out shape).  Calls on DEVICE buffers run on the GPU that owns the buffers. */
+    const int *devices;  /* ordinals when n_devices > 0 (an ordinal may repeat: one more replica on that GPU, for tests) */
+    int lanes;           /* concurrent calls per GPU: each lane has its own streams and scratch arena, so `lanes` host threads
+                            (goroutines) can be inside the library at once per GPU; further callers wait.  0 = default (2) */
+    int reserved[1];
 } kzgb200_opts;
 
 /* NewContext4096 (api.go:90-149): g1_monomial / g1_lagrange are 4096 compressed G1 points each
@@ -156,7 +165,9 @@ typedef struct kzgb200_info {
     int fk20_window, fk20_windows_per_scalar;
     uint64_t commit_table_bytes, fk20_table_bytes;
     double init_ms;
-    uint64_t kernel_launches;   /* launches issued by this context since creation */
+    uint64_t kernel_launches;   /* launches issued by this context since creation (all GPUs, all lanes) */
+    int n_devices;              /* GPUs of this context; `device` above is the first */
+    int lanes_per_device;
 } kzgb200_info;
 int kzgb200_get_info(kzgb200_ctx *ctx, kzgb200_info *out);
 
@@ -175,7 +186,9 @@ enum kzgb200_kernel_class {
 int kzgb200_last_kernel_ms(kzgb200_ctx *ctx, double out[KZGB200_N_KERNEL_CLASSES]);
 
 /* Time of the device-side part of the LAST API call on this context, measured with CUDA events
- * on the context's stream (kernels only, excluding H2D/D2H when inputs were host buffers) */
+ * on the lane's stream (kernels only, excluding H2D/D2H when inputs were host buffers); with several GPUs the
+ * maximum over the GPUs that took part (kzgb200_last_kernel_ms likewise, per class).  Meaningful when one host
+ * thread uses the context (benchmarks); concurrent callers overwrite each other's record. */
 double kzgb200_last_device_ms(kzgb200_ctx *ctx);
 
 #ifdef __cplusplus

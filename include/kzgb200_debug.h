@@ -4,6 +4,7 @@
  * Operands are plain (non-Montgomery) little-endian 32-bit limbs: 12 per Fp, 8 per Fr. */
 #ifndef KZGB200_DEBUG_H
 #define KZGB200_DEBUG_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -35,8 +36,15 @@ int kzgb200_dbg_g2_selftest(const uint8_t *in96, int *mask);
  * lists, as JSON text in a thread-local buffer; NULL if batch_offsets is not monotone / out of range */
 const char *kzgb200_dbg_plan_cell_batches_json(const uint8_t *commitments48, const uint64_t *cell_indices, size_t n_cells,
                                                const uint64_t *batch_offsets, size_t n_batches, uint64_t item, uint64_t large, uint64_t row_item);
+/* host-side sharding of a batched call over the GPUs of a context (csrc/shard_plan.hpp; no GPU involved), as JSON text in a
+ * thread-local buffer: "units" = contiguous ranges of n_units independent units over n_dev devices with at least min_per_dev
+ * each; "verdicts" = ranges of verdicts balanced by cell count (batch_offsets may be NULL); "merged" = the three-way merge of
+ * the sub-verdicts of one logical verdict (first error in index order, else VERIFY_FAILED if any, else OK) */
+const char *kzgb200_dbg_shard_plan_json(size_t n_units, size_t n_dev, size_t min_per_dev, const uint64_t *batch_offsets, size_t n_batches,
+                                        size_t min_cells_per_dev, const int32_t *sub_verdicts, size_t n_sub);
 /* dependency-free integer multiply-add microbenchmark: device-wide instructions*lanes per second.
- * mode 0: mad.lo.u32 (IMAD), 1: mad.hi.u32 (IMAD.HI), 2: mad.wide.u32 (IMAD.WIDE, 32x32+64) */
+ * mode 0: mad.lo.u32 (IMAD), 1: mad.hi.u32 (IMAD.HI), 2: mad.wide.u32 (IMAD.WIDE, 32x32+64);
+ * mode 3 / 4: a bare dependent chain of the library's Fp::mul / Fp::sqr per thread -> field operations per second */
 int kzgb200_bench_imad(int device, int mode, double *per_s, double *ms_out);
 #ifdef __cplusplus
 }

@@ -691,6 +691,31 @@ int ko_g1_msm(const uint8_t *points48, const uint8_t *scalars32, size_t n, uint8
     g1_compress(out48, msm(p.data(), s.data(), n).to_affine());
     return 0;
 }
+// out48[i] = [scalars[i]] P and out96[i] = [scalars[i]] Q for ONE base point each (compressed in/out, BE scalars):
+// what srs_insecure.go:27-58 and kzg_multi/srs.go:113-141 do with a known secret to build a test SRS
+int ko_g1_mul_many(const uint8_t *p48, const uint8_t *scalars32, size_t n, uint8_t *out48) {
+    init_all();
+    G1Affine p;
+    if (g1_decompress(p, p48, false)) return ST_BAD_G1_ENCODING;
+    G1Jac pj = G1Jac::from_affine(p);
+    for (size_t i = 0; i < n; ++i) g1_compress(out48 + 48 * i, g1_mul_fr(pj, Fr::from_bytes_be_reduce(scalars32 + 32 * i)).to_affine());
+    return 0;
+}
+int ko_g2_mul_many(const uint8_t *q96, const uint8_t *scalars32, size_t n, uint8_t *out96) {
+    init_all();
+    G2Affine q;
+    if (g2_decompress(q, q96)) return ST_BAD_G1_ENCODING;
+    G2Jac qj = G2Jac::from_affine(q);
+    for (size_t i = 0; i < n; ++i) {
+        G2Affine a = g2_mul_fr(qj, Fr::from_bytes_be_reduce(scalars32 + 32 * i)).to_affine();
+        uint8_t *b = out96 + 96 * i;
+        if (a.inf) { memset(b, 0, 96); b[0] = 0xc0; continue; }
+        a.x.c1.to_bytes_be(b); a.x.c0.to_bytes_be(b + 48);
+        b[0] |= 0x80;
+        if (a.y.lex_largest()) b[0] |= 0x20;
+    }
+    return 0;
+}
 // pairing product check over n (G1 compressed, G2 compressed) pairs: 1 if product == 1
 int ko_pairing_check(const uint8_t *g1s, const uint8_t *g2s, size_t n) {
     init_all();

@@ -19,8 +19,11 @@ def build():
 def lib():
     with _lock:
         if "lib" not in _state:
-            if not os.path.exists(SO):
-                build()
+            try:
+                build()                      # make: a no-op when the library is newer than its sources
+            except Exception:
+                if not os.path.exists(SO):
+                    raise
             L = ctypes.CDLL(SO)
             L.ko_ctx_new.restype = ctypes.c_void_p
             L.ko_ctx_new.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
@@ -37,9 +40,9 @@ def load_setup():
 class Oracle:
     """Mirrors the reference's Context method set; each method returns (status, outputs...)."""
 
-    def __init__(self):
+    def __init__(self, setup=None):
         L = lib()
-        m, l, g2 = load_setup()
+        m, l, g2 = setup if setup is not None else load_setup()
         self.L = L
         self.ctx = ctypes.c_void_p(L.ko_ctx_new(m, l, g2, len(g2) // 96))
         assert self.ctx.value, "oracle ctx_new failed"
@@ -133,6 +136,35 @@ def rand_blob(seed):
 
 
 _oracle = {}
+
+
+R_MOD = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+G1_GEN = bytes.fromhex("97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb")
+
+
+def insecure_setup(secret):
+    """(g1_monomial, g1_lagrange, g2_monomial[0..64]) for a KNOWN secret s, as the reference's tests build them
+    (internal/kzg/srs_insecure.go:19-58, internal/kzg_multi/srs.go:113-141): [s^i]G1, [L_i(s)]G1 over the natural-order
+    4096th roots of unity, [s^i]G2.  The scalars are computed with Python integers; the oracle only multiplies."""
+    L = lib()
+    n = 4096
+    w = pow(7, (R_MOD - 1) // n, R_MOD)
+    pows = [pow(secret, i, R_MOD) for i in range(n)]
+    zn = (pow(secret, n, R_MOD) - 1) * pow(n, -1, R_MOD) % R_MOD
+    lag = [zn * pow(w, i, R_MOD) % R_MOD * pow((secret - pow(w, i, R_MOD)) % R_MOD, -1, R_MOD) % R_MOD for i in range(n)]
+    be = lambda xs: b"".join(x.to_bytes(32, "big") for x in xs)
+    m = ctypes.create_string_buffer(48 * n); l = ctypes.create_string_buffer(48 * n); g2 = ctypes.create_string_buffer(96 * 65)
+    assert L.ko_g1_mul_many(G1_GEN, be(pows), ctypes.c_size_t(n), m) == 0
+    assert L.ko_g1_mul_many(G1_GEN, be(lag), ctypes.c_size_t(n), l) == 0
+    assert L.ko_g2_mul_many(load_setup()[2][:96], be(pows[:65]), ctypes.c_size_t(65), g2) == 0      # g2_monomial[0] of any setup is the G2 generator
+    return m.raw, l.raw, g2.raw
+
+
+def g1_mul_gen(k):
+    """[k]G1 compressed"""
+    out = ctypes.create_string_buffer(48)
+    assert lib().ko_g1_mul_many(G1_GEN, (k % R_MOD).to_bytes(32, "big"), ctypes.c_size_t(1), out) == 0
+    return out.raw
 
 
 def get_oracle():

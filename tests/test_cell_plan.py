@@ -108,3 +108,8 @@ def test_plan_matches_model():
     check([], [], [0, 0])
     assert plan([cm[0]] * 4, [0, 1, 2, 3], [0, 5]) is None
     assert plan([cm[0]] * 4, [0, 1, 2, 3], [3, 2]) is None
+    # offsets that leave cells outside every verdict are malformed too (such cells used to be decoded anyway and
+    # their errors folded into verdict 0)
+    assert plan([cm[0]] * 4, [0, 1, 2, 3], [1, 4]) is None
+    assert plan([cm[0]] * 4, [0, 1, 2, 3], [0, 3]) is None
+    assert plan([cm[0]] * 4, [0, 1, 2, 3], [0, 2, 3]) is None

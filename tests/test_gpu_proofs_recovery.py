@@ -63,3 +63,29 @@ def test_recover_error_statuses_in_batch(ctx):
     assert [g[0] for g in got] == [0, 8, 9, 7, 0]
     assert got[0][1] == cells and got[4][2] == proofs
     assert got[1][1] == bytes(262144) and got[2][2] == bytes(6144)
+
+
+def test_recover_cells_without_proofs(ctx):
+    """Context.RecoverCells (api_eip.go:8-15) = the out_proofs == NULL branch of kzgb200_recover_cells_and_kzg_proofs: same cells as
+    the full call and as the direct computation, same error statuses, for the 4 valid + the invalid recovery spec vectors"""
+    from golden_util import cases, resolve, BadHex
+    o = oracle_lib.get_oracle()
+    n_valid = 0
+    for c in cases("recover_cells_and_kzg_proofs"):
+        try:
+            ids = list(c["input"]["cell_indices"]); cl = [resolve(x) for x in c["input"]["cells"]]
+        except BadHex:
+            continue
+        st, cells = ctx.recover_cells(ids, cl)
+        est = o.recover_cells(ids, cl)
+        if c["output"] is None:
+            assert st != 0 and est[0] != 0, c["name"]
+        else:
+            n_valid += 1
+            assert st == 0 and cells == b"".join(resolve(x) for x in c["output"][0]) == est[1], c["name"]
+    assert n_valid >= 4
+    blob = oracle_lib.rand_blob(77 << 20)
+    st, cells, proofs = ctx.compute_cells_and_kzg_proofs(blob)
+    ids = sorted(random.Random(7).sample(range(128), 70))
+    got = ctx.recover_cells_and_kzg_proofs_batch([ids, list(range(63))], [[cells[2048 * i:2048 * i + 2048] for i in ids], [cells[2048 * i:2048 * i + 2048] for i in range(63)]], proofs=False)
+    assert got[0] == (0, cells) and got[1][0] == 9 and got[1][1] == bytes(262144)
