@@ -87,6 +87,7 @@ struct kzg_lane {
     cudaStream_t fft_streams[KZG_G1FFT_MAX_SPLIT - 1] = {nullptr};   // sub-batches of the staged G1 FFT (launch_fk20_proofs)
     cudaEvent_t ev_fork = nullptr, ev_join[KZG_G1FFT_MAX_SPLIT - 1] = {nullptr};
     size_t g1fft_split = 8;             // measured: 1 -> 40.9 ms, 2 -> 34.6, 4 -> 33.5, 8 -> 33.1 (KZGB200_G1FFT_SPLIT overrides)
+    size_t g1_dense_max = 24;           // batches up to this many blobs take the dense one-level G1 transform (KZGB200_G1_DENSE_MAX overrides)
     bool owns_tables = true;            // false for clones: setup pointers below belong to the GPU's first lane
     // setup
     G1Aff *g1_monomial = nullptr;      // natural order

@@ -25,6 +25,7 @@ namespace kzg {
 #define KZG_G1FFT_TPB 128   // measured on B200 (1024 blobs, split 8): 32 -> 37.8 ms, 64 -> 34.7 ms, 128 -> 33.1 ms
 #endif
 __device__ __constant__ uint16_t TW_PROG[128][KZG_TW_PROG_LEN];   // uploaded from H_TW_PROG (constants.inc)
+__device__ __constant__ uint16_t DENSE_PROG[65][KZG_TW_PROG_LEN]; // uploaded from H_DENSE_PROG: scalars of the dense small-batch transform
 
 // 16-byte vector moves of field elements / points (all records are 16-byte aligned)
 __device__ __forceinline__ Fp ld_fp(const Fp *p) {
@@ -84,7 +85,10 @@ static __device__ __noinline__ void jac_add_ool(G1J *a, const G1J *b) { jac_add_
 
 // *pp = [w_128^t] *pp, t block-uniform in 1..127.  Infinity in -> infinity out (Z = 0 propagates
 // through Z_2P).  Scripts/check_tw_prog.py is the big-integer model of this routine.
-static __device__ __noinline__ void jac_mul_prog(G1J *pp, int t) {
+static __device__ __noinline__ void jac_mul_prog_at(G1J *pp, const uint16_t *prog);
+static __device__ __forceinline__ void jac_mul_prog(G1J *pp, int t) { jac_mul_prog_at(pp, TW_PROG[t]); }
+// *pp = [k] *pp for the fixed scalar whose op list (constant memory, block-uniform) is prog
+static __device__ __noinline__ void jac_mul_prog_at(G1J *pp, const uint16_t *prog) {
     typedef MulCall M_;
     Fp tx[8], ty[8], tbx[8], zr[8];
     Fp ZC;                                     // Z_common * Z_2P
@@ -125,7 +129,6 @@ static __device__ __noinline__ void jac_mul_prog(G1J *pp, int t) {
             if (k) s = M_::mul(s, zr[k]);
         }
     }
-    const uint16_t *prog = TW_PROG[t];
     const int n_ops = prog[0] & 255, trailing = prog[0] >> 8;
     G1J acc;
     {
@@ -210,6 +213,43 @@ static __global__ void __launch_bounds__(KZG_G1FFT_TPB) k_g1fft_stage(const G1 *
         st_jac(w0, x);
         if (!ONLY_SUM) st_jac(w1, y);
     }
+}
+
+// ---- dense form for SMALL batches -----------------------------------------------------------------------
+// The staged transform above is a chain of 14 launches, each one ~1.1 ms of dependent doublings per thread: 16 ms however
+// small the batch (the reference is called with ONE blob, api_eip7594.go:28).  IFFT_128 -> keep 64 -> zero-pad -> FFT_128
+// is the circulant map
+//     P[m] = 64 S[m] + sum_{q : m - q odd} c_(m-q) S[q],      c_d = sum_{k<64} w^(dk) = 2 / (1 - w^d)
+// with 65 fixed scalars, so for a few blobs all 128 x 65 products [c]S[q] are computed AT ONCE (one scalar
+// multiplication deep instead of 13; 13x the arithmetic of the staged form, which an otherwise idle GPU has to spare)
+// and each output is a 65-term sum.  S arrives bit-reversed (position j holds frequency brp7(j)), P leaves bit-reversed.
+//   k_g1dense_mul: grid (ceil(blobs * 128 / 32), 65), block 32: thread = (blob, position), blockIdx.y = scalar slot
+//   k_g1dense_sum: grid (128, blobs), block 64: one output per block, tree over its 64 + 1 terms
+static __global__ void __launch_bounds__(32) k_g1dense_mul(const G1 *__restrict__ sums, G1J *__restrict__ prod, const int32_t *__restrict__ status, int nblobs) {
+    const int idx = blockIdx.x * 32 + threadIdx.x, blob = idx >> 7, pos = idx & 127, slot = blockIdx.y;
+    if (blob >= nblobs || status[blob] != ST_OK) return;
+    G1 s = sums[(size_t)blob * 128 + pos];
+    G1J y = jac_from_xyzz(s);
+    jac_mul_prog_at(&y, DENSE_PROG[slot]);
+    const int q = (int)(__brev((unsigned)pos) >> 25);
+    st_jac(prod + ((size_t)blob * 65 + slot) * 128 + q, y);
+}
+static __global__ void __launch_bounds__(64) k_g1dense_sum(const G1J *__restrict__ prod, G1 *__restrict__ dst_xyzz, const int32_t *__restrict__ status) {
+    __shared__ G1J sm[64];
+    const int blob = blockIdx.y, t = threadIdx.x;
+    if (status[blob] != ST_OK) return;
+    const int m = (int)(__brev((unsigned)blockIdx.x) >> 25);
+    const G1J *base = prod + (size_t)blob * 65 * 128;
+    const int q = 2 * t + (1 - (m & 1)), d = (m - q) & 127;
+    G1J acc = ld_jac(base + (size_t)(d >> 1) * 128 + q);
+    if (t == 0) { G1J e = ld_jac(base + (size_t)64 * 128 + m); jac_add_ool(&acc, &e); }
+    sm[t] = acc;
+    __syncthreads();
+    for (int s = 32; s > 0; s >>= 1) {
+        if (t < s) jac_add_ool(&sm[t], &sm[t + s]);
+        __syncthreads();
+    }
+    if (t == 0) dst_xyzz[(size_t)blob * 128 + blockIdx.x] = jac_to_xyzz(sm[0]);
 }
 
 }  // namespace kzg

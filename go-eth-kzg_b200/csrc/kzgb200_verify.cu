@@ -140,7 +140,7 @@ static int verify_independent(kzg_lane *c, const uint8_t *blobs, const uint8_t *
                                y32 ? y32 + off * 32 : nullptr, pf48 + off * 48, m, d_status, (G1Aff *)c->v_aff1.p, (G1Aff *)c->v_aff2.p,
                                (uint32_t *)c->zbuf.p, (uint32_t *)c->ybuf.p))) return rc;
         c->mark(KZGB200_KC_VERIFY);
-        k_verify_single_prep<<<(unsigned)((m + 63) / 64), 64, 0, c->stream>>>((const G1Aff *)c->v_aff1.p, (const G1Aff *)c->v_aff2.p, (const uint32_t *)c->zbuf.p,
+        k_verify_single_prep<<<(unsigned)((2 * m + 63) / 64), 64, 0, c->stream>>>((const G1Aff *)c->v_aff1.p, (const G1Aff *)c->v_aff2.p, (const uint32_t *)c->zbuf.p,
                                                                                (const uint32_t *)c->ybuf.p, c->g1_monomial, d_status, (G1 *)c->v_S.p, (G1 *)c->v_W.p, m);
         c->mark(KZGB200_KC_PAIRING);
         if ((rc = vm_pairing_check(c->stream, c->pairing, (const G1 *)c->v_S.p, 0, (const G1 *)c->v_W.p, 1, d_status, d_status, m))) return rc;   // e(-A, G2) e(pi, [s]G2) == 1
@@ -309,7 +309,7 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
     size_t o_idx = take(N * 8), o_batch_of = take(N * 4), o_bstart = take(nb * 8);
     size_t o_rowc = take(N * 4), o_rowoff = take((U + 1) * 8), o_browoff = take((nb + 1) * 8), o_is = take(n_items * 8), o_ie = take(n_items * 8);
     size_t o_bio = take((nb + 1) * 8), o_bst = take(nb * 4), o_ust = take(std::max<size_t>(U, 1) * 4);
-    size_t o_rowb = take(std::max<size_t>(U, 1) * 4), o_res = take(nb * 4);
+    size_t o_rowb = take(std::max<size_t>(U, 1) * 4), o_res = take(nb * 4), o_bkey = take(nb * 8);
     // without large verdicts the bucket MSM shares the interpolation's work items
     size_t o_vis = o_is, o_vie = o_ie, o_vbio = o_bio, o_lis = 0, o_lie = 0, o_lsio = 0, o_lord = 0, o_lids = 0, o_ris = 0, o_rie = 0, o_rsio = 0, o_lof = 0;
     if (n_large) {
@@ -333,6 +333,7 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
         CU(up(o_lof, large_of.data(), nb * 4));
     }
     CU(cudaMemsetAsync(M + o_ust, 0, std::max<size_t>(U, 1) * 4, c->stream));
+    CU(cudaMemsetAsync(M + o_bkey, 0xff, nb * 8, c->stream));
     if ((rc = c->v_aff1.ensure(std::max<size_t>(U, 1) * sizeof(G1Aff)))) return rc;
     if ((rc = c->v_fr.ensure(std::max<size_t>(N, 1) * sizeof(Fr)))) return rc;
     if ((rc = c->vm_digits.ensure(std::max<size_t>(N, 1) * KZG_CELL_TW))) return rc;
@@ -366,7 +367,11 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
     }
     k_cell_interp_reduce<<<(unsigned)nb, 64, 0, c->stream>>>((const Fr *)c->v_partial.p, (const uint64_t *)(M + o_bio), (uint32_t *)c->scalars.p);
     c->mark(KZGB200_KC_MSM);
-    k_msm_fixed<<<dim3(1, (unsigned)nb), 32, 32 * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p);
+    for (size_t b0 = 0; b0 < nb; b0 += 65535) {      // gridDim.y <= 65535
+        const size_t bn = std::min<size_t>(65535, nb - b0);
+        k_msm_fixed<<<dim3(1, (unsigned)bn), 32, 32 * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p + b0 * 64 * 8, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p + b0);
+    }
+    CU(cudaGetLastError());
     c->mark(KZGB200_KC_VMSM);
     // v_S[seg][b]: seg 0 = sum_k r_k pi_k, seg 1 + phi2(seg 2) = sum_k r_k h_k^64 pi_k   (kzg_verify.go:32,73-83)
     if ((rc = vm_msm_windows(c->stream, (const G1Aff *)c->v_aff2.p, (const int8_t *)c->vm_digits.p, KZG_CELL_TW, 0, KZG_CELL_TW, nullptr, KZG_VM_BUCKETS,
@@ -389,8 +394,10 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
         c->launches += 11;
     }
     c->mark(KZGB200_KC_VERIFY);
-    if (N) k_merge_status<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(d_cst, (const uint32_t *)(M + o_batch_of), d_bst, N);
-    if (U) k_merge_status<<<(unsigned)((U + 127) / 128), 128, 0, c->stream>>>(d_ust, (const uint32_t *)(M + o_rowb), d_bst, U);
+    unsigned long long *d_bkey = (unsigned long long *)(M + o_bkey);
+    if (N) k_merge_status<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(d_cst, (const uint32_t *)(M + o_batch_of), d_bkey, N, 1);
+    if (U) k_merge_status<<<(unsigned)((U + 127) / 128), 128, 0, c->stream>>>(d_ust, (const uint32_t *)(M + o_rowb), d_bkey, U, 0);
+    k_status_finish<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(d_bkey, d_bst, nb);
     k_cell_prep<<<(unsigned)((nb + 31) / 32), 32, 0, c->stream>>>((const G1 *)c->v_S.p, (const G1 *)c->sums.p, (const G1Aff *)c->v_aff1.p,
                                                                    (const uint64_t *)(M + o_rowoff), (const uint64_t *)(M + o_browoff), (const uint32_t *)(M + o_rowc),
                                                                    (const Fr *)c->v_fr.p, d_bst, n_large ? (const int32_t *)(M + o_lof) : nullptr, (const G1 *)c->vm_commsum.p, (G1 *)c->v_pa.p, (G1 *)c->v_pb.p, nb);

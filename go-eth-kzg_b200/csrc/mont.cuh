@@ -10,6 +10,10 @@
 // accumulators swap roles instead of shifting.  IMAD count per product: N*(4N+1)
 // (588 for Fp, 264 for Fr) -- the figure SURVEY.md section 8(d) uses for the roofline.
 //
+// Credit: the even/odd-accumulator row scheme and the names of its helpers (mul_n, cmad_n, madc_n_rshift,
+// mad_n_redc, final_sub) are those of supranational/sppark's mont_t.cuh (Apache-2.0), restated here from its
+// published design; the dedicated squaring (sqr) and reduce_wide are this repository's own.
+//
 // All values are kept fully reduced in [0, p).  p must leave >= 2 spare bits in the top limb
 // (true for both BLS12-381 moduli) so that 2p fits in N limbs.
 #pragma once

@@ -91,6 +91,9 @@ __device__ __forceinline__ G1Aff load_aff(const G1Aff *p) {
 // Scalars: [blob][n_groups*group_pts][8] plain limbs (table order).  out: [blob][n_groups] XYZZ.
 //   commit:  group_pts = 4096, n_groups = 1,   L = blockDim.x
 //   FK20:    group_pts = 64,   n_groups = 128, L = 8 (16 groups per 128-thread block)
+#ifndef KZG_MSM_PREFETCH
+#define KZG_MSM_PREFETCH 1
+#endif
 extern __shared__ unsigned char msm_smem[];
 static __global__ void __launch_bounds__(128) k_msm_fixed(const uint32_t *__restrict__ scalars, MsmTable tab, int group_pts,
                                                     int n_groups, int L, const int32_t *__restrict__ status, G1 *__restrict__ out) {
@@ -111,6 +114,26 @@ static __global__ void __launch_bounds__(128) k_msm_fixed(const uint32_t *__rest
                 ds.init(l);
             }
             const G1Aff *row = tab.entries + (size_t)(group * group_pts + j) * tab.row_entries;
+#if KZG_MSM_PREFETCH
+            // software pipeline: the gather of window k + 1 (a random 96-byte read of a multi-GB table: DRAM latency) is
+            // issued before the ten products of window k's addition, so it lands underneath them
+            int d = ds.next(tab.bitpos[0], tab.bits[0]);
+            G1Aff e;
+            if (d) e = load_aff(row + tab.rowoff[0] + ((d < 0 ? -d : d) - 1));
+            for (int k = 0; k < tab.W; ++k) {
+                int dn = 0;
+                G1Aff en;
+                if (k + 1 < tab.W) {
+                    dn = ds.next(tab.bitpos[k + 1], tab.bits[k + 1]);
+                    if (dn) en = load_aff(row + tab.rowoff[k + 1] + ((dn < 0 ? -dn : dn) - 1));
+                }
+                if (d) {
+                    if (d < 0) e.y = Fp::neg(e.y);
+                    g1_add_affine<MulInline>(acc, e);
+                }
+                d = dn; e = en;
+            }
+#else
             for (int k = 0; k < tab.W; ++k) {
                 int d = ds.next(tab.bitpos[k], tab.bits[k]);
                 if (d == 0) continue;
@@ -119,6 +142,7 @@ static __global__ void __launch_bounds__(128) k_msm_fixed(const uint32_t *__rest
                 if (d < 0) e.y = Fp::neg(e.y);
                 g1_add_affine<MulInline>(acc, e);
             }
+#endif
         }
     }
     // tree reduction over the L lanes of each group through shared memory

@@ -65,22 +65,33 @@ static __device__ __noinline__ Fr fr_pow_u64(Fr base, unsigned long long e) {
 // ---- n independent single-proof checks (kzg_verify.go:35-100 rewritten to fixed G2) ------------
 // status[i] must hold OK or an earlier decode error; z/y are plain limbs.
 // PA[i] = -(C - [y]G + [z]pi), PB[i] = pi; the check e(PA, G2) e(PB, [s]G2) == 1 runs in k_pairing_lanes.
+// Two threads per item: the two 255-bit scalar multiplications are independent, and a one-item call (the reference's
+// calling pattern) is pure latency -- thread 2i computes [y]G, thread 2i+1 computes [z]pi and hands it over through
+// shared memory.
 static __global__ void __launch_bounds__(64) k_verify_single_prep(const G1Aff *__restrict__ commitments, const G1Aff *__restrict__ proofs,
                                                            const uint32_t *__restrict__ z, const uint32_t *__restrict__ y,
                                                            const G1Aff *__restrict__ g1_gen, const int32_t *__restrict__ status,
                                                            G1 *__restrict__ PA, G1 *__restrict__ PB, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (status[i] != ST_OK) { PA[i] = G1::infinity(); PB[i] = G1::infinity(); return; }
-    G1 G = G1::from_affine(*g1_gen), Pi = G1::from_affine(proofs[i]), A = G1::from_affine(commitments[i]);
-    G1 yG, zPi;
-    g1_mul_scalar(&yG, &G, y + i * 8);
-    g1_mul_scalar(&zPi, &Pi, z + i * 8);
-    yG.neg_inplace();
-    g1_add(A, yG);
-    g1_add(A, zPi);                       // C - [y]G + [z]pi
+    __shared__ G1 hand[32];
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const int role = threadIdx.x & 1, slot = threadIdx.x >> 1;
+    const bool live = i < n && status[i] == ST_OK;
+    G1 part = G1::infinity();
+    if (live) {
+        G1 base = role ? G1::from_affine(proofs[i]) : G1::from_affine(*g1_gen);
+        g1_mul_scalar(&part, &base, (role ? z : y) + i * 8);
+    }
+    if (role) hand[slot] = part;
+    __syncthreads();
+    if (role || i >= n) return;
+    if (!live) { PA[i] = G1::infinity(); PB[i] = G1::infinity(); return; }
+    G1 A = G1::from_affine(commitments[i]);
+    part.neg_inplace();
+    g1_add(A, part);
+    G1 h = hand[slot];
+    g1_add(A, h);                          // C - [y]G + [z]pi
     A.neg_inplace();
-    PA[i] = A; PB[i] = Pi;
+    PA[i] = A; PB[i] = G1::from_affine(proofs[i]);
 }
 
 // ---- EIP-4844 RLC batch (kzg_verify.go:111-231) -------------------------------------------------
@@ -127,11 +138,23 @@ static __global__ void k_status_merge(int32_t *__restrict__ status, const int32_
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && status[i] == ST_OK) status[i] = later[i];
 }
-// batch_status[group_of[i]] = max(., status[i])  (any error in a batch makes the batch an error)
-static __global__ void k_merge_status(const int32_t *__restrict__ status, const uint32_t *__restrict__ group_of, int32_t *__restrict__ batch_status, size_t n) {
+// First error of a verdict in the REFERENCE's order (api_eip7594.go:190-213: every unique commitment in row order, then every
+// proof in index order, then every cell in index order): key = stage << 56 | index << 8 | status, minimum per verdict.
+// stage_arg 0: status[] are the unique commitments' decode results (index = row); 1: the per-cell slots, which hold a proof's
+// decode error (stage 1) or, if the proof was fine, the cell's NON_CANONICAL_SCALAR (stage 2).
+static __global__ void k_merge_status(const int32_t *__restrict__ status, const uint32_t *__restrict__ group_of, unsigned long long *__restrict__ batch_key, size_t n, int stage_arg) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (status[i] != ST_OK) atomicMax(&batch_status[group_of[i]], status[i]);
+    const int32_t st = status[i];
+    if (st == ST_OK) return;
+    const unsigned long long stage = stage_arg == 0 ? 0ull : (st == ST_NON_CANONICAL_SCALAR ? 2ull : 1ull);
+    atomicMin(&batch_key[group_of[i]], (stage << 56) | ((unsigned long long)i << 8) | (unsigned long long)(uint32_t)st);
+}
+// batch_status[b] keeps a host-side error (cell index out of range: checked before any decoding, api_eip7594.go:184-188), else takes the keyed first error
+static __global__ void k_status_finish(const unsigned long long *__restrict__ batch_key, int32_t *__restrict__ batch_status, size_t nb) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    if (batch_status[b] == ST_OK && batch_key[b] != ~0ull) batch_status[b] = (int32_t)(batch_key[b] & 0xffull);
 }
 // work item w = (cells [start, end) of ONE batch): partial[w][64] = sum_k r^k * interpolation poly of cell k.
 // One warp per cell, 8 warps per block.  interpolation = CosetIFFT_64(brp(evals)) on the coset

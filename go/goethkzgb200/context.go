@@ -1,7 +1,8 @@
 package goethkzgb200
 
 /*
-#cgo LDFLAGS: -lkzgb200
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../go-eth-kzg_b200 -lkzgb200 -Wl,-rpath,${SRCDIR}/../../go-eth-kzg_b200
 #include <stdlib.h>
 #include "kzgb200.h"
 */
@@ -14,9 +15,40 @@ import (
 	"unsafe"
 )
 
-// Context mirrors goethkzg.Context (api.go:17-28): immutable after creation, safe for concurrent use (the C
-// library serialises calls on one context with an internal lock).
+// Context mirrors goethkzg.Context (api.go:17-28): immutable after creation, safe for concurrent use.  Every GPU of
+// the context has Options.Lanes execution lanes (own streams and scratch); a call takes a free lane, single-blob calls
+// rotate over the GPUs, so goroutines calling the reference's one-blob methods overlap on the device(s).
 type Context struct{ h *C.kzgb200_ctx }
+
+// Options selects the GPUs and table sizes of a context (kzgb200_opts in include/kzgb200.h).  The zero value is one
+// GPU (device 0), default windows, two lanes.
+type Options struct {
+	Devices      []int // CUDA ordinals; nil = device 0; AllDevices = every visible GPU
+	Lanes        int   // concurrent calls per GPU, 0 = default
+	CommitWindow int   // bits per window of the 4096-point table, 0 = default (13)
+	FK20Window   int   // bits per window of the FK20 table, 0 = default (12)
+}
+
+// AllDevices as Options.Devices selects every visible GPU: batched calls are sharded over them inside the library.
+var AllDevices = []int{-1}
+
+func (o *Options) fill(c *C.kzgb200_opts, pin *[]C.int) {
+	if o == nil {
+		return
+	}
+	c.commit_window, c.fk20_window, c.lanes = C.int(o.CommitWindow), C.int(o.FK20Window), C.int(o.Lanes)
+	if len(o.Devices) == 1 && o.Devices[0] == -1 {
+		c.n_devices = -1
+	} else if len(o.Devices) > 0 {
+		*pin = make([]C.int, len(o.Devices))
+		for i, d := range o.Devices {
+			(*pin)[i] = C.int(d)
+		}
+		c.n_devices = C.int(len(o.Devices))
+		c.devices = (*C.int)(C.malloc(C.size_t(len(o.Devices)) * C.size_t(unsafe.Sizeof(C.int(0)))))
+		copy(unsafe.Slice(c.devices, len(o.Devices)), *pin)
+	}
+}
 
 func lastError(st int32) error {
 	return fmt.Errorf("kzgb200: status %d: %s", st, C.GoString(C.kzgb200_last_error()))
@@ -26,30 +58,52 @@ func u8(p unsafe.Pointer) *C.uint8_t { return (*C.uint8_t)(p) }
 
 // NewContext4096 replaces api.go:90-149: the JSON document goes to the library as text; decompression, the
 // bit-reversed Lagrange basis, the FK20 table and all window tables are built on the GPU.
-func NewContext4096(ts *JSONTrustedSetup) (*Context, error) {
+func NewContext4096(ts *JSONTrustedSetup) (*Context, error) { return NewContext4096WithOptions(ts, nil) }
+
+// NewContext4096WithOptions is NewContext4096 on chosen GPUs / table sizes.
+func NewContext4096WithOptions(ts *JSONTrustedSetup, o *Options) (*Context, error) {
 	text, err := json.Marshal(ts)
 	if err != nil {
 		return nil, err
 	}
 	var h *C.kzgb200_ctx
 	var opts C.kzgb200_opts
+	var pin []C.int
+	o.fill(&opts, &pin)
+	defer C.free(unsafe.Pointer(opts.devices))
 	rc := C.kzgb200_ctx_new_from_json((*C.char)(unsafe.Pointer(&text[0])), C.size_t(len(text)), &opts, &h)
 	if rc != C.KZGB200_OK {
 		return nil, errorFromStatus(int32(rc))
 	}
-	c := &Context{h}
-	runtime.SetFinalizer(c, func(c *Context) { C.kzgb200_ctx_free(c.h) })
-	return c, nil
+	return wrap(h), nil
 }
 
-// NewContext4096Secure replaces api.go:53-88.  embeddedSetupJSON is the same go:embed'ed trusted_setup.json the
-// reference ships (trusted_setup.go:38-39); it is declared in setup_embed.go next to the JSON file.
-func NewContext4096Secure() (*Context, error) {
-	var ts JSONTrustedSetup
-	if err := json.Unmarshal([]byte(embeddedSetupJSON), &ts); err != nil {
-		return nil, err
+func wrap(h *C.kzgb200_ctx) *Context {
+	c := &Context{h}
+	runtime.SetFinalizer(c, func(c *Context) { C.kzgb200_ctx_free(c.h) })
+	return c
+}
+
+// NewContext4096Secure replaces api.go:53-88 with the embedded mainnet setup (setup_embed.go: the packed bytes of the
+// same ceremony output the reference embeds as JSON, trusted_setup.go:38-39).
+func NewContext4096Secure() (*Context, error) { return NewContext4096SecureWithOptions(nil) }
+
+// NewContext4096SecureWithOptions is NewContext4096Secure on chosen GPUs / table sizes.
+func NewContext4096SecureWithOptions(o *Options) (*Context, error) {
+	if len(embeddedSetup) != 2*embeddedG1Bytes+embeddedNumG2*CompressedG2Size {
+		return nil, fmt.Errorf("kzgb200: embedded trusted setup has %d bytes", len(embeddedSetup))
 	}
-	return NewContext4096(&ts)
+	var h *C.kzgb200_ctx
+	var opts C.kzgb200_opts
+	var pin []C.int
+	o.fill(&opts, &pin)
+	defer C.free(unsafe.Pointer(opts.devices))
+	rc := C.kzgb200_ctx_new(u8(unsafe.Pointer(&embeddedSetup[0])), u8(unsafe.Pointer(&embeddedSetup[embeddedG1Bytes])),
+		u8(unsafe.Pointer(&embeddedSetup[2*embeddedG1Bytes])), embeddedNumG2, &opts, &h)
+	if rc != C.KZGB200_OK {
+		return nil, errorFromStatus(int32(rc))
+	}
+	return wrap(h), nil
 }
 
 // CheckTrustedSetupIsWellFormed replaces trusted_setup.go:45-83 (batched decode + subgroup kernels).

@@ -7,10 +7,14 @@
 // go-eth-kzg_b200/kzgb200.py (ctypes), both exercised by the test suite.  Build, once a toolchain exists:
 //
 //	python go-eth-kzg_b200/build.py                       # libkzgb200.so
-//	CGO_CFLAGS="-I$REPO/include" CGO_LDFLAGS="-L$REPO/go-eth-kzg_b200 -lkzgb200 -Wl,-rpath,$REPO/go-eth-kzg_b200" go build ./go/...
+//	cd go/goethkzgb200 && go vet . && go test .           # go.mod, the embedded setup and the cgo flags (${SRCDIR}-relative) are in place
+//
+// The reference's own conformance suite runs against this package by copying consensus_specs_test.go and tests/ from a
+// go-eth-kzg checkout next to it and replacing the package clause: the method set, the byte-array types, the sentinel
+// errors (errors.Is) and the three-way outcome convention are the same.
 //
 // Differences from the reference that a caller can observe:
-//   - every call runs on the GPU of the context; there is no CPU fallback, NewContext* fails without a device;
+//   - every call runs on the GPU(s) of the context (Options.Devices); there is no CPU fallback, NewContext* fails without a device;
 //   - numGoRoutines arguments are accepted and ignored (the reference ignores them on the EIP-7594 paths,
 //     api_eip7594.go:54,60);
 //   - batch verification draws independent 126-bit coefficients instead of powers of one random scalar

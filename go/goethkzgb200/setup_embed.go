@@ -2,9 +2,16 @@ package goethkzgb200
 
 import _ "embed"
 
-// trusted_setup.json is the reference's own file (go-eth-kzg: trusted_setup.json, embedded at
-// trusted_setup.go:38-39); copy it next to this file when building.  It is not duplicated in this repository:
-// the packed binary form used by the tests lives in go-eth-kzg_b200/data/trusted_setup_4096.bin.
+// The mainnet ceremony output in the packed form the rest of this repository uses
+// (go-eth-kzg_b200/data/trusted_setup_4096.bin, byte-identical copy): 4096 x 48 bytes g1_monomial, 4096 x 48 bytes
+// g1_lagrange, 65 x 96 bytes g2_monomial, every point in the compressed encoding of the reference's
+// trusted_setup.json (trusted_setup.go:23-27, embedded there at :38-39).  Embedding the packed bytes instead of the
+// JSON means this package builds from a fresh checkout with no file to copy in.
 //
-//go:embed trusted_setup.json
-var embeddedSetupJSON string
+//go:embed trusted_setup_4096.bin
+var embeddedSetup []byte
+
+const (
+	embeddedG1Bytes = ScalarsPerBlob * CompressedG1Size
+	embeddedNumG2   = 65
+)

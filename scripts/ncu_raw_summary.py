@@ -17,6 +17,10 @@ def main(path):
     data = rows[2:]
     name_i = hdr.index("Kernel Name")
     cols = {k: hdr.index(k) for k in KEYS if k in hdr}
+    # every warp-state (stall reason per issue) and pipe-utilisation metric of the capture as well
+    for i, k in enumerate(hdr):
+        if k not in cols and (("issue_stalled" in k and k.endswith("per_issue_active.ratio")) or k.startswith("sm__pipe_") or k.startswith("sm__inst_executed_pipe_")):
+            cols[k] = i
     names = [r[name_i].split("(")[0].replace("kzg::", "").replace("void ", "") for r in data]
     print("| metric | " + " | ".join(names) + " |")
     print("|---|" + "---|" * len(names))

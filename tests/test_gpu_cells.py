@@ -50,3 +50,22 @@ def test_bad_blob_in_batch(ctx):
     got = ctx.compute_cells_and_kzg_proofs_batch([good, bad, good])
     assert got[0][0] == 0 and got[2][0] == 0 and got[0][1:] == got[2][1:]
     assert got[1][0] == 2 and got[1][1] == bytes(262144) and got[1][2] == bytes(6144)
+
+
+def test_small_batch_paths_equal_large_batch_paths(ctx):
+    """Small batches take latency-oriented kernels (csrc/g1fft.cuh: the dense one-level G1 transform up to 24 blobs; 64 lanes per
+    FK20 group; kzgb200.cu launch_commit_msm: point-range split of the 4096-point MSM below one wave), large ones the staged /
+    one-CTA-per-blob forms.  The same blobs must give the same bytes either way, and the oracle's."""
+    o = oracle_lib.get_oracle()
+    distinct = [oracle_lib.rand_blob((300 + b) << 20) for b in range(5)]
+    blobs = [distinct[i % 5] for i in range(40)]
+    big = ctx.compute_cells_and_kzg_proofs_batch(blobs)                 # 40 > 24: staged G1 FFT, 8 lanes per group
+    for n in (1, 2, 5, 24):                                             # dense transform, 64 / 32 / 16 lanes per group
+        small = ctx.compute_cells_and_kzg_proofs_batch(blobs[:n])
+        assert small == big[:n], n
+    assert big[3] == o.compute_cells_and_kzg_proofs(distinct[3])
+    many = [distinct[i % 5] for i in range(500)]                        # 500 >= 3 x 148: one CTA per blob
+    cbig = ctx.blob_to_kzg_commitment_batch(many)
+    for n in (1, 3, 17, 100, 300):                                      # split factors 32, 32, 32, 8, 2
+        assert ctx.blob_to_kzg_commitment_batch(many[:n]) == cbig[:n], n
+    assert cbig[4] == o.blob_to_kzg_commitment(distinct[4])

@@ -186,3 +186,47 @@ def test_codec_validation_entry_points(ctx):
     blob_ok = oracle_lib.rand_blob(9 << 20)
     bad = bytearray(blob_ok); bad[32 * 4095:32 * 4096] = R.to_bytes(32, "big")
     assert ctx.check_scalars([blob_ok, bytes(bad), blob_ok], 4096) == [0, 2, 0]
+
+
+def test_cell_verifier_reports_first_error_in_reference_order(ctx):
+    """api_eip7594.go:184-213: cell indices, then every unique commitment (row order), then every proof (index order), then
+    every cell (index order) -- the FIRST failing element's error is the verdict, not the numerically largest status"""
+    import ctypes, random
+    rng = random.Random(11)
+    P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    L = oracle_lib.lib()
+    by_status = {}
+    while not (4 in by_status and 5 in by_status):
+        b = bytearray(rng.randrange(P).to_bytes(48, "big")); b[0] |= 0x80
+        st = L.ko_g1_decompress(bytes(b), ctypes.create_string_buffer(96), 1)
+        by_status.setdefault(st, bytes(b))
+    off_curve, off_subgroup, bad_enc = by_status[4], by_status[5], bytes([0xff]) * 48
+    blob = oracle_lib.rand_blob(21 << 20)
+    cm = ctx.blob_to_kzg_commitment(blob)[1]
+    _, cells, proofs = ctx.compute_cells_and_kzg_proofs(blob)
+    cl = [cells[2048 * i:2048 * i + 2048] for i in range(128)]; pl = [proofs[48 * i:48 * i + 48] for i in range(128)]
+    idx = list(range(128))
+    bad_cell = bytes([0xff]) * 32 + cl[5][32:]
+
+    def run(cms=None, cells_=None, proofs_=None, idx_=None):
+        return ctx.verify_cell_kzg_proof_batch(cms or [cm] * 128, idx_ or idx, cells_ or cl, proofs_ or pl)
+
+    assert run() == 0
+    # two bad proofs: the earlier one's status wins, whichever is numerically larger
+    p = list(pl); p[3] = bad_enc; p[10] = off_subgroup
+    assert run(proofs_=p) == 3
+    p = list(pl); p[3] = off_subgroup; p[10] = bad_enc
+    assert run(proofs_=p) == 5
+    # a bad proof late in the batch beats a bad cell early in the batch (all proofs are decoded before any cell)
+    c = list(cl); c[5] = bad_cell
+    p = list(pl); p[100] = off_curve
+    assert run(cells_=c, proofs_=p) == 4
+    assert run(cells_=c) == 2
+    # a bad commitment beats everything but the cell-index check
+    cms = [cm] * 128; cms[127] = off_curve
+    p = list(pl); p[0] = off_subgroup
+    assert run(cms=cms, cells_=c, proofs_=p) == 4
+    cms = [cm] * 128; cms[60] = off_subgroup; cms[61] = bad_enc            # two bad rows: the first-seen row first
+    assert run(cms=cms) == 5
+    i2 = list(idx); i2[77] = 128
+    assert run(cms=cms, cells_=c, proofs_=p, idx_=i2) == 7
