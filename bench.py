@@ -273,18 +273,41 @@ class Work:
     pass
 
 
-def make_work(ctx, wl, B, first_blob, torch, np, device):
+def make_work(ctx, wl, B, first_blob, torch, np, device, interleaved=False):
+    """interleaved: host buffers come from kzgb200_host_alloc_interleaved (pages spread over the NUMA nodes) instead of torch's pinned pool"""
     import kzgb200
     L = ctx.L
     P = lambda t: ctypes.c_void_p(t.data_ptr())
     SZ = ctypes.c_size_t
     dev = "cuda:%d" % device
-    pinned = lambda n, dt=torch.uint8: torch.empty(n, dtype=dt).pin_memory()
     w = Work()
+    w.host_ptrs = []
+
+    def pinned(n, dt=torch.uint8):
+        if not interleaved:
+            return torch.empty(n, dtype=dt).pin_memory()
+        nbytes = max(1, n) * torch.empty(0, dtype=dt).element_size()
+        ptr = L.kzgb200_host_alloc_interleaved(nbytes)
+        assert ptr, "kzgb200_host_alloc_interleaved failed"
+        w.host_ptrs.append(ptr)
+        return torch.frombuffer((ctypes.c_uint8 * nbytes).from_address(ptr), dtype=torch.uint8).view(dt)[:n]
+
+    def pin(t):
+        if not interleaved:
+            return t.pin_memory()
+        out = pinned(t.numel(), t.dtype)
+        out.copy_(t.reshape(-1))
+        return out
+
+    def release():
+        for ptr in w.host_ptrs:
+            L.kzgb200_host_free(ctypes.c_void_p(ptr))
+        w.host_ptrs.clear()
+    w.release = release
     w.wl, w.B, w.units = wl, B, B
     blobs = make_blobs(first_blob, B)
     w.first_blob_bytes, w.last_blob_bytes = blobs[0], blobs[-1]
-    h_blobs = torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8).pin_memory()
+    h_blobs = pin(torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8))
     del blobs
     d_blobs = h_blobs.to(dev)
     d_st = torch.zeros(max(B, 1), dtype=torch.int32, device=dev); h_st = pinned(max(B, 1), torch.int32)
@@ -307,7 +330,7 @@ def make_work(ctx, wl, B, first_blob, torch, np, device):
     elif wl == "blob_proof":
         d_c = torch.empty(48 * B, dtype=torch.uint8, device=dev)
         ctx._check(L.kzgb200_blob_to_kzg_commitment(ctx.ctx, P(d_blobs), SZ(B), P(d_c), P(d_st)))
-        h_c = d_c.cpu().pin_memory()
+        h_c = pin(d_c.cpu())
         d_o = torch.empty(48 * B, dtype=torch.uint8, device=dev); h_o = pinned(48 * B)
         def step(on_dev):
             i, c_, o, s = (d_blobs, d_c, d_o, d_st) if on_dev else (h_blobs, h_c, h_o, h_st)
@@ -319,7 +342,7 @@ def make_work(ctx, wl, B, first_blob, torch, np, device):
         d_c = torch.empty(48 * B, dtype=torch.uint8, device=dev); d_p = torch.empty(48 * B, dtype=torch.uint8, device=dev)
         ctx._check(L.kzgb200_blob_to_kzg_commitment(ctx.ctx, P(d_blobs), SZ(B), P(d_c), P(d_st)))
         ctx._check(L.kzgb200_compute_blob_kzg_proof(ctx.ctx, P(d_blobs), P(d_c), SZ(B), P(d_p), P(d_st)))
-        h_c = d_c.cpu().pin_memory(); h_p = d_p.cpu().pin_memory()
+        h_c = pin(d_c.cpu()); h_p = pin(d_p.cpu())
         res = ctypes.c_int32(-1)
         def step(on_dev):
             i, c_, p_ = (d_blobs, d_c, d_p) if on_dev else (h_blobs, h_c, h_p)
@@ -360,7 +383,7 @@ def make_work(ctx, wl, B, first_blob, torch, np, device):
                 counts = np.full(B, 64, dtype=np.uint64)
                 cells_np = d_cells.cpu().numpy().reshape(B, 128, 2048)
                 sel = np.stack([cells_np[b, ids[64 * b:64 * b + 64].astype(np.int64)] for b in range(B)])      # [B,64,2048]
-                h_in = torch.from_numpy(np.ascontiguousarray(sel.reshape(-1))).pin_memory(); d_in = h_in.to(dev)
+                h_in = pin(torch.from_numpy(np.ascontiguousarray(sel.reshape(-1)))); d_in = h_in.to(dev)
                 d_oc = torch.empty(262144 * B, dtype=torch.uint8, device=dev); d_op = torch.empty(6144 * B, dtype=torch.uint8, device=dev)
                 h_oc = pinned(262144 * B); h_op = pinned(6144 * B)
                 idp = ids.ctypes.data_as(ctypes.c_void_p); cnp = counts.ctypes.data_as(ctypes.c_void_p)
@@ -376,7 +399,7 @@ def make_work(ctx, wl, B, first_blob, torch, np, device):
                 ctx._check(L.kzgb200_blob_to_kzg_commitment(ctx.ctx, P(d_blobs), SZ(B), P(d_cm1), P(d_st)))
                 N = 128 * B
                 d_cm = d_cm1.view(B, 1, 48).expand(B, 128, 48).contiguous().view(-1)
-                h_cm = d_cm.cpu().pin_memory(); h_cells.copy_(d_cells); h_pr.copy_(d_pr)
+                h_cm = pin(d_cm.cpu()); h_cells.copy_(d_cells); h_pr.copy_(d_pr)
                 one = wl == "verify_cells_one_batch"
                 idx = np.tile(np.arange(128, dtype=np.uint64), B)
                 offs = np.array([0, N], dtype=np.uint64) if one else (np.arange(B + 1, dtype=np.uint64) * 128)
@@ -728,9 +751,14 @@ def main():
                 try:
                     mctx = kzgb200.Context(commit_window=cwc, fk20_window=fwc, devices=list(range(world)), lanes=2)
                     ip = {"context": {"devices": world, "commit_window": cwc, "fk20_window": fwc, "init_ms": mctx.info()["init_ms"]}}
+                    devs = (ctypes.c_int * world)(*range(world))
+                    for inter in (0, 1):
+                        g = ctypes.c_double()
+                        if mctx.L.kzgb200_dbg_h2d_bandwidth(devs, world, ctypes.c_size_t(256 << 20), inter, ctypes.byref(g)) == 0:
+                            ip["h2d_ceiling_GBps_%s" % ("interleaved" if inter else "plain_pinned")] = g.value
                     for name, sub, subB in (("cells_proofs_fixed_1024", "cells_proofs", 1024), ("cells_proofs_1024_per_gpu", "cells_proofs", 1024 * world),
                                             ("verify_cells_fixed_524288", "verify_cells", 4096), ("commit_fixed_4096", "commit", 4096)):
-                        sw = make_work(mctx, sub, subB, 0, torch, np, 0)
+                        sw = make_work(mctx, sub, subB, 0, torch, np, 0, interleaved=True)
                         sw.step(False); sw.step(False)
                         t0 = time.perf_counter()
                         for _ in range(4):
@@ -739,9 +767,11 @@ def main():
                         assert sw.oracle_check(), "in-process multi-GPU: " + name
                         ip[name] = {"e2e": sw.units / dt, "unit": unit_of(sub), "ms_per_step": dt * 1e3, "h2d_GBps": sw.h2d / dt / 1e9, "d2h_GBps": sw.d2h / dt / 1e9,
                                     "steps": 4, "oracle_check": "ok"}
+                        sw.keep.clear(); sw.release()
                         del sw
                         torch.cuda.empty_cache()
-                    ip["note"] = "host buffers only (one pinned buffer, sharded inside the library over the GPUs); value = units / wall-clock of the C-ABI call"
+                    ip["note"] = "host buffers only (ONE NUMA-interleaved pinned buffer per array, sharded inside the library over the GPUs); e2e = units / wall-clock of the C-ABI call; " \
+                                 "h2d_ceiling = all GPUs copying 256 MB each from one host buffer at the same time"
                     mctx.close()
                     extras["in_process"] = ip
                 except Exception as e:      # noqa: BLE001  (never lose the main line to an extra)

@@ -6,6 +6,9 @@
 // context; inputs are processed in chunks so the arena stays bounded regardless of batch size.
 #include "ctx.cuh"
 #include "g1fft.cuh"
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 std::string &kzgb200_err_slot() { static thread_local std::string s; return s; }
 
@@ -206,10 +209,75 @@ const char *kzgb200_last_error(void) { return kzgb200_err_slot().c_str(); }
 
 void *kzgb200_host_alloc(size_t bytes) {
     void *p = nullptr;
-    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return p;
 }
-void kzgb200_host_free(void *p) { if (p) cudaFreeHost(p); }
+// Pinned memory whose pages are interleaved over all NUMA nodes of the host (mmap + mbind(MPOL_INTERLEAVE) +
+// cudaHostRegister): a buffer that is read by the GPUs of BOTH sockets at once (a multi-GPU context sharding one host
+// batch) then draws on every memory controller instead of the first-touch node's.  Falls back to kzgb200_host_alloc.
+static std::mutex g_mapped_mu;
+static std::unordered_map<void *, size_t> g_mapped;
+void *kzgb200_host_alloc_interleaved(size_t bytes) {
+    const size_t len = (bytes + 4095) & ~(size_t)4095;
+    void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return kzgb200_host_alloc(bytes);
+    unsigned long mask[16];
+    for (unsigned long &m : mask) m = ~0ul;                      // every possible node; the kernel intersects with the allowed set
+    long rc = syscall(SYS_mbind, p, len, 3 /* MPOL_INTERLEAVE */, mask, (unsigned long)(sizeof mask * 8), 0u);
+    if (rc != 0) {                                               // e.g. no NUMA support / seccomp: try the online nodes only
+        unsigned long one[1] = {0};
+        FILE *f = fopen("/sys/devices/system/node/online", "r");
+        int lo = 0, hi = 0;
+        if (f) { if (fscanf(f, "%d-%d", &lo, &hi) < 2) hi = lo; fclose(f); }
+        for (int n = lo; n <= hi && n < 64; ++n) one[0] |= 1ul << n;
+        rc = hi > lo ? syscall(SYS_mbind, p, len, 3, one, 65ul, 0u) : -1;
+    }
+    memset(p, 0, len);                                           // fault the pages in under the policy
+    if (cudaHostRegister(p, len, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError(); munmap(p, len);
+        return kzgb200_host_alloc(bytes);
+    }
+    std::lock_guard<std::mutex> lk(g_mapped_mu);
+    g_mapped[p] = len;
+    return p;
+}
+void kzgb200_host_free(void *p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_mapped_mu);
+        auto it = g_mapped.find(p);
+        if (it != g_mapped.end()) {
+            cudaHostUnregister(p); munmap(p, it->second);
+            g_mapped.erase(it);
+            return;
+        }
+    }
+    cudaFreeHost(p);
+}
+
+// aggregate host -> device bandwidth of n GPUs copying AT THE SAME TIME, each its own slice of one pinned host buffer
+// (plain or NUMA-interleaved): the ceiling of every end-to-end number of a multi-GPU context
+int kzgb200_dbg_h2d_bandwidth(const int *devices, int n, size_t bytes_per_dev, int interleaved, double *gbps) {
+    if (!devices || n <= 0 || !gbps) return set_err(KZGB200_ERR_ARGS, "null argument");
+    uint8_t *h = (uint8_t *)(interleaved ? kzgb200_host_alloc_interleaved(bytes_per_dev * n) : kzgb200_host_alloc(bytes_per_dev * n));
+    if (!h) return set_err(KZGB200_ERR_CUDA, "host allocation failed");
+    std::vector<void *> d(n, nullptr);
+    std::vector<cudaStream_t> st(n);
+    for (int i = 0; i < n; ++i) { CU(cudaSetDevice(devices[i])); CU(cudaMalloc(&d[i], bytes_per_dev)); CU(cudaStreamCreate(&st[i])); }
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        for (int i = 0; i < n; ++i) { cudaSetDevice(devices[i]); cudaStreamSynchronize(st[i]); }
+        auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < n; ++i) { cudaSetDevice(devices[i]); cudaMemcpyAsync(d[i], h + (size_t)i * bytes_per_dev, bytes_per_dev, cudaMemcpyHostToDevice, st[i]); }
+        for (int i = 0; i < n; ++i) { cudaSetDevice(devices[i]); cudaStreamSynchronize(st[i]); }
+        double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (rep) best = std::max(best, (double)bytes_per_dev * n / s / 1e9);
+    }
+    for (int i = 0; i < n; ++i) { cudaSetDevice(devices[i]); cudaFree(d[i]); cudaStreamDestroy(st[i]); }
+    kzgb200_host_free(h);
+    *gbps = best;
+    return 0;
+}
 
 void lane_ctx_free(kzg_lane *c) {
     if (!c) return;

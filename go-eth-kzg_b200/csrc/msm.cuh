@@ -92,7 +92,7 @@ __device__ __forceinline__ G1Aff load_aff(const G1Aff *p) {
 //   commit:  group_pts = 4096, n_groups = 1,   L = blockDim.x
 //   FK20:    group_pts = 64,   n_groups = 128, L = 8 (16 groups per 128-thread block)
 #ifndef KZG_MSM_PREFETCH
-#define KZG_MSM_PREFETCH 1
+#define KZG_MSM_PREFETCH 0
 #endif
 extern __shared__ unsigned char msm_smem[];
 static __global__ void __launch_bounds__(128) k_msm_fixed(const uint32_t *__restrict__ scalars, MsmTable tab, int group_pts,

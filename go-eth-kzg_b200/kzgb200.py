@@ -48,7 +48,7 @@ class Info(ctypes.Structure):
 _lib = None
 
 EXPORTS = [
-    "kzgb200_ctx_new", "kzgb200_ctx_free", "kzgb200_last_error", "kzgb200_host_alloc", "kzgb200_host_free",
+    "kzgb200_ctx_new", "kzgb200_ctx_free", "kzgb200_last_error", "kzgb200_host_alloc", "kzgb200_host_alloc_interleaved", "kzgb200_host_free",
     "kzgb200_blob_to_kzg_commitment", "kzgb200_get_info", "kzgb200_last_device_ms",
     "kzgb200_compute_cells", "kzgb200_compute_cells_and_kzg_proofs", "kzgb200_last_kernel_ms",
     "kzgb200_compute_kzg_proof", "kzgb200_compute_blob_kzg_proof", "kzgb200_recover_cells_and_kzg_proofs",
@@ -69,6 +69,8 @@ def load_library():
         L.kzgb200_last_error.restype = ctypes.c_char_p
         L.kzgb200_host_alloc.restype = ctypes.c_void_p
         L.kzgb200_host_alloc.argtypes = [ctypes.c_size_t]
+        L.kzgb200_host_alloc_interleaved.restype = ctypes.c_void_p
+        L.kzgb200_host_alloc_interleaved.argtypes = [ctypes.c_size_t]
         L.kzgb200_host_free.argtypes = [ctypes.c_void_p]
         L.kzgb200_last_device_ms.restype = ctypes.c_double
         L.kzgb200_last_device_ms.argtypes = [ctypes.c_void_p]

@@ -99,8 +99,11 @@ int kzgb200_check_trusted_setup(int device, const uint8_t *g1_lagrange, size_t n
                                 const uint8_t *g2_monomial, size_t n_g2, int32_t *result, size_t *bad_index);
 const char *kzgb200_last_error(void);
 
-/* pinned host memory for zero-staging H2D/D2H */
+/* pinned host memory for zero-staging H2D/D2H (portable: usable by every GPU of a multi-GPU context).
+ * _interleaved: the pages are spread over all NUMA nodes of the host, for buffers that the GPUs of both sockets read at
+ * once (one batch sharded over a multi-GPU context); falls back to the plain allocation where mbind is unavailable. */
 void *kzgb200_host_alloc(size_t bytes);
+void *kzgb200_host_alloc_interleaved(size_t bytes);
 void kzgb200_host_free(void *p);
 
 /* Context.BlobToKZGCommitment (prove.go:13-34), batched. out48: n*48 */

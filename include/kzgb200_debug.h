@@ -42,6 +42,9 @@ const char *kzgb200_dbg_plan_cell_batches_json(const uint8_t *commitments48, con
  * the sub-verdicts of one logical verdict (first error in index order, else VERIFY_FAILED if any, else OK) */
 const char *kzgb200_dbg_shard_plan_json(size_t n_units, size_t n_dev, size_t min_per_dev, const uint64_t *batch_offsets, size_t n_batches,
                                         size_t min_cells_per_dev, const int32_t *sub_verdicts, size_t n_sub);
+/* aggregate host -> device GB/s of n GPUs copying their slices of ONE pinned host buffer at the same time (plain or
+ * NUMA-interleaved pinned memory): the ceiling of the end-to-end numbers of a multi-GPU context */
+int kzgb200_dbg_h2d_bandwidth(const int *devices, int n, size_t bytes_per_dev, int interleaved, double *gbps);
 /* dependency-free integer multiply-add microbenchmark: device-wide instructions*lanes per second.
  * mode 0: mad.lo.u32 (IMAD), 1: mad.hi.u32 (IMAD.HI), 2: mad.wide.u32 (IMAD.WIDE, 32x32+64);
  * mode 3 / 4: a bare dependent chain of the library's Fp::mul / Fp::sqr per thread -> field operations per second */
