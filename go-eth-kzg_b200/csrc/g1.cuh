@@ -21,13 +21,24 @@ static __device__ __noinline__ Fp fp_mul_ni(Fp a, Fp b) { return Fp::mul(a, b); 
 static __device__ __noinline__ Fr fr_mul_ni(Fr a, Fr b) { return Fr::mul(a, b); }
 static __device__ __noinline__ Fp fp_sqr_ni(Fp a) { return Fp::sqr(a); }
 static __device__ __noinline__ Fr fr_sqr_ni(Fr a) { return Fr::sqr(a); }
+static __device__ __noinline__ Fp fp_mam_ni(Fp a, Fp b, Fp c, Fp d) { return Fp::mul_add_mul(a, b, c, d); }
+// msub(a, b, c, d) = a*b - c*d.  The *Lazy policies compute it as a*b + (-c)*d under ONE Montgomery reduction
+// (Mont::mul_add_mul: 432 instead of 576 wide-multiply IMADs); the others as two products.
 struct MulInline {
     static __device__ __forceinline__ Fp mul(const Fp &a, const Fp &b) { return Fp::mul(a, b); }
     static __device__ __forceinline__ Fp sqr(const Fp &a) { return Fp::sqr(a); }
+    static __device__ __forceinline__ Fp msub(const Fp &a, const Fp &b, const Fp &c, const Fp &d) { return Fp::sub(Fp::mul(a, b), Fp::mul(c, d)); }
 };
 struct MulCall {
     static __device__ __forceinline__ Fp mul(const Fp &a, const Fp &b) { return fp_mul_ni(a, b); }
     static __device__ __forceinline__ Fp sqr(const Fp &a) { return fp_sqr_ni(a); }
+    static __device__ __forceinline__ Fp msub(const Fp &a, const Fp &b, const Fp &c, const Fp &d) { return Fp::sub(fp_mul_ni(a, b), fp_mul_ni(c, d)); }
+};
+struct MulInlineLazy : MulInline {
+    static __device__ __forceinline__ Fp msub(const Fp &a, const Fp &b, const Fp &c, const Fp &d) { return Fp::mul_add_mul(a, b, Fp::neg(c), d); }
+};
+struct MulCallLazy : MulCall {
+    static __device__ __forceinline__ Fp msub(const Fp &a, const Fp &b, const Fp &c, const Fp &d) { return fp_mam_ni(a, b, Fp::neg(c), d); }
 };
 
 // affine point in Montgomery form; infinity is encoded as (0,0) (not on the curve since b=4)
@@ -108,7 +119,7 @@ template <class M_ = MulCall> __device__ __forceinline__ void g1_add_affine(G1 &
     Fp PPP = M_::mul(Pd, PP);
     Fp Q = M_::mul(acc.X, PP);
     Fp X3 = Fp::sub(Fp::sub(M_::sqr(R), PPP), Fp::dbl(Q));
-    acc.Y = Fp::sub(M_::mul(R, Fp::sub(Q, X3)), M_::mul(acc.Y, PPP));
+    acc.Y = M_::msub(R, Fp::sub(Q, X3), acc.Y, PPP);
     acc.X = X3;
     acc.ZZ = M_::mul(acc.ZZ, PP);
     acc.ZZZ = M_::mul(acc.ZZZ, PPP);
@@ -133,15 +144,15 @@ template <class M_ = MulCall> __device__ __forceinline__ void g1_add(G1 &a, cons
     Fp PPP = M_::mul(Pd, PP);
     Fp Q = M_::mul(U1, PP);
     Fp X3 = Fp::sub(Fp::sub(M_::sqr(R), PPP), Fp::dbl(Q));
-    a.Y = Fp::sub(M_::mul(R, Fp::sub(Q, X3)), M_::mul(S1, PPP));
+    a.Y = M_::msub(R, Fp::sub(Q, X3), S1, PPP);
     a.X = X3;
     a.ZZ = M_::mul(M_::mul(a.ZZ, b.ZZ), PP);
     a.ZZZ = M_::mul(M_::mul(a.ZZZ, b.ZZZ), PPP);
 }
 // out-of-line full add for cold / code-size-sensitive call sites: g1_add_ool for operands in
 // shared or global memory, g1_add_v (value semantics) for register-resident operands
-static __device__ __noinline__ void g1_add_ool(G1 *a, const G1 *b) { g1_add<MulCall>(*a, *b); }
-static __device__ __noinline__ G1 g1_add_v(G1 a, G1 b) { g1_add<MulCall>(a, b); return a; }
+static __device__ __noinline__ void g1_add_ool(G1 *a, const G1 *b) { g1_add<MulCallLazy>(*a, *b); }
+static __device__ __noinline__ G1 g1_add_v(G1 a, G1 b) { g1_add<MulCallLazy>(a, b); return a; }
 
 // ---- Jacobian coordinates for doubling-heavy code (scalar multiplications, subgroup check) ----
 // Twiddle multiplications run in Jacobian coordinates (x = X/Z^2, y = Y/Z^3): a doubling is
@@ -175,7 +186,7 @@ template <class M_ = MulCall> __device__ __forceinline__ void jac_add(G1J &a, co
     }
     Fp HH = M_::sqr(H), HHH = M_::mul(H, HH), V = M_::mul(U1, HH);
     Fp X3 = Fp::sub(Fp::sub(M_::sqr(r), HHH), Fp::dbl(V));
-    a.Y = Fp::sub(M_::mul(r, Fp::sub(V, X3)), M_::mul(S1, HHH));
+    a.Y = M_::msub(r, Fp::sub(V, X3), S1, HHH);
     a.X = X3;
     a.Z = M_::mul(M_::mul(a.Z, b.Z), H);
 }

@@ -57,7 +57,7 @@ template <class M_ = MulCall> __device__ __forceinline__ void jac_madd(G1J &a, c
     }
     Fp HH = M_::sqr(H), HHH = M_::mul(H, HH), V = M_::mul(a.X, HH);
     Fp X3 = Fp::sub(Fp::sub(M_::sqr(r), HHH), Fp::dbl(V));
-    a.Y = Fp::sub(M_::mul(r, Fp::sub(V, X3)), M_::mul(a.Y, HHH));
+    a.Y = M_::msub(r, Fp::sub(V, X3), a.Y, HHH);
     a.X = X3;
     a.Z = M_::mul(a.Z, H);
 }
@@ -77,11 +77,11 @@ template <class M_ = MulCall> __device__ __forceinline__ void jac_add_full(G1J &
     }
     Fp HH = M_::sqr(H), HHH = M_::mul(H, HH), V = M_::mul(U1, HH);
     Fp X3 = Fp::sub(Fp::sub(M_::sqr(r), HHH), Fp::dbl(V));
-    a.Y = Fp::sub(M_::mul(r, Fp::sub(V, X3)), M_::mul(S1, HHH));
+    a.Y = M_::msub(r, Fp::sub(V, X3), S1, HHH);
     a.X = X3;
     a.Z = M_::mul(M_::mul(a.Z, b.Z), H);
 }
-static __device__ __noinline__ void jac_add_ool(G1J *a, const G1J *b) { jac_add_full<MulCall>(*a, *b); }
+static __device__ __noinline__ void jac_add_ool(G1J *a, const G1J *b) { jac_add_full<MulCallLazy>(*a, *b); }
 
 // *pp = [w_128^t] *pp, t block-uniform in 1..127.  Infinity in -> infinity out (Z = 0 propagates
 // through Z_2P).  Scripts/check_tw_prog.py is the big-integer model of this routine.
@@ -89,7 +89,7 @@ static __device__ __noinline__ void jac_mul_prog_at(G1J *pp, const uint16_t *pro
 static __device__ __forceinline__ void jac_mul_prog(G1J *pp, int t) { jac_mul_prog_at(pp, TW_PROG[t]); }
 // *pp = [k] *pp for the fixed scalar whose op list (constant memory, block-uniform) is prog
 static __device__ __noinline__ void jac_mul_prog_at(G1J *pp, const uint16_t *prog) {
-    typedef MulCall M_;
+    typedef MulCallLazy M_;     // Y3 = r (V - X3) - Y1 HHH under one Montgomery reduction (mont.cuh: mul_add_mul)
     Fp tx[8], ty[8], tbx[8], zr[8];
     Fp ZC;                                     // Z_common * Z_2P
     {
@@ -106,7 +106,7 @@ static __device__ __noinline__ void jac_mul_prog_at(G1J *pp, const uint16_t *pro
             Fp H = Fp::sub(U2, T.X), r = Fp::sub(S2, T.Y);
             Fp HH = M_::sqr(H), HHH = M_::mul(H, HH), V = M_::mul(T.X, HH);
             Fp X3 = Fp::sub(Fp::sub(M_::sqr(r), HHH), Fp::dbl(V));
-            T.Y = Fp::sub(M_::mul(r, Fp::sub(V, X3)), M_::mul(T.Y, HHH));
+            T.Y = M_::msub(r, Fp::sub(V, X3), T.Y, HHH);
             T.X = X3;
             T.Z = M_::mul(T.Z, H);
             tx[k] = T.X; ty[k] = T.Y; zr[k] = H;

@@ -4,6 +4,7 @@
 //
 // One context = one GPU.  All per-call scratch lives in a grow-only device arena owned by the
 // context; inputs are processed in chunks so the arena stays bounded regardless of batch size.
+#define KZG_MSM_ALL_VARIANTS 1
 #include "ctx.cuh"
 #include "g1fft.cuh"
 #include <sys/mman.h>
@@ -96,7 +97,7 @@ static __global__ void k_dbg_fp_mul(const uint32_t *a, const uint32_t *b, uint32
     Fp x, y;
     for (int k = 0; k < 12; ++k) { x.v[k] = a[i * 12 + k]; y.v[k] = b[i * 12 + k]; }
     x = Fp::to_mont(x); y = Fp::to_mont(y);
-    Fp r = op == 0 ? Fp::mul(x, y) : op == 1 ? Fp::add(x, y) : op == 2 ? Fp::sub(x, y) : op == 3 ? fp_inv(x) : Fp::sqr(x);
+    Fp r = op == 0 ? Fp::mul(x, y) : op == 1 ? Fp::add(x, y) : op == 2 ? Fp::sub(x, y) : op == 3 ? fp_inv(x) : op == 5 ? Fp::mul_add_mul(x, y, Fp::add(x, y), Fp::sub(x, y)) : Fp::sqr(x);
     r = Fp::from_mont(r);
     for (int k = 0; k < 12; ++k) out[i * 12 + k] = r.v[k];
 }
@@ -277,6 +278,29 @@ int kzgb200_dbg_h2d_bandwidth(const int *devices, int n, size_t bytes_per_dev, i
     kzgb200_host_free(h);
     *gbps = best;
     return 0;
+}
+
+// experiments: run-time tunables of the proving paths.  "msm_variant": the k_msm_fixed variant (msm.cuh; -1 = default /
+// KZGB200_MSM_VARIANT); "fk20_lanes": lanes per 64-point FK20 group for full batches (4, 8, 16; 0 = default);
+// "vmsm_policy": field-product policy of the verifiers' bucket accumulation (vmsm.cuh)
+int kzgb200_dbg_set_tunable(const char *name, int v) {
+    if (!name) return set_err(KZGB200_ERR_ARGS, "null argument");
+    if (!strcmp(name, "msm_variant")) {
+        if (v < -1 || v > 15) return set_err(KZGB200_ERR_ARGS, "variant out of range");
+        kzg::g_msm_variant_override = v;
+        return 0;
+    }
+    if (!strcmp(name, "fk20_lanes")) {
+        if (v != 0 && v != 4 && v != 8 && v != 16) return set_err(KZGB200_ERR_ARGS, "fk20_lanes must be 0, 4, 8 or 16");
+        kzg::g_fk20_lanes_override = v;
+        return 0;
+    }
+    if (!strcmp(name, "vmsm_policy")) {
+        if (v < 0 || v > 3) return set_err(KZGB200_ERR_ARGS, "vmsm_policy must be 0..3");
+        kzg::g_vmsm_policy = v;
+        return 0;
+    }
+    return set_err(KZGB200_ERR_ARGS, "unknown tunable");
 }
 
 void lane_ctx_free(kzg_lane *c) {
@@ -473,12 +497,12 @@ static int launch_commit_msm(kzg_lane *c, cudaStream_t st, const uint32_t *scala
     unsigned S = 1;
     while (S < 32 && (size_t)S * m < (size_t)3 * c->sm_count) S <<= 1;
     if (S == 1) {
-        k_msm_fixed<<<dim3(1, (unsigned)m), TPB, TPB * sizeof(G1), st>>>(scalars, c->commit_tab, N_BLOB, 1, TPB, d_status, sums);
+        launch_msm_fixed(dim3(1, (unsigned)m), TPB, st, scalars, c->commit_tab, N_BLOB, 1, TPB, d_status, sums);
         return 0;
     }
     int rc = c->msm_partial.ensure(m * S * sizeof(G1));
     if (rc) return rc;
-    k_msm_fixed<<<dim3(S, (unsigned)m), TPB, TPB * sizeof(G1), st>>>(scalars, c->commit_tab, N_BLOB / S, S, TPB, d_status, (G1 *)c->msm_partial.p);
+    launch_msm_fixed(dim3(S, (unsigned)m), TPB, st, scalars, c->commit_tab, N_BLOB / S, S, TPB, d_status, (G1 *)c->msm_partial.p);
     k_sum_groups<<<(unsigned)m, 32, 32 * sizeof(G1), st>>>((const G1 *)c->msm_partial.p, S, d_status, sums);
     c->launches += 1;
     return 0;
@@ -639,6 +663,9 @@ int lane_compute_blob_kzg_proof(kzg_lane *c, const uint8_t *blobs, const uint8_t
 // ComputeCells / ComputeCellsAndKZGProofs (api_eip7594.go:12-52)
 // -------------------------------------------------------------------------------------------
 static const size_t CELLS_CHUNK = 1024;
+#ifndef KZG_FK20_LANES
+#define KZG_FK20_LANES 8
+#endif
 
 // coefficients (c->coeffs) -> 128 compressed proofs per blob (fk20.go:76-124); buffers must be sized by the caller
 static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr *coeffs, uint32_t *scalars, G1 *sums, G1 *pxyzz,
@@ -648,10 +675,10 @@ static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr 
     // lanes per 64-point group: 8 for full batches (8 points x W windows per lane, short reduction tree); small batches
     // spread each group over up to 64 lanes so that a single blob occupies 64 CTAs instead of 8
     const int TPB = 128;
-    int L = 8;
+    int L = g_fk20_lanes_override ? g_fk20_lanes_override : KZG_FK20_LANES;
     while (L < 64 && (size_t)L * m < (size_t)2 * c->sm_count) L <<= 1;
     if (marks) c->mark(KZGB200_KC_MSM);
-    k_msm_fixed<<<dim3(128 / (TPB / L), (unsigned)m), TPB, TPB * sizeof(G1), st>>>(scalars, c->fk20_tab, 64, 128, L, d_status, sums);
+    launch_msm_fixed(dim3(128 / (TPB / L), (unsigned)m), TPB, st, scalars, c->fk20_tab, 64, 128, L, d_status, sums);
     if (marks) c->mark(KZGB200_KC_G1FFT);
     // sums (bit-reversed) --IFFT--> h, keep 64 (toeplitz.go:124), zero-pad (fk20.go:82-85) --FFT--> proofs (bit-reversed);
     // one launch per radix-2 stage, working set in c->fft_work.  The chunk is cut into independent

@@ -140,7 +140,7 @@ static int verify_independent(kzg_lane *c, const uint8_t *blobs, const uint8_t *
                                y32 ? y32 + off * 32 : nullptr, pf48 + off * 48, m, d_status, (G1Aff *)c->v_aff1.p, (G1Aff *)c->v_aff2.p,
                                (uint32_t *)c->zbuf.p, (uint32_t *)c->ybuf.p))) return rc;
         c->mark(KZGB200_KC_VERIFY);
-        k_verify_single_prep<<<(unsigned)((2 * m + 63) / 64), 64, 0, c->stream>>>((const G1Aff *)c->v_aff1.p, (const G1Aff *)c->v_aff2.p, (const uint32_t *)c->zbuf.p,
+        k_verify_single_prep<<<(unsigned)((4 * m + 63) / 64), 64, 0, c->stream>>>((const G1Aff *)c->v_aff1.p, (const G1Aff *)c->v_aff2.p, (const uint32_t *)c->zbuf.p,
                                                                                (const uint32_t *)c->ybuf.p, c->g1_monomial, d_status, (G1 *)c->v_S.p, (G1 *)c->v_W.p, m);
         c->mark(KZGB200_KC_PAIRING);
         if ((rc = vm_pairing_check(c->stream, c->pairing, (const G1 *)c->v_S.p, 0, (const G1 *)c->v_W.p, 1, d_status, d_status, m))) return rc;   // e(-A, G2) e(pi, [s]G2) == 1
@@ -232,7 +232,7 @@ int lane_verify_blob_kzg_proof_batch(kzg_lane *c, const uint8_t *blobs, const ui
     if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_CELL_TW, 32, 4, KZG_VM_SEGS, (G1 *)c->v_S.p, 2))) return rc;
     c->mark(KZGB200_KC_VERIFY);
     k_rlc_fsum<<<1, 128, 0, c->stream>>>((const Fr *)c->v_fr.p, n, (uint32_t *)c->scalars.p);
-    k_msm_fixed<<<dim3(1, 1), 32, 32 * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p);   // [sum r_i y_i] G
+    launch_msm_fixed(dim3(1, 1), 32, c->stream, (const uint32_t *)c->scalars.p, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p);   // [sum r_i y_i] G
     k_rlc_prep<<<1, 32, 0, c->stream>>>((const G1 *)c->v_S.p, (const G1 *)c->sums.p, (G1 *)c->v_pa.p, (G1 *)c->v_pb.p);
     c->mark(KZGB200_KC_PAIRING);
     if ((rc = vm_pairing_check(c->stream, c->pairing, (const G1 *)c->v_pa.p, 0, (const G1 *)c->v_pb.p, 1, nullptr, (int32_t *)c->v_st2.p, 1))) return rc;
@@ -369,7 +369,7 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
     c->mark(KZGB200_KC_MSM);
     for (size_t b0 = 0; b0 < nb; b0 += 65535) {      // gridDim.y <= 65535
         const size_t bn = std::min<size_t>(65535, nb - b0);
-        k_msm_fixed<<<dim3(1, (unsigned)bn), 32, 32 * sizeof(G1), c->stream>>>((const uint32_t *)c->scalars.p + b0 * 64 * 8, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p + b0);
+        launch_msm_fixed(dim3(1, (unsigned)bn), 32, c->stream, (const uint32_t *)c->scalars.p + b0 * 64 * 8, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p + b0);
     }
     CU(cudaGetLastError());
     c->mark(KZGB200_KC_VMSM);

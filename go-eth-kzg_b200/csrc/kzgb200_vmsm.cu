@@ -31,13 +31,18 @@ int vm_msm_windows(cudaStream_t st, const G1Aff *points, const int8_t *digits, i
                    G1 *scratch, G1 *WS, G1 *WSb) {
     if (n_items) {
         const size_t n_tasks = n_items * (size_t)nw;
+#define KZG_VMSM_LAUNCH(NB, POL) k_vmsm_buckets<NB, POL><<<(unsigned)n_items, nw, 0, st>>>(points, digits, TW, w_lo, order, item_start, item_end, scratch)
+#define KZG_VMSM_PICK(NB) do { switch (g_vmsm_policy) { case 0: KZG_VMSM_LAUNCH(NB, MulInline); break; case 2: KZG_VMSM_LAUNCH(NB, MulInlineLazy); break; \
+                                                        case 3: KZG_VMSM_LAUNCH(NB, MulCall); break; default: KZG_VMSM_LAUNCH(NB, MulCallLazy); } } while (0)
         if (nbuckets == KZG_LARGE_BUCKETS) {
-            k_vmsm_buckets<KZG_LARGE_BUCKETS><<<(unsigned)n_items, nw, 0, st>>>(points, digits, TW, w_lo, order, item_start, item_end, scratch);
+            KZG_VMSM_PICK(KZG_LARGE_BUCKETS);
             k_vmsm_bucket_reduce<KZG_LARGE_BUCKETS><<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(scratch, WS, n_tasks);
         } else {
-            k_vmsm_buckets<KZG_VM_BUCKETS><<<(unsigned)n_items, nw, 0, st>>>(points, digits, TW, w_lo, order, item_start, item_end, scratch);
+            KZG_VMSM_PICK(KZG_VM_BUCKETS);
             k_vmsm_bucket_reduce<KZG_VM_BUCKETS><<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(scratch, WS, n_tasks);
         }
+#undef KZG_VMSM_PICK
+#undef KZG_VMSM_LAUNCH
     }
     if (nb) k_vmsm_item_reduce<<<(unsigned)nb, nw, 0, st>>>(WS, batch_item_off, WSb);
     CUL(cudaGetLastError());

@@ -134,6 +134,47 @@ template <class P> struct Mont {
         for (int i = 0; i < N; ++i) r.v[i] = even[i];
         return r;
     }
+    // (a*b + c*d) / R mod p with ONE Montgomery reduction: every row adds a*b_i, c*d_i and m*p, i.e. 3N wide products
+    // per row pair instead of the 4N of two separate products (432 + 12 instead of 576 + 24 IMADs for Fp).  ONLY for moduli
+    // with 3p < 2^(32N) (Fp: p ~ 0.10 * 2^384; NOT Fr, whose 255-bit r leaves one spare bit): the running sum then stays
+    // below 3p*2^32 < 2^(32N+32), so no limb chain overflows, and the result is below (2p^2 + Rp)/R < 1.21 p: one
+    // conditional subtraction, as in mul().
+    static __device__ __forceinline__ void mad2_n_redc(uint32_t *even, uint32_t *odd, const uint32_t *a, uint32_t bi, const uint32_t *c, uint32_t di, bool first) {
+        const uint32_t *MOD = P::mod();
+        if (first) {
+            mul_n(odd, a + 1, bi);
+            mul_n(even, a, bi);
+        } else {
+            even[0] = ptx_add_cc(even[0], odd[1]);
+            madc_n_rshift(odd, a + 1, bi);
+            cmad_n(even, a, bi);
+            odd[N - 1] = ptx_addc(odd[N - 1], 0);
+        }
+        cmad_n(odd, c + 1, di);
+        cmad_n(even, c, di);
+        odd[N - 1] = ptx_addc(odd[N - 1], 0);
+        uint32_t mi = even[0] * P::inv();
+        cmad_n(odd, MOD + 1, mi);
+        cmad_n(even, MOD, mi);
+        odd[N - 1] = ptx_addc(odd[N - 1], 0);
+    }
+    static __device__ __forceinline__ Mont mul_add_mul(const Mont &a, const Mont &b, const Mont &c, const Mont &d) {
+        uint32_t even[N], odd[N];
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            mad2_n_redc(even, odd, a.v, b.v[i], c.v, d.v[i], i == 0);
+            mad2_n_redc(odd, even, a.v, b.v[i + 1], c.v, d.v[i + 1], false);
+        }
+        even[0] = ptx_add_cc(even[0], odd[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; ++i) even[i] = ptx_addc_cc(even[i], odd[i + 1]);
+        even[N - 1] = ptx_addc(even[N - 1], 0);
+        final_sub(even);
+        Mont r;
+#pragma unroll
+        for (int i = 0; i < N; ++i) r.v[i] = even[i];
+        return r;
+    }
     // Dedicated squaring: 2N^2+N -> N(N+1)/2 + N^2 + N wide products (234 vs 300 for N = 12).
     //  1. T = a^2 as 2N limbs.  Cross products a_i*a_j (i<j) land on limbs (i+j, i+j+1); they are
     //     accumulated into two arrays by the parity of i+j so every row is two contiguous carry

@@ -15,6 +15,7 @@
 // the table, so the kernel is IMAD-bound with ~100-300 GB/s of scattered HBM reads in flight.
 #pragma once
 #include "codec.cuh"
+#include <cstdlib>
 
 namespace kzg {
 
@@ -91,69 +92,212 @@ __device__ __forceinline__ G1Aff load_aff(const G1Aff *p) {
 // Scalars: [blob][n_groups*group_pts][8] plain limbs (table order).  out: [blob][n_groups] XYZZ.
 //   commit:  group_pts = 4096, n_groups = 1,   L = blockDim.x
 //   FK20:    group_pts = 64,   n_groups = 128, L = 8 (16 groups per 128-thread block)
-#ifndef KZG_MSM_PREFETCH
-#define KZG_MSM_PREFETCH 0
-#endif
+//
+// Variant V (bit mask; chosen at run time by msm_variant(), every variant is bit-exact):
+//   bit 0  field products through ONE out-of-line copy (MulCall) instead of ten inlined ones: the inlined mixed addition
+//          is ~70 KB of SASS, and ncu shows what that costs -- sm__icc_request_hit_rate 73 %, `no_instruction` the second
+//          largest stall (2.8 warps per issue) -- while the call costs ~36 register moves on the idle ALU pipe
+//   bit 1  the gather is STAGED: the 96-byte entry of item i+1 travels global -> shared with cp.async (no registers)
+//          while the ten products of item i run, so the random-HBM latency (~1.5 us) is off the critical path; the two
+//          96-byte stages per thread alias the 192 bytes per thread the reduction tree needs afterwards
+//   bit 2  Y3 = R (Q - X3) - Y1 PPP under one Montgomery reduction (Mont::mul_add_mul): 2 604 instead of 2 748 wide products
+//          per gathered addition
+//   bit 3  the accumulator lives in shared memory (g1_add_affine_smem) and the kernel is held to 128 registers: four CTAs per
+//          SM instead of three
 extern __shared__ unsigned char msm_smem[];
-static __global__ void __launch_bounds__(128) k_msm_fixed(const uint32_t *__restrict__ scalars, MsmTable tab, int group_pts,
+
+template <int V> struct MsmMul { typedef MulInline type; };
+template <> struct MsmMul<1> { typedef MulCall type; };
+template <> struct MsmMul<4> { typedef MulInlineLazy type; };
+template <> struct MsmMul<5> { typedef MulCallLazy type; };
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Fp at shared-memory slot `comp` of thread t: layout [component][16-byte piece][thread] (conflict-free 16-byte accesses)
+struct SmemAcc {
+    uint4 *base; int nthr, t;
+    __device__ __forceinline__ Fp ld(int comp) const {
+        uint4 a = base[(comp * 3 + 0) * nthr + t], b = base[(comp * 3 + 1) * nthr + t], c = base[(comp * 3 + 2) * nthr + t];
+        Fp r;
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+        r.v[8] = c.x; r.v[9] = c.y; r.v[10] = c.z; r.v[11] = c.w;
+        return r;
+    }
+    __device__ __forceinline__ void st(int comp, const Fp &r) const {
+        base[(comp * 3 + 0) * nthr + t] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+        base[(comp * 3 + 1) * nthr + t] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+        base[(comp * 3 + 2) * nthr + t] = make_uint4(r.v[8], r.v[9], r.v[10], r.v[11]);
+    }
+    __device__ __forceinline__ G1 load() const { G1 r; r.X = ld(0); r.Y = ld(1); r.ZZ = ld(2); r.ZZZ = ld(3); return r; }
+    __device__ __forceinline__ void store(const G1 &r) const { st(0, r.X); st(1, r.Y); st(2, r.ZZ); st(3, r.ZZZ); }
+};
+// acc += b with the accumulator resident in shared memory: every coordinate is loaded where it is used and stored as soon
+// as it is final, so the 48 registers of a register-resident accumulator are free for a fourth CTA per SM (variant bit 3)
+template <class M_> __device__ __forceinline__ void g1_add_affine_smem(const SmemAcc &A, const G1Aff &b) {
+    Fp ZZ = A.ld(2);
+    if (ZZ.is_zero()) { A.st(0, b.x); A.st(1, b.y); A.st(2, Fp::one()); A.st(3, Fp::one()); return; }
+    Fp U2 = M_::mul(b.x, ZZ);
+    Fp S2 = M_::mul(b.y, A.ld(3));
+    Fp Pd = Fp::sub(U2, A.ld(0));
+    Fp R = Fp::sub(S2, A.ld(1));
+    if (Pd.is_zero()) {
+        G1 acc = A.load();
+        if (R.is_zero()) g1_dbl_affine(&acc, &b);
+        else acc = G1::infinity();
+        A.store(acc);
+        return;
+    }
+    Fp PP = M_::sqr(Pd);
+    Fp PPP = M_::mul(Pd, PP);
+    Fp Q = M_::mul(A.ld(0), PP);
+    Fp X3 = Fp::sub(Fp::sub(M_::sqr(R), PPP), Fp::dbl(Q));
+    A.st(0, X3);
+    A.st(1, M_::msub(R, Fp::sub(Q, X3), A.ld(1), PPP));
+    A.st(2, M_::mul(A.ld(2), PP));
+    A.st(3, M_::mul(A.ld(3), PPP));
+}
+
+template <int V>
+static __global__ void __launch_bounds__(128, (V & 8) ? 4 : 3) k_msm_fixed(const uint32_t *__restrict__ scalars, MsmTable tab, int group_pts,
                                                     int n_groups, int L, const int32_t *__restrict__ status, G1 *__restrict__ out) {
+    typedef typename MsmMul<(V & 5)>::type M_;
     const int blob = blockIdx.y, t = threadIdx.x;
     if (status && status[blob] != ST_OK) return;
     const int lane = t & (L - 1);
     const int group = blockIdx.x * (blockDim.x / L) + t / L;
     const int total = group_pts * n_groups;
     G1 acc = G1::infinity();
+    // shared memory: [reduction tree / staging: blockDim * 192 B] [variant bit 3: accumulators, blockDim * 192 B]
+    SmemAcc A;
+    A.base = reinterpret_cast<uint4 *>(msm_smem) + 12 * blockDim.x; A.nthr = blockDim.x; A.t = t;
+    if (V & 8) A.store(acc);
     if (group < n_groups) {
         const uint32_t *sc = scalars + ((size_t)blob * total + (size_t)group * group_pts) * 8;
-        for (int j = lane; j < group_pts; j += L) {
+        if (V & 2) {
+            // staged gather: items (point j, window k) in order; the generator runs one item ahead of the consumer.
+            // Shared layout [stage][16-byte piece][thread]: consecutive threads hit consecutive 16-byte words.
+            uint4 *stage = reinterpret_cast<uint4 *>(msm_smem);
+            const int nthr = blockDim.x;
+            const int n_items = ((group_pts - lane + L - 1) / L) * tab.W;
             DigitStream ds;
-            {
-                const uint4 *q = reinterpret_cast<const uint4 *>(sc + (size_t)j * 8);
-                uint4 a = __ldg(q), b = __ldg(q + 1);
-                uint32_t l[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                ds.init(l);
-            }
-            const G1Aff *row = tab.entries + (size_t)(group * group_pts + j) * tab.row_entries;
-#if KZG_MSM_PREFETCH
-            // software pipeline: the gather of window k + 1 (a random 96-byte read of a multi-GB table: DRAM latency) is
-            // issued before the ten products of window k's addition, so it lands underneath them
-            int d = ds.next(tab.bitpos[0], tab.bits[0]);
-            G1Aff e;
-            if (d) e = load_aff(row + tab.rowoff[0] + ((d < 0 ? -d : d) - 1));
-            for (int k = 0; k < tab.W; ++k) {
-                int dn = 0;
-                G1Aff en;
-                if (k + 1 < tab.W) {
-                    dn = ds.next(tab.bitpos[k + 1], tab.bits[k + 1]);
-                    if (dn) en = load_aff(row + tab.rowoff[k + 1] + ((dn < 0 ? -dn : dn) - 1));
+            int gj = lane - L, gk = tab.W;          // generator position
+            const G1Aff *row = nullptr;
+            int dcur = 0, dnext = 0;
+            auto issue = [&](int buf) -> int {       // advances the generator, issues the copy of its item, returns the digit
+                if (gk == tab.W) {
+                    gj += L; gk = 0;
+                    const uint4 *q = reinterpret_cast<const uint4 *>(sc + (size_t)gj * 8);
+                    uint4 a = __ldg(q), b = __ldg(q + 1);
+                    uint32_t l[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    ds.init(l);
+                    row = tab.entries + (size_t)(group * group_pts + gj) * tab.row_entries;
                 }
+                int d = ds.next(tab.bitpos[gk], tab.bits[gk]);
                 if (d) {
-                    if (d < 0) e.y = Fp::neg(e.y);
-                    g1_add_affine<MulInline>(acc, e);
+                    const uint4 *src = reinterpret_cast<const uint4 *>(row + tab.rowoff[gk] + ((d < 0 ? -d : d) - 1));
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) cp_async16(stage + (buf * 6 + i) * nthr + t, src + i);
                 }
-                d = dn; e = en;
+                ++gk;
+                return d;
+            };
+            if (n_items > 0) dcur = issue(0);
+            cp_async_commit();
+            for (int it = 0, buf = 0; it < n_items; ++it, buf ^= 1) {
+                if (it + 1 < n_items) dnext = issue(buf ^ 1);
+                cp_async_commit();
+                cp_async_wait<1>();
+                if (dcur) {
+                    G1Aff e;
+                    uint4 w[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) w[i] = stage[(buf * 6 + i) * nthr + t];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        e.x.v[4 * i] = w[i].x; e.x.v[4 * i + 1] = w[i].y; e.x.v[4 * i + 2] = w[i].z; e.x.v[4 * i + 3] = w[i].w;
+                        e.y.v[4 * i] = w[3 + i].x; e.y.v[4 * i + 1] = w[3 + i].y; e.y.v[4 * i + 2] = w[3 + i].z; e.y.v[4 * i + 3] = w[3 + i].w;
+                    }
+                    if (dcur < 0) e.y = Fp::neg(e.y);
+                    if (V & 8) g1_add_affine_smem<M_>(A, e); else g1_add_affine<M_>(acc, e);
+                }
+                dcur = dnext;
             }
-#else
-            for (int k = 0; k < tab.W; ++k) {
-                int d = ds.next(tab.bitpos[k], tab.bits[k]);
-                if (d == 0) continue;
-                int mag = d < 0 ? -d : d;
-                G1Aff e = load_aff(row + tab.rowoff[k] + (mag - 1));
-                if (d < 0) e.y = Fp::neg(e.y);
-                g1_add_affine<MulInline>(acc, e);
+            cp_async_wait<0>();
+        } else {
+            for (int j = lane; j < group_pts; j += L) {
+                DigitStream ds;
+                {
+                    const uint4 *q = reinterpret_cast<const uint4 *>(sc + (size_t)j * 8);
+                    uint4 a = __ldg(q), b = __ldg(q + 1);
+                    uint32_t l[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    ds.init(l);
+                }
+                const G1Aff *row = tab.entries + (size_t)(group * group_pts + j) * tab.row_entries;
+                for (int k = 0; k < tab.W; ++k) {
+                    int d = ds.next(tab.bitpos[k], tab.bits[k]);
+                    if (d == 0) continue;
+                    int mag = d < 0 ? -d : d;
+                    G1Aff e = load_aff(row + tab.rowoff[k] + (mag - 1));
+                    if (d < 0) e.y = Fp::neg(e.y);
+                    if (V & 8) g1_add_affine_smem<M_>(A, e); else g1_add_affine<M_>(acc, e);
+                }
             }
-#endif
         }
     }
-    // tree reduction over the L lanes of each group through shared memory
+    if (V & 8) acc = A.load();
+    // tree reduction over the L lanes of each group through shared memory (the staging area is dead by now)
+    if (V & 2) __syncthreads();
     G1 *sm = reinterpret_cast<G1 *>(msm_smem);
     sm[t] = acc;
     __syncthreads();
+    // compacted: the (groups per block) * s additions of a level run on the FIRST that many threads, so whole warps go idle
+    // instead of every warp running the 14-product addition for half, a quarter, an eighth of its lanes
+    const int gpb = blockDim.x / L;
     for (int s = L >> 1; s > 0; s >>= 1) {
-        if (lane < s) g1_add_ool(&sm[t], &sm[t + s]);
+        if (t < gpb * s) {
+            const int sh = __ffs(s) - 1, g = t >> sh, l = t & (s - 1);
+            g1_add_ool(&sm[g * L + l], &sm[g * L + l + s]);
+        }
         __syncthreads();
     }
     if (lane == 0 && group < n_groups) out[(size_t)blob * n_groups + group] = sm[t];
+}
+
+// run-time choice of the variant: KZGB200_MSM_VARIANT (0..7) overrides the default; translation units that define
+// KZG_MSM_ALL_VARIANTS (kzgb200.cu: the proving paths) carry all eight, the others only the default
+#ifndef KZG_MSM_DEFAULT_VARIANT
+#define KZG_MSM_DEFAULT_VARIANT 13   /* measured on B200 (scripts/msm_variants.py, profiles/r02_msm_variants.md) */
+#endif
+inline int g_msm_variant_override = -1;       // kzgb200_dbg_set_tunable("msm_variant", v) (experiments: one context, every variant)
+inline int g_vmsm_policy = 1;                 // kzgb200_dbg_set_tunable("vmsm_policy", 0..3): see k_vmsm_buckets (vmsm.cuh)
+inline int g_fk20_lanes_override = 0;         // kzgb200_dbg_set_tunable("fk20_lanes", L): lanes per 64-point FK20 group for full batches
+static inline int msm_variant() {
+    if (g_msm_variant_override >= 0) return g_msm_variant_override;
+    static const int v = [] {
+        const char *e = getenv("KZGB200_MSM_VARIANT");
+        int x = e && *e ? atoi(e) : KZG_MSM_DEFAULT_VARIANT;
+        return (x < 0 || x > 15) ? KZG_MSM_DEFAULT_VARIANT : x;
+    }();
+    return v;
+}
+static inline void launch_msm_fixed(dim3 grid, int tpb, cudaStream_t st, const uint32_t *scalars, const MsmTable &tab, int group_pts, int n_groups, int L,
+                                    const int32_t *status, G1 *out) {
+    const size_t smem = (size_t)tpb * sizeof(G1) * ((msm_variant() & 8) ? 2 : 1);
+#ifdef KZG_MSM_ALL_VARIANTS
+    switch (msm_variant()) {
+#define KZG_MSM_CASE(V) case V: k_msm_fixed<V><<<grid, tpb, smem, st>>>(scalars, tab, group_pts, n_groups, L, status, out); break;
+        KZG_MSM_CASE(0) KZG_MSM_CASE(1) KZG_MSM_CASE(2) KZG_MSM_CASE(3) KZG_MSM_CASE(4) KZG_MSM_CASE(5) KZG_MSM_CASE(6) KZG_MSM_CASE(7)
+        KZG_MSM_CASE(8) KZG_MSM_CASE(9) KZG_MSM_CASE(10) KZG_MSM_CASE(11) KZG_MSM_CASE(12) KZG_MSM_CASE(13) KZG_MSM_CASE(14) KZG_MSM_CASE(15)
+#undef KZG_MSM_CASE
+    }
+#else
+    k_msm_fixed<KZG_MSM_DEFAULT_VARIANT><<<grid, tpb, smem, st>>>(scalars, tab, group_pts, n_groups, L, status, out);
+#endif
 }
 
 // out[blob] = sum of the S (<= 32, power of two) partial sums of a blob: one warp per blob, tree through shared memory

@@ -65,31 +65,42 @@ static __device__ __noinline__ Fr fr_pow_u64(Fr base, unsigned long long e) {
 // ---- n independent single-proof checks (kzg_verify.go:35-100 rewritten to fixed G2) ------------
 // status[i] must hold OK or an earlier decode error; z/y are plain limbs.
 // PA[i] = -(C - [y]G + [z]pi), PB[i] = pi; the check e(PA, G2) e(PB, [s]G2) == 1 runs in k_pairing_lanes.
-// Two threads per item: the two 255-bit scalar multiplications are independent, and a one-item call (the reference's
-// calling pattern) is pure latency -- thread 2i computes [y]G, thread 2i+1 computes [z]pi and hands it over through
-// shared memory.
+// Four threads per item: [y]G and [z]pi are independent, and each is GLV-split (vmsm.cuh: s = k1 + k2 * (-x^2), halves below
+// 2^127) into two 128-bit scalar multiplications, so a one-item call (the reference's calling pattern: pure latency) is ~124
+// dependent doublings deep instead of ~252.  Role 0: [k1(y)]G, 1: phi2([k2(y)]G), 2: [k1(z)]pi, 3: phi2([k2(z)]pi); the four
+// parts meet in shared memory and role 0 forms C - [y]G + [z]pi.
 static __global__ void __launch_bounds__(64) k_verify_single_prep(const G1Aff *__restrict__ commitments, const G1Aff *__restrict__ proofs,
                                                            const uint32_t *__restrict__ z, const uint32_t *__restrict__ y,
                                                            const G1Aff *__restrict__ g1_gen, const int32_t *__restrict__ status,
                                                            G1 *__restrict__ PA, G1 *__restrict__ PB, size_t n) {
-    __shared__ G1 hand[32];
-    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
-    const int role = threadIdx.x & 1, slot = threadIdx.x >> 1;
+    __shared__ G1 hand[16][3];
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const int role = threadIdx.x & 3, slot = threadIdx.x >> 2;
     const bool live = i < n && status[i] == ST_OK;
     G1 part = G1::infinity();
     if (live) {
-        G1 base = role ? G1::from_affine(proofs[i]) : G1::from_affine(*g1_gen);
-        g1_mul_scalar(&part, &base, (role ? z : y) + i * 8);
+        uint32_t k1[4], k2[4];
+        bool n1, n2;
+        glv_split(((role & 2) ? z : y) + i * 8, k1, n1, k2, n2);
+        Scalar256 ks;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { ks.v[q] = (role & 1) ? k2[q] : k1[q]; ks.v[4 + q] = 0; }
+        G1 base = (role & 2) ? G1::from_affine(proofs[i]) : G1::from_affine(*g1_gen);
+        part = g1_mul_scalar_v(base, ks, 32);
+        if ((role & 1) ? n2 : n1) part.neg_inplace();
+        if (role & 1) part = g1_phi2(part);
     }
-    if (role) hand[slot] = part;
+    if (role) hand[slot][role - 1] = part;
     __syncthreads();
     if (role || i >= n) return;
     if (!live) { PA[i] = G1::infinity(); PB[i] = G1::infinity(); return; }
+    G1 yG = part;
+    g1_add(yG, hand[slot][0]);
+    yG.neg_inplace();
     G1 A = G1::from_affine(commitments[i]);
-    part.neg_inplace();
-    g1_add(A, part);
-    G1 h = hand[slot];
-    g1_add(A, h);                          // C - [y]G + [z]pi
+    g1_add(A, yG);
+    g1_add(A, hand[slot][1]);
+    g1_add(A, hand[slot][2]);              // C - [y]G + [z]pi
     A.neg_inplace();
     PA[i] = A; PB[i] = G1::from_affine(proofs[i]);
 }

@@ -230,7 +230,11 @@ static __global__ void k_rlc_coeff_digits(Fr seed, int unit_coeff, const uint32_
 // block = one item (a run of points of ONE verdict), thread = one window.  digits: [point][TW].
 // w_lo: only windows [w_lo, w_lo + blockDim.x) of each digit row are used (so a second point set can
 // share a digit array).  Leaves the buckets of task item * nw + thread in scratch.
-template <int NB>
+// M_: field-product policy of the accumulation (g1.cuh).  MulInline is ~70 KB of SASS per loop body and ncu shows the price
+// (sm__icc_request_hit_rate 73 %, `no_instruction` 3.5 warps per issue); the default goes through the shared out-of-line
+// products and the one-reduction Y3 (kzgb200_dbg_set_tunable("vmsm_policy", 0..3) switches for measurements).
+// g_vmsm_policy (msm.cuh): 0 MulInline, 1 MulCallLazy, 2 MulInlineLazy, 3 MulCall
+template <int NB, class M_>
 static __global__ void __launch_bounds__(128) k_vmsm_buckets(const G1Aff *__restrict__ points, const int8_t *__restrict__ digits, int TW, int w_lo,
                                                       const uint32_t *__restrict__ order, const uint64_t *__restrict__ item_start,
                                                       const uint64_t *__restrict__ item_end, G1 *__restrict__ scratch) {
@@ -261,7 +265,7 @@ static __global__ void __launch_bounds__(128) k_vmsm_buckets(const G1Aff *__rest
         int d = d0;
         if (d < 0) { P.y = Fp::neg(P.y); d = -d; }
         G1 acc = load_g1(B + (d - 1));
-        g1_add_affine<MulInline>(acc, P);
+        g1_add_affine<M_>(acc, P);
         store_g1(B + (d - 1), acc);
     }
 }

@@ -45,6 +45,13 @@ const char *kzgb200_dbg_shard_plan_json(size_t n_units, size_t n_dev, size_t min
 /* aggregate host -> device GB/s of n GPUs copying their slices of ONE pinned host buffer at the same time (plain or
  * NUMA-interleaved pinned memory): the ceiling of the end-to-end numbers of a multi-GPU context */
 int kzgb200_dbg_h2d_bandwidth(const int *devices, int n, size_t bytes_per_dev, int interleaved, double *gbps);
+/* experiments: run-time tunables of the proving paths (every setting is bit-exact).
+ *   "msm_variant": k_msm_fixed variant, bit 0: out-of-line field products, bit 1: cp.async-staged gather, bit 2: one-reduction
+ *                  Y3, bit 3: accumulator in shared memory + 4 CTAs/SM; -1 = default (or the KZGB200_MSM_VARIANT environment variable)
+ *   "fk20_lanes":  lanes per 64-point FK20 group for full batches (4, 8 or 16; 0 = default)
+ *   "vmsm_policy": field products of the verifiers' bucket accumulation: 0 inlined, 1 out-of-line + one-reduction Y3 (default),
+ *                  2 inlined + one-reduction Y3, 3 out-of-line */
+int kzgb200_dbg_set_tunable(const char *name, int v);
 /* dependency-free integer multiply-add microbenchmark: device-wide instructions*lanes per second.
  * mode 0: mad.lo.u32 (IMAD), 1: mad.hi.u32 (IMAD.HI), 2: mad.wide.u32 (IMAD.WIDE, 32x32+64);
  * mode 3 / 4: a bare dependent chain of the library's Fp::mul / Fp::sqr per thread -> field operations per second */

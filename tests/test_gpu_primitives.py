@@ -28,6 +28,8 @@ def test_field_ops(dbg, field, mod):
     assert dbg.field_op(field, a, b, 1) == [(x + y) % mod for x, y in zip(a, b)]
     assert dbg.field_op(field, a, b, 2) == [(x - y) % mod for x, y in zip(a, b)]
     assert dbg.field_op(field, a, b, 4) == [x * x % mod for x in a]        # dedicated squaring
+    if field == "fp":       # sum of two products under one Montgomery reduction (needs 3p < 2^384: Fp only): x*y + (x+y)*(x-y)
+        assert dbg.field_op(field, a, b, 5) == [(x * y + (x + y) * (x - y)) % mod for x, y in zip(a, b)]
 
 
 def test_fp_inverse(dbg):
