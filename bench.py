@@ -485,28 +485,33 @@ def roofline_for(wl, info, per, B, units, world_value_per_gpu, peaks, dev_ms_per
                                      "frac": world_value_per_gpu * CANONICAL_W[wl] / peak}}
     uses_commit = wl in ("commit", "blob_proof")
     uses_fk20 = wl in ("cells_proofs", "recover")
-    IMAD_MIXED_ADD = 8 * IMAD_FP_MUL + 2 * IMAD_FP_SQR
-    blended = 10.0 / (8.0 / peaks["fp_mul"] + 2.0 / peaks["fp_sqr"])          # mixed addition = 8 mul + 2 sqr
+    # gathered mixed addition (g1.cuh g1_add_affine with the *Lazy policy): 6 mul + 2 sqr + ONE mul_add_mul (Y3 = R(Q-X3) - Y1*PPP under
+    # one Montgomery reduction: 3 x 144 wide products + 12 = 876 IMAD instead of 2 x 588)
+    IMAD_FP_MAM = 2 * 3 * 144 + 12
+    IMAD_MIXED_ADD = 6 * IMAD_FP_MUL + 2 * IMAD_FP_SQR + IMAD_FP_MAM
+    MULEQ_MIXED_ADD = 6.0 + 2.0 + 1.5                                         # in isolated-chain terms: a mul_add_mul ~ 1.5 products
+    blended = MULEQ_MIXED_ADD / (7.5 / peaks["fp_mul"] + 2.0 / peaks["fp_sqr"])
     if uses_commit or uses_fk20:
         c_used, W_used = (info["commit_window"], info["commit_windows_per_scalar"]) if uses_commit else (info["fk20_window"], info["fk20_windows_per_scalar"])
         npts = 4096 if uses_commit else 8192
         msm_imad = npts * W_used * IMAD_MIXED_ADD
         msm_ms = per.get("msm", 0.0)
         achieved = msm_imad * B / (msm_ms * 1e-3) if msm_ms else None
-        muls = npts * W_used * 10.0 * B / (msm_ms * 1e-3) if msm_ms else None
+        muls = npts * W_used * MULEQ_MIXED_ADD * B / (msm_ms * 1e-3) if msm_ms else None
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
         roof.update({"kernel": "k_msm_fixed", "achieved": achieved / 1e12 if achieved else None, "frac": achieved / peak if achieved else None,
                      "frac_of_isolated_field_op_rate": muls / blended if muls else None,
                      "fmaheavy_pct_ncu": fmaheavy_from_profiles("k_msm_fixed"),
-                     "work_model": "executed: %d pts x %d windows x (8 mul x 588 + 2 sqr x 456) IMAD = %.0f M IMAD/blob in this kernel (nominal at 588 per sqr: %.0f M); "
-                                   "frac_of_isolated_field_op_rate = Fp mul-equivalents/s over the live-measured rate of a bare chain of the same 8 mul : 2 sqr mix"
+                     "work_model": "executed: %d pts x %d windows x (6 mul x 588 + 2 sqr x 456 + 1 two-product-one-reduction x 876) IMAD = %.0f M IMAD/blob in this kernel "
+                                   "(round 1 executed 8 mul + 2 sqr = 5616 per addition; nominal 10 x 588: %.0f M); frac_of_isolated_field_op_rate = Fp mul-equivalents/s "
+                                   "over the live-measured rate of a bare chain of the same mul : sqr mix"
                                    % (npts, W_used, msm_imad / 1e6, npts * W_used * 10 * IMAD_FP_MUL / 1e6),
                      "hbm_table_gather": {"achieved": npts * W_used * 96.0 * B / (msm_ms * 1e-3) / 1e9 if msm_ms else None, "unit": "GB/s", "peak": hbm_peak}})
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("cells_proofs" if uses_fk20 else "commit")
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get("cells_proofs" if uses_fk20 else "commit")
             if tr and tr["window_bits"] == c_used:
                 roof["traffic"] = tr["bytes_per_launch"]
-                roof["traffic_note"] = "ncu dram bytes per 1024-blob launch of k_msm_fixed (profiles/r01_ncu_full_headline.md); algorithmic gather bytes %d" % tr["algorithmic_gather_bytes_per_launch"]
+                roof["traffic_note"] = "ncu dram bytes per 1024-blob launch of k_msm_fixed (%s); algorithmic gather bytes %d" % (tr.get("source", "profiles"), tr["algorithmic_gather_bytes_per_launch"])
         except Exception:
             pass
         return roof

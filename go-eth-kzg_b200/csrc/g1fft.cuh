@@ -170,8 +170,8 @@ __device__ __forceinline__ int g1fft_butterfly(int y, int log_half) {
 // SRC_XYZZ: the stage reads the MSM sums (XYZZ) instead of the working set.  DST_XYZZ: it writes
 // XYZZ points for k_finalize_g1.  ONLY_SUM: x - y is not needed (inverse transform, last stage,
 // upper half discarded: toeplitz.go:124).  UPPER_ZERO: y is the zero padding (fk20.go:82-85).
-template <bool DIT, bool INVERSE, bool SRC_XYZZ, bool DST_XYZZ, bool ONLY_SUM, bool UPPER_ZERO>
-static __global__ void __launch_bounds__(KZG_G1FFT_TPB) k_g1fft_stage(const G1 *__restrict__ src_xyzz, G1J *__restrict__ work, G1 *__restrict__ dst_xyzz,
+template <bool DIT, bool INVERSE, bool SRC_XYZZ, bool DST_XYZZ, bool ONLY_SUM, bool UPPER_ZERO, int MINB>
+static __global__ void __launch_bounds__(KZG_G1FFT_TPB, MINB) k_g1fft_stage(const G1 *__restrict__ src_xyzz, G1J *__restrict__ work, G1 *__restrict__ dst_xyzz,
                                                                       const int32_t *__restrict__ status, int nblobs, int log_half) {
     const int blob = blockIdx.x * KZG_G1FFT_TPB + threadIdx.x;
     if (blob >= nblobs || status[blob] != ST_OK) return;

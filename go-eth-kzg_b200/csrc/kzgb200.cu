@@ -295,6 +295,16 @@ int kzgb200_dbg_set_tunable(const char *name, int v) {
         kzg::g_fk20_lanes_override = v;
         return 0;
     }
+    if (!strcmp(name, "g1fft_minb")) {
+        if (v != 3 && v != 4) return set_err(KZGB200_ERR_ARGS, "g1fft_minb must be 3 or 4");
+        kzg::g_g1fft_minb = v;
+        return 0;
+    }
+    if (!strcmp(name, "g1fft_split")) {       // takes effect for lanes created afterwards? no: read per call from this global when non-zero
+        if (v < 0 || v > KZG_G1FFT_MAX_SPLIT) return set_err(KZGB200_ERR_ARGS, "g1fft_split out of range");
+        kzg::g_g1fft_split_override = v;
+        return 0;
+    }
     if (!strcmp(name, "vmsm_policy")) {
         if (v < 0 || v > 3) return set_err(KZGB200_ERR_ARGS, "vmsm_policy must be 0..3");
         kzg::g_vmsm_policy = v;
@@ -691,7 +701,7 @@ static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr 
         k_g1dense_sum<<<dim3(128, (unsigned)m), 64, 0, st>>>(prod, pxyzz, d_status);
         c->launches += 2;
     } else {
-        const size_t nsplit = std::max<size_t>(1, std::min<size_t>(c->g1fft_split, (m + 127) / 128));
+        const size_t nsplit = std::max<size_t>(1, std::min<size_t>(g_g1fft_split_override ? (size_t)g_g1fft_split_override : c->g1fft_split, (m + 127) / 128));
         const size_t per = (m + nsplit - 1) / nsplit;
         if (nsplit > 1) cudaEventRecord(c->ev_fork, st);
         for (size_t k = 0, off = 0; off < m; ++k, off += per) {
@@ -703,12 +713,15 @@ static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr 
             G1 *dst = pxyzz + off * 128;
             const int32_t *stt = d_status + off;
             const dim3 grid((unsigned)((nb + KZG_G1FFT_TPB - 1) / KZG_G1FFT_TPB), 64);
-            k_g1fft_stage<true, true, true, false, false, false><<<grid, KZG_G1FFT_TPB, 0, s>>>(src, work, nullptr, stt, nb, 0);
-            for (int lh = 1; lh < 6; ++lh) k_g1fft_stage<true, true, false, false, false, false><<<grid, KZG_G1FFT_TPB, 0, s>>>(nullptr, work, nullptr, stt, nb, lh);
-            k_g1fft_stage<true, true, false, false, true, false><<<grid, KZG_G1FFT_TPB, 0, s>>>(nullptr, work, nullptr, stt, nb, 6);
-            k_g1fft_stage<false, false, false, false, false, true><<<grid, KZG_G1FFT_TPB, 0, s>>>(nullptr, work, nullptr, stt, nb, 6);
-            for (int lh = 5; lh >= 1; --lh) k_g1fft_stage<false, false, false, false, false, false><<<grid, KZG_G1FFT_TPB, 0, s>>>(nullptr, work, nullptr, stt, nb, lh);
-            k_g1fft_stage<false, false, false, true, false, false><<<grid, KZG_G1FFT_TPB, 0, s>>>(nullptr, work, dst, stt, nb, 0);
+#define KZG_STAGE(A, B, C, D, E, F, ...) do { if (g_g1fft_minb == 4) k_g1fft_stage<A, B, C, D, E, F, 4><<<grid, KZG_G1FFT_TPB, 0, s>>>(__VA_ARGS__); \
+                                                else k_g1fft_stage<A, B, C, D, E, F, 3><<<grid, KZG_G1FFT_TPB, 0, s>>>(__VA_ARGS__); } while (0)
+            KZG_STAGE(true, true, true, false, false, false, src, work, nullptr, stt, nb, 0);
+            for (int lh = 1; lh < 6; ++lh) KZG_STAGE(true, true, false, false, false, false, nullptr, work, nullptr, stt, nb, lh);
+            KZG_STAGE(true, true, false, false, true, false, nullptr, work, nullptr, stt, nb, 6);
+            KZG_STAGE(false, false, false, false, false, true, nullptr, work, nullptr, stt, nb, 6);
+            for (int lh = 5; lh >= 1; --lh) KZG_STAGE(false, false, false, false, false, false, nullptr, work, nullptr, stt, nb, lh);
+            KZG_STAGE(false, false, false, true, false, false, nullptr, work, dst, stt, nb, 0);
+#undef KZG_STAGE
             c->launches += 14;
             if (k) { cudaEventRecord(c->ev_join[k - 1], s); cudaStreamWaitEvent(st, c->ev_join[k - 1], 0); }
         }

@@ -275,6 +275,8 @@ static __global__ void __launch_bounds__(128, (V & 8) ? 4 : 3) k_msm_fixed(const
 #endif
 inline int g_msm_variant_override = -1;       // kzgb200_dbg_set_tunable("msm_variant", v) (experiments: one context, every variant)
 inline int g_vmsm_policy = 1;                 // kzgb200_dbg_set_tunable("vmsm_policy", 0..3): see k_vmsm_buckets (vmsm.cuh)
+inline int g_g1fft_minb = 3;                  // kzgb200_dbg_set_tunable("g1fft_minb", 3 | 4): resident CTAs per SM the G1 FFT stage kernel is compiled for
+inline int g_g1fft_split_override = 0;        // kzgb200_dbg_set_tunable("g1fft_split", k): sub-batches (streams) of the staged G1 FFT; 0 = context default
 inline int g_fk20_lanes_override = 0;         // kzgb200_dbg_set_tunable("fk20_lanes", L): lanes per 64-point FK20 group for full batches
 static inline int msm_variant() {
     if (g_msm_variant_override >= 0) return g_msm_variant_override;
