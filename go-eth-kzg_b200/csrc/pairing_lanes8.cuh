@@ -1,56 +1,43 @@
-// Lane-parallel pairing product check, LATENCY form: one check runs on ONE WARP -- 8 coefficient slots x 4 sub-lanes
-// (namespace pl32; pairing_lanes8.cuh is the throughput form, 8 lanes per check; vm_pairing_check picks by batch size).
+// Lane-parallel pairing product check, THROUGHPUT form: one check runs on a group of 8 lanes of a warp (namespace pl8).
+// pairing_lanes.cuh (namespace pl32) is the latency form, one check per warp; vm_pairing_check picks by batch size.
 //
 // Replaces gnark-crypto's bls12381.PairingCheck at internal/kzg/kzg_verify.go:88,190 and
 // internal/kzg_multi/kzg_verify.go:94 (fixed G2 arguments, lines precomputed in pairing.cuh).
 //
 // Why: a batch verifier ends in ONE check per verdict, so its latency is on the critical path of
-// every call (a whole 4096-blob EIP-4844 batch waits for a single pairing), and a lone thread needs
-// ~1 us per dependent Fp product.  Fp12 is used in its flat form Fp2[w]/(w^6 - xi), xi = 1+u:
-// f = sum_{i<6} f_i w^i, and coefficient slot i (lanes 4i .. 4i+3) keeps only the Fp2 coefficient f_i in
-// registers, replicated in its four sub-lanes (tower coefficient map: flat 0,2,4 = c0.c0,c0.c1,c0.c2 and
+// every call (a whole 4096-blob EIP-4844 batch waits for a single pairing).  Fp12 is used in its
+// flat form Fp2[w]/(w^6 - xi), xi = 1+u:  f = sum_{i<6} f_i w^i, and lane i of the group keeps only
+// the Fp2 coefficient f_i in registers (tower coefficient map: flat 0,2,4 = c0.c0,c0.c1,c0.c2 and
 // flat 1,3,5 = c1.c0,c1.c1,c1.c2, since v = w^2).  Then
-//   product:        h_k = sum_{i+j=k} f_i g_j + xi sum_{i+j=k+6} f_i g_j      6 Fp2 products per slot
-//   square:         the same sum over unordered pairs                          4 Fp2 products per slot
+//   product:        h_k = sum_{i+j=k} f_i g_j + xi sum_{i+j=k+6} f_i g_j      6 Fp2 products per lane
+//   square:         the same sum over unordered pairs                          4 Fp2 products per lane
 //   sparse line:    l = a0 + a1 w^2 + w^3:  h_k = f_k a0 + [xi] f_{k-2} a1 + [xi] f_{k-3}   2 products
-//   Frobenius:      h_k = conj(f_k) gamma^k                                     1 product, slot-local
+//   Frobenius:      h_k = conj(f_k) gamma^k                                     1 product, lane-local
 //   cyclotomic sqr: Granger-Scott on the Fp4 pairs (f_j, f_{j+3})               1 square + 1 product
-// with operands exchanged by warp shuffles (24 words per Fp2), and EVERY Fp2 product is ONE Fp product deep:
-// the three Karatsuba products a0 b0, a1 b1, (a0+a1)(b0+b1) run on sub-lanes 0, 1, 2 of the slot and are
-// exchanged inside the quad (fp2_mul_q; a square is two products, fp2_sqr_q).  The critical path of a check drops
-// from ~16 k dependent Fp products (one thread) over ~4.6 k (round 1: 8 lanes, Fp2 products serial) to ~1.6 k.
-// Slots 6 and 7 carry zeros; sub-lane 3 mirrors sub-lane 2.
+// with operands exchanged by warp shuffles (24 words per Fp2).  The critical path of a check drops
+// from ~16 k dependent Fp products (one thread) to ~4.6 k.  Lanes 6 and 7 of a group carry zeros.
 #pragma once
 #include "pairing.cuh"
 
 namespace kzg {
-namespace pl32 {
+namespace pl8 {
 
-#define KZG_PL_GROUP 32
+#define KZG_PL8_GROUP 8
 
 struct PL {
-    int lane;          // lane in the warp
-    int l;             // coefficient slot = lane >> 2 (0..7)
-    int lc;            // min(l, 5): coefficient index used for addressing (idle slots mirror slot 5's pattern)
-    int sub;           // sub-lane inside the slot = lane & 3
+    unsigned mask;     // the 8 lanes of this group inside the warp
+    int l;             // lane within the group
+    int lc;            // min(l, 5): coefficient index used for addressing (idle lanes mirror lane 5's pattern)
 };
 
-// value held by coefficient slot `src` (every sub-lane reads its own counterpart: the replicas are identical)
 __device__ __forceinline__ Fp pl_shfl_fp(const PL &c, const Fp &a, int src) {
     Fp r;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) r.v[k] = __shfl_sync(0xffffffffu, a.v[k], src * 4 + c.sub);
+    for (int k = 0; k < 12; ++k) r.v[k] = __shfl_sync(c.mask, a.v[k], src, KZG_PL8_GROUP);
     return r;
 }
 __device__ __forceinline__ Fp2 pl_shfl(const PL &c, const Fp2 &a, int src) {
     Fp2 r; r.c0 = pl_shfl_fp(c, a.c0, src); r.c1 = pl_shfl_fp(c, a.c1, src);
-    return r;
-}
-// value held by sub-lane j of the caller's own slot
-__device__ __forceinline__ Fp pl_quad_fp(const PL &c, const Fp &a, int j) {
-    Fp r;
-#pragma unroll
-    for (int k = 0; k < 12; ++k) r.v[k] = __shfl_sync(0xffffffffu, a.v[k], (c.lane & ~3) + j);
     return r;
 }
 __device__ __forceinline__ Fp fp_select(bool p, const Fp &a, const Fp &b) {
@@ -64,25 +51,6 @@ __device__ __forceinline__ Fp2 fp2_select(bool p, const Fp2 &a, const Fp2 &b) {
     return r;
 }
 
-// a * b for operands replicated in the slot's sub-lanes: ONE Fp product deep (Karatsuba terms on sub-lanes 0, 1, 2)
-static __device__ __noinline__ Fp2 fp2_mul_q(PL c, Fp2 a, Fp2 b) {
-    Fp sa = Fp::add(a.c0, a.c1), sb = Fp::add(b.c0, b.c1);
-    Fp x = fp_select(c.sub == 0, a.c0, fp_select(c.sub == 1, a.c1, sa));
-    Fp y = fp_select(c.sub == 0, b.c0, fp_select(c.sub == 1, b.c1, sb));
-    Fp t = fp_mul_ni(x, y);
-    Fp t0 = pl_quad_fp(c, t, 0), t1 = pl_quad_fp(c, t, 1), t2 = pl_quad_fp(c, t, 2);
-    Fp2 r; r.c0 = Fp::sub(t0, t1); r.c1 = Fp::sub(Fp::sub(t2, t0), t1);
-    return r;
-}
-// a^2: (a0 + a1)(a0 - a1) on sub-lane 0, a0 a1 on the others
-static __device__ __noinline__ Fp2 fp2_sqr_q(PL c, Fp2 a) {
-    Fp x = fp_select(c.sub == 0, Fp::add(a.c0, a.c1), a.c0);
-    Fp y = fp_select(c.sub == 0, Fp::sub(a.c0, a.c1), a.c1);
-    Fp t = fp_mul_ni(x, y);
-    Fp2 r; r.c0 = pl_quad_fp(c, t, 0); r.c1 = Fp::dbl(pl_quad_fp(c, t, 1));
-    return r;
-}
-
 // h = f * g
 static __device__ __noinline__ Fp2 pl_mul(PL c, Fp2 f, Fp2 g) {
     Fp2 s0 = fp2_zero(), s1 = fp2_zero();
@@ -92,7 +60,7 @@ static __device__ __noinline__ Fp2 pl_mul(PL c, Fp2 f, Fp2 g) {
         bool wrap = j < 0;
         if (wrap) j += 6;
         Fp2 a = pl_shfl(c, f, i), b = pl_shfl(c, g, j);
-        Fp2 p = fp2_mul_q(c, a, b);
+        Fp2 p = fp2_mul(a, b);
         s0 = fp2_select(wrap, s0, fp2_add(s0, p));
         s1 = fp2_select(wrap, fp2_add(s1, p), s1);
     }
@@ -115,7 +83,7 @@ static __device__ __noinline__ Fp2 pl_sqr(PL c, Fp2 f) {
         int i = e & 7, j = (e >> 3) & 7, mult = (e >> 6) & 3;
         bool wrap = (e >> 8) & 1;
         Fp2 a = pl_shfl(c, f, i), b = pl_shfl(c, f, j);
-        Fp2 p = fp2_mul_q(c, a, b);
+        Fp2 p = fp2_mul(a, b);
         Fp2 p2 = fp2_dbl(p);
         p = fp2_select(mult == 2, p2, p);
         p = fp2_select(mult == 0, fp2_zero(), p);
@@ -129,27 +97,27 @@ static __device__ __noinline__ Fp2 pl_sqr(PL c, Fp2 f) {
 static __device__ __noinline__ Fp2 pl_mul_by_line(PL c, Fp2 f, Fp2 a0, Fp2 a1) {
     int l = c.lc;
     Fp2 fm2 = pl_shfl(c, f, (l + 4) % 6), fm3 = pl_shfl(c, f, (l + 3) % 6);
-    Fp2 t2 = fp2_mul_q(c, fm2, a1);
+    Fp2 t2 = fp2_mul(fm2, a1);
     t2 = fp2_select(l < 2, fp2_mul_xi(t2), t2);
     Fp2 t3 = fp2_select(l < 3, fp2_mul_xi(fm3), fm3);
-    return fp2_add(fp2_add(fp2_mul_q(c, f, a0), t2), t3);
+    return fp2_add(fp2_add(fp2_mul(f, a0), t2), t3);
 }
 
 __device__ __forceinline__ Fp2 pl_conj(const PL &c, const Fp2 &f) { return fp2_select(c.l & 1, fp2_neg(f), f); }   // f^(p^6): odd powers of w change sign
 __device__ __forceinline__ Fp2 pl_one(const PL &c) { return fp2_select(c.l == 0, fp2_one(), fp2_zero()); }
-__device__ __forceinline__ Fp2 pl_frobenius(const PL &c, const Fp2 &f, const Fp2 *g) { return fp2_mul_q(c, fp2_conj(f), g[c.lc]); }
+__device__ __forceinline__ Fp2 pl_frobenius(const PL &c, const Fp2 &f, const Fp2 *g) { return fp2_mul(fp2_conj(f), g[c.lc]); }
 
 // inverse: f^-1 = conj(f) * N^-1 with N = f conj(f) in Fp6 (flat coefficients 0, 2, 4)
 static __device__ __noinline__ Fp2 pl_inv(PL c, Fp2 f) {
     Fp2 fc = pl_conj(c, f);
     Fp2 N = pl_mul(c, f, fc);
     Fp2 n0 = pl_shfl(c, N, 0), n1 = pl_shfl(c, N, 2), n2 = pl_shfl(c, N, 4);
-    Fp2 t0 = fp2_sub(fp2_sqr_q(c, n0), fp2_mul_xi(fp2_mul_q(c, n1, n2)));
-    Fp2 t1 = fp2_sub(fp2_mul_xi(fp2_sqr_q(c, n2)), fp2_mul_q(c, n0, n1));
-    Fp2 t2 = fp2_sub(fp2_sqr_q(c, n1), fp2_mul_q(c, n0, n2));
-    Fp2 d = fp2_inv(fp2_add(fp2_add(fp2_mul_q(c, n0, t0), fp2_mul_xi(fp2_mul_q(c, n2, t1))), fp2_mul_xi(fp2_mul_q(c, n1, t2))));
+    Fp2 t0 = fp2_sub(fp2_sqr(n0), fp2_mul_xi(fp2_mul(n1, n2)));
+    Fp2 t1 = fp2_sub(fp2_mul_xi(fp2_sqr(n2)), fp2_mul(n0, n1));
+    Fp2 t2 = fp2_sub(fp2_sqr(n1), fp2_mul(n0, n2));
+    Fp2 d = fp2_inv(fp2_add(fp2_add(fp2_mul(n0, t0), fp2_mul_xi(fp2_mul(n2, t1))), fp2_mul_xi(fp2_mul(n1, t2))));
     Fp2 sel = fp2_select(c.l == 0, t0, fp2_select(c.l == 2, t1, t2));
-    Fp2 g = fp2_mul_q(c, sel, d);
+    Fp2 g = fp2_mul(sel, d);
     g = fp2_select(c.l == 0 || c.l == 2 || c.l == 4, g, fp2_zero());
     return pl_mul(c, fc, g);
 }
@@ -161,8 +129,8 @@ static __device__ __noinline__ Fp2 pl_cyc_sqr(PL c, Fp2 f) {
     int l = c.lc;
     bool hi = l >= 3;
     Fp2 other = pl_shfl(c, f, hi ? l - 3 : l + 3);
-    Fp2 sq = fp2_sqr_q(c, f);
-    Fp2 xy = fp2_mul_q(c, f, other);
+    Fp2 sq = fp2_sqr(f);
+    Fp2 xy = fp2_mul(f, other);
     Fp2 osq = pl_shfl(c, sq, hi ? l - 3 : l + 3);
     // x-lane (l < 3): tx = x^2 + xi y^2 ; y-lane: ty = 2xy
     Fp2 t = fp2_select(hi, fp2_dbl(xy), fp2_add(sq, fp2_mul_xi(osq)));
@@ -212,7 +180,7 @@ static __device__ __noinline__ Fp2 pl_miller2(PL c, const PairingConsts *pc, con
     // lane q < 4 scales one Fp component of a line: q = 0,1 -> A.c0, A.c1 times 1/y; q = 2,3 -> B.c0, B.c1 times x/y
     Fp sA = fp_select(c.l & 2, pl_shfl_fp(c, px, 0), pl_shfl_fp(c, py, 0));
     Fp sB = fp_select(c.l & 2, pl_shfl_fp(c, px, 1), pl_shfl_fp(c, py, 1));
-    const bool useA = __shfl_sync(0xffffffffu, (int)use, 0) != 0, useB = __shfl_sync(0xffffffffu, (int)use, 4) != 0;
+    const bool useA = __shfl_sync(c.mask, (int)use, 0, KZG_PL8_GROUP) != 0, useB = __shfl_sync(c.mask, (int)use, 1, KZG_PL8_GROUP) != 0;
     const G2Lines *LA = &pc->q[qa], *LB = &pc->q[qb];
     const int comp = c.l & 3;
     Fp2 f = pl_one(c);
@@ -241,28 +209,29 @@ static __device__ __noinline__ Fp2 pl_miller2(PL c, const PairingConsts *pc, con
 }
 
 // result[i] = pre_status[i] if that is an error, else OK / VERIFY_FAILED for
-//   e(A_i, Q[qa]) * e(B_i, Q[qb]) == 1.     one check per warp (KZG_PL_GROUP lanes), 4 checks per block.
-static __global__ void __launch_bounds__(128, 3) k_pairing_lanes(const PairingConsts *__restrict__ pc, const G1 *__restrict__ A, int qa, const G1 *__restrict__ B, int qb,
+//   e(A_i, Q[qa]) * e(B_i, Q[qb]) == 1.     8 lanes per check, 4 checks per warp.
+static __global__ void __launch_bounds__(128) k_pairing_lanes(const PairingConsts *__restrict__ pc, const G1 *__restrict__ A, int qa, const G1 *__restrict__ B, int qb,
                                                        const int32_t *pre_status, int32_t *result, size_t n) {   // pre_status may alias result
-    const size_t gid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one check per warp
-    if (gid >= n) return;                              // whole warp idle
-    const size_t idx = gid;
+    const size_t gid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / KZG_PL8_GROUP;
+    const size_t warp_first = ((size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) / KZG_PL8_GROUP;
+    if (warp_first >= n) return;                       // whole warp idle
+    const size_t idx = gid < n ? gid : n - 1;          // padding groups repeat the last check (keeps the warp convergent)
     PL c;
-    c.lane = threadIdx.x & 31;
-    c.l = c.lane >> 2;
+    const int lane = threadIdx.x & 31;
+    c.l = lane & (KZG_PL8_GROUP - 1);
     c.lc = c.l < 6 ? c.l : 5;
-    c.sub = c.lane & 3;
+    c.mask = 0xffu << (lane & ~(KZG_PL8_GROUP - 1));
     G1 a = A[idx], b = B[idx];
     Fp2 f = pl_miller2(c, pc, &a, qa, &b, qb);
     f = fp2_select(c.l < 6, f, fp2_zero());
     Fp2 r = pl_final_exp(c, f, pc->gamma);
     bool ok = c.l == 0 ? fp2_eq(r, fp2_one()) : (c.l < 6 ? fp2_is_zero(r) : true);
-    unsigned all = __ballot_sync(0xffffffffu, ok);
-    if (c.lane == 0) {
+    unsigned all = __ballot_sync(c.mask, ok);
+    if (gid < n && c.l == 0) {
         int32_t pre = pre_status ? pre_status[idx] : (int32_t)ST_OK;
-        result[idx] = pre != ST_OK ? pre : (all == 0xffffffffu ? (int32_t)ST_OK : (int32_t)ST_VERIFY_FAILED);
+        result[idx] = pre != ST_OK ? pre : ((all & c.mask) == c.mask ? (int32_t)ST_OK : (int32_t)ST_VERIFY_FAILED);
     }
 }
 
-}  // namespace pl32
+}  // namespace pl8
 }  // namespace kzg

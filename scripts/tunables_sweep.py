@@ -21,15 +21,18 @@ def kms(ctx, w, reps=3):
 out = {}
 ctx = kzgb200.Context(commit_window=8, fk20_window=14)
 w = make_work(ctx, "cells_proofs", 1024, 0, torch, np, 0)
-for L in (8, 4, 16):
-    assert ctx.L.kzgb200_dbg_set_tunable(b"fk20_lanes", L) == 0
+w.step(False)
+for minb, split in ((3, 8), (4, 8), (3, 4), (4, 4), (4, 2)):
+    assert ctx.L.kzgb200_dbg_set_tunable(b"g1fft_minb", minb) == 0 and ctx.L.kzgb200_dbg_set_tunable(b"g1fft_split", split) == 0
     r = kms(ctx, w); r["self_check"] = bool(w.self_check())
-    out["cells_proofs fk20_lanes=%d" % L] = r
-    print("cells_proofs fk20_lanes", L, r, flush=True)
+    out["cells_proofs g1fft_minb=%d split=%d" % (minb, split)] = r
+    print("cells_proofs g1fft_minb", minb, "split", split, r, flush=True)
+ctx.L.kzgb200_dbg_set_tunable(b"g1fft_minb", 3); ctx.L.kzgb200_dbg_set_tunable(b"g1fft_split", 0)
 ctx.L.kzgb200_dbg_set_tunable(b"fk20_lanes", 0)
 del w; torch.cuda.empty_cache()
 w = make_work(ctx, "verify_cells", 4096, 0, torch, np, 0)
-for pol in (0, 1, 2, 3):
+w.step(False)
+for pol in (0, 1):
     assert ctx.L.kzgb200_dbg_set_tunable(b"vmsm_policy", pol) == 0
     r = kms(ctx, w); r["self_check"] = bool(w.self_check())
     out["verify_cells vmsm_policy=%d" % pol] = r
@@ -37,7 +40,8 @@ for pol in (0, 1, 2, 3):
 ctx.L.kzgb200_dbg_set_tunable(b"vmsm_policy", 1)
 del w; torch.cuda.empty_cache()
 w = make_work(ctx, "verify_cells_one_batch", 4096, 0, torch, np, 0)
-for pol in (0, 1):
+w.step(False)
+for pol in (1,):
     assert ctx.L.kzgb200_dbg_set_tunable(b"vmsm_policy", pol) == 0
     r = kms(ctx, w); r["self_check"] = bool(w.self_check())
     out["verify_cells_one_batch vmsm_policy=%d" % pol] = r
