@@ -86,6 +86,9 @@ struct kzg_lane {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_piece[8] = {nullptr};
     cudaStream_t fft_streams[KZG_G1FFT_MAX_SPLIT - 1] = {nullptr};   // sub-batches of the staged G1 FFT (launch_fk20_proofs)
     cudaEvent_t ev_fork = nullptr, ev_join[KZG_G1FFT_MAX_SPLIT - 1] = {nullptr};
+    cudaStream_t prio_streams[KZG_G1FFT_MAX_SPLIT] = {nullptr};       // overlapped FK20 chains (fk20_overlap): sub-batch k on a stream of priority k (0 = highest)
+    cudaStream_t aux_stream = nullptr;  // small independent kernels that would otherwise queue behind a long one (second decode of the verifiers)
+    cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;
     size_t g1fft_split = 8;             // measured: 1 -> 40.9 ms, 2 -> 34.6, 4 -> 33.5, 8 -> 33.1 (KZGB200_G1FFT_SPLIT overrides)
     size_t g1_dense_max = 24;           // batches up to this many blobs take the dense one-level G1 transform (KZGB200_G1_DENSE_MAX overrides)
     bool owns_tables = true;            // false for clones: setup pointers below belong to the GPU's first lane
@@ -105,7 +108,7 @@ struct kzg_lane {
     DevBuf in_bytes, scalars, status, sums, out_bytes, coeffs, cells, proofs_xyzz, fft_work, in_small, in_small2, zbuf, ybuf;
     DevBuf rec_a, rec_b, rec_meta, rec_zev, rec_czinv;
     DevBuf v_aff1, v_aff2, v_fr, v_meta, v_S, v_W, v_partial, v_in2, v_in3, v_st2;
-    DevBuf vm_digits, vm_digits256, vm_colsum, vm_rowdig, vm_commsum, vm_scratch, vm_ws, vm_wsb, v_pa, v_pb, v_cst, v_st3, ev_cex, ev_total, ev_index;
+    DevBuf vm_digits, vm_digits256, vm_colsum, vm_rowdig, vm_commsum, vm_scratch, vm_ws, vm_wsb, v_pa, v_pb, v_cst, v_st3, v_pst, ev_cex, ev_total, ev_index;
     double init_ms = 0, last_device_ms = 0;
     uint64_t launches = 0;
     // per-kernel-class device timing of the last call (CUDA events on `stream`)
@@ -158,6 +161,7 @@ extern "C" {
 int lane_ctx_new(const uint8_t *g1_monomial, const uint8_t *g1_lagrange, const uint8_t *g2_monomial, size_t n_g2, const kzgb200_opts *opts, int device, kzg_lane **out);
 int lane_clone(kzg_lane *first, kzg_lane **out);      // another lane on the same GPU sharing `first`'s tables
 void lane_ctx_free(kzg_lane *c);
+void lane_quiesce(kzg_lane *c);       // after a failed call: wait for everything the call left in flight on the lane's streams, drop its event marks
 int lane_blob_to_kzg_commitment(kzg_lane *c, const uint8_t *blobs, size_t n, uint8_t *out48, int32_t *status);
 int lane_compute_blob_kzg_proof(kzg_lane *c, const uint8_t *blobs, const uint8_t *commitments48, size_t n, uint8_t *out48, int32_t *status);
 int lane_compute_kzg_proof(kzg_lane *c, const uint8_t *blobs, const uint8_t *z32, size_t n, uint8_t *out_proof48, uint8_t *out_y32, int32_t *status);

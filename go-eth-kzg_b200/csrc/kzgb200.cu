@@ -83,6 +83,11 @@ static __global__ void k_finalize_g1(const G1 *__restrict__ in, uint8_t *__restr
     }
 }
 
+// status[i] = status[i] if that is an error, else later[i]
+static __global__ void k_status_then(int32_t *__restrict__ status, const int32_t *__restrict__ later, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && status[i] == ST_OK) status[i] = later[i];
+}
 // zero the y outputs of failed items
 static __global__ void k_zero_failed(uint8_t *__restrict__ out, const int32_t *__restrict__ status, size_t n, int bytes_per_item) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,6 +328,20 @@ int kzgb200_dbg_set_tunable(const char *name, int v) {
     return set_err(KZGB200_ERR_ARGS, "unknown tunable");
 }
 
+// A call that fails half-way (a CUDA error, an allocation that did not fit) returns while kernels and copies it queued may still be
+// reading the caller's buffers or the lane's scratch; the public layer calls this before it hands the lane to the next caller.
+void lane_quiesce(kzg_lane *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
+    for (cudaStream_t q : c->fft_streams) if (q) cudaStreamSynchronize(q);
+    for (cudaStream_t q : c->prio_streams) if (q) cudaStreamSynchronize(q);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaGetLastError();
+    c->marks_reset();
+}
+
 void lane_ctx_free(kzg_lane *c) {
     if (!c) return;
     cudaSetDevice(c->device);
@@ -339,8 +358,12 @@ void lane_ctx_free(kzg_lane *c) {
     c->rec_a.release(); c->rec_b.release(); c->rec_meta.release(); c->rec_zev.release(); c->rec_czinv.release();
     c->v_aff1.release(); c->v_aff2.release(); c->v_fr.release(); c->v_meta.release(); c->v_S.release();
     c->v_W.release(); c->v_partial.release(); c->v_in2.release(); c->v_in3.release(); c->v_st2.release();
-    c->vm_digits.release(); c->vm_digits256.release(); c->vm_colsum.release(); c->vm_rowdig.release(); c->vm_commsum.release(); c->vm_scratch.release(); c->vm_ws.release(); c->vm_wsb.release(); c->v_pa.release(); c->v_pb.release(); c->v_cst.release(); c->v_st3.release(); c->ev_cex.release(); c->ev_total.release(); c->ev_index.release();
+    c->vm_digits.release(); c->vm_digits256.release(); c->vm_colsum.release(); c->vm_rowdig.release(); c->vm_commsum.release(); c->vm_scratch.release(); c->vm_ws.release(); c->vm_wsb.release(); c->v_pa.release(); c->v_pb.release(); c->v_cst.release(); c->v_st3.release(); c->v_pst.release(); c->ev_cex.release(); c->ev_total.release(); c->ev_index.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    for (cudaStream_t q : c->prio_streams) if (q) cudaStreamDestroy(q);
+    if (c->ev_aux_fork) cudaEventDestroy(c->ev_aux_fork);
+    if (c->ev_aux_join) cudaEventDestroy(c->ev_aux_join);
     for (cudaStream_t q : c->fft_streams) if (q) cudaStreamDestroy(q);
     for (cudaEvent_t e : c->ev_join) if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -364,6 +387,14 @@ static int lane_streams_init(kzg_lane *c, int device) {
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    {
+        int least = 0, greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));          // numerically lower = higher priority
+        for (int k = 0; k < KZG_G1FFT_MAX_SPLIT; ++k) CU(cudaStreamCreateWithPriority(&c->prio_streams[k], cudaStreamNonBlocking, std::min(least, greatest + k)));
+    }
+    CU(cudaEventCreateWithFlags(&c->ev_aux_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_aux_join, cudaEventDisableTiming));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
     for (cudaEvent_t &e : c->ev_piece) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -602,6 +633,7 @@ static int open_common(kzg_lane *c, const uint8_t *blobs, const uint8_t *z32, co
     if ((rc = c->sums.ensure(chunk * sizeof(G1)))) return rc;
     if ((rc = c->zbuf.ensure(chunk * 32))) return rc;
     if ((rc = c->ybuf.ensure(chunk * 32))) return rc;
+    if (!z32 && (rc = c->v_st2.ensure(chunk * sizeof(int32_t)))) return rc;
     if (!out_dev && (rc = c->out_bytes.ensure(chunk * 48))) return rc;
     const int TPB = 128;
     for (size_t off = 0; off < n; off += chunk) {
@@ -646,11 +678,26 @@ static int open_common(kzg_lane *c, const uint8_t *blobs, const uint8_t *z32, co
                 k_scalars_from_be<<<gb, 64, 0, sp>>>((const uint8_t *)d_aux + po * 32, zl, d_status + po, pm);
                 c->launches += 1;
             } else {
-                k_g1_check<<<gb, 64, 0, sp>>>((const uint8_t *)d_aux + po * 48, nullptr, d_status + po, pm, 1, 1);
+                // The commitment is only validated (decode + subgroup test, the point is discarded: prove.go:56-60), which is ~2.9 ms of one
+                // thread's latency whatever the batch, and the hash needs its BYTES only: the check runs on a side stream into a status array
+                // of its own, merged below AFTER the blob's own status (DeserializeBlob comes first in the reference, prove.go:52).
+                const size_t side = KZG_H2D_PIECES + (pc & 1);      // at most two pieces exist (bound[] above): side streams / events 4 and 5
+                cudaStream_t sv = c->fft_streams[side];
+                int32_t *d_cst = (int32_t *)c->v_st2.p + po;
+                CU(cudaEventRecord(c->ev_piece[side], sp));
+                CU(cudaStreamWaitEvent(sv, c->ev_piece[side], 0));
+                CU(cudaMemsetAsync(d_cst, 0, pm * sizeof(int32_t), sv));
+                k_g1_check<<<gb, 64, 0, sv>>>((const uint8_t *)d_aux + po * 48, nullptr, d_cst, pm, 1, 1);
+                CU(cudaEventRecord(c->ev_join[side], sv));
                 k_fiat_shamir<<<(unsigned)((pm + 31) / 32), 32, 0, sp>>>(pb, (const uint8_t *)d_aux + po * 48, zl, pm);
                 c->launches += 2;
             }
             if ((rc = vm_eval_quotient(c, sp, po, pb, zl, d_status + po, ql, d_y ? d_y + po * 32 : nullptr, nullptr, pm))) return rc;
+            if (!z32) {
+                CU(cudaStreamWaitEvent(sp, c->ev_join[KZG_H2D_PIECES + (pc & 1)], 0));
+                k_status_then<<<gb, 64, 0, sp>>>(d_status + po, (const int32_t *)c->v_st2.p + po, pm);
+                c->launches += 1;
+            }
             if (split) { CU(cudaEventRecord(c->ev_join[pc], sp)); CU(cudaStreamWaitEvent(c->stream, c->ev_join[pc], 0)); }
             c->mark(KZGB200_KC_MSM);
             if ((rc = launch_commit_msm(c, c->stream, ql, pm, d_status + po, (G1 *)c->sums.p + po))) return rc;
@@ -723,8 +770,10 @@ static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr 
         if (nsplit > 1) cudaEventRecord(c->ev_fork, st);
         for (size_t k = 0, off = 0; off < m; ++k, off += per) {
             const int nb = (int)std::min(per, m - off);
-            cudaStream_t s = k == 0 ? st : c->fft_streams[k - 1];
-            if (k) cudaStreamWaitEvent(s, c->ev_fork, 0);
+            // overlap mode: every sub-batch on a stream of its own PRIORITY (sub-batch 0 highest), so the chains are staggered -- sub-batch
+            // k's FFT stages (64 blocks each) run while the MSMs of the later sub-batches fill the rest of the GPU -- instead of all MSMs first
+            cudaStream_t s = overlap ? c->prio_streams[k] : k == 0 ? st : c->fft_streams[k - 1];
+            if (k || overlap) cudaStreamWaitEvent(s, c->ev_fork, 0);
             const G1 *src = sums + off * 128;
             G1J *work = (G1J *)c->fft_work.p + off * 128;
             G1 *dst = pxyzz + off * 128;
@@ -747,6 +796,7 @@ static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr 
 #undef KZG_STAGE
             c->launches += 14;
             if (k) { cudaEventRecord(c->ev_join[k - 1], s); cudaStreamWaitEvent(st, c->ev_join[k - 1], 0); }
+            else if (overlap) { cudaEventRecord(c->ev_aux_join, s); cudaStreamWaitEvent(st, c->ev_aux_join, 0); }
         }
     }
     size_t np = m * 128;

@@ -102,6 +102,7 @@ template <class F> int run_ranges(kzgb200_ctx *ctx, const std::vector<ShardRange
         size_t d = pinned_dev >= 0 ? (size_t)pinned_dev : (n_dev == 1 ? 0 : ctx->rr.fetch_add(1) % n_dev);
         LaneRef ref(ctx->devs[d].get());
         int rc = f(ref.l, (size_t)0, ranges[0]);
+        if (rc) { std::string keep = kzgb200_err_slot(); lane_quiesce(ref.l); kzgb200_err_slot() = keep; }
         record(ctx, {ref.l});
         return rc;
     }
@@ -112,7 +113,7 @@ template <class F> int run_ranges(kzgb200_ctx *ctx, const std::vector<ShardRange
         LaneRef ref(ctx->devs[i % n_dev].get());
         used[i] = ref.l;
         rcs[i] = f(ref.l, i, ranges[i]);
-        if (rcs[i]) errs[i] = kzgb200_err_slot();
+        if (rcs[i]) { errs[i] = kzgb200_err_slot(); lane_quiesce(ref.l); }
     };
     std::vector<std::thread> th;
     for (size_t i = 1; i < ranges.size(); ++i) th.emplace_back(body, i);

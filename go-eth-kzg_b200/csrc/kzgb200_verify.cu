@@ -105,9 +105,20 @@ static int verify_front(kzg_lane *c, const uint8_t *blobs, const uint8_t *cm48, 
         }
     }
     c->mark(KZGB200_KC_DECODE);
+    // commitments on the main stream, proofs on the aux stream: a decode is ~1.4 ms of ONE thread's latency per point and even 4096 + 4096
+    // points under-fill the GPU, so the two launches run side by side.  The proofs report into a status array of their own, merged after
+    // the commitments' (the reference decodes the commitment first: verify.go:12-41, 102-119).
+    if ((rc = c->v_pst.ensure(m * sizeof(int32_t)))) return rc;
+    int32_t *d_pst = (int32_t *)c->v_pst.p;
+    CU(cudaEventRecord(c->ev_aux_fork, c->stream));
+    CU(cudaStreamWaitEvent(c->aux_stream, c->ev_aux_fork, 0));
+    CU(cudaMemsetAsync(d_pst, 0, m * sizeof(int32_t), c->aux_stream));
+    if ((rc = vm_g1_check(c->aux_stream, (const uint8_t *)d_pf, out_pf, d_pst, m, 1, 1))) return rc;
+    CU(cudaEventRecord(c->ev_aux_join, c->aux_stream));
     if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_cm, out_cm, d_status, m, 1, 1))) return rc;
-    if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_pf, out_pf, d_status, m, 1, 1))) return rc;
-    c->launches += 2;
+    CU(cudaStreamWaitEvent(c->stream, c->ev_aux_join, 0));
+    k_status_merge<<<gb, 64, 0, c->stream>>>(d_status, d_pst, m);
+    c->launches += 3;
     c->mark(KZGB200_KC_FR);          // what is left of the side streams' hashing / evaluation after the decode
     if (blobs) {
         for (size_t p = 0; p < n_pieces; ++p) CU(cudaStreamWaitEvent(c->stream, c->ev_join[p], 0));
@@ -302,7 +313,8 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
 
     // ---- device buffers ---------------------------------------------------------------------------
     if ((rc = c->in_small2.ensure(std::max<size_t>(U, 1) * 48))) return rc;
-    if (U) CU(cudaMemcpyAsync(c->in_small2.p, uniq_bytes.data(), U * 48, cudaMemcpyHostToDevice, c->stream));
+    // the unique commitments travel and are decoded on the aux stream, underneath the proofs' decode on the main stream
+    if (U) CU(cudaMemcpyAsync(c->in_small2.p, uniq_bytes.data(), U * 48, cudaMemcpyHostToDevice, c->aux_stream));
     // meta arena layout
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) & ~(size_t)255; return at; };
@@ -332,7 +344,7 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
         CU(up(o_ris, r_item_start.data(), n_ri * 8)); CU(up(o_rie, r_item_end.data(), n_ri * 8)); CU(up(o_rsio, r_slot_item_off.data(), (n_large + 1) * 8));
         CU(up(o_lof, large_of.data(), nb * 4));
     }
-    CU(cudaMemsetAsync(M + o_ust, 0, std::max<size_t>(U, 1) * 4, c->stream));
+    CU(cudaMemsetAsync(M + o_ust, 0, std::max<size_t>(U, 1) * 4, c->aux_stream));
     CU(cudaMemsetAsync(M + o_bkey, 0xff, nb * 8, c->stream));
     if ((rc = c->v_aff1.ensure(std::max<size_t>(U, 1) * sizeof(G1Aff)))) return rc;
     if ((rc = c->v_fr.ensure(std::max<size_t>(N, 1) * sizeof(Fr)))) return rc;
@@ -355,7 +367,9 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
     if ((rc = c->sums.ensure(nb * sizeof(G1)))) return rc;
     Fr inv64; memcpy(inv64.v, H_FR_INV64, sizeof inv64.v);
     int32_t *d_ust = (int32_t *)(M + o_ust), *d_bst = (int32_t *)(M + o_bst), *d_res = (int32_t *)(M + o_res);
-    if ((rc = vm_g1_check(c->stream, (const uint8_t *)c->in_small2.p, (G1Aff *)c->v_aff1.p, d_ust, U, 1, 1))) return rc;
+    if ((rc = vm_g1_check(c->aux_stream, (const uint8_t *)c->in_small2.p, (G1Aff *)c->v_aff1.p, d_ust, U, 1, 1))) return rc;
+    CU(cudaEventRecord(c->ev_aux_join, c->aux_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_aux_join, 0));
     if (N) {
         if ((rc = vm_cell_coeff_digits(c->stream, seed_dev, (const uint32_t *)(M + o_batch_of), (const uint64_t *)(M + o_bstart), (const uint64_t *)(M + o_idx),
                                        c->roots, (Fr *)c->v_fr.p, (int8_t *)c->vm_digits.p, n_large ? (int8_t *)c->vm_digits256.p : nullptr, N))) return rc;
