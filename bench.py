@@ -645,6 +645,9 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # a CPU-side barrier for the section where rank 0 alone drives ALL GPUs from one process: a rank waiting in an NCCL barrier spins in a
+    # kernel on its GPU, which would time-slice against rank 0's work on that GPU
+    cpu_group = dist.new_group(backend="gloo") if dist else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -755,6 +758,7 @@ def main():
         torch.cuda.empty_cache()
         if world > 1:
             # ONE process, ONE context over all GPUs (kzgb200_opts.n_devices): rank 0 alone, the other ranks have released their tables and wait
+            # on the CPU (gloo), so that nothing of theirs runs on the GPUs meanwhile
             barrier()
             if rank == 0:
                 try:
@@ -785,7 +789,8 @@ def main():
                     extras["in_process"] = ip
                 except Exception as e:      # noqa: BLE001  (never lose the main line to an extra)
                     extras["in_process"] = {"error": repr(e)}
-            barrier()
+            torch.cuda.synchronize()
+            dist.barrier(group=cpu_group)
     if dist:
         dist.barrier()
         dist.destroy_process_group()

@@ -86,7 +86,6 @@ struct kzg_lane {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_piece[8] = {nullptr};
     cudaStream_t fft_streams[KZG_G1FFT_MAX_SPLIT - 1] = {nullptr};   // sub-batches of the staged G1 FFT (launch_fk20_proofs)
     cudaEvent_t ev_fork = nullptr, ev_join[KZG_G1FFT_MAX_SPLIT - 1] = {nullptr};
-    cudaStream_t prio_streams[KZG_G1FFT_MAX_SPLIT] = {nullptr};       // overlapped FK20 chains (fk20_overlap): sub-batch k on a stream of priority k (0 = highest)
     cudaStream_t aux_stream = nullptr;  // small independent kernels that would otherwise queue behind a long one (second decode of the verifiers)
     cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;
     size_t g1fft_split = 8;             // measured: 1 -> 40.9 ms, 2 -> 34.6, 4 -> 33.5, 8 -> 33.1 (KZGB200_G1FFT_SPLIT overrides)

@@ -110,6 +110,109 @@ static __global__ void k_fiat_shamir(const uint8_t *__restrict__ blobs, const ui
     for (int k = 0; k < 8; ++k) o[k] = l[k];
 }
 
+// The same hash on TWO warps per 32 blobs (round 2).  SHA-256 of one message is a chain of 2050 dependent compressions, so the kernel is
+// one thread's latency whatever the batch (3.1 ms).  A compression is 64 rounds whose critical path is ~5 dependent instructions, plus
+// the message schedule (48 words of ~7 instructions) which is NOT on that path: warp 1 (producer) fetches block b+1, byte-swaps it,
+// expands W[0..63] and stores W[t] + K[t] to shared memory while warp 0 (consumer) runs the rounds of block b from the other buffer.
+//   block = 64 threads, grid = ceil(n / 32); shared: 2 buffers x 64 words x 32 lanes = 16 KB.
+__device__ __forceinline__ void fs_message_block(uint32_t *w, int b, const uint32_t *bw, const uint32_t *cw) {
+    if (b == 0) {
+        w[0] = 0x4653424c; w[1] = 0x4f425645; w[2] = 0x52494659; w[3] = 0x5f56315f;   // "FSBLOBVERIFY_V1_"
+        w[4] = 0; w[5] = 0; w[6] = 0; w[7] = 4096;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[8 + k] = __byte_perm(bw[k], 0, 0x0123);
+    } else if (b <= 2047) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(bw + 8 + 16 * (b - 1));
+        uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
+        w[0] = __byte_perm(v0.x, 0, 0x0123); w[1] = __byte_perm(v0.y, 0, 0x0123); w[2] = __byte_perm(v0.z, 0, 0x0123); w[3] = __byte_perm(v0.w, 0, 0x0123);
+        w[4] = __byte_perm(v1.x, 0, 0x0123); w[5] = __byte_perm(v1.y, 0, 0x0123); w[6] = __byte_perm(v1.z, 0, 0x0123); w[7] = __byte_perm(v1.w, 0, 0x0123);
+        w[8] = __byte_perm(v2.x, 0, 0x0123); w[9] = __byte_perm(v2.y, 0, 0x0123); w[10] = __byte_perm(v2.z, 0, 0x0123); w[11] = __byte_perm(v2.w, 0, 0x0123);
+        w[12] = __byte_perm(v3.x, 0, 0x0123); w[13] = __byte_perm(v3.y, 0, 0x0123); w[14] = __byte_perm(v3.z, 0, 0x0123); w[15] = __byte_perm(v3.w, 0, 0x0123);
+    } else if (b == 2048) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = __byte_perm(bw[32768 - 8 + k], 0, 0x0123);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[8 + k] = __byte_perm(cw[k], 0, 0x0123);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = __byte_perm(cw[8 + k], 0, 0x0123);
+        w[4] = 0x80000000u;
+#pragma unroll
+        for (int k = 5; k < 15; ++k) w[k] = 0;
+        w[15] = 131152u * 8u;
+    }
+}
+#define KZG_FS_BLOCKS 2050
+static __global__ void __launch_bounds__(64) k_fiat_shamir2(const uint8_t *__restrict__ blobs, const uint8_t *__restrict__ commitments, uint32_t *__restrict__ z_out, size_t n) {
+    __shared__ uint32_t wk[2][64][32];
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const size_t i = (size_t)blockIdx.x * 32 + lane;
+    const size_t ii = i < n ? i : n - 1;                         // idle lanes repeat the last blob (loops stay warp-uniform), nothing is written
+    const uint32_t *bw = reinterpret_cast<const uint32_t *>(blobs + ii * 131072);
+    const uint32_t *cw = reinterpret_cast<const uint32_t *>(commitments + ii * 48);
+    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    auto produce = [&](int b) {
+        uint32_t w[16];
+        fs_message_block(w, b, bw, cw);
+        uint32_t (*dst)[32] = wk[b & 1];
+#pragma unroll
+        for (int t = 0; t < 64; ++t) {
+            if (t >= 16) {
+                uint32_t w15 = w[(t + 1) & 15], w2 = w[(t + 14) & 15];
+                uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+                uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+                w[t & 15] = w[t & 15] + s0 + w[(t + 9) & 15] + s1;
+            }
+            dst[t][lane] = w[t & 15] + SHA_K[t];
+        }
+    };
+    if (role == 1) produce(0);
+    __syncthreads();
+#pragma unroll 1
+    for (int b = 0; b < KZG_FS_BLOCKS; ++b) {
+        if (role == 1) {
+            if (b + 1 < KZG_FS_BLOCKS) produce(b + 1);
+        } else {
+            const uint32_t (*src)[32] = wk[b & 1];
+            uint32_t a = h[0], bb = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll
+            for (int t = 0; t < 64; ++t) {
+                uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+                uint32_t ch = (e & f) ^ (~e & g);
+                uint32_t t1 = hh + S1 + ch + src[t][lane];
+                uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+                uint32_t mj = (a & bb) ^ (a & c) ^ (bb & c);
+                uint32_t t2 = S0 + mj;
+                hh = g; g = f; f = e; e = d + t1; d = c; c = bb; bb = a; a = t1 + t2;
+            }
+            h[0] += a; h[1] += bb; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+        }
+        __syncthreads();
+    }
+    if (role != 0 || i >= n) return;
+    // digest (big-endian) -> integer mod r (fr.SetBytes reduces): digest < 2^256 < 3r, so <= 2 subtractions
+    uint32_t l[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) l[k] = h[7 - k];
+    for (int rep = 0; rep < 3; ++rep) {
+        if (Fr::geq_limbs(l, FR_MOD)) {
+            l[0] = ptx_sub_cc(l[0], FR_MOD[0]);
+#pragma unroll
+            for (int k = 1; k < 7; ++k) l[k] = ptx_subc_cc(l[k], FR_MOD[k]);
+            l[7] = ptx_subc(l[7], FR_MOD[7]);
+        }
+    }
+    uint32_t *o = z_out + i * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = l[k];
+}
+// launch wrapper: g_fs_variant (tunable "fiat_shamir": 2 = two-warp form (default), 1 = one thread per blob)
+static inline void launch_fiat_shamir(cudaStream_t st, const uint8_t *blobs, const uint8_t *commitments, uint32_t *z_out, size_t n) {
+    if (!n) return;
+    if (g_fs_variant == 1) k_fiat_shamir<<<(unsigned)((n + 31) / 32), 32, 0, st>>>(blobs, commitments, z_out, n);
+    else k_fiat_shamir2<<<(unsigned)((n + 31) / 32), 64, 0, st>>>(blobs, commitments, z_out, n);
+}
+
 // 32-byte big-endian scalars -> plain limbs with canonical check (DeserializeScalar, serialization.go:153-159)
 static __global__ void k_scalars_from_be(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, int32_t *__restrict__ status, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

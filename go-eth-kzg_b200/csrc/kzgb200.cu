@@ -310,14 +310,14 @@ int kzgb200_dbg_set_tunable(const char *name, int v) {
         kzg::g_g1fft_split_override = v;
         return 0;
     }
-    if (!strcmp(name, "fk20_overlap")) {
-        if (v != 0 && v != 1) return set_err(KZGB200_ERR_ARGS, "fk20_overlap must be 0 or 1");
-        kzg::g_fk20_overlap = v;
-        return 0;
-    }
     if (!strcmp(name, "pairing_lanes")) {
         if (v != 0 && v != 8 && v != 32) return set_err(KZGB200_ERR_ARGS, "pairing_lanes must be 0, 8 or 32");
         kzg::g_pairing_lanes = v;
+        return 0;
+    }
+    if (!strcmp(name, "fiat_shamir")) {
+        if (v != 1 && v != 2) return set_err(KZGB200_ERR_ARGS, "fiat_shamir must be 1 or 2");
+        kzg::g_fs_variant = v;
         return 0;
     }
     if (!strcmp(name, "vmsm_policy")) {
@@ -336,7 +336,6 @@ void lane_quiesce(kzg_lane *c) {
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     for (cudaStream_t q : c->fft_streams) if (q) cudaStreamSynchronize(q);
-    for (cudaStream_t q : c->prio_streams) if (q) cudaStreamSynchronize(q);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaGetLastError();
     c->marks_reset();
@@ -361,7 +360,6 @@ void lane_ctx_free(kzg_lane *c) {
     c->vm_digits.release(); c->vm_digits256.release(); c->vm_colsum.release(); c->vm_rowdig.release(); c->vm_commsum.release(); c->vm_scratch.release(); c->vm_ws.release(); c->vm_wsb.release(); c->v_pa.release(); c->v_pb.release(); c->v_cst.release(); c->v_st3.release(); c->v_pst.release(); c->ev_cex.release(); c->ev_total.release(); c->ev_index.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
-    for (cudaStream_t q : c->prio_streams) if (q) cudaStreamDestroy(q);
     if (c->ev_aux_fork) cudaEventDestroy(c->ev_aux_fork);
     if (c->ev_aux_join) cudaEventDestroy(c->ev_aux_join);
     for (cudaStream_t q : c->fft_streams) if (q) cudaStreamDestroy(q);
@@ -388,11 +386,6 @@ static int lane_streams_init(kzg_lane *c, int device) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
-    {
-        int least = 0, greatest = 0;
-        CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));          // numerically lower = higher priority
-        for (int k = 0; k < KZG_G1FFT_MAX_SPLIT; ++k) CU(cudaStreamCreateWithPriority(&c->prio_streams[k], cudaStreamNonBlocking, std::min(least, greatest + k)));
-    }
     CU(cudaEventCreateWithFlags(&c->ev_aux_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_aux_join, cudaEventDisableTiming));
     CU(cudaEventCreate(&c->ev0));
@@ -689,7 +682,7 @@ static int open_common(kzg_lane *c, const uint8_t *blobs, const uint8_t *z32, co
                 CU(cudaMemsetAsync(d_cst, 0, pm * sizeof(int32_t), sv));
                 k_g1_check<<<gb, 64, 0, sv>>>((const uint8_t *)d_aux + po * 48, nullptr, d_cst, pm, 1, 1);
                 CU(cudaEventRecord(c->ev_join[side], sv));
-                k_fiat_shamir<<<(unsigned)((pm + 31) / 32), 32, 0, sp>>>(pb, (const uint8_t *)d_aux + po * 48, zl, pm);
+                launch_fiat_shamir(sp, pb, (const uint8_t *)d_aux + po * 48, zl, pm);
                 c->launches += 2;
             }
             if ((rc = vm_eval_quotient(c, sp, po, pb, zl, d_status + po, ql, d_y ? d_y + po * 32 : nullptr, nullptr, pm))) return rc;
@@ -743,16 +736,12 @@ static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr 
     const int TPB = 128;
     int L = g_fk20_lanes_override ? g_fk20_lanes_override : KZG_FK20_LANES;
     while (L < 64 && (size_t)L * m < (size_t)2 * c->sm_count) L <<= 1;
-    // Overlapped form (tunable fk20_overlap = 1, NOT the default): every sub-batch runs its WHOLE chain -- circulant rows, MSM, 14 G1 FFT
-    // stages -- on a stream of its own, so that MSM CTAs could fill the draining tails of another sub-batch's FFT stages.  Measured on
-    // B200 (1024 blobs): 87.4 ms per step against 87.3 ms for the serial form in the same run -- both kernel classes already hold the
-    // fmaheavy pipe, there is nothing to fill -- so the serial form stays, which also keeps the per-class event times meaningful.
-    const bool overlap = g_fk20_overlap && m > c->g1_dense_max && m >= 256;
-    if (!overlap) {
-        k_fk20_rows<<<dim3(64, (unsigned)m), 64, 0, st>>>(coeffs, scalars, d_status, c->roots, inv128p);
-        if (marks) c->mark(KZGB200_KC_MSM);
-        launch_msm_fixed(dim3(128 / (TPB / L), (unsigned)m), TPB, st, scalars, c->fk20_tab, 64, 128, L, d_status, sums);
-    }
+    // (Running every 128-blob sub-batch's whole chain rows -> MSM -> G1 FFT on a stream of its own, so that MSM blocks fill the tails of FFT
+    // stages, was measured twice -- plain streams: 87.4 vs 87.3 ms, all MSMs still run first; priority streams that stagger the chains:
+    // 102 vs 86.4 ms -- and removed: profiles/r02_rejected_fk20_overlap.md.)
+    k_fk20_rows<<<dim3(64, (unsigned)m), 64, 0, st>>>(coeffs, scalars, d_status, c->roots, inv128p);
+    if (marks) c->mark(KZGB200_KC_MSM);
+    launch_msm_fixed(dim3(128 / (TPB / L), (unsigned)m), TPB, st, scalars, c->fk20_tab, 64, 128, L, d_status, sums);
     if (marks) c->mark(KZGB200_KC_G1FFT);
     // sums (bit-reversed) --IFFT--> h, keep 64 (toeplitz.go:124), zero-pad (fk20.go:82-85) --FFT--> proofs (bit-reversed);
     // one launch per radix-2 stage, working set in c->fft_work.  The chunk is cut into independent
@@ -770,21 +759,13 @@ static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr 
         if (nsplit > 1) cudaEventRecord(c->ev_fork, st);
         for (size_t k = 0, off = 0; off < m; ++k, off += per) {
             const int nb = (int)std::min(per, m - off);
-            // overlap mode: every sub-batch on a stream of its own PRIORITY (sub-batch 0 highest), so the chains are staggered -- sub-batch
-            // k's FFT stages (64 blocks each) run while the MSMs of the later sub-batches fill the rest of the GPU -- instead of all MSMs first
-            cudaStream_t s = overlap ? c->prio_streams[k] : k == 0 ? st : c->fft_streams[k - 1];
-            if (k || overlap) cudaStreamWaitEvent(s, c->ev_fork, 0);
+            cudaStream_t s = k == 0 ? st : c->fft_streams[k - 1];
+            if (k) cudaStreamWaitEvent(s, c->ev_fork, 0);
             const G1 *src = sums + off * 128;
             G1J *work = (G1J *)c->fft_work.p + off * 128;
             G1 *dst = pxyzz + off * 128;
             const int32_t *stt = d_status + off;
             const dim3 grid((unsigned)((nb + KZG_G1FFT_TPB - 1) / KZG_G1FFT_TPB), 64);
-            if (overlap) {
-                uint32_t *sc = scalars + off * 8192 * 8;
-                k_fk20_rows<<<dim3(64, (unsigned)nb), 64, 0, s>>>(coeffs + off * N_BLOB, sc, stt, c->roots, inv128p);
-                launch_msm_fixed(dim3(128 / (TPB / L), (unsigned)nb), TPB, s, sc, c->fk20_tab, 64, 128, L, stt, sums + off * 128);
-                c->launches += 2;
-            }
 #define KZG_STAGE(A, B, C, D, E, F, ...) do { if (g_g1fft_minb == 4) k_g1fft_stage<A, B, C, D, E, F, 4><<<grid, KZG_G1FFT_TPB, 0, s>>>(__VA_ARGS__); \
                                                 else k_g1fft_stage<A, B, C, D, E, F, 3><<<grid, KZG_G1FFT_TPB, 0, s>>>(__VA_ARGS__); } while (0)
             KZG_STAGE(true, true, true, false, false, false, src, work, nullptr, stt, nb, 0);
@@ -796,13 +777,12 @@ static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr 
 #undef KZG_STAGE
             c->launches += 14;
             if (k) { cudaEventRecord(c->ev_join[k - 1], s); cudaStreamWaitEvent(st, c->ev_join[k - 1], 0); }
-            else if (overlap) { cudaEventRecord(c->ev_aux_join, s); cudaStreamWaitEvent(st, c->ev_aux_join, 0); }
         }
     }
     size_t np = m * 128;
     if (marks) c->mark(KZGB200_KC_FINALIZE);
     k_finalize_g1<<<(unsigned)((np + 64 * KZG_FIN_BATCH - 1) / (64 * KZG_FIN_BATCH)), 64, 0, st>>>(pxyzz, d_proofs, d_status, np, 128);
-    c->launches += overlap ? 1 : 3;
+    c->launches += 3;
 }
 
 static int cells_and_proofs(kzg_lane *c, const uint8_t *blobs, size_t n, uint8_t *out_cells, uint8_t *out_proofs, int32_t *status) {

@@ -98,7 +98,7 @@ static int verify_front(kzg_lane *c, const uint8_t *blobs, const uint8_t *cm48, 
             CU(cudaStreamWaitEvent(sp, c->ev_fork, 0));
             if (blobs_host) CU(cudaStreamWaitEvent(sp, c->ev_piece[p], 0));
             const uint8_t *pb = d_blobs + po * KZGB200_BYTES_PER_BLOB;
-            k_fiat_shamir<<<(unsigned)((pm + 31) / 32), 32, 0, sp>>>(pb, (const uint8_t *)d_cm + po * 48, zl + po * 8, pm);
+            launch_fiat_shamir(sp, pb, (const uint8_t *)d_cm + po * 48, zl + po * 8, pm);
             if ((rc = vm_eval_quotient(c, sp, po, pb, zl + po * 8, d_blob_status + po, nullptr, nullptr, yl + po * 8, pm))) return rc;
             CU(cudaEventRecord(c->ev_join[p], sp));
             c->launches += 1;

@@ -277,9 +277,9 @@ inline int g_msm_variant_override = -1;       // kzgb200_dbg_set_tunable("msm_va
 inline int g_vmsm_policy = 1;                 // kzgb200_dbg_set_tunable("vmsm_policy", 0..3): see k_vmsm_buckets (vmsm.cuh)
 inline int g_g1fft_minb = 3;                  // kzgb200_dbg_set_tunable("g1fft_minb", 3 | 4): resident CTAs per SM the G1 FFT stage kernel is compiled for
 inline int g_g1fft_split_override = 0;        // kzgb200_dbg_set_tunable("g1fft_split", k): sub-batches (streams) of the staged G1 FFT; 0 = context default
-inline int g_fk20_overlap = 0;                // kzgb200_dbg_set_tunable("fk20_overlap", 0 | 1): sub-batch chains on their own streams (launch_fk20_proofs; measured: no gain)
 inline int g_pairing_lanes = 0;               // kzgb200_dbg_set_tunable("pairing_lanes", 0 | 8 | 32): see vm_pairing_check (kzgb200_vmsm.cu)
 #define KZG_PL32_RESIDENT_WARPS 10            /* pl32 up to 10 checks per SM (of its 12 resident warps); measured crossover with pl8 at ~1 700 checks on 148 SMs (profiles/r02_pairing_sweep.md) */
+inline int g_fs_variant = 2;                  // kzgb200_dbg_set_tunable("fiat_shamir", 1 | 2): see launch_fiat_shamir (kzg4844.cuh)
 inline int g_fk20_lanes_override = 0;         // kzgb200_dbg_set_tunable("fk20_lanes", L): lanes per 64-point FK20 group for full batches
 static inline int msm_variant() {
     if (g_msm_variant_override >= 0) return g_msm_variant_override;

@@ -50,9 +50,8 @@ int kzgb200_dbg_h2d_bandwidth(const int *devices, int n, size_t bytes_per_dev, i
  *                  Y3, bit 3: accumulator in shared memory + 4 CTAs/SM; -1 = default (or the KZGB200_MSM_VARIANT environment variable)
  *   "fk20_lanes":  lanes per 64-point FK20 group for full batches (4, 8 or 16; 0 = default)
  *   "g1fft_minb":  3 or 4 resident CTAs per SM for k_g1fft_stage (168 or 128 registers); "g1fft_split": sub-batches (streams), 0 = default
- *   "fk20_overlap": 1 = every 128-blob sub-batch of a full FK20 batch runs rows -> MSM -> G1 FFT on its own stream, so the kernel classes
- *                  overlap; 0 (default) = one MSM launch over the batch, then the FFTs.  Measured equal (87.4 vs 87.3 ms per 1024 blobs)
  *   "pairing_lanes": lanes per pairing check: 32 (one check per warp, latency form), 8 (throughput form), 0 = by batch size (default)
+ *   "fiat_shamir": SHA-256 of the Fiat-Shamir challenge: 2 = two warps per 32 blobs (message schedule on a producer warp; default), 1 = one thread per blob
  *   "vmsm_policy": field products of the verifiers' bucket accumulation: 0 inlined, 1 out-of-line + one-reduction Y3 (default),
  *                  2 inlined + one-reduction Y3, 3 out-of-line */
 int kzgb200_dbg_set_tunable(const char *name, int v);
