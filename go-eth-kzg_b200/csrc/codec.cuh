@@ -69,7 +69,7 @@ __device__ __forceinline__ int32_t g1_decompress(G1Aff &out, const uint8_t *in48
 // serialization.go:108-115).  Endomorphism test (M. Scott, "A note on group membership tests for
 // G1, G2 and GT on BLS pairing-friendly curves", 2021): P is in G1  <=>  phi2(P) == [-x^2]P where
 // phi2(x,y) = (beta^2 x, y) and x = -0xd201000000010000.  Cost: 126 doublings + 10 additions.
-static __device__ __noinline__ bool g1_in_subgroup(const G1Aff *pa, const uint32_t *beta2) {
+template <class M_ = MulCall> static __device__ __noinline__ bool g1_in_subgroup(const G1Aff *pa, const uint32_t *beta2) {
     G1Aff a = *pa;
     if (a.is_inf()) return true;
     G1J q; q.X = a.x; q.Y = a.y; q.Z = Fp::one();
@@ -79,8 +79,8 @@ static __device__ __noinline__ bool g1_in_subgroup(const G1Aff *pa, const uint32
         G1JT base = jac_cache(q);
 #pragma unroll 1
         for (int bit = 62; bit >= 0; --bit) {          // |x| MSB first after the leading 1
-            jac_dbl(q);
-            if ((X_ABS >> bit) & 1) jac_add(q, base);
+            jac_dbl<M_>(q);
+            if ((X_ABS >> bit) & 1) jac_add<M_>(q, base);
         }
     }
     // need q == -phi2(P) = (beta2*x, -y):  X == beta2*x*Z^2,  Y == -y*Z^3

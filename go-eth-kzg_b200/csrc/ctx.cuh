@@ -46,12 +46,12 @@ static const int N_BLOB = 4096;
 namespace kzg {
 // decompress + (optional) subgroup check of n compressed points; first error per status slot wins.
 // out may be null (validation only: prove.go:56-60 discards the point).
-static __global__ void k_g1_check(const uint8_t *__restrict__ in48, G1Aff *__restrict__ out, int32_t *__restrict__ status, size_t n, int per_status, int subgroup) {
+template <class M_ = MulCall> static __global__ void k_g1_check(const uint8_t *__restrict__ in48, G1Aff *__restrict__ out, int32_t *__restrict__ status, size_t n, int per_status, int subgroup) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     G1Aff a;
     int32_t st = g1_decompress(a, in48 + i * 48);
-    if (st == ST_OK && subgroup && !g1_in_subgroup(&a, FP_BETA2)) st = ST_NOT_IN_SUBGROUP;
+    if (st == ST_OK && subgroup && !g1_in_subgroup<M_>(&a, FP_BETA2)) st = ST_NOT_IN_SUBGROUP;
     if (st != ST_OK) atomicCAS(&status[i / per_status], (int32_t)ST_OK, st);
     if (out) out[i] = a;
 }

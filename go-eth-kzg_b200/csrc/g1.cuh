@@ -22,23 +22,36 @@ static __device__ __noinline__ Fr fr_mul_ni(Fr a, Fr b) { return Fr::mul(a, b); 
 static __device__ __noinline__ Fp fp_sqr_ni(Fp a) { return Fp::sqr(a); }
 static __device__ __noinline__ Fr fr_sqr_ni(Fr a) { return Fr::sqr(a); }
 static __device__ __noinline__ Fp fp_mam_ni(Fp a, Fp b, Fp c, Fp d) { return Fp::mul_add_mul(a, b, c, d); }
+// TWO independent squarings in one out-of-line body: ptxas interleaves their four carry chains, so a lone warp keeps the multiply pipe
+// twice as busy (the kernels that use it -- G1 FFT stages, subgroup test -- run with 2-3 warps per scheduler and are latency-limited)
+struct FpPair { Fp a, b; };
+static __device__ __noinline__ FpPair fp_sqr2_ni(Fp a, Fp b) { FpPair r; r.a = Fp::sqr(a); r.b = Fp::sqr(b); return r; }
 // msub(a, b, c, d) = a*b - c*d.  The *Lazy policies compute it as a*b + (-c)*d under ONE Montgomery reduction
 // (Mont::mul_add_mul: 432 instead of 576 wide-multiply IMADs); the others as two products.
 struct MulInline {
     static __device__ __forceinline__ Fp mul(const Fp &a, const Fp &b) { return Fp::mul(a, b); }
     static __device__ __forceinline__ Fp sqr(const Fp &a) { return Fp::sqr(a); }
     static __device__ __forceinline__ Fp msub(const Fp &a, const Fp &b, const Fp &c, const Fp &d) { return Fp::sub(Fp::mul(a, b), Fp::mul(c, d)); }
+    static __device__ __forceinline__ void sqr2(const Fp &a, const Fp &b, Fp &ra, Fp &rb) { ra = Fp::sqr(a); rb = Fp::sqr(b); }
 };
 struct MulCall {
     static __device__ __forceinline__ Fp mul(const Fp &a, const Fp &b) { return fp_mul_ni(a, b); }
     static __device__ __forceinline__ Fp sqr(const Fp &a) { return fp_sqr_ni(a); }
     static __device__ __forceinline__ Fp msub(const Fp &a, const Fp &b, const Fp &c, const Fp &d) { return Fp::sub(fp_mul_ni(a, b), fp_mul_ni(c, d)); }
+    static __device__ __forceinline__ void sqr2(const Fp &a, const Fp &b, Fp &ra, Fp &rb) { ra = fp_sqr_ni(a); rb = fp_sqr_ni(b); }
 };
+// sqr2(a, b, ra, rb): ra = a^2, rb = b^2 (independent).  MulCallLazy2 runs them in one dual body (fp_sqr2_ni), the others one after the other.
 struct MulInlineLazy : MulInline {
     static __device__ __forceinline__ Fp msub(const Fp &a, const Fp &b, const Fp &c, const Fp &d) { return Fp::mul_add_mul(a, b, Fp::neg(c), d); }
 };
 struct MulCallLazy : MulCall {
     static __device__ __forceinline__ Fp msub(const Fp &a, const Fp &b, const Fp &c, const Fp &d) { return fp_mam_ni(a, b, Fp::neg(c), d); }
+};
+struct MulCall2 : MulCall {
+    static __device__ __forceinline__ void sqr2(const Fp &a, const Fp &b, Fp &ra, Fp &rb) { FpPair r = fp_sqr2_ni(a, b); ra = r.a; rb = r.b; }
+};
+struct MulCallLazy2 : MulCallLazy {
+    static __device__ __forceinline__ void sqr2(const Fp &a, const Fp &b, Fp &ra, Fp &rb) { FpPair r = fp_sqr2_ni(a, b); ra = r.a; rb = r.b; }
 };
 
 // affine point in Montgomery form; infinity is encoded as (0,0) (not on the curve since b=4)
@@ -162,9 +175,10 @@ struct G1J { Fp X, Y, Z; };
 struct G1JT { Fp X, Y, Z, ZZ, ZZZ; };
 
 template <class M_ = MulCall> __device__ __forceinline__ void jac_dbl(G1J &p) {          // dbl-2009-l, a = 0; no-op on infinity (Z = 0 stays 0)
-    Fp A = M_::sqr(p.X), B = M_::sqr(p.Y), C = M_::sqr(B);
-    Fp t = Fp::add(p.X, B);
-    Fp D = Fp::dbl(Fp::sub(Fp::sub(M_::sqr(t), A), C));
+    Fp A, B, C, T2;
+    M_::sqr2(p.X, p.Y, A, B);
+    M_::sqr2(B, Fp::add(p.X, B), C, T2);
+    Fp D = Fp::dbl(Fp::sub(Fp::sub(T2, A), C));
     Fp E = Fp::add(Fp::dbl(A), A);
     Fp F = M_::sqr(E);
     Fp Z3 = Fp::dbl(M_::mul(p.Y, p.Z));

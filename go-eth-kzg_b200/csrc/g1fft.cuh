@@ -85,11 +85,12 @@ static __device__ __noinline__ void jac_add_ool(G1J *a, const G1J *b) { jac_add_
 
 // *pp = [w_128^t] *pp, t block-uniform in 1..127.  Infinity in -> infinity out (Z = 0 propagates
 // through Z_2P).  Scripts/check_tw_prog.py is the big-integer model of this routine.
-static __device__ __noinline__ void jac_mul_prog_at(G1J *pp, const uint16_t *prog);
-static __device__ __forceinline__ void jac_mul_prog(G1J *pp, int t) { jac_mul_prog_at(pp, TW_PROG[t]); }
+// M_ = MulCallLazy (Y3 = r (V - X3) - Y1 HHH under one Montgomery reduction, mont.cuh: mul_add_mul) or MulCallLazy2 (the doubling's
+// squarings additionally run in pairs: g1.cuh fp_sqr2_ni)
+template <class M_> static __device__ __noinline__ void jac_mul_prog_at(G1J *pp, const uint16_t *prog);
+template <class M_ = MulCallLazy> static __device__ __forceinline__ void jac_mul_prog(G1J *pp, int t) { jac_mul_prog_at<M_>(pp, TW_PROG[t]); }
 // *pp = [k] *pp for the fixed scalar whose op list (constant memory, block-uniform) is prog
-static __device__ __noinline__ void jac_mul_prog_at(G1J *pp, const uint16_t *prog) {
-    typedef MulCallLazy M_;     // Y3 = r (V - X3) - Y1 HHH under one Montgomery reduction (mont.cuh: mul_add_mul)
+template <class M_> static __device__ __noinline__ void jac_mul_prog_at(G1J *pp, const uint16_t *prog) {
     Fp tx[8], ty[8], tbx[8], zr[8];
     Fp ZC;                                     // Z_common * Z_2P
     {
@@ -170,8 +171,8 @@ __device__ __forceinline__ int g1fft_butterfly(int y, int log_half) {
 // SRC_XYZZ: the stage reads the MSM sums (XYZZ) instead of the working set.  DST_XYZZ: it writes
 // XYZZ points for k_finalize_g1.  ONLY_SUM: x - y is not needed (inverse transform, last stage,
 // upper half discarded: toeplitz.go:124).  UPPER_ZERO: y is the zero padding (fk20.go:82-85).
-template <bool DIT, bool INVERSE, bool SRC_XYZZ, bool DST_XYZZ, bool ONLY_SUM, bool UPPER_ZERO, int MINB>
-static __global__ void __launch_bounds__(KZG_G1FFT_TPB, MINB) k_g1fft_stage(const G1 *__restrict__ src_xyzz, G1J *__restrict__ work, G1 *__restrict__ dst_xyzz,
+template <bool DIT, bool INVERSE, bool SRC_XYZZ, bool DST_XYZZ, bool ONLY_SUM, bool UPPER_ZERO, class M_>
+static __global__ void __launch_bounds__(KZG_G1FFT_TPB, 3) k_g1fft_stage(const G1 *__restrict__ src_xyzz, G1J *__restrict__ work, G1 *__restrict__ dst_xyzz,
                                                                       const int32_t *__restrict__ status, int nblobs, int log_half) {
     const int blob = blockIdx.x * KZG_G1FFT_TPB + threadIdx.x;
     if (blob >= nblobs || status[blob] != ST_OK) return;
@@ -187,7 +188,7 @@ static __global__ void __launch_bounds__(KZG_G1FFT_TPB, MINB) k_g1fft_stage(cons
         else y = ld_jac(w1);
     }
     if (DIT) {
-        if (t) jac_mul_prog(&y, t);
+        if (t) jac_mul_prog<M_>(&y, t);
         if (SRC_XYZZ) { G1 q = src_xyzz[(size_t)blob * 128 + i0]; x = jac_from_xyzz(q); }
         else x = ld_jac(w0);
         G1J s = x;
@@ -204,7 +205,7 @@ static __global__ void __launch_bounds__(KZG_G1FFT_TPB, MINB) k_g1fft_stage(cons
             y.Y = Fp::neg(y.Y); jac_add_ool(&x, &y);
             y = x; x = s;
         }
-        if (t) jac_mul_prog(&y, t);
+        if (t) jac_mul_prog<M_>(&y, t);
     }
     if (DST_XYZZ) {
         dst_xyzz[(size_t)blob * 128 + i0] = jac_to_xyzz(x);
@@ -230,7 +231,7 @@ static __global__ void __launch_bounds__(32) k_g1dense_mul(const G1 *__restrict_
     if (blob >= nblobs || status[blob] != ST_OK) return;
     G1 s = sums[(size_t)blob * 128 + pos];
     G1J y = jac_from_xyzz(s);
-    jac_mul_prog_at(&y, DENSE_PROG[slot]);
+    jac_mul_prog_at<MulCallLazy>(&y, DENSE_PROG[slot]);
     const int q = (int)(__brev((unsigned)pos) >> 25);
     st_jac(prod + ((size_t)blob * 65 + slot) * 128 + q, y);
 }

@@ -300,9 +300,19 @@ int kzgb200_dbg_set_tunable(const char *name, int v) {
         kzg::g_fk20_lanes_override = v;
         return 0;
     }
-    if (!strcmp(name, "g1fft_minb")) {
-        if (v != 3 && v != 4) return set_err(KZGB200_ERR_ARGS, "g1fft_minb must be 3 or 4");
-        kzg::g_g1fft_minb = v;
+    if (!strcmp(name, "g1fft_dual")) {
+        if (v != 0 && v != 1) return set_err(KZGB200_ERR_ARGS, "g1fft_dual must be 0 or 1");
+        kzg::g_g1fft_dual = v;
+        return 0;
+    }
+    if (!strcmp(name, "decode_dual")) {
+        if (v != 0 && v != 1) return set_err(KZGB200_ERR_ARGS, "decode_dual must be 0 or 1");
+        kzg::g_decode_dual = v;
+        return 0;
+    }
+    if (!strcmp(name, "rlc_item")) {
+        if (v < 0 || v > 4096) return set_err(KZGB200_ERR_ARGS, "rlc_item out of range");
+        kzg::g_rlc_item = v;
         return 0;
     }
     if (!strcmp(name, "g1fft_split")) {       // takes effect for lanes created afterwards? no: read per call from this global when non-zero
@@ -680,7 +690,7 @@ static int open_common(kzg_lane *c, const uint8_t *blobs, const uint8_t *z32, co
                 CU(cudaEventRecord(c->ev_piece[side], sp));
                 CU(cudaStreamWaitEvent(sv, c->ev_piece[side], 0));
                 CU(cudaMemsetAsync(d_cst, 0, pm * sizeof(int32_t), sv));
-                k_g1_check<<<gb, 64, 0, sv>>>((const uint8_t *)d_aux + po * 48, nullptr, d_cst, pm, 1, 1);
+                k_g1_check<MulCall><<<gb, 64, 0, sv>>>((const uint8_t *)d_aux + po * 48, nullptr, d_cst, pm, 1, 1);
                 CU(cudaEventRecord(c->ev_join[side], sv));
                 launch_fiat_shamir(sp, pb, (const uint8_t *)d_aux + po * 48, zl, pm);
                 c->launches += 2;
@@ -766,8 +776,8 @@ static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr 
             G1 *dst = pxyzz + off * 128;
             const int32_t *stt = d_status + off;
             const dim3 grid((unsigned)((nb + KZG_G1FFT_TPB - 1) / KZG_G1FFT_TPB), 64);
-#define KZG_STAGE(A, B, C, D, E, F, ...) do { if (g_g1fft_minb == 4) k_g1fft_stage<A, B, C, D, E, F, 4><<<grid, KZG_G1FFT_TPB, 0, s>>>(__VA_ARGS__); \
-                                                else k_g1fft_stage<A, B, C, D, E, F, 3><<<grid, KZG_G1FFT_TPB, 0, s>>>(__VA_ARGS__); } while (0)
+#define KZG_STAGE(A, B, C, D, E, F, ...) do { if (g_g1fft_dual) k_g1fft_stage<A, B, C, D, E, F, MulCallLazy2><<<grid, KZG_G1FFT_TPB, 0, s>>>(__VA_ARGS__); \
+                                                else k_g1fft_stage<A, B, C, D, E, F, MulCallLazy><<<grid, KZG_G1FFT_TPB, 0, s>>>(__VA_ARGS__); } while (0)
             KZG_STAGE(true, true, true, false, false, false, src, work, nullptr, stt, nb, 0);
             for (int lh = 1; lh < 6; ++lh) KZG_STAGE(true, true, false, false, false, false, nullptr, work, nullptr, stt, nb, lh);
             KZG_STAGE(true, true, false, false, true, false, nullptr, work, nullptr, stt, nb, 6);

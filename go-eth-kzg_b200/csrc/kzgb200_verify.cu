@@ -192,7 +192,7 @@ int lane_verify_blob_kzg_proof_batch(kzg_lane *c, const uint8_t *blobs, const ui
     if (n == 0) return KZGB200_OK;                       // kzg_verify.go:120-122
     int rc;
     // work items of the bucket MSMs: runs of <= 128 points, first the proofs (verdict slot 0), then the commitments (slot 1)
-    const uint64_t RLC_ITEM = 128;
+    const uint64_t RLC_ITEM = g_rlc_item > 0 ? (uint64_t)g_rlc_item : KZG_RLC_ITEM_DEFAULT;
     std::vector<uint64_t> item_start, item_end, slot_item_off(3, 0);
     for (int slot = 0; slot < 2; ++slot) {
         for (uint64_t s0 = 0; s0 < n; s0 += RLC_ITEM) { item_start.push_back(slot * n + s0); item_end.push_back(slot * n + std::min<uint64_t>(n, s0 + RLC_ITEM)); }

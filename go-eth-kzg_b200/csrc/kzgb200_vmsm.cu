@@ -10,7 +10,8 @@
 
 int vm_g1_check(cudaStream_t st, const uint8_t *in48, G1Aff *out, int32_t *status, size_t n, int per_status, int subgroup) {
     if (!n) return 0;
-    k_g1_check<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(in48, out, status, n, per_status, subgroup);
+    if (g_decode_dual) k_g1_check<MulCall2><<<(unsigned)((n + 63) / 64), 64, 0, st>>>(in48, out, status, n, per_status, subgroup);
+    else k_g1_check<MulCall><<<(unsigned)((n + 63) / 64), 64, 0, st>>>(in48, out, status, n, per_status, subgroup);
     CUL(cudaGetLastError());
     return 0;
 }

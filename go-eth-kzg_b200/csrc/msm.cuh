@@ -275,7 +275,9 @@ static __global__ void __launch_bounds__(128, (V & 8) ? 4 : 3) k_msm_fixed(const
 #endif
 inline int g_msm_variant_override = -1;       // kzgb200_dbg_set_tunable("msm_variant", v) (experiments: one context, every variant)
 inline int g_vmsm_policy = 1;                 // kzgb200_dbg_set_tunable("vmsm_policy", 0..3): see k_vmsm_buckets (vmsm.cuh)
-inline int g_g1fft_minb = 3;                  // kzgb200_dbg_set_tunable("g1fft_minb", 3 | 4): resident CTAs per SM the G1 FFT stage kernel is compiled for
+inline int g_g1fft_dual = 0;                  // kzgb200_dbg_set_tunable("g1fft_dual", 0 | 1): paired squarings (MulCallLazy2) in the G1 FFT stage kernel; measured SLOWER (33.7 -> 35.0 ms), off
+inline int g_decode_dual = 1;                 // kzgb200_dbg_set_tunable("decode_dual", 0 | 1): the same in the subgroup test of k_g1_check (vm_g1_check); measured 29.7 -> 29.4 ms per 528 k points
+inline int g_rlc_item = 0;                    // kzgb200_dbg_set_tunable("rlc_item", n): run length of the EIP-4844 batch verdict's bucket MSM work items; 0 = default
 inline int g_g1fft_split_override = 0;        // kzgb200_dbg_set_tunable("g1fft_split", k): sub-batches (streams) of the staged G1 FFT; 0 = context default
 inline int g_pairing_lanes = 0;               // kzgb200_dbg_set_tunable("pairing_lanes", 0 | 8 | 32): see vm_pairing_check (kzgb200_vmsm.cu)
 #define KZG_PL32_RESIDENT_WARPS 10            /* pl32 up to 10 checks per SM (of its 12 resident warps); measured crossover with pl8 at ~1 700 checks on 148 SMs (profiles/r02_pairing_sweep.md) */

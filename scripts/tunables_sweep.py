@@ -22,12 +22,12 @@ out = {}
 ctx = kzgb200.Context(commit_window=8, fk20_window=14)
 w = make_work(ctx, "cells_proofs", 1024, 0, torch, np, 0)
 w.step(False)
-for minb, split in ((3, 8), (4, 8), (3, 4), (4, 4), (4, 2)):
-    assert ctx.L.kzgb200_dbg_set_tunable(b"g1fft_minb", minb) == 0 and ctx.L.kzgb200_dbg_set_tunable(b"g1fft_split", split) == 0
+for minb, split in ((3, 8), (3, 4), (3, 2)):      # (the 4-CTA/SM build of the stage kernel, "g1fft_minb", was measured in round 2 and removed: 33.85 vs 33.71 ms)
+    assert ctx.L.kzgb200_dbg_set_tunable(b"g1fft_split", split) == 0
     r = kms(ctx, w); r["self_check"] = bool(w.self_check())
     out["cells_proofs g1fft_minb=%d split=%d" % (minb, split)] = r
     print("cells_proofs g1fft_minb", minb, "split", split, r, flush=True)
-ctx.L.kzgb200_dbg_set_tunable(b"g1fft_minb", 3); ctx.L.kzgb200_dbg_set_tunable(b"g1fft_split", 0)
+ctx.L.kzgb200_dbg_set_tunable(b"g1fft_split", 0)
 ctx.L.kzgb200_dbg_set_tunable(b"fk20_lanes", 0)
 del w; torch.cuda.empty_cache()
 w = make_work(ctx, "verify_cells", 4096, 0, torch, np, 0)
