@@ -466,6 +466,28 @@ def time_work(ctx, w, steps, warmup, barrier, max_over_ranks, sampler=None):
     return {"wall": wall, "e2e_wall": e2e_wall, "dev_ms": dev_ms, "kms": kms, "launches": launches, "clocks": clocks, "steps": steps}
 
 
+def exact_pass(ctx, w, steps, barrier, max_over_ranks, world):
+    """verify_cells with the optimistic first pass (one combined check over all verdicts, kzgb200_verify.cu) switched OFF: every verdict by
+    its own random linear combination and pairing check -- what a call costs when the combined check does not pass (then on top of it)"""
+    assert ctx.L.kzgb200_dbg_set_tunable(b"optimistic", 0) == 0
+    try:
+        w.step(True)
+        kms = {}
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            w.step(True)
+            for k, v in ctx.last_kernel_ms().items():
+                kms[k] = kms.get(k, 0.0) + v
+        barrier()
+        wall = max_over_ranks(time.perf_counter() - t0)
+    finally:
+        ctx.L.kzgb200_dbg_set_tunable(b"optimistic", 1)
+    return {"value": w.units * world * steps / wall, "unit": unit_of(w.wl), "ms_per_step": wall / steps * 1e3,
+            "kernel_ms_per_step": {k: v / steps for k, v in kms.items() if v},
+            "note": "tunable optimistic = 0: per-verdict checks only (round-1 behaviour); an input whose combined check fails pays the combined pass AND this one"}
+
+
 def fmaheavy_from_profiles(kernel):
     """sm__pipe_fmaheavy_cycles_active of the committed ncu --set full capture of `kernel` (profiles/r02_ncu_pipes.json), or None"""
     try:
@@ -527,7 +549,8 @@ def roofline_for(wl, info, per, B, units, world_value_per_gpu, peaks, dev_ms_per
     DECODE = (384 * SQR + 100 * IMAD_FP_MUL) + 126 * (2 * IMAD_FP_MUL + 5 * SQR) + 10 * (11 * IMAD_FP_MUL + 3 * SQR) + 4 * IMAD_FP_MUL
     VMSM = 96 * 15 / 16 * IMAD_MIXED_ADD
     pts_decode = {"verify_cells": units + B, "verify_cells_one_batch": units + B, "verify_blob_batch": 2 * B}[wl]
-    pts_vmsm = {"verify_cells": units, "verify_cells_one_batch": units * (16 / (96 * 15 / 16)), "verify_blob_batch": 2 * B * (64 / 96)}[wl]
+    # large verdicts (and the optimistic combined pass of verify_cells): 32 of the 96 windows per point
+    pts_vmsm = {"verify_cells": units * (32 / 96), "verify_cells_one_batch": units * (32 / 96), "verify_blob_batch": 2 * B * (64 / 96)}[wl]
     models = {"decode": ("k_g1_check", pts_decode * DECODE), "vmsm": ("k_vmsm_buckets (+ reduce, combine)", pts_vmsm * VMSM)}
     top = max((k for k in per if k in models and per[k]), key=lambda k: per[k], default=None)
     roof["kernel_classes"] = {k: {"kernel": models[k][0], "ms": per[k], "executed_imad": models[k][1],
@@ -689,6 +712,7 @@ def main():
     sampler = ClockSampler(local)
     r = time_work(ctx, w, args.steps, args.warmup, barrier, max_over_ranks, sampler)
     assert w.self_check(), "self-check failed (host path vs device path / accept-reject)"
+    exact = exact_pass(ctx, w, args.steps, barrier, max_over_ranks, world) if wl == "verify_cells" else None
     oracle_ok = bool(w.oracle_check())
     assert oracle_ok, "outputs differ from the CPU oracle"
     unit = unit_of(wl)
@@ -711,6 +735,8 @@ def main():
         "roofline": roof, "oracle_check": "ok" if oracle_ok else "MISMATCH",
         "oracle_check_what": "first and last item of the batch recomputed by the CPU oracle after the timed region (and, for the verifiers, accept + corrupted-input reject on both)",
     }
+    if exact:
+        line["per_verdict_pass"] = exact
     del w
     ctx.close()
     torch.cuda.empty_cache()
@@ -731,7 +757,7 @@ def main():
             sper = {k: v / 3 for k, v in sr["kms"].items() if v}
             sval = sw.units * world * 3 / sr["wall"]
             co[sub] = {"metric": METRIC[sub], "value": sval, "unit": unit_of(sub), "e2e": sw.units * world * 3 / sr["e2e_wall"], "ms_per_step": sr["wall"] / 3 * 1e3,
-                       "kernel_ms_per_step": sper, "oracle_check": "ok",
+                       "kernel_ms_per_step": sper, "oracle_check": "ok", **({"per_verdict_pass": exact_pass(cctx, sw, 3, barrier, max_over_ranks, world)} if sub == "verify_cells" else {}),
                        "roofline": {k: v for k, v in roofline_for(sub, ci, sper, subB, sw.units, sval / world, peaks, sr["dev_ms"] / 3).items()
                                     if k in ("kernel", "achieved", "peak", "unit", "frac", "frac_of_isolated_field_op_rate", "fmaheavy_pct_ncu", "kernel_classes")}}
             del sw

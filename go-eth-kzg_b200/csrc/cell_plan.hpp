@@ -36,7 +36,8 @@ struct CellPlan {
 // batch_offsets[nb] == N are required: a cell outside every verdict would still be decoded and its errors folded
 // into verdict 0 -- ADVICE r1)
 static inline bool plan_cell_batches(const uint8_t *h_cm, const uint64_t *cell_indices, size_t N, const uint64_t *batch_offsets, size_t nb,
-                                     uint64_t item, uint64_t large, uint64_t row_item, int32_t st_bad_cell_index, CellPlan &P) {
+                                     uint64_t item, uint64_t large, uint64_t row_item, int32_t st_bad_cell_index, CellPlan &P, uint64_t l_item = 0) {
+    if (!l_item) l_item = item;               // run length of the large verdicts' column items (default: the interpolation's)
     P = CellPlan();
     P.bstatus.assign(nb, 0); P.batch_start.assign(nb, 0); P.batch_row_off.assign(nb + 1, 0); P.batch_item_off.assign(nb + 1, 0);
     P.large_of.assign(nb, -1); P.batch_of.assign(N, 0); P.row_cells.assign(N, 0); P.row_off.assign(1, 0);
@@ -91,7 +92,7 @@ static inline bool plan_cell_batches(const uint8_t *h_cm, const uint64_t *cell_i
             for (int q = 0; q < 128; ++q) fillc[q] = base + cnt[q];
             for (uint64_t k = lo; k < hi; ++k) P.l_order[fillc[cell_indices[k] & 127]++] = (uint32_t)k;
             for (int q = 0; q < 128; ++q) {
-                for (uint64_t s = base + cnt[q]; s < base + cnt[q + 1]; s += item) { P.l_item_start.push_back(s); P.l_item_end.push_back(std::min(base + cnt[q + 1], s + item)); }
+                for (uint64_t s = base + cnt[q]; s < base + cnt[q + 1]; s += l_item) { P.l_item_start.push_back(s); P.l_item_end.push_back(std::min(base + cnt[q + 1], s + l_item)); }
                 P.l_slot_item_off.push_back(P.l_item_start.size());
             }
         } else {

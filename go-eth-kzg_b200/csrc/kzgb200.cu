@@ -310,6 +310,21 @@ int kzgb200_dbg_set_tunable(const char *name, int v) {
         kzg::g_decode_dual = v;
         return 0;
     }
+    if (!strcmp(name, "large_window")) {
+        if (v != 4 && v != 8) return set_err(KZGB200_ERR_ARGS, "large_window must be 4 or 8");
+        kzg::g_large_window = v;
+        return 0;
+    }
+    if (!strcmp(name, "large_item")) {
+        if (v < 0 || v > 65536) return set_err(KZGB200_ERR_ARGS, "large_item out of range");
+        kzg::g_large_item = v;
+        return 0;
+    }
+    if (!strcmp(name, "optimistic")) {
+        if (v != 0 && v != 1) return set_err(KZGB200_ERR_ARGS, "optimistic must be 0 or 1");
+        kzg::g_optimistic = v;
+        return 0;
+    }
     if (!strcmp(name, "rlc_item")) {
         if (v < 0 || v > 4096) return set_err(KZGB200_ERR_ARGS, "rlc_item out of range");
         kzg::g_rlc_item = v;

@@ -46,7 +46,13 @@ int vm_msm_windows(cudaStream_t st, const G1Aff *points, const int8_t *digits, i
 #undef KZG_VMSM_PICK
 #undef KZG_VMSM_LAUNCH
     }
-    if (nb) k_vmsm_item_reduce<<<(unsigned)nb, nw, 0, st>>>(WS, batch_item_off, WSb);
+    if (nb) {
+        // few verdicts of many items each: four partial sums per window (see k_vmsm_item_reduce)
+        const int par = (n_items >= 8 * nb) ? (nw <= 64 ? 4 : 2) : 1;      // <= 256 threads (the full addition needs ~200 registers)
+        const size_t smem = par > 1 ? (size_t)nw * par * sizeof(G1) : 0;
+        if (smem > 48 * 1024) CUL(cudaFuncSetAttribute(k_vmsm_item_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set at every use
+        k_vmsm_item_reduce<<<(unsigned)nb, dim3(nw, par), smem, st>>>(WS, batch_item_off, WSb);
+    }
     CUL(cudaGetLastError());
     return 0;
 }

@@ -170,6 +170,7 @@ __device__ __forceinline__ void store_g1(G1 *p, const G1 &r) {
 #define KZG_ROW_TW 40         // commitment weights of a large verdict: sums of < 2^32 coefficients of 126 bits (< 2^159), 40 signed 4-bit windows
 #define KZG_ROW_ITEM 64       // ... in short runs: there are few commitments, parallelism matters more than the reduction's cost
 #define KZG_LARGE_BATCH 4096
+#define KZG_RLC_ITEM_DEFAULT 128   // EIP-4844 batch verdict: run length of the bucket MSM's work items (tunable "rlc_item")
 // per cell k: r_k = PRF(seed, batch, position in batch); rpow[k] = r_k (Montgomery, for the
 // interpolation and the commitment weights); digits[k][0..31] = r_k, digits[k][32..63], [64..95] =
 // GLV halves of r_k * h_k^64 with h_k^64 = w_128^brp7(cell index)   (kzg_multi/srs.go:60-103, kzg_verify.go:73-83)
@@ -286,16 +287,26 @@ static __global__ void __launch_bounds__(128) k_vmsm_bucket_reduce(const G1 *__r
     store_g1(WS + task, tot);
 }
 
-// WSb[b][w] = sum of WS[item][w] over the items of verdict b (usually exactly one)
-static __global__ void k_vmsm_item_reduce(const G1 *__restrict__ WS, const uint64_t *__restrict__ batch_item_off, G1 *__restrict__ WSb) {
-    const int w = threadIdx.x, nw = blockDim.x;
+// WSb[b][w] = sum of WS[item][w] over the items of verdict b (usually exactly one).  blockDim = (nw, PAR): with PAR > 1 the items are
+// dealt round-robin to PAR partial sums per window, folded through shared memory (dynamic: nw * PAR * sizeof(G1)) -- a verdict of
+// many items (the EIP-4844 batch, the columns of a large cell verdict) would otherwise be one chain of full additions per window
+static __global__ void __launch_bounds__(256) k_vmsm_item_reduce(const G1 *__restrict__ WS, const uint64_t *__restrict__ batch_item_off, G1 *__restrict__ WSb) {
+    extern __shared__ G1 ir_sm[];
+    const int w = threadIdx.x, nw = blockDim.x, par = blockDim.y, p = threadIdx.y;
     const size_t b = blockIdx.x;
     G1 acc = G1::infinity();
-    for (uint64_t it = batch_item_off[b]; it < batch_item_off[b + 1]; ++it) {
+    for (uint64_t it = batch_item_off[b] + p; it < batch_item_off[b + 1]; it += par) {
         G1 t = load_g1(WS + it * nw + w);
         g1_add<MulCall>(acc, t);
     }
-    store_g1(WSb + b * nw + w, acc);
+    if (par == 1) { store_g1(WSb + b * nw + w, acc); return; }
+    ir_sm[p * nw + w] = acc;
+    __syncthreads();
+    for (int st = par >> 1; st > 0; st >>= 1) {
+        if (p < st) g1_add_ool(&ir_sm[p * nw + w], &ir_sm[(p + st) * nw + w]);
+        __syncthreads();
+    }
+    if (p == 0) store_g1(WSb + b * nw + w, ir_sm[w]);
 }
 
 // out[seg * nb + b] = sum_{i < nw} 2^(dbl i) WSb[b][nw seg + i]   (Horner from the top window), blockIdx.y = seg

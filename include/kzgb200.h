@@ -148,7 +148,10 @@ int kzgb200_recover_cells_and_kzg_proofs(kzgb200_ctx *ctx, const uint64_t *cell_
 /* Context.VerifyCellKZGProofBatch (api_eip7594.go:163-215).  N cells total, split into n_batches
  * independent RLC verdicts: batch b covers items [batch_offsets[b], batch_offsets[b+1]).
  * commitments48 holds one commitment PER CELL (as the Go API does); de-duplication
- * (api_eip7594.go:238-265) happens inside.  results[b] in {OK, VERIFY_FAILED, error}. */
+ * (api_eip7594.go:238-265) happens inside.  results[b] in {OK, VERIFY_FAILED, error}.
+ * A call with many small verdicts (>= 8192 cells in all) first checks ALL its cells as one random linear combination; if
+ * that passes every verdict is OK (soundness error < 2^-125, the bound of a verdict's own check), otherwise the verdicts
+ * are checked one by one, so results[] never depend on the shortcut.  KZGB200_OPTIMISTIC=0 in the environment disables it. */
 int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *ctx, const uint8_t *commitments48, const uint64_t *cell_indices,
                                         const uint8_t *cells, const uint8_t *proofs48, size_t n_cells,
                                         const uint64_t *batch_offsets, size_t n_batches, int32_t *results);

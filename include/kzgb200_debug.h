@@ -55,7 +55,10 @@ int kzgb200_dbg_h2d_bandwidth(const int *devices, int n, size_t bytes_per_dev, i
  *   "pairing_lanes": lanes per pairing check: 32 (one check per warp, latency form), 8 (throughput form), 0 = by batch size (default)
  *   "fiat_shamir": SHA-256 of the Fiat-Shamir challenge: 2 = two warps per 32 blobs (message schedule on a producer warp; default), 1 = one thread per blob
  *   "vmsm_policy": field products of the verifiers' bucket accumulation: 0 inlined, 1 out-of-line + one-reduction Y3 (default),
- *                  2 inlined + one-reduction Y3, 3 out-of-line */
+ *                  2 inlined + one-reduction Y3, 3 out-of-line
+ *   "optimistic": 1 (default) = VerifyCellKZGProofBatch checks a call of many small verdicts as one combined verdict first, 0 = per-verdict checks only
+ *   "large_window": 4 (default) | 8 = window bits of the column MSMs of large (>= 4096-cell) verdicts; "large_item": run length of their work items (0 = default)
+ *   "rlc_item": run length of the EIP-4844 batch verdict's bucket-MSM work items (0 = default 128) */
 int kzgb200_dbg_set_tunable(const char *name, int v);
 /* dependency-free integer multiply-add microbenchmark: device-wide instructions*lanes per second.
  * mode 0: mad.lo.u32 (IMAD), 1: mad.hi.u32 (IMAD.HI), 2: mad.wide.u32 (IMAD.WIDE, 32x32+64);

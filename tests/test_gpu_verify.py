@@ -230,3 +230,66 @@ def test_cell_verifier_reports_first_error_in_reference_order(ctx):
     assert run(cms=cms) == 5
     i2 = list(idx); i2[77] = 128
     assert run(cms=cms, cells_=c, proofs_=p, idx_=i2) == 7
+
+
+def test_optimistic_combined_pass_agrees_with_per_verdict_checks(ctx):
+    """many small verdicts (>= 8192 cells in all) are first checked as ONE combined random linear combination
+    (kzgb200_verify.cu: optimistic pass); whatever it finds, the per-verdict results must be exactly those of the
+    per-verdict checks alone (tunable optimistic = 0): all OK, one false verdict, error statuses in the right slot"""
+    nblob = 66
+    blobs = [oracle_lib.rand_blob((300 + b) << 20) for b in range(nblob)]
+    cms = [c for _, c in ctx.blob_to_kzg_commitment_batch(blobs)]
+    full = ctx.compute_cells_and_kzg_proofs_batch(blobs)
+    commitments, idx, cells, proofs = [], [], [], []
+    for b, (st, cl, pr) in enumerate(full):
+        for i in range(128):
+            commitments.append(cms[b]); idx.append(i); cells.append(cl[2048 * i:2048 * (i + 1)]); proofs.append(pr[48 * i:48 * (i + 1)])
+    n = len(cells)                                                   # 8448 cells, 66 verdicts of 128 + one empty
+    offs = [128 * b for b in range(nblob + 1)] + [n]
+    cases = {"valid": (commitments, idx, cells, proofs)}
+    bad = list(proofs); bad[128 * 40 + 7] = proofs[128 * 40 + 8]
+    cases["false_proof"] = (commitments, idx, cells, bad)
+    badc = list(cells); badc[128 * 65 + 127] = cells[128 * 65 + 126]
+    cases["false_cell_last"] = (commitments, idx, badc, proofs)
+    bidx = list(idx); bidx[128 * 3 + 1] = 128
+    cases["bad_index"] = (commitments, bidx, cells, bad)
+    benc = list(proofs); benc[128 * 12] = bytes([0xff]) * 48
+    cases["bad_encoding"] = (commitments, idx, cells, benc)
+    expect = {"valid": {}, "false_proof": {40: 1}, "false_cell_last": {65: 1}, "bad_index": {3: 7, 40: 1}, "bad_encoding": {12: 3}}
+    for name, (cm_, ix_, ce_, pr_) in cases.items():
+        got = {}
+        for opt in (1, 0):
+            assert ctx.L.kzgb200_dbg_set_tunable(b"optimistic", opt) == 0
+            try:
+                got[opt] = ctx.verify_cell_kzg_proof_batches(cm_, ix_, ce_, pr_, offs)
+            finally:
+                ctx.L.kzgb200_dbg_set_tunable(b"optimistic", 1)
+        want = [expect[name].get(b, 0) for b in range(nblob + 1)]
+        assert got[1] == got[0] == want, (name, got)
+    # the oracle agrees on the verdict that was made false
+    o = oracle_lib.get_oracle()
+    lo = 128 * 40
+    assert o.verify_cell_kzg_proof_batch(commitments[lo:lo + 128], idx[lo:lo + 128], cells[lo:lo + 128], bad[lo:lo + 128]) == 1
+    assert o.verify_cell_kzg_proof_batch(commitments[lo:lo + 128], idx[lo:lo + 128], cells[lo:lo + 128], proofs[lo:lo + 128]) == 0
+
+
+def test_large_verdict_window_variants_agree(ctx):
+    """large verdicts: the 4-bit-window column MSM (default) against the round-1 8-bit-window form (tunable large_window = 8)"""
+    nblob = 40
+    blobs = [oracle_lib.rand_blob((400 + b) << 20) for b in range(nblob)]
+    cms = [c for _, c in ctx.blob_to_kzg_commitment_batch(blobs)]
+    full = ctx.compute_cells_and_kzg_proofs_batch(blobs)
+    commitments, idx, cells, proofs = [], [], [], []
+    for b, (st, cl, pr) in enumerate(full):
+        for i in range(128):
+            commitments.append(cms[b]); idx.append(i); cells.append(cl[2048 * i:2048 * (i + 1)]); proofs.append(pr[48 * i:48 * (i + 1)])
+    n = len(cells)
+    bad = list(proofs); bad[3000] = proofs[3001]
+    for lw in (4, 8):
+        assert ctx.L.kzgb200_dbg_set_tunable(b"large_window", lw) == 0
+        try:
+            assert ctx.verify_cell_kzg_proof_batches(commitments, idx, cells, proofs, [0, n]) == [0]
+            assert ctx.verify_cell_kzg_proof_batches(commitments, idx, cells, bad, [0, n]) == [1]
+            assert ctx.verify_cell_kzg_proof_batches(commitments, idx, cells, bad, [0, 4096, n]) == [1, 0]
+        finally:
+            ctx.L.kzgb200_dbg_set_tunable(b"large_window", 4)
