@@ -351,6 +351,7 @@ def make_work(ctx, wl, B, first_blob, torch, np, device, interleaved=False):
             assert res.value == 0, "valid batch rejected"
         def self_check():      # a corrupted proof must be rejected (Cfg2)
             bad = d_p.clone(); bad[17 * 48:18 * 48] = torch.frombuffer(bytearray(kzgb200.load_trusted_setup()[0][:48]), dtype=torch.uint8).to(dev)
+            torch.cuda.synchronize()       # the library's streams do not wait for torch's (kzgb200.h: device inputs must be complete)
             ctx._check(L.kzgb200_verify_blob_kzg_proof_batch(ctx.ctx, P(d_blobs), P(d_c), P(bad), SZ(B), ctypes.byref(res)))
             return res.value == 1
         w.h2d, w.d2h = B * (BLOB + 96), 4
@@ -417,6 +418,7 @@ def make_work(ctx, wl, B, first_blob, torch, np, device, interleaved=False):
                 def self_check():
                     ok = int(d_res.abs().sum().item()) == 0 and int(h_res.abs().sum().item()) == 0
                     badc = d_cells.clone(); badc[5 * 2048 + 40] ^= 1                                   # corrupt one cell of batch 0
+                    torch.cuda.synchronize()       # the library's streams do not wait for torch's (kzgb200.h: device inputs must be complete)
                     ctx._check(L.kzgb200_verify_cell_kzg_proof_batch(ctx.ctx, P(d_cm), ip, P(badc), P(d_pr), SZ(N), op_, SZ(nv), P(d_res)))
                     r = d_res.cpu()
                     return ok and int(r[0]) == 1 and int(r[1:].abs().sum()) == 0
@@ -432,6 +434,7 @@ def make_work(ctx, wl, B, first_blob, torch, np, device, interleaved=False):
                 w.keep += [idx, offs, d_cm, h_cm, d_res, h_res]
         w.keep += [d_cells, d_pr, h_cells, h_pr]
     w.step = step
+    torch.cuda.synchronize()       # everything torch queued for the inputs is complete before the library's own streams read them
     return w
 
 

@@ -108,6 +108,7 @@ struct kzg_lane {
     DevBuf rec_a, rec_b, rec_meta, rec_zev, rec_czinv;
     DevBuf v_aff1, v_aff2, v_fr, v_meta, v_S, v_W, v_partial, v_in2, v_in3, v_st2;
     DevBuf vm_digits, vm_digits256, vm_colsum, vm_rowdig, vm_commsum, vm_scratch, vm_ws, vm_wsb, v_pa, v_pb, v_cst, v_st3, v_pst, ev_cex, ev_total, ev_index;
+    DevBuf v_xst, vm_scratch_r, vm_ws_r, vm_wsb_r;      // cell verifier: the cells' own status slots; scratch of the row-weight MSM (runs beside the column MSM)
     double init_ms = 0, last_device_ms = 0;
     uint64_t launches = 0;
     // per-kernel-class device timing of the last call (CUDA events on `stream`)

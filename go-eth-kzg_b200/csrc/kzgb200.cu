@@ -325,6 +325,11 @@ int kzgb200_dbg_set_tunable(const char *name, int v) {
         kzg::g_optimistic = v;
         return 0;
     }
+    if (!strcmp(name, "verify_overlap")) {
+        if (v != 0 && v != 1) return set_err(KZGB200_ERR_ARGS, "verify_overlap must be 0 or 1");
+        kzg::g_verify_overlap = v;
+        return 0;
+    }
     if (!strcmp(name, "rlc_item")) {
         if (v < 0 || v > 4096) return set_err(KZGB200_ERR_ARGS, "rlc_item out of range");
         kzg::g_rlc_item = v;
@@ -382,7 +387,7 @@ void lane_ctx_free(kzg_lane *c) {
     c->rec_a.release(); c->rec_b.release(); c->rec_meta.release(); c->rec_zev.release(); c->rec_czinv.release();
     c->v_aff1.release(); c->v_aff2.release(); c->v_fr.release(); c->v_meta.release(); c->v_S.release();
     c->v_W.release(); c->v_partial.release(); c->v_in2.release(); c->v_in3.release(); c->v_st2.release();
-    c->vm_digits.release(); c->vm_digits256.release(); c->vm_colsum.release(); c->vm_rowdig.release(); c->vm_commsum.release(); c->vm_scratch.release(); c->vm_ws.release(); c->vm_wsb.release(); c->v_pa.release(); c->v_pb.release(); c->v_cst.release(); c->v_st3.release(); c->v_pst.release(); c->ev_cex.release(); c->ev_total.release(); c->ev_index.release();
+    c->vm_digits.release(); c->vm_digits256.release(); c->vm_colsum.release(); c->vm_rowdig.release(); c->vm_commsum.release(); c->vm_scratch.release(); c->vm_ws.release(); c->vm_wsb.release(); c->v_pa.release(); c->v_pb.release(); c->v_cst.release(); c->v_st3.release(); c->v_pst.release(); c->v_xst.release(); c->vm_scratch_r.release(); c->vm_ws_r.release(); c->vm_wsb_r.release(); c->ev_cex.release(); c->ev_total.release(); c->ev_index.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->ev_aux_fork) cudaEventDestroy(c->ev_aux_fork);
@@ -410,7 +415,12 @@ static int lane_streams_init(kzg_lane *c, int device) {
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    {   // the aux stream carries short latency-bound chains that run BESIDE a long pipe-bound kernel of the main stream (second decode of the
+        // verifiers, the cell verifier's interpolation chain): highest priority, so that its blocks are placed as soon as slots free up
+        int lo_pri = 0, hi_pri = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        CU(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi_pri));
+    }
     CU(cudaEventCreateWithFlags(&c->ev_aux_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_aux_join, cudaEventDisableTiming));
     CU(cudaEventCreate(&c->ev0));

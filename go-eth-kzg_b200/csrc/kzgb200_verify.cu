@@ -361,7 +361,8 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
     }
     if ((rc = c->v_meta.ensure(o))) return rc;
     char *M = (char *)c->v_meta.p;
-    auto up = [&](size_t at, const void *src, size_t bytes) { return bytes ? cudaMemcpyAsync(M + at, src, bytes, cudaMemcpyHostToDevice, c->stream) : cudaSuccess; };
+    // (on the aux stream: a copy from pageable memory waits for the stream it is queued on, and the main stream is busy decoding the proofs)
+    auto up = [&](size_t at, const void *src, size_t bytes) { return bytes ? cudaMemcpyAsync(M + at, src, bytes, cudaMemcpyHostToDevice, c->aux_stream) : cudaSuccess; };
     CU(up(o_idx, cell_indices, N * 8)); CU(up(o_batch_of, batch_of.data(), N * 4)); CU(up(o_bstart, batch_start.data(), nb * 8));
     CU(up(o_rowc, row_cells.data(), N * 4));
     CU(up(o_rowoff, row_off.data(), (U + 1) * 8)); CU(up(o_browoff, batch_row_off.data(), (nb + 1) * 8));
@@ -380,10 +381,14 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
     if ((rc = c->v_fr.ensure(std::max<size_t>(N, 1) * sizeof(Fr)))) return rc;
     if ((rc = c->vm_digits.ensure(std::max<size_t>(N, 1) * KZG_CELL_TW))) return rc;
     const size_t n_vm_items = n_large ? n_vs : n_items;
-    if ((rc = c->vm_scratch.ensure(std::max<size_t>(std::max(std::max(vm_scratch_bytes(n_vm_items, KZG_CELL_TW, KZG_VM_BUCKETS), vm_scratch_bytes(n_li, l_tw, l_nbk)), vm_scratch_bytes(n_ri, KZG_ROW_TW, KZG_VM_BUCKETS)), 256)))) return rc;
-    if ((rc = c->vm_ws.ensure(std::max<size_t>(std::max(std::max(n_vm_items * KZG_CELL_TW, n_li * (size_t)l_tw), n_ri * KZG_ROW_TW), 1) * sizeof(G1)))) return rc;
-    if ((rc = c->vm_wsb.ensure(std::max(std::max(nb * KZG_CELL_TW, n_slots * (size_t)l_tw), n_large * KZG_ROW_TW) * sizeof(G1)))) return rc;
+    if ((rc = c->vm_scratch.ensure(std::max<size_t>(std::max(vm_scratch_bytes(n_vm_items, KZG_CELL_TW, KZG_VM_BUCKETS), vm_scratch_bytes(n_li, l_tw, l_nbk)), 256)))) return rc;
+    if ((rc = c->vm_ws.ensure(std::max<size_t>(std::max(n_vm_items * KZG_CELL_TW, n_li * (size_t)l_tw), 1) * sizeof(G1)))) return rc;
+    if ((rc = c->vm_wsb.ensure(std::max(nb * KZG_CELL_TW, n_slots * (size_t)l_tw) * sizeof(G1)))) return rc;
+    if ((rc = c->v_xst.ensure(std::max<size_t>(N, 1) * 4))) return rc;
     if (n_large) {
+        if ((rc = c->vm_scratch_r.ensure(std::max<size_t>(vm_scratch_bytes(n_ri, KZG_ROW_TW, KZG_VM_BUCKETS), 256)))) return rc;
+        if ((rc = c->vm_ws_r.ensure(std::max<size_t>(n_ri * KZG_ROW_TW, 1) * sizeof(G1)))) return rc;
+        if ((rc = c->vm_wsb_r.ensure(n_large * KZG_ROW_TW * sizeof(G1)))) return rc;
         if (!l4 && (rc = c->vm_digits256.ensure(N * KZG_LARGE_TW))) return rc;
         if ((rc = c->vm_colsum.ensure(n_slots * sizeof(G1)))) return rc;
         if ((rc = c->vm_rowdig.ensure(std::max<size_t>(U, 1) * KZG_ROW_TW))) return rc;
@@ -397,25 +402,40 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
     if ((rc = c->sums.ensure(nb * sizeof(G1)))) return rc;
     Fr inv64; memcpy(inv64.v, H_FR_INV64, sizeof inv64.v);
     int32_t *d_ust = (int32_t *)(M + o_ust), *d_bst = (int32_t *)(M + o_bst), *d_res = (int32_t *)(M + o_res);
+    int32_t *d_xst = (int32_t *)c->v_xst.p;
+    // ---- side chain (aux stream, highest priority): everything that does not need the decoded proofs -- the commitments' decode, the
+    // coefficients, the cells' interpolation and [sum r_k I_k(s)]G, the commitment weights of large verdicts -- runs BESIDE the proofs'
+    // decode of the main stream and fills the issue slots that kernel leaves idle (87 % pipe-active on its own).  Tunable
+    // "verify_overlap" = 0 queues the same launches on the main stream instead (round-1 order) for measurements.
+    cudaStream_t sa = g_verify_overlap ? c->aux_stream : c->stream;
     if ((rc = vm_g1_check(c->aux_stream, (const uint8_t *)c->in_small2.p, (G1Aff *)c->v_aff1.p, d_ust, U, 1, 1))) return rc;
-    CU(cudaEventRecord(c->ev_aux_join, c->aux_stream));
-    CU(cudaStreamWaitEvent(c->stream, c->ev_aux_join, 0));
+    CU(cudaMemsetAsync(d_xst, 0, std::max<size_t>(N, 1) * 4, c->aux_stream));
+    if (!g_verify_overlap) { CU(cudaEventRecord(c->ev_aux_join, c->aux_stream)); CU(cudaStreamWaitEvent(c->stream, c->ev_aux_join, 0)); }
     if (N) {
-        if ((rc = vm_cell_coeff_digits(c->stream, seed_dev, (const uint32_t *)(M + o_batch_of), (const uint64_t *)(M + o_bstart), (const uint64_t *)(M + o_idx),
+        if ((rc = vm_cell_coeff_digits(sa, seed_dev, (const uint32_t *)(M + o_batch_of), (const uint64_t *)(M + o_bstart), (const uint64_t *)(M + o_idx),
                                        c->roots, (Fr *)c->v_fr.p, (int8_t *)c->vm_digits.p, (n_large && !l4) ? (int8_t *)c->vm_digits256.p : nullptr, N))) return rc;
-        if (d_cells == c->in_bytes.p) CU(cudaStreamWaitEvent(c->stream, c->ev1, 0));     // the cells have landed
-        c->mark(KZGB200_KC_FR);
-        k_cell_interp<<<(unsigned)n_items, 256, 0, c->stream>>>((const uint8_t *)d_cells, (const uint64_t *)(M + o_idx), (const Fr *)c->v_fr.p, (const uint64_t *)(M + o_is),
-                                                                (const uint64_t *)(M + o_ie), c->roots, inv64, d_cst, (Fr *)c->v_partial.p);
+        if (d_cells == c->in_bytes.p) CU(cudaStreamWaitEvent(sa, c->ev1, 0));     // the cells have landed
+        if (!g_verify_overlap) c->mark(KZGB200_KC_FR);
+        k_cell_interp<<<(unsigned)n_items, 256, 0, sa>>>((const uint8_t *)d_cells, (const uint64_t *)(M + o_idx), (const Fr *)c->v_fr.p, (const uint64_t *)(M + o_is),
+                                                         (const uint64_t *)(M + o_ie), c->roots, inv64, d_xst, (Fr *)c->v_partial.p);
         c->launches += 3;
     }
-    k_cell_interp_reduce<<<(unsigned)nb, 64, 0, c->stream>>>((const Fr *)c->v_partial.p, (const uint64_t *)(M + o_bio), (uint32_t *)c->scalars.p);
-    c->mark(KZGB200_KC_MSM);
+    k_cell_interp_reduce<<<(unsigned)nb, 64, 0, sa>>>((const Fr *)c->v_partial.p, (const uint64_t *)(M + o_bio), (uint32_t *)c->scalars.p);
+    if (!g_verify_overlap) c->mark(KZGB200_KC_MSM);
     for (size_t b0 = 0; b0 < nb; b0 += 65535) {      // gridDim.y <= 65535
         const size_t bn = std::min<size_t>(65535, nb - b0);
-        launch_msm_fixed(dim3(1, (unsigned)bn), 32, c->stream, (const uint32_t *)c->scalars.p + b0 * 64 * 8, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p + b0);
+        launch_msm_fixed(dim3(1, (unsigned)bn), 32, sa, (const uint32_t *)c->scalars.p + b0 * 64 * 8, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p + b0);
     }
     CU(cudaGetLastError());
+    if (n_large) {
+        // sum of w_row C_row over the large verdicts' unique commitments: one more bucket MSM, 40 four-bit windows over short runs
+        if ((rc = vm_row_weight_digits(sa, (const Fr *)c->v_fr.p, (const uint64_t *)(M + o_rowoff), (const uint32_t *)(M + o_rowc), (int8_t *)c->vm_rowdig.p, U))) return rc;
+        if ((rc = vm_msm_windows(sa, (const G1Aff *)c->v_aff1.p, (const int8_t *)c->vm_rowdig.p, KZG_ROW_TW, 0, KZG_ROW_TW, nullptr, KZG_VM_BUCKETS,
+                                 (const uint64_t *)(M + o_ris), (const uint64_t *)(M + o_rie), n_ri, (const uint64_t *)(M + o_rsio), n_large,
+                                 (G1 *)c->vm_scratch_r.p, (G1 *)c->vm_ws_r.p, (G1 *)c->vm_wsb_r.p))) return rc;
+        if ((rc = vm_combine(sa, (const G1 *)c->vm_wsb_r.p, KZG_ROW_TW, KZG_ROW_TW, 4, 1, (G1 *)c->vm_commsum.p, n_large))) return rc;
+    }
+    if (g_verify_overlap) { CU(cudaEventRecord(c->ev_aux_join, c->aux_stream)); CU(cudaStreamWaitEvent(c->stream, c->ev_aux_join, 0)); }
     c->mark(KZGB200_KC_VMSM);
     // v_S[seg][b]: seg 0 = sum_k r_k pi_k, seg 1 + phi2(seg 2) = sum_k r_k h_k^64 pi_k   (kzg_verify.go:32,73-83)
     if ((rc = vm_msm_windows(c->stream, (const G1Aff *)c->v_aff2.p, (const int8_t *)c->vm_digits.p, KZG_CELL_TW, 0, KZG_CELL_TW, nullptr, KZG_VM_BUCKETS,
@@ -429,17 +449,12 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
                                  (G1 *)c->vm_scratch.p, (G1 *)c->vm_ws.p, (G1 *)c->vm_wsb.p))) return rc;
         if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, l_tw, l_tw, l_dbl, 1, (G1 *)c->vm_colsum.p, n_slots))) return rc;
         if ((rc = vm_cell_columns_large(c->stream, (const G1 *)c->vm_colsum.p, (const uint32_t *)(M + o_lids), n_large, c->glv_digits, (G1 *)c->v_S.p, nb))) return rc;
-        // sum of w_row C_row over the large verdicts' unique commitments: one more bucket MSM, 40 four-bit windows over short runs
-        if ((rc = vm_row_weight_digits(c->stream, (const Fr *)c->v_fr.p, (const uint64_t *)(M + o_rowoff), (const uint32_t *)(M + o_rowc), (int8_t *)c->vm_rowdig.p, U))) return rc;
-        if ((rc = vm_msm_windows(c->stream, (const G1Aff *)c->v_aff1.p, (const int8_t *)c->vm_rowdig.p, KZG_ROW_TW, 0, KZG_ROW_TW, nullptr, KZG_VM_BUCKETS,
-                                 (const uint64_t *)(M + o_ris), (const uint64_t *)(M + o_rie), n_ri, (const uint64_t *)(M + o_rsio), n_large,
-                                 (G1 *)c->vm_scratch.p, (G1 *)c->vm_ws.p, (G1 *)c->vm_wsb.p))) return rc;
-        if ((rc = vm_combine(c->stream, (const G1 *)c->vm_wsb.p, KZG_ROW_TW, KZG_ROW_TW, 4, 1, (G1 *)c->vm_commsum.p, n_large))) return rc;
         c->launches += 11;
     }
     c->mark(KZGB200_KC_VERIFY);
     unsigned long long *d_bkey = (unsigned long long *)(M + o_bkey);
-    if (N) k_merge_status<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(d_cst, (const uint32_t *)(M + o_batch_of), d_bkey, N, 1);
+    if (N) k_merge_status<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(d_cst, (const uint32_t *)(M + o_batch_of), d_bkey, N, 1);      // the proofs' decode errors (stage 1)
+    if (N) k_merge_status<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(d_xst, (const uint32_t *)(M + o_batch_of), d_bkey, N, 1);      // the cells' NON_CANONICAL_SCALAR (stage 2)
     if (U) k_merge_status<<<(unsigned)((U + 127) / 128), 128, 0, c->stream>>>(d_ust, (const uint32_t *)(M + o_rowb), d_bkey, U, 0);
     k_status_finish<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(d_bkey, d_bst, nb);
     k_cell_prep<<<(unsigned)((nb + 31) / 32), 32, 0, c->stream>>>((const G1 *)c->v_S.p, (const G1 *)c->sums.p, (const G1Aff *)c->v_aff1.p,

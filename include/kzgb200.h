@@ -10,7 +10,9 @@
  *    cells 2048 B, commitments/proofs 48 B, scalars 32 B big-endian -- serialization.go:35-95).
  *  - Buffers may be HOST pointers (pageable or pinned; kzgb200_host_alloc gives pinned memory)
  *    or DEVICE pointers on the context's GPU; the library detects which.  Nothing is retained
- *    after the call returns.
+ *    after the call returns.  The library works on streams of its own that do NOT synchronise with the
+ *    caller's streams: device inputs must be complete (and device outputs unused) when the call is made --
+ *    synchronise the producing stream first; outputs are complete when the call returns.
  *  - Return value: KZGB200_OK or a global failure code (bad arguments, CUDA error).  Per-item
  *    outcomes are written to status[i] (int32_t), see enum kzgb200_status.  A per-item failure
  *    leaves that item's outputs zeroed.  The library never aborts and never falls back to the

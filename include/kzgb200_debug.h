@@ -58,6 +58,7 @@ int kzgb200_dbg_h2d_bandwidth(const int *devices, int n, size_t bytes_per_dev, i
  *                  2 inlined + one-reduction Y3, 3 out-of-line
  *   "optimistic": 1 (default) = VerifyCellKZGProofBatch checks a call of many small verdicts as one combined verdict first, 0 = per-verdict checks only
  *   "large_window": 4 (default) | 8 = window bits of the column MSMs of large (>= 4096-cell) verdicts; "large_item": run length of their work items (0 = default)
+ *   "verify_overlap": 1 (default) = the cell verifier's interpolation chain runs on a side stream beside the proofs' decode, 0 = one stream
  *   "rlc_item": run length of the EIP-4844 batch verdict's bucket-MSM work items (0 = default 128) */
 int kzgb200_dbg_set_tunable(const char *name, int v);
 /* dependency-free integer multiply-add microbenchmark: device-wide instructions*lanes per second.
