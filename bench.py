@@ -554,7 +554,11 @@ def roofline_for(wl, info, per, B, units, world_value_per_gpu, peaks, dev_ms_per
     pts_decode = {"verify_cells": units + B, "verify_cells_one_batch": units + B, "verify_blob_batch": 2 * B}[wl]
     # large verdicts (and the optimistic combined pass of verify_cells): 32 of the 96 windows per point
     pts_vmsm = {"verify_cells": units * (32 / 96), "verify_cells_one_batch": units * (32 / 96), "verify_blob_batch": 2 * B * (64 / 96)}[wl]
-    models = {"decode": ("k_g1_check", pts_decode * DECODE), "vmsm": ("k_vmsm_buckets (+ reduce, combine)", pts_vmsm * VMSM)}
+    # the cell verifier's "decode" span (CUDA events on the main stream) also covers the side chain that runs beside k_g1_check on the aux
+    # stream: the coset interpolation of the cells (448 Fr products of 264 IMAD per cell) -- counted, so that the fraction is of the whole span
+    INTERP = 448 * 264
+    side = units * INTERP if wl in ("verify_cells", "verify_cells_one_batch") and not per.get("fr") else 0
+    models = {"decode": ("k_g1_check" + (" + k_cell_interp (side stream)" if side else ""), pts_decode * DECODE + side), "vmsm": ("k_vmsm_buckets (+ reduce, combine)", pts_vmsm * VMSM)}
     top = max((k for k in per if k in models and per[k]), key=lambda k: per[k], default=None)
     roof["kernel_classes"] = {k: {"kernel": models[k][0], "ms": per[k], "executed_imad": models[k][1],
                                   "achieved": models[k][1] / (per[k] * 1e-3) / 1e12, "frac": models[k][1] / (per[k] * 1e-3) / peak,
