@@ -85,8 +85,7 @@ static __device__ __noinline__ void jac_add_ool(G1J *a, const G1J *b) { jac_add_
 
 // *pp = [w_128^t] *pp, t block-uniform in 1..127.  Infinity in -> infinity out (Z = 0 propagates
 // through Z_2P).  Scripts/check_tw_prog.py is the big-integer model of this routine.
-// M_ = MulCallLazy (Y3 = r (V - X3) - Y1 HHH under one Montgomery reduction, mont.cuh: mul_add_mul) or MulCallLazy2 (the doubling's
-// squarings additionally run in pairs: g1.cuh fp_sqr2_ni)
+// M_ = MulCallLazy (Y3 = r (V - X3) - Y1 HHH under one Montgomery reduction, mont.cuh: mul_add_mul)
 template <class M_> static __device__ __noinline__ void jac_mul_prog_at(G1J *pp, const uint16_t *prog);
 template <class M_ = MulCallLazy> static __device__ __forceinline__ void jac_mul_prog(G1J *pp, int t) { jac_mul_prog_at<M_>(pp, TW_PROG[t]); }
 // *pp = [k] *pp for the fixed scalar whose op list (constant memory, block-uniform) is prog
@@ -156,6 +155,119 @@ template <class M_> static __device__ __noinline__ void jac_mul_prog_at(G1J *pp,
     *pp = acc;
 }
 
+// ---- the same twiddle multiplication with every pair of independent field products in ONE out-of-line body (g1.cuh: fp_sqr2_ni,
+// fp_mul2_ni, fp_sqrmul_ni, fp_mammul_ni).  The arithmetic is identical (same products, same reductions: bit-exact); what changes is the
+// depth of the dependent chain a warp walks -- 4 calls per doubling instead of 7, 5 per mixed addition instead of 11 -- so that each warp
+// keeps about twice as many carry chains in flight.  A stage of the transform over 1024 blobs is only ~10 warps per SM of work
+// (DESIGN.md section 8), too few single-chain warps to saturate the multiply pipe; compiled for 2 CTAs per SM (255 registers: the dual
+// bodies take up to 72 argument registers) it is still ~8 dual-chain warps.
+// MEASURED (profiles/r02_rejected_dual_and_lane_split.md): 34.5 ms against 33.8 ms for the single-chain kernel at 3 CTAs per SM -- the SASS of the
+// dual bodies is interleaved as intended, but a warp gains only ~11 %, which does not pay for the third CTA.  Kept as the run-time tunable
+// "g1fft_dual" (default off); outputs are byte-identical.
+__device__ __forceinline__ void jac_dbl2(G1J &p) {            // dbl-2009-l, a = 0; no-op on infinity (Z = 0 stays 0)
+    FpPair q = fp_sqr2_ni(p.X, p.Y);
+    const Fp A = q.a, B = q.b;
+    q = fp_sqr2_ni(B, Fp::add(p.X, B));
+    const Fp C = q.a;
+    const Fp D = Fp::dbl(Fp::sub(Fp::sub(q.b, A), C));
+    const Fp E = Fp::add(Fp::dbl(A), A);
+    q = fp_sqrmul_ni(E, p.Y, p.Z);
+    p.X = Fp::sub(q.a, Fp::dbl(D));
+    p.Z = Fp::dbl(q.b);
+    p.Y = Fp::sub(fp_mul_ni(E, Fp::sub(D, p.X)), Fp::dbl(Fp::dbl(Fp::dbl(C))));
+}
+// a += (x2, y2), Jacobian + affine; a must not be the point at infinity.  hout (optional): H = Z3 / Z1
+__device__ __forceinline__ void jac_madd2(G1J &a, const Fp &x2, const Fp &y2, Fp *hout = nullptr) {
+    FpPair q = fp_sqrmul_ni(a.Z, y2, a.Z);
+    const Fp Z1Z1 = q.a;
+    q = fp_mul2_ni(x2, Z1Z1, q.b, Z1Z1);
+    const Fp H = Fp::sub(q.a, a.X), r = Fp::sub(q.b, a.Y);
+    if (hout) *hout = H;
+    if (H.is_zero()) {
+        if (r.is_zero()) { a.X = x2; a.Y = y2; a.Z = Fp::one(); jac_dbl2(a); }
+        else a.Z = Fp::zero();
+        return;
+    }
+    q = fp_sqr2_ni(H, r);
+    const Fp HH = q.a, r2 = q.b;
+    q = fp_mul2_ni(H, HH, a.X, HH);
+    const Fp HHH = q.a, V = q.b;
+    const Fp X3 = Fp::sub(Fp::sub(r2, HHH), Fp::dbl(V));
+    q = fp_mammul_ni(r, Fp::sub(V, X3), Fp::neg(a.Y), HHH, a.Z, H);
+    a.X = X3; a.Y = q.a; a.Z = q.b;
+}
+static __device__ __noinline__ void jac_mul_prog_dual_at(G1J *pp, const uint16_t *prog) {
+    Fp tx[8], ty[8], tbx[8], zr[8];
+    Fp ZC;                                     // Z_common * Z_2P
+    {
+        G1J P = *pp;
+        G1J D = P;
+        jac_dbl2(D);
+        const Fp C2 = fp_sqr_ni(D.Z);
+        FpPair q = fp_mul2_ni(C2, D.Z, P.X, C2);
+        G1J T; T.X = q.b; T.Y = fp_mul_ni(P.Y, q.a); T.Z = P.Z;      // P on the curve where 2P = (D.X, D.Y) is affine
+        tx[0] = T.X; ty[0] = T.Y;
+#pragma unroll 1
+        for (int k = 1; k < 8; ++k) {          // T_k = T_{k-1} + 2P, raw mixed addition (never degenerate: k P != +-2P); zr[k] = Z_k / Z_{k-1}
+            FpPair u = fp_sqrmul_ni(T.Z, D.Y, T.Z);
+            const Fp Z1Z1 = u.a;
+            u = fp_mul2_ni(D.X, Z1Z1, u.b, Z1Z1);
+            const Fp H = Fp::sub(u.a, T.X), r = Fp::sub(u.b, T.Y);
+            u = fp_sqr2_ni(H, r);
+            const Fp HH = u.a, r2 = u.b;
+            u = fp_mul2_ni(H, HH, T.X, HH);
+            const Fp HHH = u.a, V = u.b;
+            const Fp X3 = Fp::sub(Fp::sub(r2, HHH), Fp::dbl(V));
+            u = fp_mammul_ni(r, Fp::sub(V, X3), Fp::neg(T.Y), HHH, T.Z, H);
+            T.X = X3; T.Y = u.a; T.Z = u.b;
+            tx[k] = T.X; ty[k] = T.Y; zr[k] = H;
+        }
+        ZC = fp_mul_ni(T.Z, D.Z);
+    }
+    {
+        Fp beta;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) beta.v[i] = FP_BETA[i];
+        tbx[7] = fp_mul_ni(tx[7], beta);
+        Fp s = zr[7];                          // s = Z_7 / Z_k
+#pragma unroll 1
+        for (int k = 6; k >= 0; --k) {
+            FpPair u = fp_sqrmul_ni(s, s, zr[k ? k : 1]);          // s^2 and the next s (unused after k = 0)
+            const Fp s2 = u.a, s_next = u.b;
+            u = fp_mul2_ni(tx[k], s2, s2, s);
+            const Fp x = u.a;
+            tx[k] = x;
+            u = fp_mul2_ni(x, beta, ty[k], u.b);
+            tbx[k] = u.a; ty[k] = u.b;
+            s = s_next;
+        }
+    }
+    const int n_ops = prog[0] & 255, trailing = prog[0] >> 8;
+    G1J acc;
+    {
+        uint32_t op = prog[1];
+        int idx = (op >> 8) & 7;
+        acc.X = (op & 0x1000u) ? tbx[idx] : tx[idx];
+        acc.Y = (op & 0x0800u) ? Fp::neg(ty[idx]) : ty[idx];
+        acc.Z = Fp::one();
+    }
+#pragma unroll 1
+    for (int k = 2; k <= n_ops; ++k) {
+        uint32_t op = prog[k];
+#pragma unroll 1
+        for (int d = op & 255; d > 0; --d) jac_dbl2(acc);
+        int idx = (op >> 8) & 7;
+        Fp ex = (op & 0x1000u) ? tbx[idx] : tx[idx];
+        Fp ey = ty[idx];
+        if (op & 0x0800u) ey = Fp::neg(ey);
+        jac_madd2(acc, ex, ey);
+    }
+#pragma unroll 1
+    for (int d = trailing; d > 0; --d) jac_dbl2(acc);
+    acc.Z = fp_mul_ni(acc.Z, ZC);
+    *pp = acc;
+}
+
 // butterfly number of the y-th block of a stage: non-trivial twiddles first
 __device__ __forceinline__ int g1fft_butterfly(int y, int log_half) {
     const int half = 1 << log_half;
@@ -171,8 +283,8 @@ __device__ __forceinline__ int g1fft_butterfly(int y, int log_half) {
 // SRC_XYZZ: the stage reads the MSM sums (XYZZ) instead of the working set.  DST_XYZZ: it writes
 // XYZZ points for k_finalize_g1.  ONLY_SUM: x - y is not needed (inverse transform, last stage,
 // upper half discarded: toeplitz.go:124).  UPPER_ZERO: y is the zero padding (fk20.go:82-85).
-template <bool DIT, bool INVERSE, bool SRC_XYZZ, bool DST_XYZZ, bool ONLY_SUM, bool UPPER_ZERO, class M_>
-static __global__ void __launch_bounds__(KZG_G1FFT_TPB, 3) k_g1fft_stage(const G1 *__restrict__ src_xyzz, G1J *__restrict__ work, G1 *__restrict__ dst_xyzz,
+template <bool DIT, bool INVERSE, bool SRC_XYZZ, bool DST_XYZZ, bool ONLY_SUM, bool UPPER_ZERO, bool DUAL>
+static __global__ void __launch_bounds__(KZG_G1FFT_TPB, DUAL ? 2 : 3) k_g1fft_stage(const G1 *__restrict__ src_xyzz, G1J *__restrict__ work, G1 *__restrict__ dst_xyzz,
                                                                       const int32_t *__restrict__ status, int nblobs, int log_half) {
     const int blob = blockIdx.x * KZG_G1FFT_TPB + threadIdx.x;
     if (blob >= nblobs || status[blob] != ST_OK) return;
@@ -188,7 +300,7 @@ static __global__ void __launch_bounds__(KZG_G1FFT_TPB, 3) k_g1fft_stage(const G
         else y = ld_jac(w1);
     }
     if (DIT) {
-        if (t) jac_mul_prog<M_>(&y, t);
+        if (t) { if (DUAL) jac_mul_prog_dual_at(&y, TW_PROG[t]); else jac_mul_prog<MulCallLazy>(&y, t); }
         if (SRC_XYZZ) { G1 q = src_xyzz[(size_t)blob * 128 + i0]; x = jac_from_xyzz(q); }
         else x = ld_jac(w0);
         G1J s = x;
@@ -205,7 +317,7 @@ static __global__ void __launch_bounds__(KZG_G1FFT_TPB, 3) k_g1fft_stage(const G
             y.Y = Fp::neg(y.Y); jac_add_ool(&x, &y);
             y = x; x = s;
         }
-        if (t) jac_mul_prog<M_>(&y, t);
+        if (t) { if (DUAL) jac_mul_prog_dual_at(&y, TW_PROG[t]); else jac_mul_prog<MulCallLazy>(&y, t); }
     }
     if (DST_XYZZ) {
         dst_xyzz[(size_t)blob * 128 + i0] = jac_to_xyzz(x);

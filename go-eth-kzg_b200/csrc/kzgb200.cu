@@ -801,8 +801,8 @@ static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr 
             G1 *dst = pxyzz + off * 128;
             const int32_t *stt = d_status + off;
             const dim3 grid((unsigned)((nb + KZG_G1FFT_TPB - 1) / KZG_G1FFT_TPB), 64);
-#define KZG_STAGE(A, B, C, D, E, F, ...) do { if (g_g1fft_dual) k_g1fft_stage<A, B, C, D, E, F, MulCallLazy2><<<grid, KZG_G1FFT_TPB, 0, s>>>(__VA_ARGS__); \
-                                                else k_g1fft_stage<A, B, C, D, E, F, MulCallLazy><<<grid, KZG_G1FFT_TPB, 0, s>>>(__VA_ARGS__); } while (0)
+#define KZG_STAGE(A, B, C, D, E, F, ...) do { if (g_g1fft_dual) k_g1fft_stage<A, B, C, D, E, F, true><<<grid, KZG_G1FFT_TPB, 0, s>>>(__VA_ARGS__); \
+                                                else k_g1fft_stage<A, B, C, D, E, F, false><<<grid, KZG_G1FFT_TPB, 0, s>>>(__VA_ARGS__); } while (0)
             KZG_STAGE(true, true, true, false, false, false, src, work, nullptr, stt, nb, 0);
             for (int lh = 1; lh < 6; ++lh) KZG_STAGE(true, true, false, false, false, false, nullptr, work, nullptr, stt, nb, lh);
             KZG_STAGE(true, true, false, false, true, false, nullptr, work, nullptr, stt, nb, 6);

@@ -275,7 +275,7 @@ static __global__ void __launch_bounds__(128, (V & 8) ? 4 : 3) k_msm_fixed(const
 #endif
 inline int g_msm_variant_override = -1;       // kzgb200_dbg_set_tunable("msm_variant", v) (experiments: one context, every variant)
 inline int g_vmsm_policy = 1;                 // kzgb200_dbg_set_tunable("vmsm_policy", 0..3): see k_vmsm_buckets (vmsm.cuh)
-inline int g_g1fft_dual = 0;                  // kzgb200_dbg_set_tunable("g1fft_dual", 0 | 1): paired squarings (MulCallLazy2) in the G1 FFT stage kernel; measured SLOWER (33.7 -> 35.0 ms), off
+inline int g_g1fft_dual = 0;                  // kzgb200_dbg_set_tunable("g1fft_dual", 0 | 1): G1 FFT stage kernel with every pair of independent field products in one dual body, 2 CTAs/SM (g1fft.cuh: jac_mul_prog_dual_at); measured SLOWER (33.8 -> 34.5 ms), off
 inline int g_decode_dual = 1;                 // kzgb200_dbg_set_tunable("decode_dual", 0 | 1): the same in the subgroup test of k_g1_check (vm_g1_check); measured 29.7 -> 29.4 ms per 528 k points
 inline int g_large_window = 4;                // kzgb200_dbg_set_tunable("large_window", 4 | 8): window bits of the large verdicts' column MSMs (kzgb200_verify.cu)
 inline int g_large_item = 0;                  // kzgb200_dbg_set_tunable("large_item", n): run length of their work items; 0 = default (128 / 512)

@@ -50,8 +50,8 @@ int kzgb200_dbg_h2d_bandwidth(const int *devices, int n, size_t bytes_per_dev, i
  *                  Y3, bit 3: accumulator in shared memory + 4 CTAs/SM; -1 = default (or the KZGB200_MSM_VARIANT environment variable)
  *   "fk20_lanes":  lanes per 64-point FK20 group for full batches (4, 8 or 16; 0 = default)
  *   "g1fft_split": sub-batches (streams) of the staged G1 FFT, 0 = context default
- *   "g1fft_dual", "decode_dual": 1 = the squarings of a Jacobian doubling run in PAIRS inside one out-of-line body (more ILP per warp)
- *                  in the G1 FFT stage kernel / in the subgroup test of the decode kernel
+ *   "g1fft_dual": 1 = the G1 FFT stage kernel runs every pair of independent field products of a doubling / addition inside one out-of-line
+ *                  body at 2 CTAs per SM (default 0: measured slower); "decode_dual": 1 (default) = paired squarings in the subgroup test
  *   "pairing_lanes": lanes per pairing check: 32 (one check per warp, latency form), 8 (throughput form), 0 = by batch size (default)
  *   "fiat_shamir": SHA-256 of the Fiat-Shamir challenge: 2 = two warps per 32 blobs (message schedule on a producer warp; default), 1 = one thread per blob
  *   "vmsm_policy": field products of the verifiers' bucket accumulation: 0 inlined, 1 out-of-line + one-reduction Y3 (default),
