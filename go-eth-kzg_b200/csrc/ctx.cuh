@@ -46,7 +46,7 @@ static const int N_BLOB = 4096;
 namespace kzg {
 // decompress + (optional) subgroup check of n compressed points; first error per status slot wins.
 // out may be null (validation only: prove.go:56-60 discards the point).
-template <class M_ = MulCall> static __global__ void k_g1_check(const uint8_t *__restrict__ in48, G1Aff *__restrict__ out, int32_t *__restrict__ status, size_t n, int per_status, int subgroup) {
+template <class M_ = MulCall, int MINB = 4> static __global__ void __launch_bounds__(64, MINB) k_g1_check(const uint8_t *__restrict__ in48, G1Aff *__restrict__ out, int32_t *__restrict__ status, size_t n, int per_status, int subgroup) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     G1Aff a;

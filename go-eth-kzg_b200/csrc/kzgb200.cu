@@ -330,6 +330,11 @@ int kzgb200_dbg_set_tunable(const char *name, int v) {
         kzg::g_verify_overlap = v;
         return 0;
     }
+    if (!strcmp(name, "decode_minb")) {
+        if (v != 4 && v != 6 && v != 8) return set_err(KZGB200_ERR_ARGS, "decode_minb must be 4, 6 or 8");
+        kzg::g_decode_minb = v;
+        return 0;
+    }
     if (!strcmp(name, "rlc_item")) {
         if (v < 0 || v > 4096) return set_err(KZGB200_ERR_ARGS, "rlc_item out of range");
         kzg::g_rlc_item = v;
@@ -715,7 +720,7 @@ static int open_common(kzg_lane *c, const uint8_t *blobs, const uint8_t *z32, co
                 CU(cudaEventRecord(c->ev_piece[side], sp));
                 CU(cudaStreamWaitEvent(sv, c->ev_piece[side], 0));
                 CU(cudaMemsetAsync(d_cst, 0, pm * sizeof(int32_t), sv));
-                k_g1_check<MulCall><<<gb, 64, 0, sv>>>((const uint8_t *)d_aux + po * 48, nullptr, d_cst, pm, 1, 1);
+                k_g1_check<MulCall, 4><<<gb, 64, 0, sv>>>((const uint8_t *)d_aux + po * 48, nullptr, d_cst, pm, 1, 1);
                 CU(cudaEventRecord(c->ev_join[side], sv));
                 launch_fiat_shamir(sp, pb, (const uint8_t *)d_aux + po * 48, zl, pm);
                 c->launches += 2;

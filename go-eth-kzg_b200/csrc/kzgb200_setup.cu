@@ -147,7 +147,7 @@ extern "C" int kzgb200_check_trusted_setup(int device, const uint8_t *g1_lagrang
     if (n_lagrange) CUS(cudaMemcpy(d_in, g1_lagrange, n_lagrange * 48, cudaMemcpyHostToDevice));
     if (n_monomial) CUS(cudaMemcpy(d_in + n_lagrange * 48, g1_monomial, n_monomial * 48, cudaMemcpyHostToDevice));
     if (n_g2) CUS(cudaMemcpy(d_in + n1 * 48, g2_monomial, n_g2 * 96, cudaMemcpyHostToDevice));
-    if (n1) k_g1_check<MulCall><<<(unsigned)((n1 + 63) / 64), 64>>>(d_in, nullptr, d_st, n1, 1, 1);
+    if (n1) k_g1_check<MulCall, 4><<<(unsigned)((n1 + 63) / 64), 64>>>(d_in, nullptr, d_st, n1, 1, 1);
     if (n_g2) k_g2_check<<<(unsigned)((n_g2 + 31) / 32), 32>>>(d_in + n1 * 48, d_st + n1, n_g2, 1);
     CUS(cudaGetLastError());
     std::vector<int32_t> st(n);
@@ -171,7 +171,7 @@ extern "C" int lane_check_g1_points(kzg_lane *c, const uint8_t *points48, size_t
     if (!st_dev && (rc = c->status.ensure(n * sizeof(int32_t)))) return rc;
     int32_t *d_st = st_dev ? status : (int32_t *)c->status.p;
     CUS(cudaMemsetAsync(d_st, 0, n * sizeof(int32_t), c->stream));
-    k_g1_check<MulCall><<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>((const uint8_t *)d_in, nullptr, d_st, n, 1, 1);
+    k_g1_check<MulCall, 4><<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>((const uint8_t *)d_in, nullptr, d_st, n, 1, 1);
     c->launches += 1;
     CUS(cudaGetLastError());
     if (!st_dev) CUS(cudaMemcpyAsync(status, d_st, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));

@@ -10,8 +10,13 @@
 
 int vm_g1_check(cudaStream_t st, const uint8_t *in48, G1Aff *out, int32_t *status, size_t n, int per_status, int subgroup) {
     if (!n) return 0;
-    if (g_decode_dual) k_g1_check<MulCall2><<<(unsigned)((n + 63) / 64), 64, 0, st>>>(in48, out, status, n, per_status, subgroup);
-    else k_g1_check<MulCall><<<(unsigned)((n + 63) / 64), 64, 0, st>>>(in48, out, status, n, per_status, subgroup);
+    // tunables "decode_dual" (paired squarings in the subgroup test) and "decode_minb" (resident CTAs of 64 threads per SM the kernel is compiled
+    // for: 4 -> 255 registers, 6 -> 168, 8 -> 128)
+    const unsigned grid = (unsigned)((n + 63) / 64);
+#define KZG_DECODE(M, B) k_g1_check<M, B><<<grid, 64, 0, st>>>(in48, out, status, n, per_status, subgroup)
+    if (g_decode_dual) { if (g_decode_minb == 8) KZG_DECODE(MulCall2, 8); else if (g_decode_minb == 6) KZG_DECODE(MulCall2, 6); else KZG_DECODE(MulCall2, 4); }
+    else { if (g_decode_minb == 8) KZG_DECODE(MulCall, 8); else if (g_decode_minb == 6) KZG_DECODE(MulCall, 6); else KZG_DECODE(MulCall, 4); }
+#undef KZG_DECODE
     CUL(cudaGetLastError());
     return 0;
 }
