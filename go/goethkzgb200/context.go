@@ -407,6 +407,8 @@ func (c *Context) ComputeCellsAndKZGProofsBatch(blobs []*Blob) (cells, proofs []
 }
 
 // VerifyCellKZGProofBatches returns one verdict per batch: batch b covers items [offsets[b], offsets[b+1]).
+// (The engine checks a call of many small batches as one combined random linear combination first and falls back to the
+// per-batch checks only if that does not pass; the results are the same either way.  KZGB200_OPTIMISTIC=0 disables it.)
 func (c *Context) VerifyCellKZGProofBatches(commitments []KZGCommitment, cellIndices []uint64, cells []*Cell, proofs []KZGProof, offsets []uint64) ([]error, error) {
 	n := len(cells)
 	if len(commitments) != n || len(cellIndices) != n || len(proofs) != n || len(offsets) == 0 {
