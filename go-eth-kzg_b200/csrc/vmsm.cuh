@@ -248,7 +248,8 @@ static __global__ void __launch_bounds__(128) k_vmsm_buckets(const G1Aff *__rest
         for (int j = 0; j < NB; ++j) {
             uint4 *q = reinterpret_cast<uint4 *>(B + j);
 #pragma unroll
-            for (int i = 6; i < 12; ++i) q[i] = z;          // ZZ = ZZZ = 0: infinity
+            for (int i = 0; i < 12; ++i) q[i] = z;          // ZZ = ZZZ = 0: infinity (X, Y cleared too: the accumulation loads whole buckets, and
+                                                            // compute-sanitizer --tool initcheck flags the read of never-written coordinates)
         }
     }
     const uint64_t s = item_start[blockIdx.x], e = item_end[blockIdx.x];
