@@ -318,7 +318,11 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
         h_cm = h_cm_copy.data();
     }
     // (pure host code in cell_plan.hpp; the GPU is already decoding the proofs meanwhile)
-    const uint64_t ITEM = 512;
+    // work items = runs of <= ITEM cells of one verdict (interpolation: one CTA per item; small verdicts' bucket MSM: 96 window-threads per item).
+    // A big call is pipe-bound and wants long runs (the bucket reduction costs 16 full additions per item and window); a small call is ONE
+    // thread's latency per item -- 128 cells as one item are 128 dependent additions (0.9 ms) -- and wants many short ones: aim at ~30 k tasks.
+    uint64_t ITEM = 512;
+    while (ITEM > 16 && (N / ITEM) * 96 < 30000) ITEM >>= 1;
     // large verdicts: per (verdict, column) bucket MSM of the 126-bit coefficients.  Default: the SAME signed 4-bit digits as the small
     // verdicts (windows 0..31 of the digit rows), runs of 128 cells -> 32 x N/128 tasks of 128 + 16 additions, one full warp per item.
     // (Round 1 used 16 signed 8-bit windows over runs of 512: 16 x N/512 half-warp tasks of 512 + 256 additions -- 18.3 ms per
@@ -397,6 +401,7 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
     if ((rc = c->v_S.ensure(KZG_VM_SEGS * nb * sizeof(G1)))) return rc;
     if ((rc = c->v_pa.ensure(nb * sizeof(G1)))) return rc;
     if ((rc = c->v_pb.ensure(nb * sizeof(G1)))) return rc;
+    if ((rc = c->v_W.ensure(nb * sizeof(G1)))) return rc;
     if ((rc = c->v_partial.ensure(std::max<size_t>(n_items, 1) * 64 * sizeof(Fr)))) return rc;
     if ((rc = c->scalars.ensure(nb * 64 * 32))) return rc;
     if ((rc = c->sums.ensure(nb * sizeof(G1)))) return rc;
@@ -414,6 +419,7 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
     if (N) {
         if ((rc = vm_cell_coeff_digits(sa, seed_dev, (const uint32_t *)(M + o_batch_of), (const uint64_t *)(M + o_bstart), (const uint64_t *)(M + o_idx),
                                        c->roots, (Fr *)c->v_fr.p, (int8_t *)c->vm_digits.p, (n_large && !l4) ? (int8_t *)c->vm_digits256.p : nullptr, N))) return rc;
+        if (g_verify_overlap) CU(cudaEventRecord(c->ev_fork, sa));                  // the digits are ready: the bucket MSM of the main stream needs nothing else of this chain
         if (d_cells == c->in_bytes.p) CU(cudaStreamWaitEvent(sa, c->ev1, 0));     // the cells have landed
         if (!g_verify_overlap) c->mark(KZGB200_KC_FR);
         k_cell_interp<<<(unsigned)n_items, 256, 0, sa>>>((const uint8_t *)d_cells, (const uint64_t *)(M + o_idx), (const Fr *)c->v_fr.p, (const uint64_t *)(M + o_is),
@@ -427,6 +433,10 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
         launch_msm_fixed(dim3(1, (unsigned)bn), 32, sa, (const uint32_t *)c->scalars.p + b0 * 64 * 8, c->mono64_tab, 64, 1, 32, nullptr, (G1 *)c->sums.p + b0);
     }
     CU(cudaGetLastError());
+    // sum of w_row C_row of every small verdict: one scalar multiplication per unique commitment, one thread per verdict (latency, hidden here)
+    k_cell_row_weights<<<(unsigned)((nb + 31) / 32), 32, 0, sa>>>((const G1Aff *)c->v_aff1.p, (const uint64_t *)(M + o_rowoff), (const uint64_t *)(M + o_browoff),
+                                                                  (const uint32_t *)(M + o_rowc), (const Fr *)c->v_fr.p, d_bst, n_large ? (const int32_t *)(M + o_lof) : nullptr,
+                                                                  (G1 *)c->v_W.p, nb);
     if (n_large) {
         // sum of w_row C_row over the large verdicts' unique commitments: one more bucket MSM, 40 four-bit windows over short runs
         if ((rc = vm_row_weight_digits(sa, (const Fr *)c->v_fr.p, (const uint64_t *)(M + o_rowoff), (const uint32_t *)(M + o_rowc), (int8_t *)c->vm_rowdig.p, U))) return rc;
@@ -435,7 +445,7 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
                                  (G1 *)c->vm_scratch_r.p, (G1 *)c->vm_ws_r.p, (G1 *)c->vm_wsb_r.p))) return rc;
         if ((rc = vm_combine(sa, (const G1 *)c->vm_wsb_r.p, KZG_ROW_TW, KZG_ROW_TW, 4, 1, (G1 *)c->vm_commsum.p, n_large))) return rc;
     }
-    if (g_verify_overlap) { CU(cudaEventRecord(c->ev_aux_join, c->aux_stream)); CU(cudaStreamWaitEvent(c->stream, c->ev_aux_join, 0)); }
+    if (g_verify_overlap) { CU(cudaEventRecord(c->ev_aux_join, c->aux_stream)); if (N) CU(cudaStreamWaitEvent(c->stream, c->ev_fork, 0)); }
     c->mark(KZGB200_KC_VMSM);
     // v_S[seg][b]: seg 0 = sum_k r_k pi_k, seg 1 + phi2(seg 2) = sum_k r_k h_k^64 pi_k   (kzg_verify.go:32,73-83)
     if ((rc = vm_msm_windows(c->stream, (const G1Aff *)c->v_aff2.p, (const int8_t *)c->vm_digits.p, KZG_CELL_TW, 0, KZG_CELL_TW, nullptr, KZG_VM_BUCKETS,
@@ -451,15 +461,15 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
         if ((rc = vm_cell_columns_large(c->stream, (const G1 *)c->vm_colsum.p, (const uint32_t *)(M + o_lids), n_large, c->glv_digits, (G1 *)c->v_S.p, nb))) return rc;
         c->launches += 11;
     }
+    if (g_verify_overlap) CU(cudaStreamWaitEvent(c->stream, c->ev_aux_join, 0));      // the rest of the side chain: statuses, [sum r I(s)]G, commitment weights
     c->mark(KZGB200_KC_VERIFY);
     unsigned long long *d_bkey = (unsigned long long *)(M + o_bkey);
     if (N) k_merge_status<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(d_cst, (const uint32_t *)(M + o_batch_of), d_bkey, N, 1);      // the proofs' decode errors (stage 1)
     if (N) k_merge_status<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(d_xst, (const uint32_t *)(M + o_batch_of), d_bkey, N, 1);      // the cells' NON_CANONICAL_SCALAR (stage 2)
     if (U) k_merge_status<<<(unsigned)((U + 127) / 128), 128, 0, c->stream>>>(d_ust, (const uint32_t *)(M + o_rowb), d_bkey, U, 0);
     k_status_finish<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(d_bkey, d_bst, nb);
-    k_cell_prep<<<(unsigned)((nb + 31) / 32), 32, 0, c->stream>>>((const G1 *)c->v_S.p, (const G1 *)c->sums.p, (const G1Aff *)c->v_aff1.p,
-                                                                   (const uint64_t *)(M + o_rowoff), (const uint64_t *)(M + o_browoff), (const uint32_t *)(M + o_rowc),
-                                                                   (const Fr *)c->v_fr.p, d_bst, n_large ? (const int32_t *)(M + o_lof) : nullptr, (const G1 *)c->vm_commsum.p, (G1 *)c->v_pa.p, (G1 *)c->v_pb.p, nb);
+    k_cell_prep<<<(unsigned)((nb + 31) / 32), 32, 0, c->stream>>>((const G1 *)c->v_S.p, (const G1 *)c->sums.p, (const G1 *)c->v_W.p,
+                                                                   d_bst, n_large ? (const int32_t *)(M + o_lof) : nullptr, (const G1 *)c->vm_commsum.p, (G1 *)c->v_pa.p, (G1 *)c->v_pb.p, nb);
     c->mark(KZGB200_KC_PAIRING);
     if ((rc = vm_pairing_check(c->stream, c->pairing, (const G1 *)c->v_pa.p, 2, (const G1 *)c->v_pb.p, 0, d_bst, d_res, nb))) return rc;
     c->launches += 10;   // + bucket reduce and item reduce inside vm_msm_windows

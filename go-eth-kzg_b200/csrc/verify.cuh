@@ -240,11 +240,38 @@ static __global__ void k_cell_interp_reduce(const Fr *__restrict__ partial, cons
     Fr p = fr_from_mont(tot);
     for (int q = 0; q < 8; ++q) interp[((size_t)b * 64 + j) * 8 + q] = p.v[q];
 }
-// per batch: final combination; PA[b], PB[b] feed k_pairing_lanes (qa = 2, qb = 0).  rows: CSR of the batch's cells grouped by unique commitment.
+// per (small) verdict: comm[b] = sum over its unique commitments of [w_row] C_row, w_row = sum of r_k over the row's cells (kzg_verify.go:37-45).
+// One thread per verdict, a ~134-bit scalar multiplication per row: pure latency (1.9 ms), which is why it is a kernel of its own on the
+// verifier's side chain instead of a step of k_cell_prep after the bucket MSM.  host_status: the statuses known before any decoding (cell
+// index range); rows whose commitment failed to decode are the point at infinity and contribute nothing (the verdict is an error anyway).
+static __global__ void __launch_bounds__(32) k_cell_row_weights(const G1Aff *__restrict__ uniq_commit, const uint64_t *__restrict__ row_off,
+                                                           const uint64_t *__restrict__ batch_row_off, const uint32_t *__restrict__ row_cells,
+                                                           const Fr *__restrict__ rpow, const int32_t *__restrict__ host_status,
+                                                           const int32_t *__restrict__ large_of /*may be null*/, G1 *__restrict__ comm, size_t n_batches) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_batches) return;
+    G1 comms = G1::infinity();
+    if (host_status[b] == ST_OK && !(large_of && large_of[b] >= 0)) {
+        for (uint64_t row = batch_row_off[b]; row < batch_row_off[b + 1]; ++row) {
+            Fr wsum = Fr::zero();
+            for (uint64_t q = row_off[row]; q < row_off[row + 1]; ++q) wsum = Fr::add(wsum, rpow[row_cells[q]]);
+            Fr wp = fr_from_mont(wsum);
+            G1Aff ca = uniq_commit[row];
+            if (ca.is_inf()) continue;
+            G1 C = G1::from_affine(ca), t;
+            int top = 0;                              // the weight is a sum of 126-bit coefficients: ~134 bits for 128 cells
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (wp.v[q]) top = q;
+            g1_mul_scalar(&t, &C, wp.v, 8 * (top + 1));
+            g1_add(comms, t);
+        }
+    }
+    comm[b] = comms;
+}
+// per batch: final combination; PA[b], PB[b] feed k_pairing_lanes (qa = 2, qb = 0).  comm_small[b]: k_cell_row_weights; comm_large[lb]: the bucket MSM
+// over a large verdict's commitments.
 static __global__ void __launch_bounds__(32) k_cell_prep(const G1 *__restrict__ comb /*[seg][batch]: seg 0 = sum r pi, 1 and 2 = GLV halves of sum r h^64 pi*/, const G1 *__restrict__ interp_commit,
-                                                    const G1Aff *__restrict__ uniq_commit, const uint64_t *__restrict__ row_off,
-                                                    const uint64_t *__restrict__ batch_row_off, const uint32_t *__restrict__ row_cells,
-                                                    const Fr *__restrict__ rpow, const int32_t *__restrict__ batch_status,
+                                                    const G1 *__restrict__ comm_small, const int32_t *__restrict__ batch_status,
                                                     const int32_t *__restrict__ large_of /*may be null*/, const G1 *__restrict__ comm_large,
                                                     G1 *__restrict__ PA, G1 *__restrict__ PB, size_t n_batches) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -252,20 +279,8 @@ static __global__ void __launch_bounds__(32) k_cell_prep(const G1 *__restrict__ 
     if (batch_status[b] != ST_OK) { PA[b] = G1::infinity(); PB[b] = G1::infinity(); return; }
     G1 sumS = comb[b], sumW = comb[n_batches + b];
     g1_add(sumW, g1_phi2(comb[2 * n_batches + b]));
-    G1 comms = G1::infinity();
     const int lb = large_of ? large_of[b] : -1;
-    if (lb >= 0) comms = comm_large[lb];          // large verdict: sum of w_row C_row came from a bucket MSM over its commitments
-    else for (uint64_t row = batch_row_off[b]; row < batch_row_off[b + 1]; ++row) {
-        Fr wsum = Fr::zero();
-        for (uint64_t q = row_off[row]; q < row_off[row + 1]; ++q) wsum = Fr::add(wsum, rpow[row_cells[q]]);
-        Fr wp = fr_from_mont(wsum);
-        G1 C = G1::from_affine(uniq_commit[row]), t;
-        int top = 0;                              // the weight is a sum of 126-bit coefficients: ~134 bits for 128 cells
-#pragma unroll
-        for (int q = 0; q < 8; ++q) if (wp.v[q]) top = q;
-        g1_mul_scalar(&t, &C, wp.v, 8 * (top + 1));
-        g1_add(comms, t);
-    }
+    G1 comms = lb >= 0 ? comm_large[lb] : comm_small[b];
     G1 I = interp_commit[b];
     I.neg_inplace();
     g1_add(comms, I);
