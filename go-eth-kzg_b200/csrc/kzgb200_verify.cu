@@ -482,11 +482,18 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
 }
 
 // unit-test hook (host only, no GPU): the plan of plan_cell_batches as JSON text (thread-local buffer), or NULL on malformed offsets
+const char *kzgb200_dbg_plan_cell_batches_json_l(const uint8_t *commitments48, const uint64_t *cell_indices, size_t N, const uint64_t *batch_offsets, size_t nb,
+                                                 uint64_t item, uint64_t large, uint64_t row_item, uint64_t l_item);
 const char *kzgb200_dbg_plan_cell_batches_json(const uint8_t *commitments48, const uint64_t *cell_indices, size_t N, const uint64_t *batch_offsets, size_t nb,
                                                uint64_t item, uint64_t large, uint64_t row_item) {
+    return kzgb200_dbg_plan_cell_batches_json_l(commitments48, cell_indices, N, batch_offsets, nb, item, large, row_item, 0);
+}
+// the same with the run length of the large verdicts' column items given separately (0 = item)
+const char *kzgb200_dbg_plan_cell_batches_json_l(const uint8_t *commitments48, const uint64_t *cell_indices, size_t N, const uint64_t *batch_offsets, size_t nb,
+                                                 uint64_t item, uint64_t large, uint64_t row_item, uint64_t l_item) {
     static thread_local std::string out;
     CellPlan P;
-    if (!plan_cell_batches(commitments48, cell_indices, N, batch_offsets, nb, item, large, row_item, KZGB200_BAD_CELL_INDEX, P)) return nullptr;
+    if (!plan_cell_batches(commitments48, cell_indices, N, batch_offsets, nb, item, large, row_item, KZGB200_BAD_CELL_INDEX, P, l_item)) return nullptr;
     out.clear();
     auto arr = [&](const char *name, auto &v, bool last = false) {
         out += "\""; out += name; out += "\": [";

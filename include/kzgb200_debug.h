@@ -36,6 +36,9 @@ int kzgb200_dbg_g2_selftest(const uint8_t *in96, int *mask);
  * lists, as JSON text in a thread-local buffer; NULL if batch_offsets is not monotone / out of range */
 const char *kzgb200_dbg_plan_cell_batches_json(const uint8_t *commitments48, const uint64_t *cell_indices, size_t n_cells,
                                                const uint64_t *batch_offsets, size_t n_batches, uint64_t item, uint64_t large, uint64_t row_item);
+/* the same with the run length of the large verdicts' column work items given separately (0 = item) */
+const char *kzgb200_dbg_plan_cell_batches_json_l(const uint8_t *commitments48, const uint64_t *cell_indices, size_t n_cells,
+                                                 const uint64_t *batch_offsets, size_t n_batches, uint64_t item, uint64_t large, uint64_t row_item, uint64_t l_item);
 /* host-side sharding of a batched call over the GPUs of a context (csrc/shard_plan.hpp; no GPU involved), as JSON text in a
  * thread-local buffer: "units" = contiguous ranges of n_units independent units over n_dev devices with at least min_per_dev
  * each; "verdicts" = ranges of verdicts balanced by cell count (batch_offsets may be NULL); "merged" = the three-way merge of

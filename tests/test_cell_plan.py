@@ -9,15 +9,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _lib():
     L = ctypes.CDLL(os.path.join(ROOT, "go-eth-kzg_b200", "libkzgb200.so"))
     L.kzgb200_dbg_plan_cell_batches_json.restype = ctypes.c_char_p
+    L.kzgb200_dbg_plan_cell_batches_json_l.restype = ctypes.c_char_p
     return L
 
 
-def plan(commitments, idx, offs, item=512, large=4096, row_item=64):
+def plan(commitments, idx, offs, item=512, large=4096, row_item=64, l_item=None):
     n, nb = len(commitments), len(offs) - 1
     a = (ctypes.c_uint64 * max(n, 1))(*idx)
     o = (ctypes.c_uint64 * (nb + 1))(*offs)
     u64 = ctypes.c_uint64
-    r = _lib().kzgb200_dbg_plan_cell_batches_json(b"".join(commitments), a, ctypes.c_size_t(n), o, ctypes.c_size_t(nb), u64(item), u64(large), u64(row_item))
+    if l_item is None:
+        r = _lib().kzgb200_dbg_plan_cell_batches_json(b"".join(commitments), a, ctypes.c_size_t(n), o, ctypes.c_size_t(nb), u64(item), u64(large), u64(row_item))
+    else:
+        r = _lib().kzgb200_dbg_plan_cell_batches_json_l(b"".join(commitments), a, ctypes.c_size_t(n), o, ctypes.c_size_t(nb), u64(item), u64(large), u64(row_item), u64(l_item))
     return None if r is None else json.loads(r)
 
 
@@ -56,8 +60,9 @@ def model(commitments, idx, offs, item, large, row_item):
     return P
 
 
-def check(commitments, idx, offs, item=512, large=4096, row_item=64):
-    got, exp = plan(commitments, idx, offs, item, large, row_item), model(commitments, idx, offs, item, large, row_item)
+def check(commitments, idx, offs, item=512, large=4096, row_item=64, l_item=None):
+    got, exp = plan(commitments, idx, offs, item, large, row_item, l_item), model(commitments, idx, offs, item, large, row_item)
+    l_run = l_item or item                                             # run length of the large verdicts' column items
     assert got is not None
     for k in ("bstatus", "batch_start", "batch_row_off", "batch_item_off", "vs_batch_item_off", "large_of", "large_ids", "batch_of", "row_batch"):
         assert got[k] == exp[k], k
@@ -74,7 +79,7 @@ def check(commitments, idx, offs, item=512, large=4096, row_item=64):
             cells = []
             for it in its:
                 s, e = got["l_item_start"][it], got["l_item_end"][it]
-                assert 0 < e - s <= item
+                assert 0 < e - s <= l_run
                 cells += got["l_order"][s:e]
             assert cells == g, (lb, q)
             slot += 1
@@ -104,6 +109,9 @@ def test_plan_matches_model():
     i3 = [rng.randrange(128) for _ in range(n)]
     got = check(c3, i3, [0, 50, 900, 1000], item=16, large=200, row_item=2)
     assert got["large_of"] == [-1, 0, -1]
+    # the engine's shape: long interpolation runs, short column runs for the large verdicts (kzgb200_verify.cu: ITEM = 512, L_ITEM = 128)
+    got = check(c3, i3, [0, 50, 900, 1000], item=64, large=200, row_item=2, l_item=4)
+    assert max(e - s for s, e in zip(got["l_item_start"], got["l_item_end"])) == 4
     # nothing at all, and malformed offsets
     check([], [], [0, 0])
     assert plan([cm[0]] * 4, [0, 1, 2, 3], [0, 5]) is None
