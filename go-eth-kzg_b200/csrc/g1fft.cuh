@@ -365,4 +365,56 @@ static __global__ void __launch_bounds__(64) k_g1dense_sum(const G1J *__restrict
     if (t == 0) dst_xyzz[(size_t)blob * 128 + blockIdx.x] = jac_to_xyzz(sm[0]);
 }
 
+// ---- two-level form for the batches just above the dense form's range (25 .. 32 blobs per GPU) --------------------------------
+// Between the dense form (13 x the arithmetic, one multiplication deep: pays up to ~24 blobs) and the staged form (the minimum
+// arithmetic, 14 multiplications deep: 16 ms however small the batch) sits the Cooley-Tukey split 128 = 16 x 8 with every level
+// done densely: all products of a level at once, then short sums.  With w = w_128, S[f] the MSM sums (frequency f at position
+// brp7(f)), h = IFFT_128(S)[0..63] (1/128 folded into the scalars), P = FFT_128(h, zero-padded), P[k] leaving at position brp7(k):
+//   I1:  A[f2][m1] = sum_{f1 < 16} S[8 f1 + f2] w^(-8 f1 m1)          128 outputs x 16 terms
+//   I2:  h[m]      = sum_{f2 < 8}  A[f2][m mod 16] w^(-f2 m), m < 64    64 outputs x  8 terms
+//   F1:  B[b][k1]  = sum_{a < 8}   h[8 a + b] w^(8 a k1)              128 outputs x  8 terms
+//   F2:  P[k]      = sum_{b < 8}   B[b][k mod 16] w^(b k)             128 outputs x  8 terms
+// ~4 100 non-trivial twiddle multiplications per blob (staged: 642, dense: 8 320), four multiplications deep.  MEASURED: 9.2 ms for
+// 25-32 blobs (staged: 16.2 ms), 15.5 ms for 33-64 (a full wave of the GPU is 57 k twiddle multiplications = 2.5 ms of the multiply
+// pipe, and 64 blobs x 4 100 are 4.6 waves), 22 ms for 96: it pays up to 32 blobs (kzg_lane::g1_two_level_max).  Same group elements
+// as the other two forms, so the compressed proofs are byte-identical.
+//   k_g1lvl_mul: grid (ceil(blobs / 32), n_out * R), block 32: thread = blob, block = (output o, term j): the twiddle is block-uniform
+//   k_g1lvl_sum: one thread per (blob, output): R-term sum
+struct G1Level { int n_out, R; };
+__device__ __forceinline__ void g1lvl_term(int level, int o, int j, int &src, int &e) {
+    switch (level) {
+    case 0: { const int f2 = o >> 4, m1 = o & 15; src = (int)(__brev((unsigned)(8 * j + f2)) >> 25); e = (128 - ((8 * j * m1) & 127)) & 127; break; }   // I1: src = position of S[8 j + f2]
+    case 1: { src = (j << 4) + (o & 15); e = (128 - ((j * o) & 127)) & 127; break; }                                                                  // I2: A[j][o mod 16]
+    case 2: { const int b = o >> 4, k1 = o & 15; src = 8 * j + b; e = (8 * j * k1) & 127; break; }                                                      // F1: h[8 j + b]
+    default: { src = (j << 4) + (o & 15); e = (j * o) & 127; break; }                                                                                  // F2: B[j][o mod 16]
+    }
+}
+template <int LEVEL>
+static __global__ void __launch_bounds__(32) k_g1lvl_mul(const G1 *__restrict__ sums, const G1J *__restrict__ in, G1J *__restrict__ prod, const int32_t *__restrict__ status,
+                                                     int nblobs, int R) {
+    const int blob = blockIdx.x * 32 + threadIdx.x;
+    if (blob >= nblobs || status[blob] != ST_OK) return;
+    const int o = blockIdx.y / R, j = blockIdx.y - o * R;
+    int src, e;
+    g1lvl_term(LEVEL, o, j, src, e);
+    G1J y;
+    if (LEVEL == 0) { G1 q = sums[(size_t)blob * 128 + src]; y = jac_from_xyzz(q); }
+    else y = ld_jac(in + (size_t)blob * 128 + src);
+    if (e) jac_mul_prog_at<MulCallLazy>(&y, TW_PROG[e]);
+    st_jac(prod + ((size_t)blob * gridDim.y + blockIdx.y), y);
+}
+// out[blob][o] = sum_j prod[blob][o][j]; LAST: written as XYZZ at position brp7(o) for k_finalize_g1
+template <bool LAST>
+static __global__ void __launch_bounds__(64) k_g1lvl_sum(const G1J *__restrict__ prod, G1J *__restrict__ out, G1 *__restrict__ dst_xyzz, const int32_t *__restrict__ status,
+                                                     int nblobs, int n_out, int R) {
+    const int idx = blockIdx.x * 64 + threadIdx.x, blob = idx / n_out, o = idx - blob * n_out;
+    if (blob >= nblobs || status[blob] != ST_OK) return;
+    const G1J *p = prod + ((size_t)blob * n_out + o) * R;
+    G1J acc = ld_jac(p);
+#pragma unroll 1
+    for (int j = 1; j < R; ++j) { G1J t = ld_jac(p + j); jac_add_ool(&acc, &t); }
+    if (LAST) dst_xyzz[(size_t)blob * 128 + (int)(__brev((unsigned)o) >> 25)] = jac_to_xyzz(acc);
+    else st_jac(out + (size_t)blob * 128 + o, acc);
+}
+
 }  // namespace kzg

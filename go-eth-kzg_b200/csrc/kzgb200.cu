@@ -335,6 +335,11 @@ int kzgb200_dbg_set_tunable(const char *name, int v) {
         kzg::g_decode_minb = v;
         return 0;
     }
+    if (!strcmp(name, "g1_two_level_max")) {
+        if (v < -1 || v > 1024) return set_err(KZGB200_ERR_ARGS, "g1_two_level_max out of range");
+        kzg::g_g1_two_level_max = v;
+        return 0;
+    }
     if (!strcmp(name, "rlc_item")) {
         if (v < 0 || v > 4096) return set_err(KZGB200_ERR_ARGS, "rlc_item out of range");
         kzg::g_rlc_item = v;
@@ -436,6 +441,7 @@ static int lane_streams_init(kzg_lane *c, int device) {
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     if (const char *e = getenv("KZGB200_G1FFT_SPLIT")) c->g1fft_split = (size_t)std::min(std::max(atoi(e), 1), KZG_G1FFT_MAX_SPLIT);
     if (const char *e = getenv("KZGB200_G1_DENSE_MAX")) c->g1_dense_max = (size_t)std::max(atoi(e), 0);
+    if (const char *e = getenv("KZGB200_G1_TWO_LEVEL_MAX")) c->g1_two_level_max = (size_t)std::max(atoi(e), 0);
     return 0;
 }
 
@@ -768,6 +774,13 @@ static const size_t CELLS_CHUNK = 1024;
 #endif
 
 // coefficients (c->coeffs) -> 128 compressed proofs per blob (fk20.go:76-124); buffers must be sized by the caller
+// which form of the G1 transform a chunk of m blobs takes, and the points of working storage (c->fft_work) it needs
+static inline size_t g1_two_level_max(const kzg_lane *c) { return g_g1_two_level_max >= 0 ? (size_t)g_g1_two_level_max : c->g1_two_level_max; }
+static inline size_t g1fft_work_points(const kzg_lane *c, size_t m) {
+    if (m <= c->g1_dense_max) return m * 128 * 65;                  // dense: all 65 x 128 products
+    if (m <= g1_two_level_max(c)) return m * 128 * (2 + 16);        // two-level: two working sets + the 16 x 128 products of level I1
+    return m * 128;                                                 // staged: the working set
+}
 static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr *coeffs, uint32_t *scalars, G1 *sums, G1 *pxyzz,
                                const int32_t *d_status, uint8_t *d_proofs, bool marks) {
     Fr inv128p; memcpy(inv128p.v, H_FR_INV128_PLAIN, sizeof inv128p.v);
@@ -793,6 +806,19 @@ static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr 
         k_g1dense_mul<<<dim3((unsigned)((m * 128 + 31) / 32), 65), 32, 0, st>>>(sums, prod, d_status, (int)m);
         k_g1dense_sum<<<dim3(128, (unsigned)m), 64, 0, st>>>(prod, pxyzz, d_status);
         c->launches += 2;
+    } else if (m <= g1_two_level_max(c)) {
+        // a medium batch: the two-level form (g1fft.cuh), four twiddle multiplications deep instead of fourteen
+        G1J *wa = (G1J *)c->fft_work.p, *wb = wa + m * 128, *prod = wb + m * 128;      // sized by g1fft_work_points
+        const unsigned gx = (unsigned)((m + 31) / 32);
+        k_g1lvl_mul<0><<<dim3(gx, 128 * 16), 32, 0, st>>>(sums, nullptr, prod, d_status, (int)m, 16);
+        k_g1lvl_sum<false><<<(unsigned)((m * 128 + 63) / 64), 64, 0, st>>>(prod, wa, nullptr, d_status, (int)m, 128, 16);
+        k_g1lvl_mul<1><<<dim3(gx, 64 * 8), 32, 0, st>>>(nullptr, wa, prod, d_status, (int)m, 8);
+        k_g1lvl_sum<false><<<(unsigned)((m * 64 + 63) / 64), 64, 0, st>>>(prod, wb, nullptr, d_status, (int)m, 64, 8);
+        k_g1lvl_mul<2><<<dim3(gx, 128 * 8), 32, 0, st>>>(nullptr, wb, prod, d_status, (int)m, 8);
+        k_g1lvl_sum<false><<<(unsigned)((m * 128 + 63) / 64), 64, 0, st>>>(prod, wa, nullptr, d_status, (int)m, 128, 8);
+        k_g1lvl_mul<3><<<dim3(gx, 128 * 8), 32, 0, st>>>(nullptr, wa, prod, d_status, (int)m, 8);
+        k_g1lvl_sum<true><<<(unsigned)((m * 128 + 63) / 64), 64, 0, st>>>(prod, nullptr, pxyzz, d_status, (int)m, 128, 8);
+        c->launches += 8;
     } else {
         const size_t nsplit = std::max<size_t>(1, std::min<size_t>(g_g1fft_split_override ? (size_t)g_g1fft_split_override : c->g1fft_split, (m + 127) / 128));
         const size_t per = (m + nsplit - 1) / nsplit;
@@ -842,7 +868,7 @@ static int cells_and_proofs(kzg_lane *c, const uint8_t *blobs, size_t n, uint8_t
         if ((rc = c->scalars.ensure(chunk * 8192 * 32))) return rc;
         if ((rc = c->sums.ensure(chunk * 128 * sizeof(G1)))) return rc;
         if ((rc = c->proofs_xyzz.ensure(chunk * 128 * sizeof(G1)))) return rc;
-        if ((rc = c->fft_work.ensure(chunk * 128 * (chunk <= c->g1_dense_max ? 65 : 1) * sizeof(G1J)))) return rc;
+        if ((rc = c->fft_work.ensure(g1fft_work_points(c, chunk) * sizeof(G1J)))) return rc;
         if (!proofs_dev && (rc = c->out_bytes.ensure(chunk * 128 * 48))) return rc;
     }
     Fr inv4096; memcpy(inv4096.v, H_FR_INV4096, sizeof inv4096.v);
@@ -946,7 +972,7 @@ int lane_recover_cells_and_kzg_proofs(kzg_lane *c, const uint64_t *cell_ids, con
         if ((rc = c->scalars.ensure(chunk * 8192 * 32))) return rc;
         if ((rc = c->sums.ensure(chunk * 128 * sizeof(G1)))) return rc;
         if ((rc = c->proofs_xyzz.ensure(chunk * 128 * sizeof(G1)))) return rc;
-        if ((rc = c->fft_work.ensure(chunk * 128 * (chunk <= c->g1_dense_max ? 65 : 1) * sizeof(G1J)))) return rc;
+        if ((rc = c->fft_work.ensure(g1fft_work_points(c, chunk) * sizeof(G1J)))) return rc;
         if (!proofs_dev && (rc = c->out_bytes.ensure(chunk * 128 * 48))) return rc;
     }
     Fr inv8192; memcpy(inv8192.v, H_FR_INV8192, sizeof inv8192.v);

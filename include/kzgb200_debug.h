@@ -62,6 +62,7 @@ int kzgb200_dbg_h2d_bandwidth(const int *devices, int n, size_t bytes_per_dev, i
  *   "optimistic": 1 (default) = VerifyCellKZGProofBatch checks a call of many small verdicts as one combined verdict first, 0 = per-verdict checks only
  *   "large_window": 4 (default) | 8 = window bits of the column MSMs of large (>= 4096-cell) verdicts; "large_item": run length of their work items (0 = default)
  *   "verify_overlap": 1 (default) = the cell verifier's interpolation chain runs on a side stream beside the proofs' decode, 0 = one stream
+ *   "g1_two_level_max": chunks of up to this many blobs take the two-level (16 x 8) G1 transform instead of the staged one (-1 = default 32, 0 = never)
  *   "rlc_item": run length of the EIP-4844 batch verdict's bucket-MSM work items (0 = default 128) */
 int kzgb200_dbg_set_tunable(const char *name, int v);
 /* dependency-free integer multiply-add microbenchmark: device-wide instructions*lanes per second.

@@ -69,3 +69,29 @@ def test_small_batch_paths_equal_large_batch_paths(ctx):
     for n in (1, 3, 17, 100, 300):                                      # split factors 32, 32, 32, 8, 2
         assert ctx.blob_to_kzg_commitment_batch(many[:n]) == cbig[:n], n
     assert cbig[4] == o.blob_to_kzg_commitment(distinct[4])
+
+
+def test_two_level_g1_transform_equals_staged_and_oracle(ctx):
+    """Batches of 25 .. 32 blobs take the two-level 16 x 8 G1 transform (csrc/g1fft.cuh: k_g1lvl_mul / k_g1lvl_sum).  The same
+    blobs through the staged radix-2 form (tunable g1_two_level_max = 0) and through the CPU oracle must give the same bytes; a blob
+    with an invalid scalar in the middle of the batch keeps its error status and zeroed outputs."""
+    o = oracle_lib.get_oracle()
+    distinct = [oracle_lib.rand_blob((500 + b) << 20) for b in range(7)]
+    zero = bytes(131072)                                                # constant-zero blob: every MSM sum is the point at infinity
+    blobs = [distinct[i % 7] for i in range(45)] + [zero]
+    bad = bytes([0xff]) * 32 + distinct[0][32:]
+    blobs[17] = bad
+    assert ctx.L.kzgb200_dbg_set_tunable(b"g1_two_level_max", 64) == 0  # (the default threshold is 32 blobs)
+    try:
+        two = ctx.compute_cells_and_kzg_proofs_batch(blobs)             # 46 blobs: two-level
+        ctx.L.kzgb200_dbg_set_tunable(b"g1_two_level_max", 0)
+        staged = ctx.compute_cells_and_kzg_proofs_batch(blobs)
+    finally:
+        ctx.L.kzgb200_dbg_set_tunable(b"g1_two_level_max", -1)
+    assert two == staged
+    assert two[17][0] == 2 and two[17][2] == bytes(6144)
+    for i in (3, 44, 45):
+        assert two[i] == o.compute_cells_and_kzg_proofs(blobs[i]), i
+    # default threshold: 25 and 32 blobs two-level, 33 staged (sizes around the 32-blob block granularity of the level kernels)
+    for n in (25, 32, 33):
+        assert ctx.compute_cells_and_kzg_proofs_batch(blobs[:n]) == staged[:n], n
