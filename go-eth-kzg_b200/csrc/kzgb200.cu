@@ -555,7 +555,7 @@ int lane_clone(kzg_lane *f, kzg_lane **out) {
     c->g1_monomial = f->g1_monomial; c->g1_lagrange_brp = f->g1_lagrange_brp; c->g2_bytes = f->g2_bytes;
     c->commit_tab = f->commit_tab; c->fk20_tab = f->fk20_tab; c->mono64_tab = f->mono64_tab;
     c->roots = f->roots; c->glv_digits = f->glv_digits; c->pow7 = f->pow7; c->ipow7 = f->ipow7; c->pairing = f->pairing;
-    c->g1fft_split = f->g1fft_split;
+    c->g1fft_split = f->g1fft_split; c->g1_dense_max = f->g1_dense_max; c->g1_two_level_max = f->g1_two_level_max;
     *out = c;
     return KZGB200_OK;
 }
