@@ -380,15 +380,54 @@ static __global__ void __launch_bounds__(64) k_g1dense_sum(const G1J *__restrict
 // as the other two forms, so the compressed proofs are byte-identical.
 //   k_g1lvl_mul: grid (ceil(blobs / 32), n_out * R), block 32: thread = blob, block = (output o, term j): the twiddle is block-uniform
 //   k_g1lvl_sum: one thread per (blob, output): R-term sum
-struct G1Level { int n_out, R; };
-__device__ __forceinline__ void g1lvl_term(int level, int o, int j, int &src, int &e) {
+__host__ __device__ __forceinline__ int g1_brp7(int x) {      // 7-bit reversal (host + device: the index maps below are unit-tested on the CPU)
+    x = ((x & 0x55) << 1) | ((x >> 1) & 0x55); x = ((x & 0x33) << 2) | ((x >> 2) & 0x33); x = ((x & 0x0f) << 4) | ((x >> 4) & 0x0f);
+    return (x >> 1) & 127;
+}
+__host__ __device__ __forceinline__ void g1lvl_term(int level, int o, int j, int &src, int &e) {
     switch (level) {
-    case 0: { const int f2 = o >> 4, m1 = o & 15; src = (int)(__brev((unsigned)(8 * j + f2)) >> 25); e = (128 - ((8 * j * m1) & 127)) & 127; break; }   // I1: src = position of S[8 j + f2]
+    case 0: { const int f2 = o >> 4, m1 = o & 15; src = g1_brp7(8 * j + f2); e = (128 - ((8 * j * m1) & 127)) & 127; break; }   // I1: src = position of S[8 j + f2]
     case 1: { src = (j << 4) + (o & 15); e = (128 - ((j * o) & 127)) & 127; break; }                                                                  // I2: A[j][o mod 16]
     case 2: { const int b = o >> 4, k1 = o & 15; src = 8 * j + b; e = (8 * j * k1) & 127; break; }                                                      // F1: h[8 j + b]
     default: { src = (j << 4) + (o & 15); e = (j * o) & 127; break; }                                                                                  // F2: B[j][o mod 16]
     }
 }
+// ---- the same idea one step further for 33 .. ~160 blobs: 128 = 4 x 4 x 4 x 2, eight levels of 4- or 2-term sums ------------------
+// Splitting the size-16 transform of the form above as 4 x 4 and its size-8 transform (with the twiddle) as 4 x 2 (indices
+// f = 8 (4 a + b) + f2, f2 = 2 p + q on the input side, k = k1 + 16 u + 64 v, k1 = c + 4 d on the output side, W = w^(-1) for the
+// inverse and w for the forward transform):
+//   B[f2][b][c]  = sum_{a < 4} x[8 (4 a + b) + f2] W^(32 a c)              (forward: a < 2, the upper half of h is the zero padding)
+//   A[f2][k1]    = sum_{b < 4} B[f2][b][k1 mod 4]  W^(8 b k1)
+//   C[k1][q][u]  = sum_{p < 4} A[2 p + q][k1]      W^(2 p (k1 + 16 u))
+//   X[k]         = sum_{q < 2} C[k mod 16][q][(k / 16) mod 4] W^(q k)        (inverse: k < 64 only)
+// ~2 000 non-trivial twiddle multiplications per blob (half of the 16 x 8 form, three times the staged form), eight multiplications deep
+// (staged: fourteen).  Levels 0-3 are the inverse transform, 4-7 the forward one; level l has G1LVL8_NOUT[l] outputs of G1LVL8_R[l] terms.
+__host__ __device__ __forceinline__ void g1lvl8_term(int level, int o, int j, int &src, int &e) {
+    const int l = level & 3;
+    int ex;
+    if (l == 0) { const int f2 = o >> 4, b = (o >> 2) & 3, c = o & 3; src = 8 * (4 * j + b) + f2; ex = 32 * j * c; }
+    else if (l == 1) { const int f2 = o >> 4, k1 = o & 15; src = f2 * 16 + j * 4 + (k1 & 3); ex = 8 * j * k1; }
+    else if (l == 2) { const int k1 = o >> 3, q = (o >> 2) & 1, u = o & 3; src = (2 * j + q) * 16 + k1; ex = 2 * j * (k1 + 16 * u); }
+    else { const int k1 = o & 15, u = (o >> 4) & 3; src = k1 * 8 + j * 4 + u; ex = j * o; }
+    ex &= 127;
+    e = level < 4 ? (128 - ex) & 127 : ex;
+    if (level == 0) src = g1_brp7(src);      // the MSM sums arrive bit-reversed: frequency f at position brp7(f)
+}
+template <int LEVEL>
+static __global__ void __launch_bounds__(32) k_g1lvl8_mul(const G1 *__restrict__ sums, const G1J *__restrict__ in, G1J *__restrict__ prod, const int32_t *__restrict__ status,
+                                                      int nblobs, int R) {
+    const int blob = blockIdx.x * 32 + threadIdx.x;
+    if (blob >= nblobs || status[blob] != ST_OK) return;
+    const int o = blockIdx.y / R, j = blockIdx.y - o * R;
+    int src, e;
+    g1lvl8_term(LEVEL, o, j, src, e);
+    G1J y;
+    if (LEVEL == 0) { G1 q = sums[(size_t)blob * 128 + src]; y = jac_from_xyzz(q); }
+    else y = ld_jac(in + (size_t)blob * 128 + src);
+    if (e) jac_mul_prog_at<MulCallLazy>(&y, TW_PROG[e]);
+    st_jac(prod + ((size_t)blob * gridDim.y + blockIdx.y), y);
+}
+
 template <int LEVEL>
 static __global__ void __launch_bounds__(32) k_g1lvl_mul(const G1 *__restrict__ sums, const G1J *__restrict__ in, G1J *__restrict__ prod, const int32_t *__restrict__ status,
                                                      int nblobs, int R) {

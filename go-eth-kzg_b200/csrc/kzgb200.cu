@@ -285,6 +285,14 @@ int kzgb200_dbg_h2d_bandwidth(const int *devices, int n, size_t bytes_per_dev, i
     return 0;
 }
 
+// unit-test hook (host only): source index and twiddle exponent of term j of output o at `level` of the multi-level G1 transforms
+// (g1fft.cuh; form 0: 16 x 8, four levels; form 1: 4 x 4 x 4 x 2, eight levels)
+int kzgb200_dbg_g1_level_term(int form, int level, int o, int j, int *src, int *e) {
+    if (!src || !e || form < 0 || form > 1 || level < 0 || level >= (form ? 8 : 4) || o < 0 || o > 127 || j < 0 || j > 15) return set_err(KZGB200_ERR_ARGS, "bad argument");
+    if (form) kzg::g1lvl8_term(level, o, j, *src, *e); else kzg::g1lvl_term(level, o, j, *src, *e);
+    return 0;
+}
+
 // experiments: run-time tunables of the proving paths.  "msm_variant": the k_msm_fixed variant (msm.cuh; -1 = default /
 // KZGB200_MSM_VARIANT); "fk20_lanes": lanes per 64-point FK20 group for full batches (4, 8, 16; 0 = default);
 // "vmsm_policy": field-product policy of the verifiers' bucket accumulation (vmsm.cuh)
@@ -333,6 +341,11 @@ int kzgb200_dbg_set_tunable(const char *name, int v) {
     if (!strcmp(name, "decode_minb")) {
         if (v != 4 && v != 6 && v != 8) return set_err(KZGB200_ERR_ARGS, "decode_minb must be 4, 6 or 8");
         kzg::g_decode_minb = v;
+        return 0;
+    }
+    if (!strcmp(name, "g1_chain4_max")) {
+        if (v < -1 || v > 4096) return set_err(KZGB200_ERR_ARGS, "g1_chain4_max out of range");
+        kzg::g_g1_chain4_max = v;
         return 0;
     }
     if (!strcmp(name, "g1_two_level_max")) {
@@ -442,6 +455,7 @@ static int lane_streams_init(kzg_lane *c, int device) {
     if (const char *e = getenv("KZGB200_G1FFT_SPLIT")) c->g1fft_split = (size_t)std::min(std::max(atoi(e), 1), KZG_G1FFT_MAX_SPLIT);
     if (const char *e = getenv("KZGB200_G1_DENSE_MAX")) c->g1_dense_max = (size_t)std::max(atoi(e), 0);
     if (const char *e = getenv("KZGB200_G1_TWO_LEVEL_MAX")) c->g1_two_level_max = (size_t)std::max(atoi(e), 0);
+    if (const char *e = getenv("KZGB200_G1_CHAIN4_MAX")) c->g1_chain4_max = (size_t)std::max(atoi(e), 0);
     return 0;
 }
 
@@ -555,7 +569,7 @@ int lane_clone(kzg_lane *f, kzg_lane **out) {
     c->g1_monomial = f->g1_monomial; c->g1_lagrange_brp = f->g1_lagrange_brp; c->g2_bytes = f->g2_bytes;
     c->commit_tab = f->commit_tab; c->fk20_tab = f->fk20_tab; c->mono64_tab = f->mono64_tab;
     c->roots = f->roots; c->glv_digits = f->glv_digits; c->pow7 = f->pow7; c->ipow7 = f->ipow7; c->pairing = f->pairing;
-    c->g1fft_split = f->g1fft_split; c->g1_dense_max = f->g1_dense_max; c->g1_two_level_max = f->g1_two_level_max;
+    c->g1fft_split = f->g1fft_split; c->g1_dense_max = f->g1_dense_max; c->g1_two_level_max = f->g1_two_level_max; c->g1_chain4_max = f->g1_chain4_max;
     *out = c;
     return KZGB200_OK;
 }
@@ -776,9 +790,11 @@ static const size_t CELLS_CHUNK = 1024;
 // coefficients (c->coeffs) -> 128 compressed proofs per blob (fk20.go:76-124); buffers must be sized by the caller
 // which form of the G1 transform a chunk of m blobs takes, and the points of working storage (c->fft_work) it needs
 static inline size_t g1_two_level_max(const kzg_lane *c) { return g_g1_two_level_max >= 0 ? (size_t)g_g1_two_level_max : c->g1_two_level_max; }
+static inline size_t g1_chain4_max(const kzg_lane *c) { return g_g1_chain4_max >= 0 ? (size_t)g_g1_chain4_max : c->g1_chain4_max; }
 static inline size_t g1fft_work_points(const kzg_lane *c, size_t m) {
     if (m <= c->g1_dense_max) return m * 128 * 65;                  // dense: all 65 x 128 products
     if (m <= g1_two_level_max(c)) return m * 128 * (2 + 16);        // two-level: two working sets + the 16 x 128 products of level I1
+    if (m <= g1_chain4_max(c)) return m * 128 * (2 + 4);            // 4 x 4 x 4 x 2: two working sets + 4 x 128 products
     return m * 128;                                                 // staged: the working set
 }
 static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr *coeffs, uint32_t *scalars, G1 *sums, G1 *pxyzz,
@@ -819,6 +835,18 @@ static void launch_fk20_proofs(kzg_lane *c, cudaStream_t st, size_t m, const Fr 
         k_g1lvl_mul<3><<<dim3(gx, 128 * 8), 32, 0, st>>>(nullptr, wa, prod, d_status, (int)m, 8);
         k_g1lvl_sum<true><<<(unsigned)((m * 128 + 63) / 64), 64, 0, st>>>(prod, nullptr, pxyzz, d_status, (int)m, 128, 8);
         c->launches += 8;
+    } else if (m <= g1_chain4_max(c)) {
+        // a medium batch: the 4 x 4 x 4 x 2 form (g1fft.cuh), eight twiddle multiplications deep instead of fourteen
+        G1J *wa = (G1J *)c->fft_work.p, *wb = wa + m * 128, *prod = wb + m * 128;      // sized by g1fft_work_points
+        const unsigned gx = (unsigned)((m + 31) / 32);
+        static const int NOUT[8] = {128, 128, 128, 64, 128, 128, 128, 128}, RR[8] = {4, 4, 4, 2, 2, 4, 4, 2};
+#define KZG_LVL8(L, IN, OUT, LASTF) do { \
+            k_g1lvl8_mul<L><<<dim3(gx, NOUT[L] * RR[L]), 32, 0, st>>>(sums, IN, prod, d_status, (int)m, RR[L]); \
+            k_g1lvl_sum<LASTF><<<(unsigned)((m * NOUT[L] + 63) / 64), 64, 0, st>>>(prod, OUT, pxyzz, d_status, (int)m, NOUT[L], RR[L]); } while (0)
+        KZG_LVL8(0, nullptr, wa, false); KZG_LVL8(1, wa, wb, false); KZG_LVL8(2, wb, wa, false); KZG_LVL8(3, wa, wb, false);
+        KZG_LVL8(4, wb, wa, false); KZG_LVL8(5, wa, wb, false); KZG_LVL8(6, wb, wa, false); KZG_LVL8(7, wa, nullptr, true);
+#undef KZG_LVL8
+        c->launches += 16;
     } else {
         const size_t nsplit = std::max<size_t>(1, std::min<size_t>(g_g1fft_split_override ? (size_t)g_g1fft_split_override : c->g1fft_split, (m + 127) / 128));
         const size_t per = (m + nsplit - 1) / nsplit;

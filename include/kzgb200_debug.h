@@ -48,6 +48,9 @@ const char *kzgb200_dbg_shard_plan_json(size_t n_units, size_t n_dev, size_t min
 /* aggregate host -> device GB/s of n GPUs copying their slices of ONE pinned host buffer at the same time (plain or
  * NUMA-interleaved pinned memory): the ceiling of the end-to-end numbers of a multi-GPU context */
 int kzgb200_dbg_h2d_bandwidth(const int *devices, int n, size_t bytes_per_dev, int interleaved, double *gbps);
+/* host-only unit-test hook: source index and twiddle exponent (of w_128) of term j of output o at `level` of the multi-level forms of the
+ * FK20 G1 transform (csrc/g1fft.cuh; form 0: 128 = 16 x 8, levels 0..3; form 1: 128 = 4 x 4 x 4 x 2, levels 0..7) */
+int kzgb200_dbg_g1_level_term(int form, int level, int o, int j, int *src, int *e);
 /* experiments: run-time tunables of the proving paths (every setting is bit-exact).
  *   "msm_variant": k_msm_fixed variant, bit 0: out-of-line field products, bit 1: cp.async-staged gather, bit 2: one-reduction
  *                  Y3, bit 3: accumulator in shared memory + 4 CTAs/SM; -1 = default (or the KZGB200_MSM_VARIANT environment variable)
@@ -63,6 +66,7 @@ int kzgb200_dbg_h2d_bandwidth(const int *devices, int n, size_t bytes_per_dev, i
  *   "large_window": 4 (default) | 8 = window bits of the column MSMs of large (>= 4096-cell) verdicts; "large_item": run length of their work items (0 = default)
  *   "verify_overlap": 1 (default) = the cell verifier's interpolation chain runs on a side stream beside the proofs' decode, 0 = one stream
  *   "g1_two_level_max": chunks of up to this many blobs take the two-level (16 x 8) G1 transform instead of the staged one (-1 = default 32, 0 = never)
+ *   "g1_chain4_max": chunks above g1_two_level_max and up to this many blobs take the 4 x 4 x 4 x 2 G1 transform (-1 = default, 0 = never)
  *   "rlc_item": run length of the EIP-4844 batch verdict's bucket-MSM work items (0 = default 128) */
 int kzgb200_dbg_set_tunable(const char *name, int v);
 /* dependency-free integer multiply-add microbenchmark: device-wide instructions*lanes per second.

@@ -1,5 +1,5 @@
-"""G1 transform of FK20 for medium batches: two-level 16 x 8 form (default up to 160 blobs) against the staged radix-2 form
-(tunable g1_two_level_max = 0); kernel-class ms from the library's CUDA events, device-resident blobs, min of 3.  Run on a GPU box."""
+"""G1 transform of FK20 for medium batches: the two-level 16 x 8 form and the 4 x 4 x 4 x 2 form against the staged radix-2 form
+(tunables g1_two_level_max, g1_chain4_max); kernel-class ms from the library's CUDA events, device-resident blobs, min of 3.  Run on a GPU box."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "go-eth-kzg_b200")); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
@@ -8,11 +8,11 @@ from bench import make_work
 
 out = {}
 ctx = kzgb200.Context(commit_window=8, fk20_window=13)
-for n in (25, 32, 48, 64, 96, 128, 160, 192, 256):
+for n in (25, 32, 33, 64, 96, 128, 160, 192, 256):
     w = make_work(ctx, "cells_proofs", n, 0, torch, np, 0)
     row = {}
-    for name, v in (("two_level", 1024), ("staged", 0)):
-        assert ctx.L.kzgb200_dbg_set_tunable(b"g1_two_level_max", v) == 0
+    for name, v, v4 in (("two_level", 1024, 0), ("chain4", 0, 1024), ("staged", 0, 0)):
+        assert ctx.L.kzgb200_dbg_set_tunable(b"g1_two_level_max", v) == 0 and ctx.L.kzgb200_dbg_set_tunable(b"g1_chain4_max", v4) == 0
         w.step(True)
         best = None
         for _ in range(3):
@@ -24,9 +24,10 @@ for n in (25, 32, 48, 64, 96, 128, 160, 192, 256):
         w.step(False)
         best["checks"] = bool(w.self_check()) and bool(w.oracle_check())
         row[name] = best
-    ctx.L.kzgb200_dbg_set_tunable(b"g1_two_level_max", -1)
+    ctx.L.kzgb200_dbg_set_tunable(b"g1_two_level_max", -1); ctx.L.kzgb200_dbg_set_tunable(b"g1_chain4_max", -1)
     out[n] = row
-    print(n, "two_level", row["two_level"]["g1fft"], row["two_level"]["total"], "staged", row["staged"]["g1fft"], row["staged"]["total"], row["two_level"]["checks"], row["staged"]["checks"], flush=True)
+    print(n, "two_level", row["two_level"]["g1fft"], "chain4", row["chain4"]["g1fft"], "staged", row["staged"]["g1fft"], "totals", row["two_level"]["total"], row["chain4"]["total"], row["staged"]["total"],
+          row["two_level"]["checks"], row["chain4"]["checks"], row["staged"]["checks"], flush=True)
     del w; torch.cuda.empty_cache()
 ctx.close()
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "g1_midbatch_sweep.json"), "w"), indent=1)

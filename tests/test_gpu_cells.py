@@ -89,6 +89,13 @@ def test_two_level_g1_transform_equals_staged_and_oracle(ctx):
     finally:
         ctx.L.kzgb200_dbg_set_tunable(b"g1_two_level_max", -1)
     assert two == staged
+    # the 4 x 4 x 4 x 2 form (k_g1lvl8_mul) on the same blobs
+    assert ctx.L.kzgb200_dbg_set_tunable(b"g1_two_level_max", 0) == 0 and ctx.L.kzgb200_dbg_set_tunable(b"g1_chain4_max", 64) == 0
+    try:
+        chain4 = ctx.compute_cells_and_kzg_proofs_batch(blobs)
+    finally:
+        ctx.L.kzgb200_dbg_set_tunable(b"g1_two_level_max", -1); ctx.L.kzgb200_dbg_set_tunable(b"g1_chain4_max", -1)
+    assert chain4 == staged
     assert two[17][0] == 2 and two[17][2] == bytes(6144)
     for i in (3, 44, 45):
         assert two[i] == o.compute_cells_and_kzg_proofs(blobs[i]), i
