@@ -89,7 +89,8 @@ struct kzg_lane {
     cudaStream_t aux_stream = nullptr;  // small independent kernels that would otherwise queue behind a long one (second decode of the verifiers)
     cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;
     size_t g1fft_split = 8;             // measured: 1 -> 40.9 ms, 2 -> 34.6, 4 -> 33.5, 8 -> 33.1 (KZGB200_G1FFT_SPLIT overrides)
-    size_t g1_chain4_max = 0;           // ... then up to this many the 4 x 4 x 4 x 2 form (KZGB200_G1_CHAIN4_MAX overrides); 0 until measured
+    size_t g1_chain4_max = 64;          // ... then up to this many the 4 x 4 x 4 x 2 form (KZGB200_G1_CHAIN4_MAX overrides).  Measured, g1fft class in ms for
+                                        // two-level / 4x4x4x2 / staged: 25-32 blobs 9.2 / 10.3 / 16.2, 33-64: 15.5 / 12.6 / 16.2, 65-96: 22.0 / 18.5 / 16.2, 128: 27.3 / 20.1 / 16.3
     size_t g1_two_level_max = 32;       // ... up to this many the two-level 16 x 8 form, beyond it the staged radix-2 form (KZGB200_G1_TWO_LEVEL_MAX overrides).
                                         // Measured (profiles/r02_g1_midbatch_sweep.json), two-level / staged: 25-32 blobs 9.2 / 16.2 ms, 33-64: 15.5 / 16.2, 96: 22.0 / 16.2
     size_t g1_dense_max = 24;           // batches up to this many blobs take the dense one-level G1 transform (KZGB200_G1_DENSE_MAX overrides)

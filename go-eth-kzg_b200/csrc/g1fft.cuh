@@ -401,7 +401,9 @@ __host__ __device__ __forceinline__ void g1lvl_term(int level, int o, int j, int
 //   C[k1][q][u]  = sum_{p < 4} A[2 p + q][k1]      W^(2 p (k1 + 16 u))
 //   X[k]         = sum_{q < 2} C[k mod 16][q][(k / 16) mod 4] W^(q k)        (inverse: k < 64 only)
 // ~2 000 non-trivial twiddle multiplications per blob (half of the 16 x 8 form, three times the staged form), eight multiplications deep
-// (staged: fourteen).  Levels 0-3 are the inverse transform, 4-7 the forward one; level l has G1LVL8_NOUT[l] outputs of G1LVL8_R[l] terms.
+// (staged: fourteen).  Levels 0-3 are the inverse transform, 4-7 the forward one (outputs x terms: 128x4, 128x4, 128x4, 64x2, 128x2, 128x4, 128x4, 128x2).
+// MEASURED: 12.6 ms for 33-64 blobs (staged 16.2, 16 x 8 form 15.5), 18.5 ms for 65-96 (a level is one partial wave whose blocks share the
+// pipe: its duration is the longest twiddle multiplication under that contention, not the average), so it is used for 33-64 blobs.
 __host__ __device__ __forceinline__ void g1lvl8_term(int level, int o, int j, int &src, int &e) {
     const int l = level & 3;
     int ex;

@@ -72,7 +72,7 @@ def test_small_batch_paths_equal_large_batch_paths(ctx):
 
 
 def test_two_level_g1_transform_equals_staged_and_oracle(ctx):
-    """Batches of 25 .. 32 blobs take the two-level 16 x 8 G1 transform (csrc/g1fft.cuh: k_g1lvl_mul / k_g1lvl_sum).  The same
+    """Batches of 25 .. 32 blobs take the two-level 16 x 8 G1 transform, 33 .. 64 the 4 x 4 x 4 x 2 one (csrc/g1fft.cuh: k_g1lvl_mul / k_g1lvl_sum).  The same
     blobs through the staged radix-2 form (tunable g1_two_level_max = 0) and through the CPU oracle must give the same bytes; a blob
     with an invalid scalar in the middle of the batch keeps its error status and zeroed outputs."""
     o = oracle_lib.get_oracle()
@@ -99,6 +99,6 @@ def test_two_level_g1_transform_equals_staged_and_oracle(ctx):
     assert two[17][0] == 2 and two[17][2] == bytes(6144)
     for i in (3, 44, 45):
         assert two[i] == o.compute_cells_and_kzg_proofs(blobs[i]), i
-    # default threshold: 25 and 32 blobs two-level, 33 staged (sizes around the 32-blob block granularity of the level kernels)
-    for n in (25, 32, 33):
+    # default thresholds: 25 and 32 blobs two-level, 33 and 46 the 4 x 4 x 4 x 2 form (sizes around the 32-blob block granularity of the level kernels)
+    for n in (25, 32, 33, 46):
         assert ctx.compute_cells_and_kzg_proofs_batch(blobs[:n]) == staged[:n], n
