@@ -21,7 +21,8 @@
 // Cost per point and window: 10 Fp products, against ~13 for a windowed scalar multiplication of
 // each point on its own (4 doublings + 15/16 addition per window) -- and no per-point table.
 // Verdicts with thousands of cells take a second shape (KZG_LARGE_BATCH): cells grouped by cell index,
-// 8-bit windows over the coefficients only, the column twiddle applied to 128 column sums.
+// the SAME signed 4-bit digits of the coefficients (windows 0..31) in runs of 128 cells, the column twiddle applied to 128 column sums
+// (kzgb200_verify.cu; the round-1 form -- 16 signed 8-bit windows, 128 buckets, recode256 below -- is kept behind the tunable "large_window").
 #pragma once
 #include "kzg4844.cuh"
 #include "fk20.cuh"      // constants.inc: FP_BETA2
@@ -78,7 +79,7 @@ template <int ND> __device__ __forceinline__ void recode16(int8_t *out, const ui
 }
 
 // signed base-256 recoding of a value < 2^(8 ND - 1): ND digits in [-128, 127] (a digit of -128 means bucket 128,
-// negated); used for verdicts with thousands of points, where 8-bit windows pay
+// negated); the round-1 form of the large verdicts (tunable "large_window" = 8), kept for measurements
 template <int ND> __device__ __forceinline__ void recode256(int8_t *out, const uint32_t *limbs) {
     uint32_t carry = 0;
 #pragma unroll
@@ -165,7 +166,7 @@ __device__ __forceinline__ void store_g1(G1 *p, const G1 &r) {
 // ---- coefficients and digits ------------------------------------------------------------------
 #define KZG_CELL_TW 96        // windows per point: 32 (r_k, 126 bits) + 2 x 32 (GLV halves of the 255-bit scalar)
 #define KZG_VM_SEGS 3         // ... = three 32-window segments
-#define KZG_LARGE_TW 16       // verdicts with >= KZG_LARGE_BATCH cells: 16 signed 8-bit windows of r_k, 128 buckets
+#define KZG_LARGE_TW 16       // round-1 form of verdicts with >= KZG_LARGE_BATCH cells (tunable "large_window" = 8): 16 signed 8-bit windows of r_k, 128 buckets
 #define KZG_LARGE_BUCKETS 128
 #define KZG_ROW_TW 40         // commitment weights of a large verdict: sums of < 2^32 coefficients of 126 bits (< 2^159), 40 signed 4-bit windows
 #define KZG_ROW_ITEM 64       // ... in short runs: there are few commitments, parallelism matters more than the reduction's cost
