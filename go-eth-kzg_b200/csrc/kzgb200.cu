@@ -353,6 +353,11 @@ int kzgb200_dbg_set_tunable(const char *name, int v) {
         kzg::g_g1_two_level_max = v;
         return 0;
     }
+    if (!strcmp(name, "proof_pieces")) {
+        if (v < 2 || v > 4) return set_err(KZGB200_ERR_ARGS, "proof_pieces out of range");     // KZG_H2D_PIECES
+        kzg::g_proof_pieces = v;
+        return 0;
+    }
     if (!strcmp(name, "rlc_item")) {
         if (v < 0 || v > 4096) return set_err(KZGB200_ERR_ARGS, "rlc_item out of range");
         kzg::g_rlc_item = v;
@@ -706,10 +711,19 @@ static int open_common(kzg_lane *c, const uint8_t *blobs, const uint8_t *z32, co
         CU(cudaMemsetAsync(d_status, 0, m * sizeof(int32_t), c->stream));
         if (d_y) CU(cudaMemsetAsync(d_y, 0, m * 32, c->stream));
         if ((rc = vm_eval_scratch(c, m))) return rc;
-        // host input: two pieces, one wave of MSM CTAs first, then the rest, whose H2D, hash and evaluation run under the
-        // first piece's MSM (for device input the same split was measured 1.5 % slower than one launch: not used)
+        // host input: three pieces (3, then 6 waves of MSM CTAs, then the rest), each one's H2D, hash and evaluation running under the
+        // previous piece's MSM (for device input the same split was measured 1.5 % slower than one launch: not used)
         size_t bound[KZG_H2D_PIECES + 1] = {0, m, m, m, m};
-        if (!in_dev && m >= (size_t)8 * c->sm_count) bound[1] = (size_t)3 * c->sm_count;
+        if (!in_dev && m >= (size_t)8 * c->sm_count) {
+            bound[1] = (size_t)3 * c->sm_count;
+            // tunable "proof_pieces" (2..4): further pieces of 2x, 3x .. the first one.  The evaluation kernels need a whole SM's registers per
+            // CTA, so a piece's evaluation only starts when the previous piece's MSM has drained: smaller later pieces expose less of it.
+            for (int q = 2; q < g_proof_pieces && q < KZG_H2D_PIECES; ++q) {
+                const size_t nxt = bound[q - 1] + (size_t)q * 3 * c->sm_count;
+                if (nxt + (size_t)3 * c->sm_count >= m) break;
+                bound[q] = nxt;
+            }
+        }
         const bool split = bound[1] < m;
         if (split) CU(cudaEventRecord(c->ev_fork, c->stream));         // staged aux input and cleared status are visible to the side streams
         for (size_t pc = 0; pc < KZG_H2D_PIECES && bound[pc] < m; ++pc) {

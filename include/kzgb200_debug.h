@@ -67,6 +67,7 @@ int kzgb200_dbg_g1_level_term(int form, int level, int o, int j, int *src, int *
  *   "verify_overlap": 1 (default) = the cell verifier's interpolation chain runs on a side stream beside the proofs' decode, 0 = one stream
  *   "g1_two_level_max": chunks of up to this many blobs take the two-level (16 x 8) G1 transform instead of the staged one (-1 = default 32, 0 = never)
  *   "g1_chain4_max": chunks above g1_two_level_max and up to this many blobs take the 4 x 4 x 4 x 2 G1 transform (-1 = default 64, 0 = never)
+ *   "proof_pieces": 2..4 (default 3) = pieces the host-buffer ComputeKZGProof / ComputeBlobKZGProof paths cut their input into
  *   "rlc_item": run length of the EIP-4844 batch verdict's bucket-MSM work items (0 = default 128) */
 int kzgb200_dbg_set_tunable(const char *name, int v);
 /* dependency-free integer multiply-add microbenchmark: device-wide instructions*lanes per second.
