@@ -1054,10 +1054,17 @@ int lane_recover_cells_and_kzg_proofs(kzg_lane *c, const uint64_t *cell_ids, con
         k_inv_combine<<<dim3(4096 / 256, (unsigned)m), 256, 0, c->stream>>>(A, (Fr *)c->coeffs.p, d_status, c->roots, c->ipow7, inv8192, 0);
         k_cells_from_coeffs<<<dim3(2, (unsigned)m), KZG_NTT_THREADS, 4096 * 32, c->stream>>>((const Fr *)c->coeffs.p, d_cells, d_status, c->roots);
         c->launches += 8;
+        // the cells are final here: their D2H (the bulk of the output bytes) runs on the copy stream underneath the FK20 kernels, as in cells_and_proofs
+        if (!cells_dev) {
+            CU(cudaEventRecord(c->ev0, c->stream));
+            CU(cudaStreamWaitEvent(c->copy_stream, c->ev0, 0));
+            CU(cudaMemcpyAsync(out_cells + off * 262144, d_cells, m * 262144, cudaMemcpyDeviceToHost, c->copy_stream));
+            CU(cudaEventRecord(c->ev1, c->copy_stream));
+        }
         if (out_proofs) launch_fk20_proofs(c, c->stream, m, (const Fr *)c->coeffs.p, (uint32_t *)c->scalars.p, (G1 *)c->sums.p, (G1 *)c->proofs_xyzz.p, d_status, d_proofs, true);
         c->mark(-1);
         CU(cudaGetLastError());
-        if (!cells_dev) CU(cudaMemcpyAsync(out_cells + off * 262144, d_cells, m * 262144, cudaMemcpyDeviceToHost, c->stream));
+        if (!cells_dev) CU(cudaStreamWaitEvent(c->stream, c->ev1, 0));      // (also: the staging buffer is reused by the next chunk)
         if (out_proofs && !proofs_dev) CU(cudaMemcpyAsync(out_proofs + off * 6144, d_proofs, m * 6144, cudaMemcpyDeviceToHost, c->stream));
         if (!st_dev) CU(cudaMemcpyAsync(status + off, d_status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
