@@ -702,8 +702,21 @@ static int open_common(kzg_lane *c, const uint8_t *blobs, const uint8_t *z32, co
         // piece (latency-bound: one thread per SHA-256) runs on a side stream, under the previous piece's MSM.
         const bool in_dev = is_device_ptr(blobs);
         if (!in_dev && (rc = c->in_bytes.ensure(m * KZGB200_BYTES_PER_BLOB))) return rc;
-        if (z32) { if ((rc = stage_in(c, z32 + off * 32, m * 32, c->in_small, &d_aux))) return rc; }
-        else { if ((rc = stage_in(c, commitments + off * 48, m * 48, c->in_small, &d_aux))) return rc; }
+        {
+            // host blobs: the small input travels on the COPY stream ahead of the blob pieces and the main stream waits for it through an event.
+            // Queued on the main stream it was observed to complete only after the blob pieces queued behind it on the copy stream, which
+            // held back ev_fork and with it every piece's hash (kzgb200_verify.cu: verify_front has the measurement).
+            const void *src = z32 ? (const void *)(z32 + off * 32) : (const void *)(commitments + off * 48);
+            const size_t bytes = m * (z32 ? 32 : 48);
+            if (in_dev || is_device_ptr(src)) { if ((rc = stage_in(c, src, bytes, c->in_small, &d_aux))) return rc; }
+            else {
+                if ((rc = c->in_small.ensure(bytes))) return rc;
+                CU(cudaMemcpyAsync(c->in_small.p, src, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+                CU(cudaEventRecord(c->ev0, c->copy_stream));
+                CU(cudaStreamWaitEvent(c->stream, c->ev0, 0));
+                d_aux = c->in_small.p;
+            }
+        }
         int32_t *d_status = st_dev ? status + off : (int32_t *)c->status.p;
         uint8_t *d_out = out_dev ? out_proof + off * 48 : (uint8_t *)c->out_bytes.p;
         uint8_t *d_y = !out_y ? nullptr : y_dev ? out_y + off * 32 : (uint8_t *)c->ybuf.p;

@@ -9,6 +9,8 @@
 #include "ctx.cuh"
 #include "verify.cuh"
 #include "cell_plan.hpp"
+#include <chrono>
+#include <cstdio>
 
 namespace kzg {
 static __global__ void k_dbg_g1_mul(const uint8_t *p48, const uint8_t *s32, uint8_t *out48, int n) {
@@ -38,6 +40,14 @@ static __global__ void k_dbg_dump_pairing(const PairingConsts *pc, uint32_t *out
 }
 }  // namespace kzg
 
+// KZGB200_TRACE=1: host wall-clock (ms since the first call) at a few points of the verifiers, to stderr
+static inline void trace_pt(const char *what) {
+    static const bool on = [] { const char *e = getenv("KZGB200_TRACE"); return e && *e == '1'; }();
+    if (!on) return;
+    static const auto t0 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[kzgb200 trace] %9.3f ms  %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), what);
+}
+
 extern "C" {
 
 // -------------------------------------------------------------------------------------------
@@ -57,9 +67,24 @@ static int verify_front(kzg_lane *c, const uint8_t *blobs, const uint8_t *cm48, 
                         size_t m, int32_t *d_status, G1Aff *out_cm, G1Aff *out_pf, uint32_t *zl, uint32_t *yl) {
     int rc;
     const void *d_cm, *d_pf, *d_z = nullptr, *d_y = nullptr;
-    if ((rc = stage_in(c, cm48, m * 48, c->in_small, &d_cm))) return rc;
-    if ((rc = stage_in(c, pf48, m * 48, c->in_small2, &d_pf))) return rc;
+    trace_pt("verify_front: begin");
     const bool blobs_host = blobs && !is_device_ptr(blobs);
+    // With host blobs, the small inputs travel on the COPY stream ahead of the blob pieces and the main stream waits for them through an
+    // event: queued on the main stream they were observed to complete only after the 0.5 GB of blob pieces queued behind them on the copy
+    // stream (KZGB200_TRACE), which held back the event every side stream waits for -- no hashing under the H2D at all.
+    cudaStream_t s_small = blobs_host ? c->copy_stream : c->stream;
+    auto stage_small = [&](const void *user, size_t bytes, DevBuf &buf, const void **dev) -> int {
+        if (bytes == 0) { *dev = buf.p; return 0; }
+        if (is_device_ptr(user)) { *dev = user; return 0; }
+        int r = buf.ensure(bytes);
+        if (r) return r;
+        CU(cudaMemcpyAsync(buf.p, user, bytes, cudaMemcpyHostToDevice, s_small));
+        *dev = buf.p;
+        return 0;
+    };
+    if ((rc = stage_small(cm48, m * 48, c->in_small, &d_cm))) return rc;
+    if ((rc = stage_small(pf48, m * 48, c->in_small2, &d_pf))) return rc;
+    if (blobs_host) { CU(cudaEventRecord(c->ev0, c->copy_stream)); CU(cudaStreamWaitEvent(c->stream, c->ev0, 0)); }
     const size_t piece = blobs_host ? ((m + VERIFY_MAX_PIECES - 1) / VERIFY_MAX_PIECES + 31) & ~(size_t)31 : m;
     const size_t n_pieces = blobs ? (m + piece - 1) / piece : 0;
     if (blobs_host) {
@@ -71,6 +96,7 @@ static int verify_front(kzg_lane *c, const uint8_t *blobs, const uint8_t *cm48, 
             CU(cudaEventRecord(c->ev_piece[p], c->copy_stream));
         }
     }
+    trace_pt("verify_front: blob pieces queued");
     if (!blobs) {
         if ((rc = stage_in(c, z32, m * 32, c->v_in2, &d_z))) return rc;
         if ((rc = stage_in(c, y32, m * 32, c->v_in3, &d_y))) return rc;
@@ -125,6 +151,7 @@ static int verify_front(kzg_lane *c, const uint8_t *blobs, const uint8_t *cm48, 
         k_status_merge<<<gb, 64, 0, c->stream>>>(d_status, d_blob_status, m);      // commitment / proof errors come first (verify.go:102-119)
         c->launches += 1;
     }
+    trace_pt("verify_front: all queued");
     return 0;
 }
 
@@ -226,6 +253,7 @@ int lane_verify_blob_kzg_proof_batch(kzg_lane *c, const uint8_t *blobs, const ui
         if ((rc = verify_front(c, blobs + off * KZGB200_BYTES_PER_BLOB, cm48 + off * 48, nullptr, nullptr, pf48 + off * 48, m, (int32_t *)c->status.p + off,
                                d_cm_aff + off, d_pf_aff + off, (uint32_t *)c->zbuf.p + off * 8, (uint32_t *)c->ybuf.p + off * 8))) return rc;
         CU(cudaStreamSynchronize(c->stream));
+        trace_pt("batch: front synchronised");
     }
     std::vector<int32_t> h_status(n);
     CU(cudaMemcpyAsync(h_status.data(), c->status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
