@@ -28,6 +28,8 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
+#include <atomic>
+#include <thread>
 
 using namespace kzg;
 
@@ -79,8 +81,13 @@ struct InitTemps {
     ~InitTemps() { for (void *p : ptrs) if (p) cudaFree(p); }
 };
 
+// A gate between two lanes of one GPU (kzgb200_api.cu: tail overlap of the cell verifier): the first lane records `ev` on its main stream once its
+// long decode kernel is queued, the second lane makes its kernel streams wait for it.  state: 0 = nothing yet, 1 = ev recorded, 2 = released without one.
+struct LaneGate { cudaEvent_t ev = nullptr; std::atomic<int> state{0}; };
+
 #define KZG_G1FFT_MAX_SPLIT 8
 struct kzg_lane {
+    LaneGate *gate_signal = nullptr, *gate_wait = nullptr;      // set by the public layer around ONE call, consumed by lane_verify_cell_kzg_proof_batch
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_piece[8] = {nullptr};

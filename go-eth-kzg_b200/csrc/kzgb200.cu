@@ -358,6 +358,16 @@ int kzgb200_dbg_set_tunable(const char *name, int v) {
         kzg::g_proof_pieces = v;
         return 0;
     }
+    if (!strcmp(name, "tail_split")) {
+        if (v != 0 && v != 1) return set_err(KZGB200_ERR_ARGS, "tail_split must be 0 or 1");
+        kzg::g_tail_split = v;
+        return 0;
+    }
+    if (!strcmp(name, "tail_min_cells")) {
+        if (v < 16) return set_err(KZGB200_ERR_ARGS, "tail_min_cells out of range");
+        kzg::g_tail_min_cells = v;
+        return 0;
+    }
     if (!strcmp(name, "rlc_item")) {
         if (v < 0 || v > 4096) return set_err(KZGB200_ERR_ARGS, "rlc_item out of range");
         kzg::g_rlc_item = v;

@@ -349,28 +349,82 @@ int kzgb200_verify_cell_kzg_proof_batch(kzgb200_ctx *ctx, const uint8_t *commitm
     if (pin == -2) return set_err(KZGB200_ERR_ARGS, "a device buffer lives on a GPU that is not part of this context");
     const size_t n_dev = ctx->devs.size();
     const bool may_split = pin < 0 && n_dev > 1 && ctx->split.verify_cells > 0;
-    if (may_split && nb == 1 && N >= 2 * ctx->split.verify_cells) {
-        // one large verdict: contiguous cell ranges, one sub-verdict per GPU
-        std::vector<ShardRange> rg = shard_units(N, n_dev, ctx->split.verify_cells);
-        std::vector<int32_t> sub(rg.size(), KZGB200_OK);
-        int rc = run_ranges(ctx, rg, -1, [&](kzg_lane *l, size_t i, ShardRange r) {
-            const uint64_t off[2] = {0, r.hi - r.lo};
-            return lane_verify_cell_kzg_proof_batch(l, commitments48 + r.lo * 48, cell_indices + r.lo, cells + r.lo * 2048, proofs48 + r.lo * 48, r.hi - r.lo, off, 1, &sub[i]);
-        });
-        if (rc) return rc;
-        results[0] = merge_sub_verdicts(sub.data(), sub.size());
-        return KZGB200_OK;
-    }
+    const bool one = nb == 1;          // one verdict: the units below are CELLS (sub-verdicts merged at the end), else VERDICTS
+    // ---- shares: one per GPU (host buffers, several GPUs), else the whole call on the GPU that owns the buffers / the next in rotation
     std::vector<ShardRange> rg;
-    if (may_split && nb > 1) rg = shard_verdicts(batch_offsets, nb, n_dev, ctx->split.verify_cells);
-    else rg.assign(1, ShardRange{0, nb});
-    return run_ranges(ctx, rg, pin, [&](kzg_lane *l, size_t, ShardRange r) {
-        const uint64_t c0 = batch_offsets[r.lo], c1 = batch_offsets[r.hi];
-        if (c0 == 0) return lane_verify_cell_kzg_proof_batch(l, commitments48, cell_indices, cells, proofs48, c1, batch_offsets + r.lo, r.hi - r.lo, results + r.lo);
-        std::vector<uint64_t> off(r.hi - r.lo + 1);
-        for (size_t b = r.lo; b <= r.hi; ++b) off[b - r.lo] = batch_offsets[b] - c0;
-        return lane_verify_cell_kzg_proof_batch(l, commitments48 + c0 * 48, cell_indices + c0, cells + c0 * 2048, proofs48 + c0 * 48, c1 - c0, off.data(), r.hi - r.lo, results + r.lo);
-    });
+    if (may_split && one && N >= 2 * ctx->split.verify_cells) rg = shard_units(N, n_dev, ctx->split.verify_cells);
+    else if (may_split && !one) rg = shard_verdicts(batch_offsets, nb, n_dev, ctx->split.verify_cells);
+    else rg.assign(1, ShardRange{0, one ? N : nb});
+    const size_t solo_dev = pin >= 0 ? (size_t)pin : (n_dev == 1 ? 0 : ctx->rr.fetch_add(1) % n_dev);
+    // ---- tail overlap: a share of >= 128 Ki cells is cut once more, 7/8 + 1/8, onto two lanes of the SAME GPU.  The verdict of a big share ends in
+    // ~8 ms of dependent chains (Horner over the windows, column twiddles, one pairing) during which the GPU idles; the small part's kernels are
+    // gated behind the big part's decode (LaneGate) and fill exactly that time.  MEASURED on 524 288 cells: 47.35 ms against 47.2 ms on one lane --
+    // the small part's decode saturates the multiply pipe of every SM, and the big part's one-warp chains, sharing schedulers with it, stretch by
+    // as much as the overlap saves (vmsm class 11.2 -> 15.5 ms).  Kept behind the tunable "tail_split" (default OFF) with its test.
+    struct Part { size_t dev; ShardRange r; LaneGate *sig, *wait; };
+    std::vector<Part> parts;
+    std::vector<std::unique_ptr<LaneGate>> gates;
+    auto cells_of = [&](const ShardRange &r) { return one ? (uint64_t)(r.hi - r.lo) : batch_offsets[r.hi] - batch_offsets[r.lo]; };
+    for (size_t i = 0; i < rg.size(); ++i) {
+        const size_t dev = rg.size() > 1 ? i % n_dev : solo_dev;
+        const ShardRange r = rg[i];
+        size_t cut = r.hi;
+        if (kzg::g_tail_split && ctx->lanes_per_dev >= 2 && cells_of(r) >= (uint64_t)kzg::g_tail_min_cells) {
+            if (one) cut = r.lo + (r.hi - r.lo) / 8 * 7;
+            else {
+                const uint64_t target = batch_offsets[r.lo] + cells_of(r) / 8 * 7;
+                cut = (size_t)(std::lower_bound(batch_offsets + r.lo, batch_offsets + r.hi, target) - batch_offsets);
+            }
+        }
+        if (cut > r.lo && cut < r.hi) {
+            gates.emplace_back(new LaneGate());
+            cudaSetDevice(ctx->devs[dev]->device);
+            if (cudaEventCreateWithFlags(&gates.back()->ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); gates.back()->state = 2; }
+            parts.push_back({dev, {r.lo, cut}, gates.back().get(), nullptr});
+            parts.push_back({dev, {cut, r.hi}, nullptr, gates.back().get()});
+        } else parts.push_back({dev, r, nullptr, nullptr});
+    }
+    std::vector<int32_t> sub(parts.size(), KZGB200_OK);
+    std::vector<int> rcs(parts.size(), 0);
+    std::vector<std::string> errs(parts.size());
+    std::vector<kzg_lane *> used(parts.size(), nullptr);
+    auto body = [&](size_t i) {
+        const Part &p = parts[i];
+        LaneRef ref(ctx->devs[p.dev].get());
+        kzg_lane *l = ref.l;
+        used[i] = l;
+        l->gate_signal = p.sig; l->gate_wait = p.wait;
+        if (one) {
+            const uint64_t off[2] = {0, p.r.hi - p.r.lo};
+            rcs[i] = lane_verify_cell_kzg_proof_batch(l, commitments48 + p.r.lo * 48, cell_indices + p.r.lo, cells + p.r.lo * 2048, proofs48 + p.r.lo * 48,
+                                                      p.r.hi - p.r.lo, off, 1, rg.size() == 1 && parts.size() == 1 ? results : &sub[i]);
+        } else {
+            const uint64_t c0 = batch_offsets[p.r.lo], c1 = batch_offsets[p.r.hi];
+            std::vector<uint64_t> off(p.r.hi - p.r.lo + 1);
+            for (size_t b = p.r.lo; b <= p.r.hi; ++b) off[b - p.r.lo] = batch_offsets[b] - c0;
+            rcs[i] = lane_verify_cell_kzg_proof_batch(l, commitments48 + c0 * 48, cell_indices + c0, cells + c0 * 2048, proofs48 + c0 * 48, c1 - c0, off.data(),
+                                                      p.r.hi - p.r.lo, results + p.r.lo);
+        }
+        l->gate_signal = nullptr; l->gate_wait = nullptr;
+        if (p.sig && p.sig->state.load() == 0) p.sig->state.store(2);          // the big part ended without queueing its decode: release the small one
+        if (rcs[i]) { errs[i] = kzgb200_err_slot(); lane_quiesce(l); }
+    };
+    {
+        std::vector<std::thread> th;
+        for (size_t i = 1; i < parts.size(); ++i) th.emplace_back(body, i);
+        body(0);
+        for (auto &t : th) t.join();
+    }
+    for (auto &g : gates) if (g->ev) cudaEventDestroy(g->ev);
+    record(ctx, used);
+    for (size_t i = 0; i < parts.size(); ++i) if (rcs[i]) { kzgb200_err_slot() = errs[i]; return rcs[i]; }
+    if (one && parts.size() > 1) {
+        // sub-verdicts of ONE verdict (each with its own random coefficients), merged in index order
+        const int32_t merged = merge_sub_verdicts(sub.data(), sub.size());
+        if (ptr_device(results) >= 0) { if (cudaMemcpy(results, &merged, sizeof merged, cudaMemcpyHostToDevice) != cudaSuccess) return set_err(KZGB200_ERR_CUDA, "cudaMemcpy(result)"); }
+        else results[0] = merged;
+    }
+    return KZGB200_OK;
 }
 
 int kzgb200_check_g1_points(kzgb200_ctx *ctx, const uint8_t *points48, size_t n, int32_t *status) {

@@ -319,6 +319,17 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
             c->timing_reset();
         }
     }
+    // ---- gate (tail overlap, kzgb200_api.cu): this call is the SMALL part of a share that was cut in two on one GPU; its kernels wait until the
+    // big part's decode has run, so that they fill the GPU while the big part walks its latency-bound tails (Horner, column twiddles, pairing)
+    if (c->gate_wait) {
+        LaneGate *g = c->gate_wait;
+        c->gate_wait = nullptr;                                     // consumed: the optimistic inner call / the exact pass do not wait again
+        while (g->state.load(std::memory_order_acquire) == 0) std::this_thread::yield();
+        if (g->state.load(std::memory_order_acquire) == 1) {
+            CU(cudaStreamWaitEvent(c->stream, g->ev, 0));
+            CU(cudaStreamWaitEvent(c->aux_stream, g->ev, 0));
+        }
+    }
     // ---- device first: the proofs' decode + subgroup check (the longest kernel of the call) needs nothing from
     // the host bookkeeping below, and the cells' H2D rides the copy stream meanwhile ------------------
     const void *d_cells = cells, *d_proofs = nullptr;
@@ -329,6 +340,10 @@ int lane_verify_cell_kzg_proof_batch(kzg_lane *c, const uint8_t *commitments48, 
     if ((rc = stage_in(c, proofs48, N * 48, c->in_small, &d_proofs))) return rc;
     CU(cudaMemsetAsync(d_cst, 0, std::max<size_t>(N, 1) * 4, c->stream));
     if ((rc = vm_g1_check(c->stream, (const uint8_t *)d_proofs, (G1Aff *)c->v_aff2.p, d_cst, N, 1, 1))) return rc;
+    if (c->gate_signal && c->gate_signal->state.load(std::memory_order_acquire) == 0) {      // the BIG part: its decode is queued
+        CU(cudaEventRecord(c->gate_signal->ev, c->stream));
+        c->gate_signal->state.store(1, std::memory_order_release);
+    }
     if (N && !is_device_ptr(cells)) {
         if ((rc = c->in_bytes.ensure(N * 2048))) return rc;
         // (every entry point ends with a stream synchronise under the context lock, so the staging buffer is free)

@@ -285,6 +285,8 @@ inline int g_decode_minb = 4;                 // kzgb200_dbg_set_tunable("decode
 inline int g_g1_two_level_max = -1;           // kzgb200_dbg_set_tunable("g1_two_level_max", n): chunks of up to n blobs take the two-level G1 transform (g1fft.cuh); -1 = context default, 0 = never
 inline int g_g1_chain4_max = -1;              // kzgb200_dbg_set_tunable("g1_chain4_max", n): chunks of up to n blobs (above g1_two_level_max) take the 4 x 4 x 4 x 2 G1 transform; -1 = context default, 0 = never
 inline int g_proof_pieces = 3;                // kzgb200_dbg_set_tunable("proof_pieces", 2..4): H2D pieces of the host-buffer ComputeKZGProof / ComputeBlobKZGProof paths; measured per 4096 blobs: 2 -> 118.4, 3 -> 109.3, 4 -> 110.3 ms
+inline int g_tail_split = 0;                  // kzgb200_dbg_set_tunable("tail_split", 0 | 1): see kzgb200_verify_cell_kzg_proof_batch (kzgb200_api.cu).  MEASURED: no gain (47.35 vs 47.2 ms), default off
+inline int g_tail_min_cells = 128 << 10;        // kzgb200_dbg_set_tunable("tail_min_cells", n): smallest share the tail overlap cuts in two (tests lower it)
 inline int g_rlc_item = 0;                    // kzgb200_dbg_set_tunable("rlc_item", n): run length of the EIP-4844 batch verdict's bucket MSM work items; 0 = default
 inline int g_g1fft_split_override = 0;        // kzgb200_dbg_set_tunable("g1fft_split", k): sub-batches (streams) of the staged G1 FFT; 0 = context default
 inline int g_pairing_lanes = 0;               // kzgb200_dbg_set_tunable("pairing_lanes", 0 | 8 | 32): see vm_pairing_check (kzgb200_vmsm.cu)

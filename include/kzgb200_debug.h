@@ -68,6 +68,9 @@ int kzgb200_dbg_g1_level_term(int form, int level, int o, int j, int *src, int *
  *   "g1_two_level_max": chunks of up to this many blobs take the two-level (16 x 8) G1 transform instead of the staged one (-1 = default 32, 0 = never)
  *   "g1_chain4_max": chunks above g1_two_level_max and up to this many blobs take the 4 x 4 x 4 x 2 G1 transform (-1 = default 64, 0 = never)
  *   "proof_pieces": 2..4 (default 3) = pieces the host-buffer ComputeKZGProof / ComputeBlobKZGProof paths cut their input into
+ *   "tail_split": 1 = a share of >= "tail_min_cells" cells of VerifyCellKZGProofBatch is cut 7/8 + 1/8 onto two lanes of its GPU, the small part gated
+ *                  behind the big part's decode so that it runs during the big part's latency-bound tails; 0 (default: measured, no gain) = one lane per share
+ *   "tail_min_cells": smallest share (in cells) that "tail_split" cuts in two (default 131072)
  *   "rlc_item": run length of the EIP-4844 batch verdict's bucket-MSM work items (0 = default 128) */
 int kzgb200_dbg_set_tunable(const char *name, int v);
 /* dependency-free integer multiply-add microbenchmark: device-wide instructions*lanes per second.

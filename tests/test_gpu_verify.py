@@ -293,3 +293,32 @@ def test_large_verdict_window_variants_agree(ctx):
             assert ctx.verify_cell_kzg_proof_batches(commitments, idx, cells, bad, [0, 4096, n]) == [1, 0]
         finally:
             ctx.L.kzgb200_dbg_set_tunable(b"large_window", 4)
+
+
+def test_tail_overlap_split_agrees_with_one_lane(ctx):
+    """(an option, off by default: measured without gain) a big share of VerifyCellKZGProofBatch is cut 7/8 + 1/8 onto two lanes of one GPU, the small part gated behind the big part's decode
+    (kzgb200_api.cu, LaneGate).  With the threshold lowered so that 10 240 cells are cut (8 960 + 1 280: the big part still takes the optimistic pass), results must equal the one-lane results: many verdicts
+    (all valid; a false verdict in the big part; one in the small part; an error) and one large verdict (valid, false in either part)."""
+    nblob = 80
+    blobs = [oracle_lib.rand_blob((600 + b) << 20) for b in range(nblob)]
+    cms = [c for _, c in ctx.blob_to_kzg_commitment_batch(blobs)]
+    full = ctx.compute_cells_and_kzg_proofs_batch(blobs)
+    commitments, idx, cells, proofs = [], [], [], []
+    for b, (st, cl, pr) in enumerate(full):
+        for i in range(128):
+            commitments.append(cms[b]); idx.append(i); cells.append(cl[2048 * i:2048 * (i + 1)]); proofs.append(pr[48 * i:48 * (i + 1)])
+    n = len(cells)
+    offs = [128 * b for b in range(nblob + 1)]
+    bad_big = list(proofs); bad_big[128 * 10 + 3] = proofs[128 * 10 + 4]
+    bad_small = list(cells); bad_small[128 * 78 + 100] = cells[128 * 78 + 99]            # verdict 78 of 80 lies in the last eighth (the cut is at verdict 70)
+    bad_enc = list(proofs); bad_enc[128 * 79 + 5] = bytes([0xff]) * 48
+    cases = [(proofs, cells, {}), (bad_big, cells, {10: 1}), (proofs, bad_small, {78: 1}), (bad_enc, cells, {79: 3}), (bad_big, bad_small, {10: 1, 78: 1})]
+    for tail in (1, 0):
+        assert ctx.L.kzgb200_dbg_set_tunable(b"tail_split", tail) == 0 and ctx.L.kzgb200_dbg_set_tunable(b"tail_min_cells", 2048) == 0
+        try:
+            for pr_, ce_, want in cases:
+                assert ctx.verify_cell_kzg_proof_batches(commitments, idx, ce_, pr_, offs) == [want.get(b, 0) for b in range(nblob)], (tail, want)
+                one = ctx.verify_cell_kzg_proof_batches(commitments, idx, ce_, pr_, [0, n])
+                assert one == [max(want.values()) if want else 0] or (3 in want.values() and one == [3]), (tail, want, one)
+        finally:
+            ctx.L.kzgb200_dbg_set_tunable(b"tail_split", 0); ctx.L.kzgb200_dbg_set_tunable(b"tail_min_cells", 128 << 10)
